@@ -400,7 +400,8 @@ def evaluate_pipeline(params, news_tokens, hist_rows, cand_offsets, cand_rows, l
     D = params[EMB_KEY].shape[1]
     table = np.zeros((Nn + 1, D), dtype=params[EMB_KEY].dtype)  # last row = PADDED_NEWS
     for s in range(0, Nn, batch):
-        table[s:s + batch] = news_encoder_forward(params, news_tokens[s:s + batch], num_heads)[0]
+        e = min(s + batch, Nn)
+        table[s:e] = news_encoder_forward(params, news_tokens[s:e], num_heads)[0]
     if news_owner is not None:
         table[:Nn] = table[news_owner]
     I = hist_rows.shape[0]
