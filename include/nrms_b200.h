@@ -1,0 +1,159 @@
+/*
+ * nrms_b200.h -- C-ABI of the B200-native NRMS hot path (libnrms_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry
+ * point replaces the PyTorch op sequence of one reference function (file:line relative
+ * to the reference tree, Maguire1999/NewsRecommendationSystem):
+ *
+ *   nrms_news_encoder_fwd/bwd   NewsEncoder.forward            src/model/NRMS/news_encoder.py:27-48
+ *   nrms_user_encoder_fwd/bwd   UserEncoder.forward            src/model/NRMS/user_encoder.py:15-26
+ *       (both = MultiHeadSelfAttention.forward  src/model/general/attention/multihead_self.py:46-76,
+ *               ScaledDotProductAttention.forward :15-23,
+ *               AdditiveAttention.forward        src/model/general/attention/additive.py:27-53)
+ *   nrms_score_fwd/bwd          DotProductClickPredictor.forward  src/model/general/click_predictor/dot_product.py:8-19
+ *   nrms_score_csr              the per-impression get_prediction loop   src/evaluate.py:245-260
+ *   nrms_ce_loss_fwd_bwd        CrossEntropyLoss(y_pred, zeros)    src/train.py:126,205-206
+ *   nrms_adam_step              torch.optim.Adam(lr=1e-4).step()   src/train.py:127-128,233 (AdamW: decoupled=1)
+ *   nrms_rank_metrics           calculate_single_user_metric + nanmean  src/evaluate.py:24-42,160-168,270-272
+ *
+ * Conventions
+ *   - All pointers are DEVICE pointers unless the name ends in _host.  Buffers are
+ *     caller-owned (torch-allocated); the library never frees or keeps a pointer after
+ *     the call returns.  All fp32 row pointers must be 16-byte aligned.
+ *   - Calls are asynchronous on `stream` (a cudaStream_t passed as void*); no call syncs.
+ *   - Return value: 0 = ok, nonzero = error (NRMS_E_*); text via nrms_last_error()
+ *     (thread-local).  No exception crosses the ABI.  There is no CPU fallback.
+ *   - Model dimensions are compile-time: D=300, H=15 (d_k=d_v=20), query dim 200
+ *     (src/config.py:14-45); sequence length S is 20 (titles) or 50 (click history).
+ *   - Packed weights: wqkv = rows [W_Q; W_K; W_V] -> [900,300] (nn.Linear "out,in" layout),
+ *     bqkv [900], wa [200,300], ba [200], qa [200].
+ */
+#ifndef NRMS_B200_H
+#define NRMS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRMS_D 300
+#define NRMS_H 15
+#define NRMS_DH 20
+#define NRMS_QD 200
+
+enum {
+  NRMS_OK = 0,
+  NRMS_E_INVALID = 1,     /* bad argument / null pointer / misaligned */
+  NRMS_E_UNSUPPORTED = 2, /* shape not supported by the compiled kernels */
+  NRMS_E_WORKSPACE = 3,   /* workspace / stash too small */
+  NRMS_E_CUDA = 4         /* CUDA runtime error (launch failure etc.) */
+};
+
+/* arithmetic mode of the dense contractions */
+enum {
+  NRMS_MODE_FP32 = 0, /* CUDA-core FFMA everywhere: reference-exact fp32 (up to summation order) */
+  NRMS_MODE_TF32 = 1  /* tcgen05 kind::tf32 projections (operands rounded to TF32, fp32 accumulate in TMEM) */
+};
+
+const char* nrms_last_error(void);
+int nrms_abi_version(void);
+
+/* ---- sizes ------------------------------------------------------------------------- */
+/* Bytes of the saved-for-backward stash of one encoder call over n_seq sequences of length S
+ * (X, QKV, C, T, w).  The same stash is written by *_fwd (when non-NULL) and read by *_bwd. */
+size_t nrms_encoder_stash_bytes(int64_t n_seq, int S);
+/* Scratch bytes for one encoder fwd / bwd call (mode-dependent). */
+size_t nrms_encoder_fwd_workspace_bytes(int64_t n_seq, int S, int mode, int training);
+size_t nrms_encoder_bwd_workspace_bytes(int64_t n_seq, int S, int mode);
+
+/* ---- encoders ---------------------------------------------------------------------- */
+/* News encoder forward: tokens int64 [n_titles, L] -> out fp32 [n_titles, 300].
+ * emb: [num_words, 300].  stash: NULL for inference, else nrms_encoder_stash_bytes bytes.
+ * dropout_p in [0,1): 0 = eval mode.  (seed, offset) key the in-kernel Philox stream. */
+int nrms_news_encoder_fwd(const int64_t* tokens, int64_t n_titles, int L,
+                          const float* emb, int64_t num_words,
+                          const float* wqkv, const float* bqkv,
+                          const float* wa, const float* ba, const float* qa,
+                          float* out, void* stash,
+                          void* workspace, size_t workspace_bytes,
+                          float dropout_p, uint64_t seed, uint64_t offset,
+                          int mode, void* stream);
+
+/* News encoder backward.  d_out [n_titles,300].  Gradients are ACCUMULATED (+=) into
+ * d_emb [num_words,300] (row 0 = padding_idx is never touched), d_wqkv [900,300],
+ * d_bqkv [900], d_wa [200,300], d_ba [200], d_qa [200]. */
+int nrms_news_encoder_bwd(const float* d_out, const int64_t* tokens, int64_t n_titles, int L,
+                          int64_t num_words,
+                          const float* wqkv, const float* wa, const float* qa,
+                          const void* stash,
+                          float* d_emb, float* d_wqkv, float* d_bqkv,
+                          float* d_wa, float* d_ba, float* d_qa,
+                          void* workspace, size_t workspace_bytes,
+                          float dropout_p, uint64_t seed, uint64_t offset,
+                          int mode, void* stream);
+
+/* User encoder forward.  Input rows are either dense x [n_users, S, 300] (rows == NULL) or
+ * gathered from a table: x = table [n_rows,300], rows int32 [n_users, S] (evaluate.py:220-224;
+ * the PADDED_NEWS zero vector is a zero row of the table). */
+int nrms_user_encoder_fwd(const float* x, const int32_t* rows, int64_t n_users, int S,
+                          const float* wqkv, const float* bqkv,
+                          const float* wa, const float* ba, const float* qa,
+                          float* out, void* stash,
+                          void* workspace, size_t workspace_bytes,
+                          int mode, void* stream);
+
+/* User encoder backward (dense input only).  d_x [n_users,S,300] is OVERWRITTEN; weight
+ * gradients are accumulated (+=). */
+int nrms_user_encoder_bwd(const float* d_out, int64_t n_users, int S,
+                          const float* wqkv, const float* wa, const float* qa,
+                          const void* stash,
+                          float* d_x, float* d_wqkv, float* d_bqkv,
+                          float* d_wa, float* d_ba, float* d_qa,
+                          void* workspace, size_t workspace_bytes,
+                          int mode, void* stream);
+
+/* ---- click predictor --------------------------------------------------------------- */
+/* scores[b,c] = cand[b,c,:] . user[b,:]     cand [B,C,X], user [B,X] */
+int nrms_score_fwd(const float* cand, const float* user, int64_t B, int C, int X,
+                   float* scores, void* stream);
+/* d_cand [B,C,X] and d_user [B,X] are overwritten. */
+int nrms_score_bwd(const float* d_scores, const float* cand, const float* user,
+                   int64_t B, int C, int X, float* d_cand, float* d_user, void* stream);
+/* CSR form used by evaluate: impression i owns candidates [offsets[i], offsets[i+1]);
+ * scores[k] = table[cand_rows[k], :] . user_vec[i, :]   (X = 300). */
+int nrms_score_csr(const float* table, const int32_t* cand_rows, const int64_t* offsets,
+                   const float* user_vec, int64_t n_impressions, float* scores, void* stream);
+
+/* ---- loss / optimizer --------------------------------------------------------------- */
+/* loss = mean_b( -log_softmax(logits[b,:])[0] ); d_logits = d(loss)/d(logits) * grad_scale. */
+int nrms_ce_loss_fwd_bwd(const float* logits, int64_t B, int C, float grad_scale,
+                         float* loss, float* d_logits, void* stream);
+/* One Adam/AdamW update over n contiguous elements.  step is 1-based.  grad_scale multiplies
+ * g first (1/world_size for data-parallel averaging).  decoupled=1 -> AdamW. */
+int nrms_adam_step(float* p, const float* g, float* m, float* v, int64_t n,
+                   float lr, float beta1, float beta2, float eps, float weight_decay,
+                   int decoupled, int64_t step, float grad_scale, void* stream);
+
+/* ---- evaluate helpers ---------------------------------------------------------------- */
+/* Row gather: dst[i,:] = src[rows[i],:] (width floats per row, width % 4 == 0). */
+int nrms_gather_rows(const float* src, const int64_t* rows, int64_t n, int width,
+                     float* dst, void* stream);
+/* Per-impression AUC / MRR / nDCG@5 / nDCG@10 (fp64) on CSR (labels int8 in {0,1});
+ * single-class impressions give NaN x4.  per_impression [n,4] (may be NULL);
+ * sums_counts [8] = {sum auc, mrr, ndcg5, ndcg10, count auc, mrr, ndcg5, ndcg10} over non-NaN
+ * rows (nanmean numerators/denominators), overwritten. */
+int nrms_rank_metrics(const float* scores, const int8_t* labels, const int64_t* offsets,
+                      int64_t n_impressions, double* per_impression, double* sums_counts,
+                      void* stream);
+
+/* ---- generic dense contraction (exposed for tests / profiling) ---------------------- */
+/* C[M,N] = A[M,K] * B[N,K]^T (+ bias[N] if non-NULL); row-major, lda/ldb/ldc in floats. */
+int nrms_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias,
+                 float* C, int64_t ldc, int64_t M, int N, int K, int mode, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRMS_B200_H */

@@ -1,0 +1,79 @@
+"""ctypes binding of libnrms_b200.so (the C-ABI declared in include/nrms_b200.h).
+
+There is NO fallback: if the shared library is missing or a call fails this module raises.
+Build it with `python newsrecommendationsystem_b200/csrc/build.py` (or `__graft_entry__.build()`).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnrms_b200.so")
+
+MODE_FP32 = 0
+MODE_TF32 = 1
+MODES = {"fp32": MODE_FP32, "tf32": MODE_TF32}
+
+_vp, _i64, _i32, _f32, _u64, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/nrms_b200.h one to one
+SIGNATURES = {
+    "nrms_last_error": (C.c_char_p, []),
+    "nrms_abi_version": (_i32, []),
+    "nrms_encoder_stash_bytes": (_sz, [_i64, _i32]),
+    "nrms_encoder_fwd_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
+    "nrms_encoder_bwd_workspace_bytes": (_sz, [_i64, _i32, _i32]),
+    "nrms_news_encoder_fwd": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
+                                     _f32, _u64, _u64, _i32, _vp]),
+    "nrms_news_encoder_bwd": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                     _vp, _sz, _f32, _u64, _u64, _i32, _vp]),
+    "nrms_user_encoder_fwd": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),
+    "nrms_user_encoder_bwd": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
+                                     _i32, _vp]),
+    "nrms_score_fwd": (_i32, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "nrms_score_bwd": (_i32, [_vp, _vp, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
+    "nrms_score_csr": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
+    "nrms_ce_loss_fwd_bwd": (_i32, [_vp, _i64, _i32, _f32, _vp, _vp, _vp]),
+    "nrms_adam_step": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _i64, _f32, _vp]),
+    "nrms_gather_rows": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp]),
+    "nrms_rank_metrics": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "nrms_gemm_nt": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _i32, _i32, _i32, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise loudly if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the NRMS B200 CUDA library is not built. "
+            "Run `python newsrecommendationsystem_b200/csrc/build.py` (nvcc, sm_100a). There is no CPU fallback.")
+    import torch  # noqa: F401  (brings libcudart.so.12 into the process before dlopen)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().nrms_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libnrms_b200 {what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    """Raw device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)

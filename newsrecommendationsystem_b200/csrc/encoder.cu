@@ -1,0 +1,354 @@
+// Host side of the encoder entry points (C-ABI): argument checks, stash/workspace carving and
+// the launch sequence.  Kernels live in encoder_kernels.cuh / sgemm.cuh / tc_gemm.cuh.
+#include "common.cuh"
+#include "encoder_kernels.cuh"
+#include "sgemm.cuh"
+#include "tc_api.cuh"
+
+namespace nrms {
+
+// ---- stash layout: X [rows,300] | QKV [rows,900] | C [rows,300] | T [rows,200] | w [rows] ----
+struct Stash {
+  float *x, *qkv, *c, *t, *w;
+  size_t bytes;
+};
+static Stash carve_stash(void* base, int64_t rows) {
+  Stash s;
+  char* p = reinterpret_cast<char*>(base);
+  size_t off = 0;
+  auto take = [&](size_t nfloat) {
+    float* r = reinterpret_cast<float*>(p + off);
+    off += align_up(nfloat * sizeof(float), 256);
+    return r;
+  };
+  s.x = take((size_t)rows * D);
+  s.qkv = take((size_t)rows * D3);
+  s.c = take((size_t)rows * D);
+  s.t = take((size_t)rows * QD);
+  s.w = take((size_t)rows);
+  s.bytes = off;
+  return s;
+}
+
+constexpr int64_t INFER_CHUNK_ROWS = 2048 * 20;  // rows processed per pass in inference (reference batch 2048 titles)
+constexpr int REDUCE_BLOCKS = 296;
+
+struct BwdWs {
+  float *d_c, *d_u, *d_qkv, *d_x, *partial;
+  size_t bytes;
+};
+static BwdWs carve_bwd(void* base, int64_t rows, bool need_dx) {
+  BwdWs s;
+  char* p = reinterpret_cast<char*>(base);
+  size_t off = 0;
+  auto take = [&](size_t nfloat) {
+    float* r = reinterpret_cast<float*>(p + off);
+    off += align_up(nfloat * sizeof(float), 256);
+    return r;
+  };
+  s.d_c = take((size_t)rows * D);
+  s.d_u = take((size_t)rows * QD);
+  s.d_qkv = take((size_t)rows * D3);
+  s.d_x = need_dx ? take((size_t)rows * D) : nullptr;
+  s.partial = take((size_t)REDUCE_BLOCKS * D3);
+  s.bytes = off;
+  return s;
+}
+
+template <int S, int HC>
+static cudaError_t launch_attention_fwd(const float* qkv, float* ctx, int64_t n_seq, float p, uint64_t seed,
+                                        uint64_t offset, cudaStream_t st) {
+  constexpr int threads = ((S * HC + 31) / 32) * 32;
+  const size_t smem = 2 * S * HC * DH * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<S, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  int64_t gx = n_seq < (int64_t)num_sms() * 8 ? n_seq : (int64_t)num_sms() * 8;
+  dim3 grid((unsigned)gx, H / HC);
+  const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  attention_fwd_kernel<S, HC><<<grid, threads, smem, st>>>(qkv, ctx, n_seq, p, scale, seed, offset);
+  return cudaGetLastError();
+}
+
+template <int S, int HC>
+static cudaError_t launch_attention_bwd(const float* qkv, const float* d_ctx, float* d_qkv, int64_t n_seq, float p,
+                                        uint64_t seed, uint64_t offset, cudaStream_t st) {
+  constexpr int threads = ((S * HC + 31) / 32) * 32;
+  const size_t smem = (4 * S * HC * DH + 2 * HC * S) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel<S, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  int64_t gx = n_seq < (int64_t)num_sms() * 4 ? n_seq : (int64_t)num_sms() * 4;
+  dim3 grid((unsigned)gx, H / HC);
+  const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  attention_bwd_kernel<S, HC><<<grid, threads, smem, st>>>(qkv, d_ctx, d_qkv, n_seq, p, scale, seed, offset);
+  return cudaGetLastError();
+}
+
+static int gemm_nt_bias(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C,
+                        int64_t ldc, int64_t M, int N, int K, int mode, cudaStream_t st) {
+  if (mode == NRMS_MODE_TF32) return tc_gemm_nt(A, lda, B, ldb, bias, C, ldc, M, N, K, st);
+  cudaError_t e = sgemm_launch<0, 0, EPI_STORE>(A, lda, B, ldb, bias, C, ldc, M, N, K, 1, st);
+  if (e != cudaSuccess) return cuda_fail(e, "sgemm_nt");
+  return NRMS_OK;
+}
+
+// Forward over `n_seq` sequences whose input rows X are already materialised in st.x.
+static int encoder_core_fwd(const Stash& s, int64_t n_seq, int S, const float* wqkv, const float* bqkv,
+                            const float* wa, const float* ba, const float* qa, float* out, float p2,
+                            uint64_t seed, uint64_t offset, int64_t row_base, int mode, cudaStream_t st) {
+  const int64_t rows = n_seq * S;
+  int rc = gemm_nt_bias(s.x, D, wqkv, D, bqkv, s.qkv, D3, rows, D3, D, mode, st);
+  if (rc) return rc;
+  // dropout #2 mask indices are global row indices: offset the Philox counter by row_base*D/4
+  const uint64_t off2 = offset + (uint64_t)row_base * D / 4;
+  cudaError_t e;
+  if (S == 20) e = launch_attention_fwd<20, 15>(s.qkv, s.c, n_seq, p2, seed, off2, st);
+  else e = launch_attention_fwd<50, 5>(s.qkv, s.c, n_seq, p2, seed, off2, st);
+  if (e != cudaSuccess) return cuda_fail(e, "attention_fwd");
+  rc = gemm_nt_bias(s.c, D, wa, D, ba, s.t, QD, rows, QD, D, mode, st);
+  if (rc) return rc;
+  int64_t gx = n_seq < (int64_t)num_sms() * 8 ? n_seq : (int64_t)num_sms() * 8;
+  if (S == 20) additive_fwd_kernel<20><<<(unsigned)gx, 256, 0, st>>>(s.c, s.t, qa, s.w, out, n_seq);
+  else additive_fwd_kernel<50><<<(unsigned)gx, 256, 0, st>>>(s.c, s.t, qa, s.w, out, n_seq);
+  NRMS_LAUNCH_CHECK("additive_fwd");
+  return NRMS_OK;
+}
+
+// Backward over the whole stash.  d_x (rows x 300) receives dL/dX.
+static int encoder_core_bwd(const Stash& s, const BwdWs& w, const float* d_out, int64_t n_seq, int S,
+                            const float* wqkv, const float* wa, const float* qa, float* d_x, float* d_wqkv,
+                            float* d_bqkv, float* d_wa, float* d_ba, float* d_qa, float p2, uint64_t seed,
+                            uint64_t offset, int mode, cudaStream_t st) {
+  (void)mode;  // backward contractions run in fp32 on the CUDA cores
+  const int64_t rows = n_seq * S;
+  int nb = (int)(n_seq < REDUCE_BLOCKS ? n_seq : REDUCE_BLOCKS);
+  if (S == 20) additive_bwd_kernel<20><<<nb, 256, 0, st>>>(d_out, s.c, s.t, s.w, qa, w.d_c, w.d_u, w.partial, n_seq);
+  else additive_bwd_kernel<50><<<nb, 256, 0, st>>>(d_out, s.c, s.t, s.w, qa, w.d_c, w.d_u, w.partial, n_seq);
+  NRMS_LAUNCH_CHECK("additive_bwd");
+  partial_reduce_accum_kernel<<<1, 256, 0, st>>>(w.partial, nb, QD, d_qa);
+  NRMS_LAUNCH_CHECK("dqa_reduce");
+  // d_ba = colsum(dU)
+  int cb = (int)(rows < REDUCE_BLOCKS ? rows : REDUCE_BLOCKS);
+  colsum_partial_kernel<<<cb, 256, 0, st>>>(w.d_u, rows, QD, w.partial);
+  NRMS_LAUNCH_CHECK("colsum_du");
+  partial_reduce_accum_kernel<<<1, 256, 0, st>>>(w.partial, cb, QD, d_ba);
+  NRMS_LAUNCH_CHECK("dba_reduce");
+  // d_wa[200,300] += dU^T C   (reduction over rows, split-K + fp32 atomics)
+  int splits = (int)((rows + 4095) / 4096);
+  if (splits > 64) splits = 64;
+  cudaError_t e = sgemm_launch<1, 1, EPI_ATOMIC>(w.d_u, QD, s.c, D, nullptr, d_wa, D, QD, D, rows, splits, st);
+  if (e != cudaSuccess) return cuda_fail(e, "sgemm dWa");
+  // d_c += dU * Wa   ([rows,200] x [200,300])
+  e = sgemm_launch<0, 1, EPI_ACCUM>(w.d_u, QD, wa, D, nullptr, w.d_c, D, rows, D, QD, 1, st);
+  if (e != cudaSuccess) return cuda_fail(e, "sgemm dC");
+  // attention backward (applies the dropout-2 mask to d_c on load)
+  if (S == 20) e = launch_attention_bwd<20, 15>(s.qkv, w.d_c, w.d_qkv, n_seq, p2, seed, offset, st);
+  else e = launch_attention_bwd<50, 5>(s.qkv, w.d_c, w.d_qkv, n_seq, p2, seed, offset, st);
+  if (e != cudaSuccess) return cuda_fail(e, "attention_bwd");
+  // d_bqkv = colsum(dQKV)
+  colsum_partial_kernel<<<cb, 256, 0, st>>>(w.d_qkv, rows, D3, w.partial);
+  NRMS_LAUNCH_CHECK("colsum_dqkv");
+  partial_reduce_accum_kernel<<<(D3 + 255) / 256, 256, 0, st>>>(w.partial, cb, D3, d_bqkv);
+  NRMS_LAUNCH_CHECK("dbqkv_reduce");
+  // d_wqkv[900,300] += dQKV^T X
+  e = sgemm_launch<1, 1, EPI_ATOMIC>(w.d_qkv, D3, s.x, D, nullptr, d_wqkv, D, D3, D, rows, splits, st);
+  if (e != cudaSuccess) return cuda_fail(e, "sgemm dWqkv");
+  // d_x = dQKV * Wqkv   ([rows,900] x [900,300])
+  e = sgemm_launch<0, 1, EPI_STORE>(w.d_qkv, D3, wqkv, D, nullptr, d_x, D, rows, D, D3, 1, st);
+  if (e != cudaSuccess) return cuda_fail(e, "sgemm dX");
+  return NRMS_OK;
+}
+
+static int check_common(int S, int mode) {
+  NRMS_CHECK_ARG(S == 20 || S == 50, NRMS_E_UNSUPPORTED, "sequence length %d unsupported (compiled: 20, 50)", S);
+  NRMS_CHECK_ARG(mode == NRMS_MODE_FP32 || mode == NRMS_MODE_TF32, NRMS_E_INVALID, "bad mode %d", mode);
+  return NRMS_OK;
+}
+
+}  // namespace nrms
+
+using namespace nrms;
+
+extern "C" {
+
+size_t nrms_encoder_stash_bytes(int64_t n_seq, int S) {
+  if (n_seq <= 0 || S <= 0) return 0;
+  return carve_stash(nullptr, n_seq * S).bytes;
+}
+
+size_t nrms_encoder_fwd_workspace_bytes(int64_t n_seq, int S, int mode, int training) {
+  if (n_seq <= 0 || S <= 0) return 0;
+  if (training) return 256;
+  if (mode == NRMS_MODE_TF32) {
+    size_t fused = tc_fused_workspace_bytes(n_seq, S);
+    if (fused != (size_t)-1) return fused + 256;
+  }
+  int64_t chunk_seq = INFER_CHUNK_ROWS / S;
+  if (n_seq < chunk_seq) chunk_seq = n_seq;
+  return carve_stash(nullptr, chunk_seq * S).bytes + 256;
+}
+
+size_t nrms_encoder_bwd_workspace_bytes(int64_t n_seq, int S, int mode) {
+  (void)mode;
+  if (n_seq <= 0 || S <= 0) return 0;
+  return carve_bwd(nullptr, n_seq * S, true).bytes + 256;
+}
+
+int nrms_news_encoder_fwd(const int64_t* tokens, int64_t n_titles, int L, const float* emb, int64_t num_words,
+                          const float* wqkv, const float* bqkv, const float* wa, const float* ba, const float* qa,
+                          float* out, void* stash, void* workspace, size_t workspace_bytes, float dropout_p,
+                          uint64_t seed, uint64_t offset, int mode, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (int rc = check_common(L, mode)) return rc;
+  NRMS_CHECK_ARG(L == 20, NRMS_E_UNSUPPORTED, "news encoder compiled for title length 20, got %d", L);
+  NRMS_CHECK_ARG(n_titles >= 0 && num_words > 0, NRMS_E_INVALID, "bad sizes");
+  if (n_titles == 0) return NRMS_OK;
+  NRMS_CHECK_ARG(tokens && emb && wqkv && bqkv && wa && ba && qa && out, NRMS_E_INVALID, "null pointer");
+  NRMS_CHECK_ARG(aligned16(emb) && aligned16(wqkv) && aligned16(bqkv) && aligned16(wa) && aligned16(ba) && aligned16(out),
+                 NRMS_E_INVALID, "pointers must be 16-byte aligned");
+  NRMS_CHECK_ARG(dropout_p >= 0.f && dropout_p < 1.f, NRMS_E_INVALID, "dropout_p out of range");
+  const float scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+
+  if (stash) {  // training: everything kept for backward
+    NRMS_CHECK_ARG(aligned16(stash), NRMS_E_INVALID, "stash misaligned");
+    Stash s = carve_stash(stash, n_titles * L);
+    const int64_t rows = n_titles * L;
+    int64_t gb = (rows + 7) / 8;
+    if (gb > (int64_t)num_sms() * 16) gb = (int64_t)num_sms() * 16;
+    gather_embedding_kernel<<<(unsigned)gb, 256, 0, st>>>(tokens, rows, emb, s.x, dropout_p, scale, seed, offset);
+    NRMS_LAUNCH_CHECK("gather_embedding");
+    return encoder_core_fwd(s, n_titles, L, wqkv, bqkv, wa, ba, qa, out, dropout_p, seed, offset, 0, mode, st);
+  }
+  // inference
+  if (mode == NRMS_MODE_TF32 && dropout_p == 0.f && tc_fused_workspace_bytes(n_titles, L) != (size_t)-1) {
+    return tc_news_encoder_fused(tokens, n_titles, emb, num_words, wqkv, bqkv, wa, ba, qa, out, workspace,
+                                 workspace_bytes, st);
+  }
+  const int64_t chunk_seq = INFER_CHUNK_ROWS / L;
+  const int64_t first = n_titles < chunk_seq ? n_titles : chunk_seq;
+  NRMS_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= carve_stash(nullptr, first * L).bytes,
+                 NRMS_E_WORKSPACE, "workspace too small: need %zu bytes", carve_stash(nullptr, first * L).bytes);
+  for (int64_t s0 = 0; s0 < n_titles; s0 += chunk_seq) {
+    const int64_t n = (n_titles - s0 < chunk_seq) ? (n_titles - s0) : chunk_seq;
+    Stash s = carve_stash(workspace, n * L);
+    const int64_t rows = n * L;
+    int64_t gb = (rows + 7) / 8;
+    if (gb > (int64_t)num_sms() * 16) gb = (int64_t)num_sms() * 16;
+    // global row index keys the dropout stream, so a chunked pass equals a single pass
+    gather_embedding_kernel<<<(unsigned)gb, 256, 0, st>>>(tokens + s0 * L, rows, emb, s.x, dropout_p, scale, seed,
+                                                          offset + (uint64_t)s0 * L * D / 4);
+    NRMS_LAUNCH_CHECK("gather_embedding");
+    int rc = encoder_core_fwd(s, n, L, wqkv, bqkv, wa, ba, qa, out + s0 * D, dropout_p, seed, offset, s0 * L, mode, st);
+    if (rc) return rc;
+  }
+  return NRMS_OK;
+}
+
+int nrms_news_encoder_bwd(const float* d_out, const int64_t* tokens, int64_t n_titles, int L, int64_t num_words,
+                          const float* wqkv, const float* wa, const float* qa, const void* stash, float* d_emb,
+                          float* d_wqkv, float* d_bqkv, float* d_wa, float* d_ba, float* d_qa, void* workspace,
+                          size_t workspace_bytes, float dropout_p, uint64_t seed, uint64_t offset, int mode,
+                          void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (int rc = check_common(L, mode)) return rc;
+  NRMS_CHECK_ARG(L == 20, NRMS_E_UNSUPPORTED, "news encoder compiled for title length 20, got %d", L);
+  if (n_titles == 0) return NRMS_OK;
+  NRMS_CHECK_ARG(n_titles > 0 && num_words > 0, NRMS_E_INVALID, "bad sizes");
+  NRMS_CHECK_ARG(d_out && tokens && wqkv && wa && qa && stash && d_emb && d_wqkv && d_bqkv && d_wa && d_ba && d_qa,
+                 NRMS_E_INVALID, "null pointer");
+  NRMS_CHECK_ARG(aligned16(d_out) && aligned16(stash) && aligned16(d_emb) && aligned16(d_wqkv) && aligned16(d_wa),
+                 NRMS_E_INVALID, "pointers must be 16-byte aligned");
+  const int64_t rows = n_titles * L;
+  NRMS_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= carve_bwd(nullptr, rows, true).bytes,
+                 NRMS_E_WORKSPACE, "workspace too small: need %zu bytes", carve_bwd(nullptr, rows, true).bytes);
+  Stash s = carve_stash(const_cast<void*>(stash), rows);
+  BwdWs w = carve_bwd(workspace, rows, true);
+  int rc = encoder_core_bwd(s, w, d_out, n_titles, L, wqkv, wa, qa, w.d_x, d_wqkv, d_bqkv, d_wa, d_ba, d_qa,
+                            dropout_p, seed, offset, mode, st);
+  if (rc) return rc;
+  const float scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
+  int64_t gb = (rows + 7) / 8;
+  if (gb > (int64_t)num_sms() * 16) gb = (int64_t)num_sms() * 16;
+  scatter_embedding_grad_kernel<<<(unsigned)gb, 256, 0, st>>>(tokens, rows, w.d_x, d_emb, dropout_p, scale, seed, offset);
+  NRMS_LAUNCH_CHECK("scatter_embedding_grad");
+  return NRMS_OK;
+}
+
+int nrms_user_encoder_fwd(const float* x, const int32_t* rows_idx, int64_t n_users, int S, const float* wqkv,
+                          const float* bqkv, const float* wa, const float* ba, const float* qa, float* out,
+                          void* stash, void* workspace, size_t workspace_bytes, int mode, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (int rc = check_common(S, mode)) return rc;
+  NRMS_CHECK_ARG(n_users >= 0, NRMS_E_INVALID, "bad sizes");
+  if (n_users == 0) return NRMS_OK;
+  NRMS_CHECK_ARG(x && wqkv && bqkv && wa && ba && qa && out, NRMS_E_INVALID, "null pointer");
+  NRMS_CHECK_ARG(aligned16(x) && aligned16(wqkv) && aligned16(bqkv) && aligned16(wa) && aligned16(ba) && aligned16(out),
+                 NRMS_E_INVALID, "pointers must be 16-byte aligned");
+  if (stash) {
+    NRMS_CHECK_ARG(rows_idx == nullptr, NRMS_E_UNSUPPORTED, "indexed input is inference-only");
+    NRMS_CHECK_ARG(aligned16(stash), NRMS_E_INVALID, "stash misaligned");
+    Stash s = carve_stash(stash, n_users * S);
+    NRMS_CUDA(cudaMemcpyAsync(s.x, x, (size_t)n_users * S * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return encoder_core_fwd(s, n_users, S, wqkv, bqkv, wa, ba, qa, out, 0.f, 0, 0, 0, mode, st);
+  }
+  const int64_t chunk_seq = INFER_CHUNK_ROWS / S;
+  const int64_t first = n_users < chunk_seq ? n_users : chunk_seq;
+  NRMS_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= carve_stash(nullptr, first * S).bytes,
+                 NRMS_E_WORKSPACE, "workspace too small: need %zu bytes", carve_stash(nullptr, first * S).bytes);
+  for (int64_t s0 = 0; s0 < n_users; s0 += chunk_seq) {
+    const int64_t n = (n_users - s0 < chunk_seq) ? (n_users - s0) : chunk_seq;
+    Stash s = carve_stash(workspace, n * S);
+    const int64_t rows = n * S;
+    if (rows_idx) {
+      int64_t gb = (rows + 7) / 8;
+      if (gb > (int64_t)num_sms() * 16) gb = (int64_t)num_sms() * 16;
+      gather_rows_kernel<int32_t><<<(unsigned)gb, 256, 0, st>>>(x, rows_idx + s0 * S, rows, DV4, s.x);
+      NRMS_LAUNCH_CHECK("gather_rows");
+    } else {
+      s.x = const_cast<float*>(x) + s0 * S * D;  // dense input is read in place
+    }
+    int rc = encoder_core_fwd(s, n, S, wqkv, bqkv, wa, ba, qa, out + s0 * D, 0.f, 0, 0, 0, mode, st);
+    if (rc) return rc;
+  }
+  return NRMS_OK;
+}
+
+int nrms_user_encoder_bwd(const float* d_out, int64_t n_users, int S, const float* wqkv, const float* wa,
+                          const float* qa, const void* stash, float* d_x, float* d_wqkv, float* d_bqkv, float* d_wa,
+                          float* d_ba, float* d_qa, void* workspace, size_t workspace_bytes, int mode, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (int rc = check_common(S, mode)) return rc;
+  if (n_users == 0) return NRMS_OK;
+  NRMS_CHECK_ARG(n_users > 0, NRMS_E_INVALID, "bad sizes");
+  NRMS_CHECK_ARG(d_out && wqkv && wa && qa && stash && d_x && d_wqkv && d_bqkv && d_wa && d_ba && d_qa, NRMS_E_INVALID,
+                 "null pointer");
+  NRMS_CHECK_ARG(aligned16(d_out) && aligned16(stash) && aligned16(d_x) && aligned16(d_wqkv) && aligned16(d_wa),
+                 NRMS_E_INVALID, "pointers must be 16-byte aligned");
+  const int64_t rows = n_users * S;
+  NRMS_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= carve_bwd(nullptr, rows, false).bytes,
+                 NRMS_E_WORKSPACE, "workspace too small: need %zu bytes", carve_bwd(nullptr, rows, false).bytes);
+  Stash s = carve_stash(const_cast<void*>(stash), rows);
+  BwdWs w = carve_bwd(workspace, rows, false);
+  return encoder_core_bwd(s, w, d_out, n_users, S, wqkv, wa, qa, d_x, d_wqkv, d_bqkv, d_wa, d_ba, d_qa, 0.f, 0, 0, mode,
+                          st);
+}
+
+int nrms_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
+                 int64_t M, int N, int K, int mode, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  NRMS_CHECK_ARG(A && B && C, NRMS_E_INVALID, "null pointer");
+  NRMS_CHECK_ARG(M >= 0 && N > 0 && K > 0 && (N % 4) == 0 && (K % 4) == 0 && (lda % 4) == 0 && (ldb % 4) == 0 && (ldc % 4) == 0,
+                 NRMS_E_UNSUPPORTED, "N, K and leading dimensions must be multiples of 4");
+  NRMS_CHECK_ARG(aligned16(A) && aligned16(B) && aligned16(C) && (!bias || aligned16(bias)), NRMS_E_INVALID,
+                 "pointers must be 16-byte aligned");
+  return gemm_nt_bias(A, lda, B, ldb, bias, C, ldc, M, N, K, mode, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,415 @@
+// Device kernels of the decomposed encoder pipeline (everything except the dense contractions):
+// embedding gather / scatter, multi-head exp-softmax attention fwd/bwd, additive pooling fwd/bwd,
+// deterministic column sums.  Math follows the reference exactly (see include/nrms_b200.h for the
+// file:line map): scores = QK^T / sqrt(20); e = exp(scores) (no max subtraction);
+// attn = e / (sum e + 1e-8); ctx = attn V; pooling = stable softmax over tanh(linear(c)) . q.
+#pragma once
+#include "common.cuh"
+
+namespace nrms {
+
+constexpr float SQRT_DH = 4.47213595499957939f;  // np.sqrt(20) rounded to fp32 by the cast
+constexpr float ATTN_EPS = 1e-8f;
+constexpr uint32_t DROPOUT_STREAM_EMB = 1, DROPOUT_STREAM_CTX = 2;
+
+// ----------------------------------------------------------------------------------------
+// a1: embedding gather (+ dropout #1).  One warp per token row: 75 coalesced float4.
+// ----------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256)
+gather_embedding_kernel(const int64_t* __restrict__ tokens, int64_t n_rows, const float* __restrict__ emb,
+                        float* __restrict__ x, float p, float scale, uint64_t seed, uint64_t offset) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = warp; r < n_rows; r += nwarps) {
+    const int64_t tok = tokens[r];
+    const float4* src = reinterpret_cast<const float4*>(emb + tok * D);
+    float4* dst = reinterpret_cast<float4*>(x + r * D);
+#pragma unroll
+    for (int l = lane; l < DV4; l += 32) {
+      float4 v = __ldg(src + l);
+      if (p > 0.f) {
+        float4 m = dropout_mask4((uint64_t)r * D + 4 * l, DROPOUT_STREAM_EMB, p, scale, seed, offset);
+        v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+      }
+      dst[l] = v;
+    }
+  }
+}
+
+// generic row gather with int32/int64 indices (user-encoder indexed input, evaluate tables)
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ src, const IdxT* __restrict__ rows, int64_t n, int width4,
+                   float* __restrict__ dst) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = warp; r < n; r += nwarps) {
+    const float4* s = reinterpret_cast<const float4*>(src) + (int64_t)rows[r] * width4;
+    float4* d = reinterpret_cast<float4*>(dst) + r * width4;
+    for (int l = lane; l < width4; l += 32) d[l] = __ldg(s + l);
+  }
+}
+
+// embedding backward: dE[tok] += dX[row] * mask1 ; token 0 (padding_idx) skipped.
+static __global__ void __launch_bounds__(256)
+scatter_embedding_grad_kernel(const int64_t* __restrict__ tokens, int64_t n_rows, const float* __restrict__ dx,
+                              float* __restrict__ d_emb, float p, float scale, uint64_t seed, uint64_t offset) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r = warp; r < n_rows; r += nwarps) {
+    const int64_t tok = tokens[r];
+    if (tok == 0) continue;
+    const float4* src = reinterpret_cast<const float4*>(dx + r * D);
+    float4* dst = reinterpret_cast<float4*>(d_emb + tok * D);
+#pragma unroll
+    for (int l = lane; l < DV4; l += 32) {
+      float4 v = src[l];
+      if (p > 0.f) {
+        float4 m = dropout_mask4((uint64_t)r * D + 4 * l, DROPOUT_STREAM_EMB, p, scale, seed, offset);
+        v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+      }
+      atomicAdd(dst + l, v);
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// a3/a4: attention forward.  CTA = (sequence, chunk of HC heads); thread = (head, query i).
+// K,V slices staged in smem (every read is a warp broadcast), q_i and the context in registers.
+// ----------------------------------------------------------------------------------------
+template <int S, int HC>
+__global__ void __launch_bounds__(((S * HC + 31) / 32) * 32)
+attention_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ ctx, int64_t n_seq,
+                     float p, float scale, uint64_t seed, uint64_t offset) {
+  constexpr int W = HC * DH;  // columns of this head chunk
+  extern __shared__ __align__(16) float smem[];
+  float* Ks = smem;          // [S][W]
+  float* Vs = smem + S * W;  // [S][W]
+  const int hc = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int hl = tid / S, i = tid % S;
+  const bool active = tid < S * HC;
+  constexpr int W4 = W / 4;
+
+  for (int64_t seq = blockIdx.x; seq < n_seq; seq += gridDim.x) {
+    const float* base = qkv + seq * S * D3;
+    __syncthreads();
+    for (int f = tid; f < S * W4 * 2; f += blockDim.x) {
+      int which = f / (S * W4);  // 0 = K, 1 = V
+      int g = f % (S * W4);
+      int j = g / W4, c4 = g % W4;
+      float4 v = *reinterpret_cast<const float4*>(base + (int64_t)j * D3 + (1 + which) * D + hc * W + c4 * 4);
+      *reinterpret_cast<float4*>((which ? Vs : Ks) + j * W + c4 * 4) = v;
+    }
+    __syncthreads();
+    if (!active) continue;
+    float q[DH], acc[DH];
+    {
+      const float4* qp = reinterpret_cast<const float4*>(base + (int64_t)i * D3 + hc * W + hl * DH);
+#pragma unroll
+      for (int c = 0; c < DH / 4; ++c) {
+        float4 v = qp[c];
+        q[4 * c] = v.x; q[4 * c + 1] = v.y; q[4 * c + 2] = v.z; q[4 * c + 3] = v.w;
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < DH; ++d) acc[d] = 0.f;
+    float Z = 0.f;
+#pragma unroll 2
+    for (int j = 0; j < S; ++j) {
+      const float4* kp = reinterpret_cast<const float4*>(Ks + j * W + hl * DH);
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < DH / 4; ++c) {
+        float4 k = kp[c];
+        s = fmaf(q[4 * c], k.x, s); s = fmaf(q[4 * c + 1], k.y, s);
+        s = fmaf(q[4 * c + 2], k.z, s); s = fmaf(q[4 * c + 3], k.w, s);
+      }
+      const float e = expf(s / SQRT_DH);
+      Z += e;
+      const float4* vp = reinterpret_cast<const float4*>(Vs + j * W + hl * DH);
+#pragma unroll
+      for (int c = 0; c < DH / 4; ++c) {
+        float4 v = vp[c];
+        acc[4 * c] = fmaf(e, v.x, acc[4 * c]); acc[4 * c + 1] = fmaf(e, v.y, acc[4 * c + 1]);
+        acc[4 * c + 2] = fmaf(e, v.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(e, v.w, acc[4 * c + 3]);
+      }
+    }
+    const float inv = 1.f / (Z + ATTN_EPS);
+    const int64_t row = seq * S + i;
+    const int col = hc * W + hl * DH;
+    float4* op = reinterpret_cast<float4*>(ctx + row * D + col);
+#pragma unroll
+    for (int c = 0; c < DH / 4; ++c) {
+      float4 o = make_float4(acc[4 * c] * inv, acc[4 * c + 1] * inv, acc[4 * c + 2] * inv, acc[4 * c + 3] * inv);
+      if (p > 0.f) {
+        float4 m = dropout_mask4((uint64_t)row * D + col + 4 * c, DROPOUT_STREAM_CTX, p, scale, seed, offset);
+        o.x *= m.x; o.y *= m.y; o.z *= m.z; o.w *= m.w;
+      }
+      op[c] = o;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// attention backward.  Phase 1: thread (h,i) -> Zinv_i, delta_i, dQ_i.  Phase 2: thread (h,j)
+// -> dK_j, dV_j (recomputing the probabilities; nothing S x S is stored).
+//   attn = e/(Z+eps)  =>  ds_ij = attn_ij (dattn_ij - sum_k attn_ik dattn_ik) / sqrt(d)
+// ----------------------------------------------------------------------------------------
+template <int S, int HC>
+__global__ void __launch_bounds__(((S * HC + 31) / 32) * 32)
+attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_ctx, float* __restrict__ d_qkv,
+                     int64_t n_seq, float p, float scale, uint64_t seed, uint64_t offset) {
+  constexpr int W = HC * DH;
+  constexpr int W4 = W / 4;
+  extern __shared__ __align__(16) float smem[];
+  float* Qs = smem;
+  float* Ks = Qs + S * W;
+  float* Vs = Ks + S * W;
+  float* Gs = Vs + S * W;     // d_ctx (after dropout-2 mask)
+  float* Zi = Gs + S * W;     // [HC*S] 1/(Z+eps)
+  float* De = Zi + HC * S;    // [HC*S] delta
+  const int hc = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int hl = tid / S, i = tid % S;
+  const bool active = tid < S * HC;
+
+  for (int64_t seq = blockIdx.x; seq < n_seq; seq += gridDim.x) {
+    const float* base = qkv + seq * S * D3;
+    __syncthreads();
+    for (int f = tid; f < S * W4 * 4; f += blockDim.x) {
+      int which = f / (S * W4);  // 0 Q, 1 K, 2 V, 3 dCtx
+      int g = f % (S * W4);
+      int j = g / W4, c4 = g % W4;
+      float4 v;
+      if (which < 3) {
+        v = *reinterpret_cast<const float4*>(base + (int64_t)j * D3 + which * D + hc * W + c4 * 4);
+      } else {
+        const int64_t row = seq * S + j;
+        const int col = hc * W + c4 * 4;
+        v = *reinterpret_cast<const float4*>(d_ctx + row * D + col);
+        if (p > 0.f) {
+          float4 m = dropout_mask4((uint64_t)row * D + col, DROPOUT_STREAM_CTX, p, scale, seed, offset);
+          v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+        }
+      }
+      *reinterpret_cast<float4*>(smem + which * S * W + j * W + c4 * 4) = v;
+    }
+    __syncthreads();
+
+    float a[DH], b[DH], r[DH];
+    // ---- phase 1 ---------------------------------------------------------------------
+    if (active) {
+#pragma unroll
+      for (int d = 0; d < DH; ++d) { a[d] = Qs[i * W + hl * DH + d]; b[d] = Gs[i * W + hl * DH + d]; r[d] = 0.f; }
+      float Z = 0.f, num = 0.f;
+      for (int j = 0; j < S; ++j) {
+        const float4* kp = reinterpret_cast<const float4*>(Ks + j * W + hl * DH);
+        const float4* vp = reinterpret_cast<const float4*>(Vs + j * W + hl * DH);
+        float s = 0.f, da = 0.f;
+#pragma unroll
+        for (int c = 0; c < DH / 4; ++c) {
+          float4 k = kp[c], v = vp[c];
+          s = fmaf(a[4 * c], k.x, s); s = fmaf(a[4 * c + 1], k.y, s); s = fmaf(a[4 * c + 2], k.z, s); s = fmaf(a[4 * c + 3], k.w, s);
+          da = fmaf(b[4 * c], v.x, da); da = fmaf(b[4 * c + 1], v.y, da); da = fmaf(b[4 * c + 2], v.z, da); da = fmaf(b[4 * c + 3], v.w, da);
+        }
+        const float e = expf(s / SQRT_DH);
+        Z += e;
+        num = fmaf(e, da, num);
+      }
+      const float zinv = 1.f / (Z + ATTN_EPS);
+      const float delta = num * zinv;
+      Zi[hl * S + i] = zinv;
+      De[hl * S + i] = delta;
+      for (int j = 0; j < S; ++j) {
+        const float4* kp = reinterpret_cast<const float4*>(Ks + j * W + hl * DH);
+        const float4* vp = reinterpret_cast<const float4*>(Vs + j * W + hl * DH);
+        float s = 0.f, da = 0.f;
+#pragma unroll
+        for (int c = 0; c < DH / 4; ++c) {
+          float4 k = kp[c], v = vp[c];
+          s = fmaf(a[4 * c], k.x, s); s = fmaf(a[4 * c + 1], k.y, s); s = fmaf(a[4 * c + 2], k.z, s); s = fmaf(a[4 * c + 3], k.w, s);
+          da = fmaf(b[4 * c], v.x, da); da = fmaf(b[4 * c + 1], v.y, da); da = fmaf(b[4 * c + 2], v.z, da); da = fmaf(b[4 * c + 3], v.w, da);
+        }
+        const float at = expf(s / SQRT_DH) * zinv;
+        const float ds = at * (da - delta) / SQRT_DH;
+#pragma unroll
+        for (int c = 0; c < DH / 4; ++c) {
+          float4 k = kp[c];
+          r[4 * c] = fmaf(ds, k.x, r[4 * c]); r[4 * c + 1] = fmaf(ds, k.y, r[4 * c + 1]);
+          r[4 * c + 2] = fmaf(ds, k.z, r[4 * c + 2]); r[4 * c + 3] = fmaf(ds, k.w, r[4 * c + 3]);
+        }
+      }
+      float4* op = reinterpret_cast<float4*>(d_qkv + (seq * S + i) * D3 + hc * W + hl * DH);
+#pragma unroll
+      for (int c = 0; c < DH / 4; ++c) op[c] = make_float4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+    }
+    __syncthreads();
+    // ---- phase 2 (thread index i now plays the key/value row j) ---------------------------
+    if (active) {
+      const int j = i;
+      float dk[DH], dv[DH];
+#pragma unroll
+      for (int d = 0; d < DH; ++d) { a[d] = Ks[j * W + hl * DH + d]; b[d] = Vs[j * W + hl * DH + d]; dk[d] = 0.f; dv[d] = 0.f; }
+      for (int ii = 0; ii < S; ++ii) {
+        const float4* qp = reinterpret_cast<const float4*>(Qs + ii * W + hl * DH);
+        const float4* gp = reinterpret_cast<const float4*>(Gs + ii * W + hl * DH);
+        float s = 0.f, da = 0.f;
+#pragma unroll
+        for (int c = 0; c < DH / 4; ++c) {
+          float4 qv = qp[c], g = gp[c];
+          s = fmaf(qv.x, a[4 * c], s); s = fmaf(qv.y, a[4 * c + 1], s); s = fmaf(qv.z, a[4 * c + 2], s); s = fmaf(qv.w, a[4 * c + 3], s);
+          da = fmaf(g.x, b[4 * c], da); da = fmaf(g.y, b[4 * c + 1], da); da = fmaf(g.z, b[4 * c + 2], da); da = fmaf(g.w, b[4 * c + 3], da);
+        }
+        const float at = expf(s / SQRT_DH) * Zi[hl * S + ii];
+        const float ds = at * (da - De[hl * S + ii]) / SQRT_DH;
+#pragma unroll
+        for (int c = 0; c < DH / 4; ++c) {
+          float4 qv = qp[c], g = gp[c];
+          dk[4 * c] = fmaf(ds, qv.x, dk[4 * c]); dk[4 * c + 1] = fmaf(ds, qv.y, dk[4 * c + 1]);
+          dk[4 * c + 2] = fmaf(ds, qv.z, dk[4 * c + 2]); dk[4 * c + 3] = fmaf(ds, qv.w, dk[4 * c + 3]);
+          dv[4 * c] = fmaf(at, g.x, dv[4 * c]); dv[4 * c + 1] = fmaf(at, g.y, dv[4 * c + 1]);
+          dv[4 * c + 2] = fmaf(at, g.z, dv[4 * c + 2]); dv[4 * c + 3] = fmaf(at, g.w, dv[4 * c + 3]);
+        }
+      }
+      float* orow = d_qkv + (seq * S + j) * D3 + hc * W + hl * DH;
+      float4* ok = reinterpret_cast<float4*>(orow + D);
+      float4* ov = reinterpret_cast<float4*>(orow + 2 * D);
+#pragma unroll
+      for (int c = 0; c < DH / 4; ++c) {
+        ok[c] = make_float4(dk[4 * c], dk[4 * c + 1], dk[4 * c + 2], dk[4 * c + 3]);
+        ov[c] = make_float4(dv[4 * c], dv[4 * c + 1], dv[4 * c + 2], dv[4 * c + 3]);
+      }
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// a5: additive pooling forward.  t holds linear(c)+bias on entry and tanh(.) on exit.
+// ----------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(256)
+additive_fwd_kernel(const float* __restrict__ c, float* __restrict__ t, const float* __restrict__ qa,
+                    float* __restrict__ w, float* __restrict__ out, int64_t n_seq) {
+  __shared__ float sc[S];
+  __shared__ float wv[S];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int64_t seq = blockIdx.x; seq < n_seq; seq += gridDim.x) {
+    for (int i = warp; i < S; i += 8) {
+      float* trow = t + (seq * S + i) * QD;
+      float part = 0.f;
+      for (int q = lane; q < QD; q += 32) {
+        float v = tanhf(trow[q]);
+        trow[q] = v;
+        part = fmaf(v, __ldg(qa + q), part);
+      }
+      part = warp_sum(part);
+      if (lane == 0) sc[i] = part;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      float m = -INFINITY;
+      for (int i = lane; i < S; i += 32) m = fmaxf(m, sc[i]);
+      m = warp_max(m);
+      float sum = 0.f;
+      for (int i = lane; i < S; i += 32) { float e = expf(sc[i] - m); wv[i] = e; sum += e; }
+      sum = warp_sum(sum);
+      for (int i = lane; i < S; i += 32) { float x = wv[i] / sum; wv[i] = x; w[seq * S + i] = x; }
+    }
+    __syncthreads();
+    for (int d = tid; d < D; d += 256) {
+      const float* cp = c + seq * S * D + d;
+      float acc = 0.f;
+#pragma unroll 5
+      for (int i = 0; i < S; ++i) acc = fmaf(wv[i], cp[(int64_t)i * D], acc);
+      out[seq * D + d] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+// additive pooling backward (everything except the two contractions dU*Wa and dU^T*C):
+//   d_c[i,:]  = w_i * d_out           (first term; the GEMM adds dU * Wa afterwards)
+//   d_u[i,q]  = ds_i * qa[q] * (1 - t^2)
+//   partial_dqa[block, q] = sum over this block's sequences of ds_i * t[i,q]
+template <int S>
+__global__ void __launch_bounds__(256)
+additive_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ c, const float* __restrict__ t,
+                    const float* __restrict__ w, const float* __restrict__ qa,
+                    float* __restrict__ d_c, float* __restrict__ d_u, float* __restrict__ partial_dqa,
+                    int64_t n_seq) {
+  __shared__ float dwv[S];
+  __shared__ float dsv[S];
+  __shared__ float wv[S];
+  __shared__ __align__(16) float go[D];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float dqa_acc = 0.f;
+  const float qv = (tid < QD) ? qa[tid] : 0.f;
+  for (int64_t seq = blockIdx.x; seq < n_seq; seq += gridDim.x) {
+    for (int d = tid; d < D; d += 256) go[d] = d_out[seq * D + d];
+    if (tid < S) wv[tid] = w[seq * S + tid];
+    __syncthreads();
+    for (int i = warp; i < S; i += 8) {
+      const float* cp = c + (seq * S + i) * D;
+      float part = 0.f;
+      for (int d = lane; d < D; d += 32) part = fmaf(go[d], cp[d], part);
+      part = warp_sum(part);
+      if (lane == 0) dwv[i] = part;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      float dot = 0.f;
+      for (int i = lane; i < S; i += 32) dot = fmaf(wv[i], dwv[i], dot);
+      dot = warp_sum(dot);
+      for (int i = lane; i < S; i += 32) dsv[i] = wv[i] * (dwv[i] - dot);
+    }
+    __syncthreads();
+    if (tid < QD) {
+      for (int i = 0; i < S; ++i) {
+        const int64_t row = seq * S + i;
+        const float tv = t[row * QD + tid];
+        const float ds = dsv[i];
+        d_u[row * QD + tid] = ds * qv * (1.f - tv * tv);
+        dqa_acc = fmaf(ds, tv, dqa_acc);
+      }
+    }
+    for (int f = tid; f < S * DV4; f += 256) {
+      const int i = f / DV4, l = f % DV4;
+      const float wi = wv[i];
+      float4 g = *reinterpret_cast<const float4*>(go + 4 * l);
+      *reinterpret_cast<float4*>(d_c + (seq * S + i) * D + 4 * l) = make_float4(wi * g.x, wi * g.y, wi * g.z, wi * g.w);
+    }
+    __syncthreads();
+  }
+  if (tid < QD) partial_dqa[(int64_t)blockIdx.x * QD + tid] = dqa_acc;
+}
+
+// ----------------------------------------------------------------------------------------
+// deterministic column sums: partial[b, col] over a contiguous row range, then a fixed-order
+// final accumulate  out[col] += sum_b partial[b, col].
+// ----------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256)
+colsum_partial_kernel(const float* __restrict__ x, int64_t n_rows, int N, float* __restrict__ partial) {
+  const int64_t per = (n_rows + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = (int64_t)blockIdx.x * per;
+  const int64_t r1 = (r0 + per < n_rows) ? r0 + per : n_rows;
+  for (int col = threadIdx.x; col < N; col += blockDim.x) {
+    float acc = 0.f;
+    for (int64_t r = r0; r < r1; ++r) acc += x[r * N + col];
+    partial[(int64_t)blockIdx.x * N + col] = acc;
+  }
+}
+
+static __global__ void __launch_bounds__(256)
+partial_reduce_accum_kernel(const float* __restrict__ partial, int n_blocks, int N, float* __restrict__ out) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= N) return;
+  float acc = 0.f;
+  for (int b = 0; b < n_blocks; ++b) acc += partial[(int64_t)b * N + col];
+  out[col] += acc;
+}
+
+}  // namespace nrms

@@ -1,0 +1,19 @@
+// Host-side entry points of the tensor-core (tcgen05) kernels, called from encoder.cu.
+#pragma once
+#include "common.cuh"
+
+namespace nrms {
+
+// C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]); operands rounded to TF32 (rna) on the way into shared
+// memory, fp32 accumulation in TMEM.  Same layout contract as sgemm (multiples of 4, 16B aligned).
+int tc_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
+               int64_t M, int N, int K, cudaStream_t st);
+
+// Fused news-encoder forward (inference): gather -> QKV (tcgen05) -> attention -> additive pooling
+// in one kernel.  tc_fused_workspace_bytes returns (size_t)-1 when the fused path does not apply.
+size_t tc_fused_workspace_bytes(int64_t n_seq, int S);
+int tc_news_encoder_fused(const int64_t* tokens, int64_t n_titles, const float* emb, int64_t num_words,
+                          const float* wqkv, const float* bqkv, const float* wa, const float* ba, const float* qa,
+                          float* out, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+}  // namespace nrms

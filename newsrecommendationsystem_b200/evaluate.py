@@ -1,0 +1,157 @@
+"""Device-resident evaluate pipeline (reference src/evaluate.py:171-272).
+
+The reference walks Python dicts of GPU row views, stacks 102,400 tensors per user batch and
+launches one bmm + .tolist() per impression.  Here the same semantics run on integer tables:
+
+  stage A  news table  [N_news+1, 300]; last row = PADDED_NEWS zeros (evaluate.py:203-204);
+           duplicate news ids resolve to their FIRST row (evaluate.py:197-201)
+  stage B  user vectors from int32 history rows [I, 50] (first 50 clicks, LEFT padded,
+           evaluate.py:111-124), gathered inside the library
+  stage C  CSR scoring (evaluate.py:245-260), `max_count` keeps the reference's off-by-one
+           (:247-249 processes max_count-1 impressions)
+  stage D  AUC / MRR / nDCG@5 / nDCG@10 per impression on the GPU + nanmean (:160-168,267-272)
+
+With torch.distributed initialised (one process per GPU) the news rows and the impressions are
+split into contiguous blocks per rank; the table is all-gathered (NCCL) and the eight metric
+sums/counts are all-reduced.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+def first_occurrence_rows(news_ids) -> np.ndarray:
+    """owner[i] = first row whose id equals news_ids[i]  (evaluate.py:197-201 'if id not in')."""
+    ids = np.asarray(news_ids)
+    _, first_idx, inverse = np.unique(ids, return_index=True, return_inverse=True)
+    return first_idx[inverse].astype(np.int64)
+
+
+def build_history(clicked_rows_list, num_clicked=50, pad_row=-1) -> np.ndarray:
+    """UserDataset.__getitem__ (evaluate.py:111-124): FIRST `num_clicked` clicks, LEFT padded."""
+    out = np.full((len(clicked_rows_list), num_clicked), pad_row, dtype=np.int64)
+    for i, h in enumerate(clicked_rows_list):
+        h = list(h)[:num_clicked]
+        if h:
+            out[i, num_clicked - len(h):] = h
+    return out
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+def shard_range(n, rank, world):
+    """Contiguous block [lo, hi) of rank `rank` (blocks of ceil(n/world))."""
+    per = (n + world - 1) // world
+    lo = min(rank * per, n)
+    return lo, min(lo + per, n)
+
+
+def shard_impressions_by_candidates(cand_offsets: np.ndarray, world: int):
+    """Impression block boundaries [world+1] balancing the number of CANDIDATES per rank."""
+    total = int(cand_offsets[-1])
+    targets = (np.arange(1, world) * total) // world
+    cuts = np.searchsorted(cand_offsets, targets, side="left")
+    return np.concatenate([[0], cuts, [len(cand_offsets) - 1]]).astype(np.int64)
+
+
+class EvalInputs:
+    """Evaluate inputs resident on one device (built once; the timed pipeline touches only these).
+
+    news_tokens  int64 [N_news, L]        hist_rows  int32 [I, 50]  (pad -> N_news, the zero row)
+    cand_rows    int32 [sumC]             cand_offsets int64 [I+1]   labels int8 [sumC]
+    """
+
+    def __init__(self, news_tokens, hist_rows, cand_offsets, cand_rows, labels, news_ids=None, device="cuda"):
+        n_news = int(news_tokens.shape[0])
+        hist = np.asarray(hist_rows, dtype=np.int64).copy()
+        cand = np.asarray(cand_rows, dtype=np.int64)
+        if news_ids is not None:          # first occurrence wins
+            owner = first_occurrence_rows(news_ids)
+            valid = hist >= 0
+            hist[valid] = owner[hist[valid]]
+            cand = owner[cand]
+        hist[hist < 0] = n_news           # PADDED_NEWS -> the all-zero last row of the table
+        self.n_news = n_news
+        self.n_impressions = int(hist.shape[0])
+        self.device = torch.device(device)
+        t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(self.device)
+        self.news_tokens = t(news_tokens, torch.int64)
+        self.hist_rows = t(hist, torch.int32)
+        self.cand_rows = t(cand, torch.int32)
+        self.cand_offsets = t(cand_offsets, torch.int64)
+        self.labels = t(labels, torch.int8)
+        self.cand_offsets_host = np.asarray(cand_offsets, dtype=np.int64)
+
+
+@torch.no_grad()
+def encode_news_table(model, news_tokens: torch.Tensor) -> torch.Tensor:
+    """Stage A.  Returns [N_news+1, 300] with a zero last row.  Multi-rank: each rank encodes its
+    contiguous row block straight into its slot of the (padded) table, then one all_gather."""
+    dist = _dist()
+    n = news_tokens.shape[0]
+    dev = news_tokens.device
+    was_training = model.training
+    model.eval()
+    try:
+        if dist is None:
+            table = torch.empty((n + 1, ops.D), dtype=torch.float32, device=dev)
+            table[:n] = model.get_news_vector({"title": news_tokens})
+            table[n].zero_()
+            return table
+        world, rank = dist.get_world_size(), dist.get_rank()
+        per = (n + world - 1) // world
+        padded = torch.zeros((world * per + 1, ops.D), dtype=torch.float32, device=dev)
+        lo, hi = shard_range(n, rank, world)
+        if hi > lo:
+            padded[lo:hi] = model.get_news_vector({"title": news_tokens[lo:hi]})
+        dist.all_gather_into_tensor(padded[:world * per].view(-1), padded[rank * per:(rank + 1) * per].reshape(-1).clone())
+        table = padded[:n + 1]
+        table[n].zero_()
+        return table
+    finally:
+        model.train(was_training)
+
+
+@torch.no_grad()
+def evaluate_tensors(model, inputs: EvalInputs, max_count=None, return_details=False):
+    """evaluate() on resident tensors -> (AUC, MRR, nDCG@5, nDCG@10) as Python floats.
+
+    One D2H read (the 8 sums/counts) at the very end; no per-impression host work."""
+    dist = _dist()
+    table = encode_news_table(model, inputs.news_tokens)
+    n_imp = inputs.n_impressions
+    if max_count is not None:
+        n_imp = max(0, min(n_imp, int(max_count) - 1))
+    lo, hi = 0, n_imp
+    if dist is not None:
+        bounds = shard_impressions_by_candidates(inputs.cand_offsets_host[:n_imp + 1], dist.get_world_size())
+        lo, hi = int(bounds[dist.get_rank()]), int(bounds[dist.get_rank() + 1])
+    dev = inputs.device
+    if hi > lo:
+        user_vec = model.user_encoder.forward_indexed(table, inputs.hist_rows[lo:hi])
+        c0, c1 = int(inputs.cand_offsets_host[lo]), int(inputs.cand_offsets_host[hi])
+        offs = (inputs.cand_offsets[lo:hi + 1] - c0).contiguous()
+        scores = ops.score_csr(table, inputs.cand_rows[c0:c1], offs, user_vec)
+        per, sums = ops.rank_metrics(scores, inputs.labels[c0:c1], offs)
+    else:
+        user_vec = torch.empty((0, ops.D), device=dev)
+        scores = torch.empty((0,), device=dev)
+        per = torch.empty((0, 4), dtype=torch.float64, device=dev)
+        sums = torch.zeros((8,), dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(sums)
+    s = sums.cpu().numpy()
+    with np.errstate(all="ignore"):
+        means = tuple(float(x) for x in (s[:4] / s[4:]))
+    if return_details:
+        return means, dict(table=table, user_vectors=user_vec, scores=scores, per_impression=per,
+                           impression_range=(lo, hi))
+    return means

@@ -1,0 +1,53 @@
+"""NewsEncoder (reference src/model/NRMS/news_encoder.py:10-48) on libnrms_b200."""
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ...config import resolve_mode
+from ..general.attention.multihead_self import MultiHeadSelfAttention
+from ..general.attention.additive import AdditiveAttention
+
+
+class NewsEncoder(nn.Module):
+    def __init__(self, config, pretrained_word_embedding):
+        super().__init__()
+        self.config = config
+        if pretrained_word_embedding is None:
+            self.word_embedding = nn.Embedding(config.num_words, config.word_embedding_dim, padding_idx=0)
+        else:
+            self.word_embedding = nn.Embedding.from_pretrained(pretrained_word_embedding, freeze=False,
+                                                               padding_idx=0)
+        self.multihead_self_attention = MultiHeadSelfAttention(config.word_embedding_dim,
+                                                               config.num_attention_heads)
+        self.additive_attention = AdditiveAttention(config.query_vector_dim, config.word_embedding_dim)
+        self.precision = None          # None -> config.precision / $NRMS_B200_PRECISION / "tf32"
+        self._dropout_calls = 0
+        self.dropout_seed = 0x5EED
+
+    def _check_dims(self):
+        c = self.config
+        if (c.word_embedding_dim, c.num_attention_heads, c.query_vector_dim) != (ops.D, ops.H, ops.QD):
+            raise RuntimeError("libnrms_b200 is compiled for word_embedding_dim=300, num_attention_heads=15, "
+                               "query_vector_dim=200 (reference src/config.py:33-45)")
+
+    def encode_tokens(self, title):
+        """title: integer tensor [n, num_words_title] (any device) -> fp32 [n, 300]."""
+        self._check_dims()
+        dev = self.word_embedding.weight.device
+        title = title.to(dev, non_blocking=True)
+        wqkv, bqkv = self.multihead_self_attention.packed()
+        p = float(self.config.dropout_probability) if self.training else 0.0
+        offset = 0
+        if p > 0.0:
+            # a fresh Philox offset per call (n*20*300/4 counters per dropout site)
+            offset = self._dropout_calls
+            self._dropout_calls += (title.numel() * ops.D) // 4 + 1
+        return ops.news_encoder(title, self.word_embedding.weight, wqkv, bqkv,
+                                self.additive_attention.linear.weight, self.additive_attention.linear.bias,
+                                self.additive_attention.attention_query_vector,
+                                dropout_p=p, seed=self.dropout_seed, offset=offset,
+                                mode=resolve_mode(self.config, self.precision))
+
+    def forward(self, news):
+        """news: {"title": batch_size * num_words_title} -> batch_size, word_embedding_dim"""
+        return self.encode_tokens(news["title"])

@@ -1,0 +1,24 @@
+"""AdditiveAttention parameter container.
+
+Mirror of reference src/model/general/attention/additive.py:6-53: Linear(candidate_dim ->
+query_dim), query vector ~ U(-0.1, 0.1).  `writer/tag/names` are accepted and ignored (NRMS
+passes none: src/model/NRMS/news_encoder.py:24-25).
+"""
+import torch
+import torch.nn as nn
+
+
+class AdditiveAttention(nn.Module):
+    def __init__(self, query_vector_dim, candidate_vector_dim, writer=None, tag=None, names=None):
+        super().__init__()
+        self.linear = nn.Linear(candidate_vector_dim, query_vector_dim)
+        self.attention_query_vector = nn.Parameter(torch.empty(query_vector_dim).uniform_(-0.1, 0.1))
+        self.writer = writer
+        self.tag = tag
+        self.names = names
+        self.local_step = 1
+
+    def forward(self, candidate_vector):
+        raise NotImplementedError(
+            "AdditiveAttention is fused into the encoder kernels of libnrms_b200; call the owning "
+            "NewsEncoder / UserEncoder")

@@ -1,0 +1,39 @@
+"""MultiHeadSelfAttention parameter container + standalone forward.
+
+Mirror of reference src/model/general/attention/multihead_self.py:26-76: three nn.Linear
+(W_Q, W_K, W_V; xavier_uniform weights, :41-44), no output projection.  Inside NewsEncoder /
+UserEncoder the projections, the exp-softmax attention and the pooling run inside
+libnrms_b200; this class owns the parameters so state_dict keys match the reference.
+"""
+import torch
+import torch.nn as nn
+
+
+class MultiHeadSelfAttention(nn.Module):
+    def __init__(self, d_model, num_attention_heads):
+        super().__init__()
+        assert d_model % num_attention_heads == 0
+        self.d_model = d_model
+        self.num_attention_heads = num_attention_heads
+        self.d_k = d_model // num_attention_heads
+        self.d_v = d_model // num_attention_heads
+        self.W_Q = nn.Linear(d_model, d_model)
+        self.W_K = nn.Linear(d_model, d_model)
+        self.W_V = nn.Linear(d_model, d_model)
+        self._initialize_weights()
+
+    def _initialize_weights(self):
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight, gain=1)
+
+    def packed(self):
+        """([W_Q;W_K;W_V] [3D,D], [b_Q;b_K;b_V] [3D]) -- autograd splits the gradients back."""
+        return (torch.cat([self.W_Q.weight, self.W_K.weight, self.W_V.weight], dim=0),
+                torch.cat([self.W_Q.bias, self.W_K.bias, self.W_V.bias], dim=0))
+
+    def forward(self, Q, K=None, V=None, length=None):
+        raise NotImplementedError(
+            "MultiHeadSelfAttention is fused into the encoder kernels of libnrms_b200; call the owning "
+            "NewsEncoder / UserEncoder (the reference never calls this block on its own in NRMS, and never "
+            "passes K, V or length: src/model/NRMS/news_encoder.py:41, user_encoder.py:23)")

@@ -1,0 +1,275 @@
+"""torch.autograd.Function wrappers over the C-ABI (forward AND backward run in libnrms_b200).
+
+PyTorch is plumbing here: it owns device memory, streams and autograd bookkeeping; every
+arithmetic step is a hand-written sm_100a kernel behind `include/nrms_b200.h`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+D, H, QD = 300, 15, 200
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("newsrecommendationsystem_b200 ops need CUDA tensors (there is no CPU fallback); "
+                               "move the model/inputs to a B200 device")
+
+
+def _f32c(t):
+    return t.detach().contiguous().float()
+
+
+def _bytes(n, device):
+    # at least 256 B so that data_ptr() is a real, 256-byte aligned allocation
+    return torch.empty(max(int(n), 256), dtype=torch.uint8, device=device)
+
+
+def pack_qkv(wq, bq, wk, bk, wv, bv):
+    """[W_Q; W_K; W_V] -> [900,300], [b_Q; b_K; b_V] -> [900] (autograd-transparent)."""
+    return torch.cat([wq, wk, wv], dim=0), torch.cat([bq, bk, bv], dim=0)
+
+
+class _NewsEncoderFn(torch.autograd.Function):
+    """NewsEncoder.forward (reference src/model/NRMS/news_encoder.py:27-48)."""
+
+    @staticmethod
+    def forward(ctx, tokens, emb, wqkv, bqkv, wa, ba, qa, dropout_p, seed, offset, mode):
+        lib = _lib.load()
+        _require_cuda(tokens, emb, wqkv, bqkv, wa, ba, qa)
+        tokens = tokens.contiguous()
+        if tokens.dtype != torch.int64:
+            tokens = tokens.long()
+        n, L = tokens.shape
+        dev = emb.device
+        emb_c, wqkv_c, bqkv_c, wa_c, ba_c, qa_c = map(_f32c, (emb, wqkv, bqkv, wa, ba, qa))
+        out = torch.empty((n, D), dtype=torch.float32, device=dev)
+        needs_grad = any(ctx.needs_input_grad)
+        stash = None
+        if needs_grad:
+            stash = _bytes(lib.nrms_encoder_stash_bytes(n, L), dev)
+        ws_bytes = lib.nrms_encoder_fwd_workspace_bytes(n, L, mode, 1 if needs_grad else 0)
+        ws = _bytes(ws_bytes, dev)
+        check(lib.nrms_news_encoder_fwd(ptr(tokens), n, L, ptr(emb_c), emb_c.shape[0], ptr(wqkv_c), ptr(bqkv_c),
+                                        ptr(wa_c), ptr(ba_c), ptr(qa_c), ptr(out), ptr(stash), ptr(ws), ws.numel(),
+                                        float(dropout_p), int(seed), int(offset), mode, stream_ptr(dev)),
+              "nrms_news_encoder_fwd")
+        if needs_grad:
+            ctx.save_for_backward(tokens, wqkv_c, wa_c, qa_c, stash)
+            ctx.meta = (n, L, emb_c.shape[0], float(dropout_p), int(seed), int(offset), mode)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        tokens, wqkv, wa, qa, stash = ctx.saved_tensors
+        n, L, V, p, seed, offset, mode = ctx.meta
+        dev = d_out.device
+        d_out = d_out.contiguous().float()
+        d_emb = torch.zeros((V, D), dtype=torch.float32, device=dev)
+        d_wqkv = torch.zeros((3 * D, D), dtype=torch.float32, device=dev)
+        d_bqkv = torch.zeros((3 * D,), dtype=torch.float32, device=dev)
+        d_wa = torch.zeros((QD, D), dtype=torch.float32, device=dev)
+        d_ba = torch.zeros((QD,), dtype=torch.float32, device=dev)
+        d_qa = torch.zeros((QD,), dtype=torch.float32, device=dev)
+        ws = _bytes(lib.nrms_encoder_bwd_workspace_bytes(n, L, mode), dev)
+        check(lib.nrms_news_encoder_bwd(ptr(d_out), ptr(tokens), n, L, V, ptr(wqkv), ptr(wa), ptr(qa), ptr(stash),
+                                        ptr(d_emb), ptr(d_wqkv), ptr(d_bqkv), ptr(d_wa), ptr(d_ba), ptr(d_qa),
+                                        ptr(ws), ws.numel(), p, seed, offset, mode, stream_ptr(dev)),
+              "nrms_news_encoder_bwd")
+        return None, d_emb, d_wqkv, d_bqkv, d_wa, d_ba, d_qa, None, None, None, None
+
+
+class _UserEncoderFn(torch.autograd.Function):
+    """UserEncoder.forward (reference src/model/NRMS/user_encoder.py:15-26), dense input."""
+
+    @staticmethod
+    def forward(ctx, x, wqkv, bqkv, wa, ba, qa, mode):
+        lib = _lib.load()
+        _require_cuda(x, wqkv, bqkv, wa, ba, qa)
+        n, S, d = x.shape
+        if d != D:
+            raise RuntimeError(f"user encoder compiled for dim {D}, got {d}")
+        dev = x.device
+        x_c, wqkv_c, bqkv_c, wa_c, ba_c, qa_c = map(_f32c, (x, wqkv, bqkv, wa, ba, qa))
+        out = torch.empty((n, D), dtype=torch.float32, device=dev)
+        needs_grad = any(ctx.needs_input_grad)
+        stash = _bytes(lib.nrms_encoder_stash_bytes(n, S), dev) if needs_grad else None
+        ws = _bytes(lib.nrms_encoder_fwd_workspace_bytes(n, S, mode, 1 if needs_grad else 0), dev)
+        check(lib.nrms_user_encoder_fwd(ptr(x_c), None, n, S, ptr(wqkv_c), ptr(bqkv_c), ptr(wa_c), ptr(ba_c),
+                                        ptr(qa_c), ptr(out), ptr(stash), ptr(ws), ws.numel(), mode, stream_ptr(dev)),
+              "nrms_user_encoder_fwd")
+        if needs_grad:
+            ctx.save_for_backward(wqkv_c, wa_c, qa_c, stash)
+            ctx.meta = (n, S, mode)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        wqkv, wa, qa, stash = ctx.saved_tensors
+        n, S, mode = ctx.meta
+        dev = d_out.device
+        d_out = d_out.contiguous().float()
+        d_x = torch.empty((n, S, D), dtype=torch.float32, device=dev)
+        d_wqkv = torch.zeros((3 * D, D), dtype=torch.float32, device=dev)
+        d_bqkv = torch.zeros((3 * D,), dtype=torch.float32, device=dev)
+        d_wa = torch.zeros((QD, D), dtype=torch.float32, device=dev)
+        d_ba = torch.zeros((QD,), dtype=torch.float32, device=dev)
+        d_qa = torch.zeros((QD,), dtype=torch.float32, device=dev)
+        ws = _bytes(lib.nrms_encoder_bwd_workspace_bytes(n, S, mode), dev)
+        check(lib.nrms_user_encoder_bwd(ptr(d_out), n, S, ptr(wqkv), ptr(wa), ptr(qa), ptr(stash), ptr(d_x),
+                                        ptr(d_wqkv), ptr(d_bqkv), ptr(d_wa), ptr(d_ba), ptr(d_qa), ptr(ws),
+                                        ws.numel(), mode, stream_ptr(dev)),
+              "nrms_user_encoder_bwd")
+        return d_x, d_wqkv, d_bqkv, d_wa, d_ba, d_qa, None
+
+
+class _ScoreFn(torch.autograd.Function):
+    """DotProductClickPredictor.forward (reference .../click_predictor/dot_product.py:8-19)."""
+
+    @staticmethod
+    def forward(ctx, cand, user):
+        lib = _lib.load()
+        _require_cuda(cand, user)
+        B, Cn, X = cand.shape
+        cand_c, user_c = _f32c(cand), _f32c(user)
+        scores = torch.empty((B, Cn), dtype=torch.float32, device=cand.device)
+        check(lib.nrms_score_fwd(ptr(cand_c), ptr(user_c), B, Cn, X, ptr(scores), stream_ptr(cand.device)),
+              "nrms_score_fwd")
+        ctx.save_for_backward(cand_c, user_c)
+        return scores
+
+    @staticmethod
+    def backward(ctx, d_scores):
+        lib = _lib.load()
+        cand, user = ctx.saved_tensors
+        B, Cn, X = cand.shape
+        d_scores = d_scores.contiguous().float()
+        d_cand = torch.empty_like(cand)
+        d_user = torch.empty_like(user)
+        check(lib.nrms_score_bwd(ptr(d_scores), ptr(cand), ptr(user), B, Cn, X, ptr(d_cand), ptr(d_user),
+                                 stream_ptr(cand.device)), "nrms_score_bwd")
+        return d_cand, d_user
+
+
+class _CrossEntropyLabel0Fn(torch.autograd.Function):
+    """CrossEntropyLoss()(y_pred, zeros) (reference src/train.py:126,205-206)."""
+
+    @staticmethod
+    def forward(ctx, logits):
+        lib = _lib.load()
+        _require_cuda(logits)
+        lg = _f32c(logits)
+        B, Cn = lg.shape
+        loss = torch.empty((), dtype=torch.float32, device=lg.device)
+        d_logits = torch.empty_like(lg)
+        check(lib.nrms_ce_loss_fwd_bwd(ptr(lg), B, Cn, 1.0, ptr(loss), ptr(d_logits), stream_ptr(lg.device)),
+              "nrms_ce_loss_fwd_bwd")
+        ctx.save_for_backward(d_logits)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (d_logits,) = ctx.saved_tensors
+        return d_logits * g
+
+
+# ---- functional API ---------------------------------------------------------------------------
+def news_encoder(tokens, emb, wqkv, bqkv, wa, ba, qa, dropout_p=0.0, seed=0, offset=0, mode=_lib.MODE_TF32):
+    return _NewsEncoderFn.apply(tokens, emb, wqkv, bqkv, wa, ba, qa, dropout_p, seed, offset, mode)
+
+
+def user_encoder(x, wqkv, bqkv, wa, ba, qa, mode=_lib.MODE_TF32):
+    return _UserEncoderFn.apply(x, wqkv, bqkv, wa, ba, qa, mode)
+
+
+@torch.no_grad()
+def user_encoder_indexed(table, rows, wqkv, bqkv, wa, ba, qa, mode=_lib.MODE_TF32):
+    """Inference-only user encoder whose input rows are gathered from `table` [n_rows,300] by
+    int32 `rows` [n_users,S] (replaces the dict/stack loops of reference src/evaluate.py:220-224)."""
+    lib = _lib.load()
+    _require_cuda(table, rows)
+    if rows.dtype != torch.int32:
+        rows = rows.int()
+    rows = rows.contiguous()
+    n, S = rows.shape
+    dev = table.device
+    out = torch.empty((n, D), dtype=torch.float32, device=dev)
+    ws = _bytes(lib.nrms_encoder_fwd_workspace_bytes(n, S, mode, 0), dev)
+    args = [_f32c(t) for t in (table, wqkv, bqkv, wa, ba, qa)]
+    check(lib.nrms_user_encoder_fwd(ptr(args[0]), ptr(rows), n, S, ptr(args[1]), ptr(args[2]), ptr(args[3]),
+                                    ptr(args[4]), ptr(args[5]), ptr(out), None, ptr(ws), ws.numel(), mode,
+                                    stream_ptr(dev)), "nrms_user_encoder_fwd(indexed)")
+    return out
+
+
+def click_score(cand, user):
+    return _ScoreFn.apply(cand, user)
+
+
+def cross_entropy_label0(logits):
+    return _CrossEntropyLabel0Fn.apply(logits)
+
+
+@torch.no_grad()
+def score_csr(table, cand_rows, offsets, user_vec):
+    lib = _lib.load()
+    _require_cuda(table, cand_rows, offsets, user_vec)
+    n_imp = offsets.numel() - 1
+    scores = torch.empty((cand_rows.numel(),), dtype=torch.float32, device=table.device)
+    check(lib.nrms_score_csr(ptr(table), ptr(cand_rows), ptr(offsets), ptr(user_vec), n_imp, ptr(scores),
+                             stream_ptr(table.device)), "nrms_score_csr")
+    return scores
+
+
+@torch.no_grad()
+def rank_metrics(scores, labels, offsets):
+    """-> (per_impression [n,4] fp64 with NaN rows for single-class impressions, sums_counts [8] fp64)."""
+    lib = _lib.load()
+    _require_cuda(scores, labels, offsets)
+    n_imp = offsets.numel() - 1
+    per = torch.empty((n_imp, 4), dtype=torch.float64, device=scores.device)
+    sc = torch.empty((8,), dtype=torch.float64, device=scores.device)
+    check(lib.nrms_rank_metrics(ptr(scores), ptr(labels), ptr(offsets), n_imp, ptr(per), ptr(sc),
+                                stream_ptr(scores.device)), "nrms_rank_metrics")
+    return per, sc
+
+
+@torch.no_grad()
+def gather_rows(src, rows):
+    lib = _lib.load()
+    _require_cuda(src, rows)
+    rows = rows.contiguous().long()
+    out = torch.empty((rows.numel(), src.shape[1]), dtype=torch.float32, device=src.device)
+    check(lib.nrms_gather_rows(ptr(src), ptr(rows), rows.numel(), src.shape[1], ptr(out), stream_ptr(src.device)),
+          "nrms_gather_rows")
+    return out
+
+
+@torch.no_grad()
+def adam_step_(p, g, m, v, step, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=False,
+               grad_scale=1.0):
+    lib = _lib.load()
+    _require_cuda(p, g, m, v)
+    check(lib.nrms_adam_step(ptr(p), ptr(g), ptr(m), ptr(v), p.numel(), lr, betas[0], betas[1], eps, weight_decay,
+                             1 if decoupled else 0, int(step), grad_scale, stream_ptr(p.device)), "nrms_adam_step")
+
+
+@torch.no_grad()
+def gemm_nt(a, b, bias=None, mode=_lib.MODE_TF32):
+    """C = A @ B^T (+bias) through the library's contraction kernels (tests / profiling)."""
+    lib = _lib.load()
+    _require_cuda(a, b)
+    M, K = a.shape
+    N = b.shape[0]
+    c = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    check(lib.nrms_gemm_nt(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(bias), ptr(c), c.stride(0), M, N, K, mode,
+                           stream_ptr(a.device)), "nrms_gemm_nt")
+    return c

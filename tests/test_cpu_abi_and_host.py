@@ -1,0 +1,115 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/nrms_b200.h declares
+(no compute calls), the ctypes table matches the header, argument validation returns error codes
+without touching a GPU, and the host-side evaluate helpers follow the reference's indexing rules."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "nrms_b200.h")
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b(nrms_[a-z0-9_]+)\s*\(", src)
+    return sorted(set(names))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from newsrecommendationsystem_b200 import _lib
+    return _lib.load()
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    from newsrecommendationsystem_b200 import _lib
+    declared = header_functions()
+    assert len(declared) >= 17
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in nrms_b200.h but not exported"
+    assert sorted(_lib.SIGNATURES) == declared, "ctypes table and header disagree"
+
+
+def test_argument_count_matches_header():
+    from newsrecommendationsystem_b200 import _lib
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for name, (_, args) in _lib.SIGNATURES.items():
+        m = re.search(r"\b" + name + r"\s*\(([^)]*)\)", src)
+        assert m, name
+        params = m.group(1).strip()
+        n = 0 if params in ("", "void") else len(params.split(","))
+        assert n == len(args), (name, n, len(args))
+
+
+def test_version_and_error_paths_without_gpu(lib):
+    assert lib.nrms_abi_version() == 1
+    # invalid arguments are rejected before any CUDA call; message is retrievable
+    rc = lib.nrms_score_fwd(None, None, 4, 0, 300, None, None)
+    assert rc == 1 and b"bad sizes" in lib.nrms_last_error()
+    rc = lib.nrms_news_encoder_fwd(None, 8, 21, None, 10, None, None, None, None, None, None, None, None, 0,
+                                   0.0, 0, 0, 0, None)
+    assert rc == 2 and b"unsupported" in lib.nrms_last_error()
+    rc = lib.nrms_adam_step(None, None, None, None, 16, 1e-4, 0.9, 0.999, 1e-8, 0.0, 0, 0, 1.0, None)
+    assert rc == 1
+    assert lib.nrms_encoder_stash_bytes(7040, 20) >= 7040 * 20 * (300 + 900 + 300 + 200 + 1) * 4
+    assert lib.nrms_encoder_bwd_workspace_bytes(128, 50, 0) > 0
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from newsrecommendationsystem_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libnrms_b200.so")
+    with pytest.raises(ImportError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "newsrecommendationsystem_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("# oracle", ""), os.path.join(dirpath, f)
+
+
+def test_first_occurrence_and_history_match_oracle():
+    from newsrecommendationsystem_b200 import evaluate as E
+    from oracle import nrms_oracle as O
+    ids = np.array([5, 9, 5, 7, 9, 9, 1])
+    assert E.first_occurrence_rows(ids).tolist() == O.first_occurrence_rows(ids).tolist() == [0, 1, 0, 3, 1, 1, 6]
+    hs = [[1, 2, 3], list(range(100, 160)), []]
+    assert np.array_equal(E.build_history(hs), O.build_history(hs))
+
+
+def test_sharding_helpers():
+    from newsrecommendationsystem_b200 import evaluate as E
+    assert [E.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert [E.shard_range(2, r, 4) for r in range(4)] == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    offs = np.array([0, 10, 12, 40, 41, 80, 100])
+    b = E.shard_impressions_by_candidates(offs, 4)
+    assert b[0] == 0 and b[-1] == 6 and (np.diff(b) >= 0).all()
+    loads = [offs[b[i + 1]] - offs[b[i]] for i in range(4)]
+    assert sum(loads) == 100 and max(loads) <= 60
+
+
+def test_synthetic_shapes():
+    from newsrecommendationsystem_b200 import synthetic
+    toks = synthetic.make_news(1000)
+    assert toks.shape == (1000, 20) and toks.dtype == np.int64 and (toks[:, 0] > 0).all() and toks.max() < 70976
+    imp = synthetic.make_impressions(3000, 1000)
+    C_ = np.diff(imp["cand_offsets"])
+    assert C_.min() >= 2 and C_.max() <= 300 and 25 < C_.mean() < 50
+    h = imp["hist_rows"]
+    pads = (h < 0)
+    assert (pads[:, :-1] >= pads[:, 1:]).all()          # pads are a LEFT prefix
+    lab = imp["labels"]
+    o = imp["cand_offsets"]
+    assert lab[o[0]:o[1]].max() == 1 and lab[o[999]:o[1000]].max() == 0   # every 1000th single-class
+    cand, clicked = synthetic.make_train_batch(16, toks, k_neg=4)
+    assert cand.shape == (16, 5, 20) and clicked.shape == (16, 50, 20)

@@ -1,0 +1,374 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) vs the numpy oracle and the committed
+reference-generated golden fixtures.  Run on the B200 box: pytest -m gpu.
+
+Tolerances (north_star): gathers / indexing bit-exact; news & user vectors <= 1e-3 max row-wise
+relative L2 in TF32 mode (<= 2e-5 in FP32 mode); metrics equal to 3 decimals.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2_rows
+from oracle import nrms_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_VEC = {"fp32": 2e-5, "tf32": 1e-3}
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from newsrecommendationsystem_b200 import _lib
+    return _lib.load()
+
+
+class Cfg:
+    num_words = 401
+    word_embedding_dim = 300
+    num_attention_heads = 15
+    query_vector_dim = 200
+    dropout_probability = 0.2
+    num_words_title = 20
+    num_clicked_news_a_user = 50
+
+
+def make_model(golden_sd, dev, precision, cfg=Cfg):
+    from newsrecommendationsystem_b200 import NRMS
+    m = NRMS(cfg)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in golden_sd.items()})   # reference keys/shapes
+    m.to(dev).eval()
+    m.set_precision(precision)
+    return m
+
+
+def t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_library_loaded_and_versioned(lib):
+    assert lib.nrms_abi_version() == 1
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("shape", [(128, 256, 32), (1000, 900, 300), (257, 200, 300), (61, 300, 900), (4096, 900, 300)])
+def test_gemm_nt(dev, mode, shape):
+    from newsrecommendationsystem_b200 import ops, _lib
+    M, N, K = shape
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N)
+    a = torch.randn(M, K, generator=g).to(dev)
+    b = (torch.randn(N, K, generator=g) * 0.1).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    c = ops.gemm_nt(a, b, bias, mode=_lib.MODES[mode])
+    ref = (a.double() @ b.double().T + bias.double())
+    err = (c.double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    # TF32: operands rounded to 11-bit significands -> ~2^-11 relative per product, averaged over K
+    tol = 2e-6 if mode == "fp32" else 2e-3
+    assert err / scale < tol, (mode, shape, err, scale)
+
+
+def test_gather_bit_exact(dev, lib, golden, golden_sd):
+    """Embedding gather inside nrms_news_encoder_fwd (training stash X) is a bit-exact row copy."""
+    from newsrecommendationsystem_b200._lib import ptr, stream_ptr, check, MODE_FP32
+    from newsrecommendationsystem_b200 import ops
+    toks = t(golden["fwd/tokens"], dev)
+    n, L = toks.shape
+    sd = {k: t(v, dev) for k, v in golden_sd.items()}
+    p = O.enc_keys("news_encoder")
+    wqkv = torch.cat([sd[p["Wq"]], sd[p["Wk"]], sd[p["Wv"]]]).contiguous()
+    bqkv = torch.cat([sd[p["bq"]], sd[p["bk"]], sd[p["bv"]]]).contiguous()
+    stash = torch.zeros(lib.nrms_encoder_stash_bytes(n, L), dtype=torch.uint8, device=dev)
+    ws = torch.zeros(max(256, lib.nrms_encoder_fwd_workspace_bytes(n, L, MODE_FP32, 1)), dtype=torch.uint8, device=dev)
+    out = torch.empty(n, 300, device=dev)
+    check(lib.nrms_news_encoder_fwd(ptr(toks), n, L, ptr(sd[O.EMB_KEY]), sd[O.EMB_KEY].shape[0], ptr(wqkv), ptr(bqkv),
+                                    ptr(sd[p["Wa"]]), ptr(sd[p["ba"]]), ptr(sd[p["qa"]]), ptr(out), ptr(stash),
+                                    ptr(ws), ws.numel(), 0.0, 0, 0, MODE_FP32, stream_ptr(dev)))
+    torch.cuda.synchronize()
+    x = stash[: n * L * 300 * 4].view(torch.float32).view(n, L, 300).cpu().numpy()
+    assert np.array_equal(x.view(np.uint32), golden["fwd/gathered"].view(np.uint32))
+    # the standalone gather entry point is bit-exact too
+    g2 = ops.gather_rows(sd[O.EMB_KEY], toks.reshape(-1)).cpu().numpy().reshape(n, L, 300)
+    assert np.array_equal(g2.view(np.uint32), golden["fwd/gathered"].view(np.uint32))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_news_vectors_golden(dev, golden, golden_sd, precision):
+    m = make_model(golden_sd, dev, precision)
+    with torch.no_grad():
+        nv = m.get_news_vector({"title": torch.from_numpy(golden["fwd/tokens"])})   # CPU input, like the DataLoader
+    err = rel_l2_rows(nv.cpu().numpy(), golden["fwd/news_vectors"])
+    assert err < TOL_VEC[precision], err
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_user_vectors_golden(dev, golden, golden_sd, precision):
+    m = make_model(golden_sd, dev, precision)
+    with torch.no_grad():
+        uv = m.get_user_vector(t(golden["fwd/user_input"], dev))
+    err = rel_l2_rows(uv.cpu().numpy(), golden["fwd/user_vectors"])
+    assert err < TOL_VEC[precision], err
+
+
+def test_scores_golden(dev, golden, golden_sd):
+    m = make_model(golden_sd, dev, "fp32")
+    nv, uv = t(golden["fwd/news_vectors"], dev), t(golden["fwd/user_vectors"], dev)
+    with torch.no_grad():
+        s = m.get_prediction(nv[:23], uv[0])
+        sb = m.click_predictor(nv[:36].reshape(9, 4, 300), uv)
+    np.testing.assert_allclose(s.cpu().numpy(), golden["fwd/scores_single"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(sb.cpu().numpy(), golden["fwd/scores_batched"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("n", [1, 6, 7, 130, 2049])
+def test_news_encoder_vs_oracle_ragged_sizes(dev, golden_sd, precision, n):
+    """Batch sizes around the tile boundaries (1 title, partial tiles, > one inference chunk)."""
+    from newsrecommendationsystem_b200 import synthetic
+    toks = synthetic.make_news(n, num_words=Cfg.num_words, seed=100 + n)
+    if n > 6:
+        toks[3] = 0          # all-pad title
+    ref, _ = O.news_encoder_forward(golden_sd, toks)
+    m = make_model(golden_sd, dev, precision)
+    with torch.no_grad():
+        nv = m.get_news_vector({"title": torch.from_numpy(toks)})
+    assert rel_l2_rows(nv.cpu().numpy(), ref) < TOL_VEC[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_user_encoder_indexed_equals_dense(dev, golden_sd, precision):
+    rng = np.random.default_rng(5)
+    table = rng.standard_normal((301, 300)).astype(np.float32) * 0.3
+    table[300] = 0
+    rows = rng.integers(0, 300, size=(67, 50))
+    rows[4, :31] = 300
+    rows[9] = 300
+    ref, _ = O.user_encoder_forward(golden_sd, table[rows])
+    m = make_model(golden_sd, dev, precision)
+    tb = t(table, dev)
+    with torch.no_grad():
+        a = m.user_encoder.forward_indexed(tb, t(rows.astype(np.int32), dev))
+        b = m.get_user_vector(tb[t(rows, dev)])
+    assert rel_l2_rows(a.cpu().numpy(), ref) < TOL_VEC[precision]
+    assert torch.equal(a, b)      # the in-library gather is a pure copy
+
+
+# ---------------------------------------------------------------------------------------------
+def _train_once(golden, golden_sd, dev, precision, adamw=False, steps=1):
+    from newsrecommendationsystem_b200.train import TrainStep
+    m = make_model(golden_sd, dev, precision)
+    m.eval()   # goldens were produced in eval mode (dropout = identity), grads still flow
+    ts = TrainStep(m, lr=1e-4, adamw=adamw, weight_decay=0.01 if adamw else 0.0)
+    cand, clicked = golden["train/cand"], golden["train/clicked"]
+    titles = torch.from_numpy(np.concatenate([cand, clicked], axis=1))
+    losses, grads = [], None
+    for _ in range(steps):
+        loss = ts.step_tokens(titles, cand.shape[1])
+        losses.append(float(loss.item()))
+        if grads is None:
+            grads = {k: p.grad.detach().clone().cpu().numpy() for k, p in m.named_parameters()}
+    return m, losses, grads
+
+
+def test_train_step_fp32_matches_reference(dev, golden, golden_sd):
+    m, losses, grads = _train_once(golden, golden_sd, dev, "fp32", steps=2)
+    assert abs(losses[0] - float(golden["train/loss"])) < 1e-5
+    assert abs(losses[1] - float(golden["train/loss2"])) < 2e-5
+    for k, g in grads.items():
+        ref = golden["train/grad/" + k]
+        got = g if "embedding" in k else (g[:48] if g.ndim == 2 else g)
+        scale = np.abs(ref).max() + 1e-12
+        assert np.abs(got - ref).max() < 2e-4 * scale + 1e-8, (k, np.abs(got - ref).max(), scale)
+    assert not grads[O.EMB_KEY][0].any()
+    sd = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+    for k, v in sd.items():
+        ref = golden["train/adam2/" + k]
+        got = v[:48] if v.ndim == 2 else v
+        gs = float(np.abs(golden["train/grad/" + k]).mean())
+        d = np.abs(got.astype(np.float64) - ref)
+        assert d.max() <= 2.5e-4, k                      # never more than ~2 lr per step off
+        if gs >= 1e-5:                                    # tensors whose Adam update is well conditioned
+            assert (d <= 1e-6).mean() >= 0.8 and d.mean() < 2e-6, (k, d.mean())
+
+
+def test_train_logits_tf32(dev, golden, golden_sd):
+    m = make_model(golden_sd, dev, "tf32")
+    cand, clicked = golden["train/cand"], golden["train/clicked"]
+    titles = torch.from_numpy(np.concatenate([cand, clicked], axis=1))
+    with torch.no_grad():
+        logits = m.forward_tokens(titles, cand.shape[1])
+    np.testing.assert_allclose(logits.cpu().numpy(), golden["train/logits"], rtol=0, atol=2e-3)
+
+
+def test_reference_list_of_dict_api(dev, golden, golden_sd):
+    """model(candidate_news, clicked_news) with the reference's list-of-dict minibatch (train.py:202-203)."""
+    m = make_model(golden_sd, dev, "fp32")
+    cand, clicked = golden["train/cand"], golden["train/clicked"]
+    cn = [{"title": torch.from_numpy(cand[:, i])} for i in range(cand.shape[1])]
+    cl = [{"title": torch.from_numpy(clicked[:, i])} for i in range(clicked.shape[1])]
+    with torch.no_grad():
+        y = m(cn, cl)
+    np.testing.assert_allclose(y.cpu().numpy(), golden["train/logits"], rtol=0, atol=2e-5)
+
+
+def test_adam_kernel_elementwise(dev, golden, golden_sd):
+    from newsrecommendationsystem_b200 import ops
+    for k in golden_sd:
+        if "embedding" in k:
+            continue
+        p0 = golden_sd[k][:48] if golden_sd[k].ndim == 2 else golden_sd[k]
+        g = golden["train/grad/" + k]
+        for tag, kw in (("adam1", {}), ("adamw1", dict(weight_decay=0.01, decoupled=True))):
+            p = t(p0.reshape(-1).copy(), dev)
+            m_ = torch.zeros_like(p)
+            v_ = torch.zeros_like(p)
+            ops.adam_step_(p, t(g.reshape(-1).copy(), dev), m_, v_, 1, lr=1e-4, **kw)
+            np.testing.assert_allclose(p.cpu().numpy().reshape(p0.shape), golden[f"train/{tag}/" + k], rtol=0,
+                                       atol=2e-8, err_msg=k)
+
+
+def test_ce_loss_and_score_backward_vs_oracle(dev):
+    from newsrecommendationsystem_b200 import ops
+    rng = np.random.default_rng(3)
+    cand = rng.standard_normal((17, 5, 300)).astype(np.float32)
+    user = rng.standard_normal((17, 300)).astype(np.float32)
+    ct, ut = t(cand, dev).requires_grad_(), t(user, dev).requires_grad_()
+    logits = ops.click_score(ct, ut)
+    loss = ops.cross_entropy_label0(logits)
+    loss.backward()
+    lo = O.click_score(cand, user)
+    l_ref, dl = O.cross_entropy_label0(lo)
+    assert abs(float(loss.item()) - float(l_ref)) < 1e-4 * abs(float(l_ref))
+    np.testing.assert_allclose(ct.grad.cpu().numpy(), dl[:, :, None] * user[:, None, :], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(ut.grad.cpu().numpy(), np.einsum("bc,bcx->bx", dl, cand), rtol=1e-4, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+def test_rank_metrics_golden(dev, golden):
+    from newsrecommendationsystem_b200 import ops
+    per, sums = ops.rank_metrics(t(golden["metric/scores"], dev), t(golden["metric/labels"], dev),
+                                 t(golden["metric/offsets"], dev))
+    per = per.cpu().numpy()
+    offs = golden["metric/offsets"]
+    for i in range(len(offs) - 1):
+        a, b = offs[i], offs[i + 1]
+        y, sc = golden["metric/labels"][a:b], golden["metric/scores"][a:b]
+        want = O.single_user_metric(y.astype(np.int64), sc.tolist())
+        if np.isnan(want).any():
+            assert np.isnan(per[i]).all()
+        else:
+            np.testing.assert_allclose(per[i], want, rtol=1e-12)          # == oracle (reversed-stable ties)
+            ref = golden["metric/results"][i]
+            if len(np.intersect1d(sc[y == 1], sc[y == 0])) == 0:
+                np.testing.assert_allclose(per[i], ref, rtol=1e-12)      # == reference, tie-free cases
+            else:
+                np.testing.assert_allclose(per[i][0], ref[0], rtol=1e-12)  # AUC is tie-order free
+    s = sums.cpu().numpy()
+    np.testing.assert_allclose(s[:4] / s[4:], np.nanmean(per, axis=0), rtol=1e-12)
+
+
+def test_rank_metrics_long_impression_and_empty(dev):
+    """C above the shared-memory staging cap (512) takes the global-memory path; n=0 is legal."""
+    from newsrecommendationsystem_b200 import ops
+    rng = np.random.default_rng(9)
+    C_ = [700, 3, 513, 2]
+    offs = np.concatenate([[0], np.cumsum(C_)]).astype(np.int64)
+    sc = rng.standard_normal(offs[-1]).astype(np.float32)
+    lb = (rng.random(offs[-1]) < 0.2).astype(np.int8)
+    lb[offs[:-1]] = 1
+    lb[offs[:-1] + 1] = 0
+    per, _ = ops.rank_metrics(t(sc, dev), t(lb, dev), t(offs, dev))
+    for i in range(4):
+        a, b = offs[i], offs[i + 1]
+        np.testing.assert_allclose(per[i].cpu().numpy(), O.single_user_metric(lb[a:b].astype(np.int64), sc[a:b].tolist()),
+                                   rtol=1e-12)
+    per0, s0 = ops.rank_metrics(t(sc[:0], dev), t(lb[:0], dev), t(offs[:1], dev))
+    assert per0.shape == (0, 4) and float(s0.sum().item()) == 0.0
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_evaluate_pipeline_golden(dev, golden, golden_sd, precision):
+    from newsrecommendationsystem_b200.evaluate import EvalInputs, evaluate_tensors
+    m = make_model(golden_sd, dev, precision)
+    inp = EvalInputs(golden["eval/news_tokens"], golden["eval/hist_rows"], golden["eval/cand_offsets"],
+                     golden["eval/cand_rows"], golden["eval/labels"], news_ids=golden["eval/news_ids"], device=dev)
+    means, det = evaluate_tensors(m, inp, max_count=int(golden["eval/max_count"]), return_details=True)
+    ref_per = golden["eval/per_impression"]
+    per = det["per_impression"].cpu().numpy()
+    assert per.shape == ref_per.shape                       # max_count - 1 impressions (off-by-one kept)
+    assert np.array_equal(np.isnan(per), np.isnan(ref_per))
+    scores = det["scores"].cpu().numpy()
+    np.testing.assert_allclose(scores, golden["eval/scores"], rtol=0, atol=5e-5 if precision == "fp32" else 3e-3)
+    if precision == "fp32":
+        np.testing.assert_allclose(per, ref_per, rtol=1e-9, atol=1e-12, equal_nan=True)
+    np.testing.assert_allclose(means, golden["eval/means"], atol=5e-4 if precision == "fp32" else 5e-3)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_evaluate_pipeline_vs_oracle_medium(dev, golden_sd, precision):
+    """3k news / 2k impressions: metric means agree with the oracle to 3 decimals."""
+    from newsrecommendationsystem_b200 import synthetic
+    from newsrecommendationsystem_b200.evaluate import EvalInputs, evaluate_tensors
+    Nn, I = 3000, 2000
+    ntok = synthetic.make_news(Nn, num_words=Cfg.num_words, seed=41)
+    imp = synthetic.make_impressions(I, Nn, seed=42, single_class_every=50)
+    ref_means, ref_per, ref_scores, ref_table, ref_uv = O.evaluate_pipeline(
+        golden_sd, ntok, imp["hist_rows"], imp["cand_offsets"], imp["cand_rows"], imp["labels"])
+    m = make_model(golden_sd, dev, precision)
+    inp = EvalInputs(ntok, imp["hist_rows"], imp["cand_offsets"], imp["cand_rows"], imp["labels"], device=dev)
+    means, det = evaluate_tensors(m, inp, return_details=True)
+    assert rel_l2_rows(det["table"][:Nn].cpu().numpy(), ref_table[:Nn]) < TOL_VEC[precision]
+    assert not det["table"][Nn].any()
+    assert rel_l2_rows(det["user_vectors"].cpu().numpy(), ref_uv) < TOL_VEC[precision]
+    np.testing.assert_allclose(means, ref_means, atol=5e-4)
+    assert np.array_equal(np.isnan(det["per_impression"].cpu().numpy()), np.isnan(ref_per))
+
+
+def test_dropout_determinism_and_scale(dev, golden_sd):
+    """Train-mode dropout: same (seed, offset) -> same result; different offset -> different;
+    backward regenerates the same masks (gradient of sum(out) wrt a scaled input is consistent)."""
+    from newsrecommendationsystem_b200 import ops, _lib, synthetic
+    sd = {k: t(v, dev) for k, v in golden_sd.items()}
+    p = O.enc_keys("news_encoder")
+    wqkv = torch.cat([sd[p["Wq"]], sd[p["Wk"]], sd[p["Wv"]]]).contiguous()
+    bqkv = torch.cat([sd[p["bq"]], sd[p["bk"]], sd[p["bv"]]]).contiguous()
+    toks = t(synthetic.make_news(64, num_words=Cfg.num_words, seed=77), dev)
+    args = (sd[O.EMB_KEY], wqkv, bqkv, sd[p["Wa"]], sd[p["ba"]], sd[p["qa"]])
+    a = ops.news_encoder(toks, *args, dropout_p=0.2, seed=11, offset=5, mode=_lib.MODE_FP32)
+    b = ops.news_encoder(toks, *args, dropout_p=0.2, seed=11, offset=5, mode=_lib.MODE_FP32)
+    c = ops.news_encoder(toks, *args, dropout_p=0.2, seed=11, offset=6, mode=_lib.MODE_FP32)
+    e = ops.news_encoder(toks, *args, dropout_p=0.0, mode=_lib.MODE_FP32)
+    assert torch.equal(a, b) and not torch.equal(a, c) and not torch.equal(a, e)
+    # directional finite difference through the dropout path (masks fixed by seed/offset)
+    emb = sd[O.EMB_KEY].clone().requires_grad_()
+    out = ops.news_encoder(toks, emb, *args[1:], dropout_p=0.2, seed=11, offset=5, mode=_lib.MODE_FP32)
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    direction = torch.randn_like(emb)
+    direction[0] = 0
+    eps = 1e-2
+    with torch.no_grad():
+        f1 = (ops.news_encoder(toks, emb + eps * direction, *args[1:], dropout_p=0.2, seed=11, offset=5,
+                               mode=_lib.MODE_FP32) * w).sum().double()
+        f0 = (ops.news_encoder(toks, emb - eps * direction, *args[1:], dropout_p=0.2, seed=11, offset=5,
+                               mode=_lib.MODE_FP32) * w).sum().double()
+    fd = float((f1 - f0) / (2 * eps))
+    an = float((emb.grad.double() * direction.double()).sum())
+    assert abs(fd - an) < 2e-2 * max(1.0, abs(an)), (fd, an)
+
+
+def test_unsupported_shape_and_cpu_inputs_fail_loudly(dev, golden_sd):
+    from newsrecommendationsystem_b200 import ops
+    m = make_model(golden_sd, dev, "fp32")
+    with pytest.raises(RuntimeError):
+        m.get_news_vector({"title": torch.zeros(4, 21, dtype=torch.long)})     # title length 21 not compiled
+    with pytest.raises(RuntimeError):
+        ops.click_score(torch.zeros(2, 3, 300), torch.zeros(2, 300))           # CPU tensors: no fallback
