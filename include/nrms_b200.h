@@ -59,6 +59,8 @@ enum {
 
 const char* nrms_last_error(void);
 int nrms_abi_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t nrms_launch_count(void);
 
 /* ---- sizes ------------------------------------------------------------------------- */
 /* Bytes of the saved-for-backward stash of one encoder call over n_seq sequences of length S
@@ -141,7 +143,7 @@ int nrms_adam_step(float* p, const float* g, float* m, float* v, int64_t n,
 int nrms_gather_rows(const float* src, const int64_t* rows, int64_t n, int width,
                      float* dst, void* stream);
 /* Per-impression AUC / MRR / nDCG@5 / nDCG@10 (fp64) on CSR (labels int8 in {0,1});
- * single-class impressions give NaN x4.  per_impression [n,4] (may be NULL);
+ * single-class impressions give NaN x4.  per_impression [n,4] (required when n > 0);
  * sums_counts [8] = {sum auc, mrr, ndcg5, ndcg10, count auc, mrr, ndcg5, ndcg10} over non-NaN
  * rows (nanmean numerators/denominators), overwritten. */
 int nrms_rank_metrics(const float* scores, const int8_t* labels, const int64_t* offsets,

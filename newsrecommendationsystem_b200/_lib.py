@@ -21,6 +21,7 @@ _vp, _i64, _i32, _f32, _u64, _sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.
 SIGNATURES = {
     "nrms_last_error": (C.c_char_p, []),
     "nrms_abi_version": (_i32, []),
+    "nrms_launch_count": (_i64, []),
     "nrms_encoder_stash_bytes": (_sz, [_i64, _i32]),
     "nrms_encoder_fwd_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "nrms_encoder_bwd_workspace_bytes": (_sz, [_i64, _i32, _i32]),

@@ -18,6 +18,7 @@ constexpr int DV4 = D / 4;     // 75 float4 per 300-wide row
 // ---- error plumbing (thread-local message, int codes; nothing throws across the ABI) ----
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+void count_launch();  // bumps the per-process kernel-launch counter (nrms_launch_count)
 
 #define NRMS_CHECK_ARG(cond, code, ...)          \
   do {                                           \
@@ -37,6 +38,7 @@ int cuda_fail(cudaError_t e, const char* what);
   do {                                                          \
     cudaError_t e__ = cudaGetLastError();                       \
     if (e__ != cudaSuccess) return nrms::cuda_fail(e__, name);  \
+    nrms::count_launch();                                       \
   } while (0)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }

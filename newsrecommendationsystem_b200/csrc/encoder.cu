@@ -70,6 +70,7 @@ static cudaError_t launch_attention_fwd(const float* qkv, float* ctx, int64_t n_
   dim3 grid((unsigned)gx, H / HC);
   const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
   attention_fwd_kernel<S, HC><<<grid, threads, smem, st>>>(qkv, ctx, n_seq, p, scale, seed, offset);
+  count_launch();
   return cudaGetLastError();
 }
 
@@ -88,6 +89,7 @@ static cudaError_t launch_attention_bwd(const float* qkv, const float* d_ctx, fl
   dim3 grid((unsigned)gx, H / HC);
   const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
   attention_bwd_kernel<S, HC><<<grid, threads, smem, st>>>(qkv, d_ctx, d_qkv, n_seq, p, scale, seed, offset);
+  count_launch();
   return cudaGetLastError();
 }
 

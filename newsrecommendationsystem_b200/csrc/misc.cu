@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "encoder_kernels.cuh"
 #include <math.h>
+#include <atomic>
 
 namespace nrms {
 
@@ -14,6 +15,9 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int cuda_fail(cudaError_t e, const char* what) {
   set_error("CUDA error in %s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
@@ -278,6 +282,7 @@ extern "C" {
 
 const char* nrms_last_error(void) { return g_err; }
 int nrms_abi_version(void) { return 1; }
+int64_t nrms_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 int nrms_score_fwd(const float* cand, const float* user, int64_t B, int C, int X, float* scores, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -364,6 +369,10 @@ int nrms_rank_metrics(const float* scores, const int8_t* labels, const int64_t* 
                       double* per_impression, double* sums_counts, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   NRMS_CHECK_ARG(n_impressions >= 0, NRMS_E_INVALID, "bad sizes");
+  if (n_impressions == 0) {
+    if (sums_counts) NRMS_CUDA(cudaMemsetAsync(sums_counts, 0, 8 * sizeof(double), st));
+    return NRMS_OK;
+  }
   NRMS_CHECK_ARG(per_impression != nullptr, NRMS_E_INVALID, "per_impression buffer [n,4] is required");
   if (n_impressions > 0) {
     NRMS_CHECK_ARG(scores && labels && offsets, NRMS_E_INVALID, "null pointer");

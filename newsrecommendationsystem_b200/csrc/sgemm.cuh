@@ -154,6 +154,7 @@ inline cudaError_t sgemm_launch(const float* A, int64_t lda, const float* B, int
   }
   dim3 grid((unsigned)((M + SG_BM - 1) / SG_BM), (N + SG_BN - 1) / SG_BN, splits);
   sgemm_kernel<AT, BT, EPI><<<grid, SG_THREADS, 0, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K, k_chunk);
+  count_launch();
   return cudaGetLastError();
 }
 

@@ -62,14 +62,15 @@ def shard_impressions_by_candidates(cand_offsets: np.ndarray, world: int):
     return np.concatenate([[0], cuts, [len(cand_offsets) - 1]]).astype(np.int64)
 
 
-class EvalInputs:
-    """Evaluate inputs resident on one device (built once; the timed pipeline touches only these).
+class EvalHost:
+    """Evaluate inputs preprocessed on the host into the library's index formats, in pinned
+    memory (when CUDA is available) so `EvalInputs.from_host` is a handful of async H2D copies.
 
     news_tokens  int64 [N_news, L]        hist_rows  int32 [I, 50]  (pad -> N_news, the zero row)
     cand_rows    int32 [sumC]             cand_offsets int64 [I+1]   labels int8 [sumC]
     """
 
-    def __init__(self, news_tokens, hist_rows, cand_offsets, cand_rows, labels, news_ids=None, device="cuda"):
+    def __init__(self, news_tokens, hist_rows, cand_offsets, cand_rows, labels, news_ids=None):
         n_news = int(news_tokens.shape[0])
         hist = np.asarray(hist_rows, dtype=np.int64).copy()
         cand = np.asarray(cand_rows, dtype=np.int64)
@@ -81,14 +82,41 @@ class EvalInputs:
         hist[hist < 0] = n_news           # PADDED_NEWS -> the all-zero last row of the table
         self.n_news = n_news
         self.n_impressions = int(hist.shape[0])
-        self.device = torch.device(device)
-        t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt).to(self.device)
+        pin = torch.cuda.is_available()
+
+        def t(a, dt):
+            x = torch.as_tensor(np.ascontiguousarray(a), dtype=dt)
+            return x.pin_memory() if pin else x
         self.news_tokens = t(news_tokens, torch.int64)
         self.hist_rows = t(hist, torch.int32)
         self.cand_rows = t(cand, torch.int32)
         self.cand_offsets = t(cand_offsets, torch.int64)
         self.labels = t(labels, torch.int8)
         self.cand_offsets_host = np.asarray(cand_offsets, dtype=np.int64)
+
+    def nbytes(self):
+        return sum(x.numel() * x.element_size() for x in
+                   (self.news_tokens, self.hist_rows, self.cand_rows, self.cand_offsets, self.labels))
+
+
+class EvalInputs:
+    """Evaluate inputs resident on one device (the timed pipeline touches only these)."""
+
+    def __init__(self, news_tokens, hist_rows, cand_offsets, cand_rows, labels, news_ids=None, device="cuda"):
+        self._fill(EvalHost(news_tokens, hist_rows, cand_offsets, cand_rows, labels, news_ids), device)
+
+    @classmethod
+    def from_host(cls, host: EvalHost, device="cuda"):
+        self = cls.__new__(cls)
+        self._fill(host, device)
+        return self
+
+    def _fill(self, host, device):
+        self.device = torch.device(device)
+        self.n_news, self.n_impressions = host.n_news, host.n_impressions
+        for name in ("news_tokens", "hist_rows", "cand_rows", "cand_offsets", "labels"):
+            setattr(self, name, getattr(host, name).to(self.device, non_blocking=True))
+        self.cand_offsets_host = host.cand_offsets_host
 
 
 @torch.no_grad()
@@ -121,12 +149,16 @@ def encode_news_table(model, news_tokens: torch.Tensor) -> torch.Tensor:
 
 
 @torch.no_grad()
-def evaluate_tensors(model, inputs: EvalInputs, max_count=None, return_details=False):
+def evaluate_tensors(model, inputs: EvalInputs, max_count=None, return_details=False, mark=None):
     """evaluate() on resident tensors -> (AUC, MRR, nDCG@5, nDCG@10) as Python floats.
 
-    One D2H read (the 8 sums/counts) at the very end; no per-impression host work."""
+    One D2H read (the 8 sums/counts) at the very end; no per-impression host work.
+    `mark(name)` (optional) is called at stage boundaries (bench.py records CUDA events there)."""
     dist = _dist()
+    mark = mark or (lambda name: None)
+    mark("start")
     table = encode_news_table(model, inputs.news_tokens)
+    mark("news")
     n_imp = inputs.n_impressions
     if max_count is not None:
         n_imp = max(0, min(n_imp, int(max_count) - 1))
@@ -137,10 +169,13 @@ def evaluate_tensors(model, inputs: EvalInputs, max_count=None, return_details=F
     dev = inputs.device
     if hi > lo:
         user_vec = model.user_encoder.forward_indexed(table, inputs.hist_rows[lo:hi])
+        mark("users")
         c0, c1 = int(inputs.cand_offsets_host[lo]), int(inputs.cand_offsets_host[hi])
         offs = (inputs.cand_offsets[lo:hi + 1] - c0).contiguous()
         scores = ops.score_csr(table, inputs.cand_rows[c0:c1], offs, user_vec)
+        mark("score")
         per, sums = ops.rank_metrics(scores, inputs.labels[c0:c1], offs)
+        mark("metrics")
     else:
         user_vec = torch.empty((0, ops.D), device=dev)
         scores = torch.empty((0,), device=dev)

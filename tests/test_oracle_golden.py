@@ -167,3 +167,15 @@ def test_layernorm_matches_torch():
     np.testing.assert_allclose(dx, xt.grad.numpy(), atol=5e-5)
     np.testing.assert_allclose(dg, gt.grad.numpy(), rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose(db, bt.grad.numpy(), rtol=1e-4, atol=1e-4)
+
+
+def test_torch_port_matches_golden(golden, golden_sd):
+    """bench.py's CPU baseline (torch-CPU port of the reference op sequence) is pinned too."""
+    from oracle import torch_port as TP
+    nv = TP.news_vectors(golden_sd, golden["fwd/tokens"]).numpy()
+    assert rel_l2_rows(nv, golden["fwd/news_vectors"]) < 1e-6
+    uv = TP.user_vectors(golden_sd, golden["fwd/user_input"]).numpy()
+    assert rel_l2_rows(uv, golden["fwd/user_vectors"]) < 1e-6
+    import torch
+    s = TP.prediction(torch.from_numpy(golden["fwd/news_vectors"][:23]), torch.from_numpy(golden["fwd/user_vectors"][0]))
+    np.testing.assert_allclose(s, golden["fwd/scores_single"], rtol=1e-5, atol=1e-6)
