@@ -1,148 +1,234 @@
 // Generic TF32 tensor-core GEMM for sm_100a:  C[M,N] = A[M,K] * B[N,K]^T (+ bias).
 //
-//   CTA tile 128 x 256, K streamed in 32-float (128-byte) chunks through a 2-stage
-//   shared-memory ring in the canonical UMMA SWIZZLE_128B K-major layout.
-//   warps 0-3 : producers (ld.global.v4 -> cvt.rna.tf32 -> swizzled st.shared -> proxy fence ->
-//               mbarrier arrive), then the epilogue (tcgen05.ld -> +bias -> st.global)
-//   warp  4   : TMEM allocation + single-thread tcgen05.mma issue, tcgen05.commit to free stages
-//   Accumulator: 128 lanes x 256 fp32 columns of TMEM.  Two CTAs are resident per SM (2 x 96 KB
-//   smem, 2 x 256 TMEM columns) so one CTA's epilogue overlaps the other's main loop.
+// Persistent, warp-specialised, TMA-fed:
+//   warp 0     : TMA producer.  One thread issues cp.async.bulk.tensor.2d loads of a 128x32 (A) and a
+//                256x32 (B) fp32 box per 128-byte K chunk into a 4-stage ring; the tensor maps use
+//                SWIZZLE_128B, i.e. exactly the canonical UMMA K-major layout; out-of-bounds rows / K
+//                tail are zero-filled by the TMA unit.
+//   warp 1     : TMEM allocation (512 columns = two 256-column accumulator stages) and single-thread
+//                tcgen05.mma.kind::tf32 issue; tcgen05.commit releases smem stages / publishes accumulators.
+//   warps 2..5 : epilogue: tcgen05.ld (32 lanes x 16 columns) -> +bias -> st.global, overlapped with the
+//                next tile's main loop through the second accumulator stage.
+// Tiles are walked n-fastest so the A tile of an M block stays L2-resident across its N tiles.
+// The tensor maps are typed TFLOAT32: the TMA unit rounds the fp32 operands to TF32 while copying, so
+// callers pass plain fp32 tensors (no pre-rounding pass) and the tensor core never truncates.
+#include <cuda.h>
+#include <stdlib.h>
 #include "tc_common.cuh"
 #include "tc_api.cuh"
 
 namespace nrms {
 using namespace tc;
 
-constexpr int TG_BM = 128, TG_BN = 256, TG_BK = 32, TG_STAGES = 2;
+constexpr int TG_BM = 128, TG_BN = 256, TG_BK = 32, TG_STAGES = 4;
 constexpr int TG_A_BYTES = TG_BM * TG_BK * 4;  // 16 KB
 constexpr int TG_B_BYTES = TG_BN * TG_BK * 4;  // 32 KB
 constexpr int TG_STAGE_BYTES = TG_A_BYTES + TG_B_BYTES;
-constexpr int TG_THREADS = 160;
-constexpr int TG_SMEM = TG_STAGES * TG_STAGE_BYTES + 1024 /*align slack*/ + 64 /*barriers*/;
+constexpr int TG_THREADS = 192;
+constexpr int TG_SMEM = TG_STAGES * TG_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
-__global__ void __launch_bounds__(TG_THREADS)
-tc_gemm_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
-                  const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int64_t M, int N, int K) {
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(TG_THREADS, 1)
+tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int64_t M, int N, int K,
+                  uint32_t stage_tx_bytes) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;          // SWIZZLE_128B tiles need 1024-byte alignment
+  const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw);
-  const uint32_t bars = base + TG_STAGES * TG_STAGE_BYTES;  // full[2], empty[2], tmem_full, tmem_ptr
-  const uint32_t full_bar = bars, empty_bar = bars + 8 * TG_STAGES, tmem_full_bar = bars + 16 * TG_STAGES;
+  const uint32_t bars = base + TG_STAGES * TG_STAGE_BYTES;
+  const uint32_t full_bar = bars;                          // [STAGES]
+  const uint32_t empty_bar = bars + 8 * TG_STAGES;         // [STAGES]
+  const uint32_t tfull_bar = bars + 16 * TG_STAGES;        // [2]
+  const uint32_t tempty_bar = tfull_bar + 16;              // [2]
   volatile uint32_t* tmem_ptr_smem =
-      reinterpret_cast<volatile uint32_t*>(base_ptr + TG_STAGES * TG_STAGE_BYTES + 16 * TG_STAGES + 8);
+      reinterpret_cast<volatile uint32_t*>(base_ptr + TG_STAGES * TG_STAGE_BYTES + 16 * TG_STAGES + 32);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int64_t m0 = (int64_t)blockIdx.x * TG_BM;
-  const int n0 = blockIdx.y * TG_BN;
-  int n_valid = N - n0;
-  if (n_valid > TG_BN) n_valid = TG_BN;
-  const int n_mma = (n_valid + 15) & ~15;  // UMMA N (multiple of 16 for M=128); padded B rows are zero
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = (N + TG_BN - 1) / TG_BN;
+  const int64_t m_tiles = (M + TG_BM - 1) / TG_BM;
+  const int64_t total_tiles = m_tiles * n_tiles;
   const int num_chunks = (K + TG_BK - 1) / TG_BK;
 
   if (tid == 0) {
     for (int s = 0; s < TG_STAGES; ++s) {
-      mbar_init(full_bar + 8 * s, 128);
+      mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar + 8 * a, 1);
+      mbar_init(tempty_bar + 8 * a, 4);
+    }
     mbar_fence_init();
   }
-  if (warp == 4) tmem_alloc(smem_u32((const void*)tmem_ptr_smem), 256);
+  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_ptr_smem), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (warp < 4) {
-    // ------------------------------ producers ------------------------------------------
-    for (int kc = 0; kc < num_chunks; ++kc) {
-      const int s = kc % TG_STAGES;
-      const uint32_t ph = (kc / TG_STAGES) & 1;
-      mbar_wait(empty_bar + 8 * s, ph ^ 1);
-      uint8_t* sa = base_ptr + s * TG_STAGE_BYTES;
-      uint8_t* sb = sa + TG_A_BYTES;
-      const int k0 = kc * TG_BK;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int idx = tid + 128 * i;
-        const int r = idx >> 3, c = idx & 7;
-        const int64_t m = m0 + r;
-        const int k = k0 + 4 * c;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < M && k < K) v = to_tf32(__ldg(reinterpret_cast<const float4*>(A + m * lda + k)));
-        *reinterpret_cast<float4*>(sa + r * 128 + ((c ^ (r & 7)) << 4)) = v;
-      }
-      for (int idx = tid; idx < n_mma * 8; idx += 128) {
-        const int r = idx >> 3, c = idx & 7;
-        const int k = k0 + 4 * c;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < n_valid && k < K) v = to_tf32(__ldg(reinterpret_cast<const float4*>(B + (int64_t)(n0 + r) * ldb + k)));
-        *reinterpret_cast<float4*>(sb + r * 128 + ((c ^ (r & 7)) << 4)) = v;
-      }
-      fence_proxy_async_smem();
-      mbar_arrive(full_bar + 8 * s);
-    }
-    // ------------------------------ epilogue -------------------------------------------
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const int64_t m = m0 + tid;
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int col = 0; col < n_mma; col += 16) {
-      float v[16];
-      tmem_ld16(trow + col, v);
-      if (m < M) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int n = n0 + col + 4 * q;
-          if (n < N) {
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
-            *reinterpret_cast<float4*>(C + m * ldc + n) =
-                make_float4(v[4 * q] + b4.x, v[4 * q + 1] + b4.y, v[4 * q + 2] + b4.z, v[4 * q + 3] + b4.w);
-          }
+  if (warp == 0) {
+    // ------------------------------ TMA producer ---------------------------------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m0 = (int)(t / n_tiles) * TG_BM;
+        const int n0 = (int)(t % n_tiles) * TG_BN;
+        for (int kc = 0; kc < num_chunks; ++kc, ++it) {
+          const int s = it % TG_STAGES;
+          const uint32_t ph = (it / TG_STAGES) & 1;
+          mbar_wait(empty_bar + 8 * s, ph ^ 1);
+          mbar_expect_tx(full_bar + 8 * s, stage_tx_bytes);
+          const uint32_t sa = base + s * TG_STAGE_BYTES;
+          tma_load_2d(sa, &tmap_a, kc * TG_BK, m0, full_bar + 8 * s);
+          tma_load_2d(sa + TG_A_BYTES, &tmap_b, kc * TG_BK, n0, full_bar + 8 * s);
         }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer -----------------------------------------
+    uint32_t it = 0, tile_it = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
+      const int n0 = (int)(t % n_tiles) * TG_BN;
+      int n_valid = N - n0;
+      if (n_valid > TG_BN) n_valid = TG_BN;
+      const int n_mma = (n_valid + 15) & ~15;
+      const uint32_t idesc = umma_idesc_tf32(TG_BM, n_mma);
+      const uint32_t as = tile_it & 1;
+      mbar_wait(tempty_bar + 8 * as, ((tile_it >> 1) & 1) ^ 1);   // epilogue drained this accumulator stage
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * TG_BN;
+      for (int kc = 0; kc < num_chunks; ++kc, ++it) {
+        const int s = it % TG_STAGES;
+        const uint32_t ph = (it / TG_STAGES) & 1;
+        mbar_wait(full_bar + 8 * s, ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = base + s * TG_STAGE_BYTES;
+          const uint32_t sb = sa + TG_A_BYTES;
+          int ksteps = (K - kc * TG_BK + 7) / 8;
+          if (ksteps > 4) ksteps = 4;
+          for (int ks = 0; ks < ksteps; ++ks)
+            umma_tf32_ss(d_tmem, umma_desc_k_sw128(sa + ks * 32), umma_desc_k_sw128(sb + ks * 32), idesc,
+                         (kc | ks) ? 1u : 0u);
+          umma_commit(empty_bar + 8 * s);
+          if (kc == num_chunks - 1) umma_commit(tfull_bar + 8 * as);
+        }
+        __syncwarp();
       }
     }
   } else {
-    // ------------------------------ MMA issuer (warp 4) --------------------------------
-    const uint32_t idesc = umma_idesc_tf32(TG_BM, n_mma);
-    for (int kc = 0; kc < num_chunks; ++kc) {
-      const int s = kc % TG_STAGES;
-      const uint32_t ph = (kc / TG_STAGES) & 1;
-      mbar_wait(full_bar + 8 * s, ph);
+    // ------------------------------ epilogue (warps 2..5) ------------------------------
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    uint32_t tile_it = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
+      const int64_t m0 = (t / n_tiles) * TG_BM;
+      const int n0 = (int)(t % n_tiles) * TG_BN;
+      int n_valid = N - n0;
+      if (n_valid > TG_BN) n_valid = TG_BN;
+      const uint32_t as = tile_it & 1;
+      mbar_wait(tfull_bar + 8 * as, (tile_it >> 1) & 1);
       tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sa = base + s * TG_STAGE_BYTES;
-        const uint32_t sb = sa + TG_A_BYTES;
-        int ksteps = (K - kc * TG_BK + 7) / 8;
-        if (ksteps > 4) ksteps = 4;
-        for (int ks = 0; ks < ksteps; ++ks) {
-          umma_tf32_ss(tmem_base, umma_desc_k_sw128(sa + ks * 32), umma_desc_k_sw128(sb + ks * 32), idesc,
-                       (kc | ks) ? 1u : 0u);
+      const int64_t m = m0 + q * 32 + lane;
+      const uint32_t trow = tmem_base + as * TG_BN + ((uint32_t)(q * 32) << 16);
+      for (int col = 0; col < n_valid; col += 16) {
+        float v[16];
+        tmem_ld16(trow + col, v);
+        if (m < M) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int n = n0 + col + 4 * j;
+            if (n < N) {
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+              *reinterpret_cast<float4*>(C + m * ldc + n) =
+                  make_float4(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w);
+            }
+          }
         }
-        umma_commit(empty_bar + 8 * s);                       // stage reusable once these MMAs retire
-        if (kc == num_chunks - 1) umma_commit(tmem_full_bar);  // accumulator complete
       }
+      tc_fence_before();
       __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * as);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---- host: tensor maps ---------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major [rows, cols] (row stride ld floats) -> SWIZZLE_128B boxes of box_rows x 32 floats
+int make_tmap_k_major(CUtensorMap* out, const float* base, int64_t rows, int cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  NRMS_CHECK_ARG(fn != nullptr, NRMS_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  static int dtype_override = -1;
+  if (dtype_override < 0) {
+    // CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 makes the TMA unit ROUND fp32 to TF32 on the way into shared
+    // memory (measured, profiles/tma_round_probe.py: max error 3.1e-4 vs 8.1e-4 with plain FLOAT32, where
+    // the tensor core truncates the low 13 mantissa bits).  NRMS_TMA_TF32_DTYPE=0 selects FLOAT32 (debug).
+    const char* e = getenv("NRMS_TMA_TF32_DTYPE");
+    dtype_override = (e && e[0] == '0') ? 0 : 1;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(out, dtype_override ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NRMS_CHECK_ARG(r == CUDA_SUCCESS, NRMS_E_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return NRMS_OK;
 }
 
 int tc_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
                int64_t M, int N, int K, cudaStream_t st) {
   if (M <= 0) return NRMS_OK;
+  NRMS_CHECK_ARG(M < (1ll << 31), NRMS_E_UNSUPPORTED, "M too large for one tensor map");
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_gemm_nt_kernel)");
     configured = true;
   }
-  dim3 grid((unsigned)((M + TG_BM - 1) / TG_BM), (N + TG_BN - 1) / TG_BN);
-  tc_gemm_nt_kernel<<<grid, TG_THREADS, TG_SMEM, st>>>(A, lda, B, ldb, bias, C, ldc, M, N, K);
+  alignas(64) CUtensorMap ta, tb;
+  // boxes never exceed the tensor extent (rows past it would only feed outputs that are not stored)
+  const int box_a = M < TG_BM ? (int)M : TG_BM;
+  const int box_b = N < TG_BN ? N : TG_BN;
+  if (int rc = make_tmap_k_major(&ta, A, M, K, lda, box_a)) return rc;
+  if (int rc = make_tmap_k_major(&tb, B, N, K, ldb, box_b)) return rc;
+  const uint32_t stage_tx = (uint32_t)(box_a + box_b) * TG_BK * 4;
+  const int64_t tiles = ((M + TG_BM - 1) / TG_BM) * ((N + TG_BN - 1) / TG_BN);
+  int grid = num_sms();
+  if (tiles < grid) grid = (int)tiles;
+  tc_gemm_nt_kernel<<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, bias, C, ldc, M, N, K, stage_tx);
   NRMS_LAUNCH_CHECK("tc_gemm_nt");
   return NRMS_OK;
 }
