@@ -230,8 +230,7 @@ int nrms_news_encoder_fwd(const int64_t* tokens, int64_t n_titles, int L, const 
   }
   // inference
   if (mode == NRMS_MODE_TF32 && dropout_p == 0.f && tc_fused_workspace_bytes(n_titles, L) != (size_t)-1) {
-    return tc_news_encoder_fused(tokens, n_titles, emb, num_words, wqkv, bqkv, wa, ba, qa, out, workspace,
-                                 workspace_bytes, st);
+    return tc_encoder_fused(emb, tokens, 1, n_titles, L, wqkv, bqkv, wa, ba, qa, out, workspace, workspace_bytes, st);
   }
   const int64_t chunk_seq = INFER_CHUNK_ROWS / L;
   const int64_t first = n_titles < chunk_seq ? n_titles : chunk_seq;
@@ -299,6 +298,10 @@ int nrms_user_encoder_fwd(const float* x, const int32_t* rows_idx, int64_t n_use
     Stash s = carve_stash(stash, n_users * S);
     NRMS_CUDA(cudaMemcpyAsync(s.x, x, (size_t)n_users * S * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return encoder_core_fwd(s, n_users, S, wqkv, bqkv, wa, ba, qa, out, 0.f, 0, 0, 0, mode, st);
+  }
+  if (mode == NRMS_MODE_TF32 && tc_fused_workspace_bytes(n_users, S) != (size_t)-1) {
+    return tc_encoder_fused(x, rows_idx, rows_idx ? 2 : 0, n_users, S, wqkv, bqkv, wa, ba, qa, out, workspace,
+                            workspace_bytes, st);
   }
   const int64_t chunk_seq = INFER_CHUNK_ROWS / S;
   const int64_t first = n_users < chunk_seq ? n_users : chunk_seq;

@@ -9,11 +9,13 @@ namespace nrms {
 int tc_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
                int64_t M, int N, int K, cudaStream_t st);
 
-// Fused news-encoder forward (inference): gather -> QKV (tcgen05) -> attention -> additive pooling
-// in one kernel.  tc_fused_workspace_bytes returns (size_t)-1 when the fused path does not apply.
+// Fused tensor-core encoder forward (inference): gather -> QKV (tcgen05) -> attention (K1), then
+// additive GEMM (tcgen05) -> tanh/softmax/pool (K2).  Input rows come from `src` [*,300]:
+//   idx_kind 0: dense rows (sequence s, position i -> row s*S+i), 1: int64 ids, 2: int32 ids.
+// tc_fused_workspace_bytes returns (size_t)-1 when the fused path does not apply (S not 20/50).
 size_t tc_fused_workspace_bytes(int64_t n_seq, int S);
-int tc_news_encoder_fused(const int64_t* tokens, int64_t n_titles, const float* emb, int64_t num_words,
-                          const float* wqkv, const float* bqkv, const float* wa, const float* ba, const float* qa,
-                          float* out, void* workspace, size_t workspace_bytes, cudaStream_t st);
+int tc_encoder_fused(const float* src, const void* idx, int idx_kind, int64_t n_seq, int S, const float* wqkv,
+                     const float* bqkv, const float* wa, const float* ba, const float* qa, float* out,
+                     void* workspace, size_t workspace_bytes, cudaStream_t st);
 
 }  // namespace nrms

@@ -1,15 +1,505 @@
-// Fused tcgen05 news-encoder forward (inference).  Placeholder until the fused kernel lands:
-// reports "not applicable" so encoder.cu takes the decomposed path with tc_gemm_nt.
+// Fused tensor-core encoder forward (inference) for sm_100a.  Two persistent kernels per chunk of
+// sequences; the only intermediate that leaves the SM is the attention context C (L2-resident chunk).
+//
+//  K1  encoder_attn_kernel<S,SPT>:  tile = SPT sequences (S*SPT <= 128 rows: 6 titles or 2 users)
+//      workers (4 warps): gather the tile's input rows (embedding rows by token id, news-vector rows by
+//        int32 index, or dense rows) with coalesced float4 loads, round to TF32 and store them into the
+//        resident A tile in the UMMA SWIZZLE_128B K-major layout (10 chunks of 32 floats);
+//      producer (1 thread): streams W_Q/W_K/W_V through a 2-stage TMA ring, three 64-row boxes per K
+//        chunk (heads 3p..3p+2 of Q, K and V) -> B tile of 192 rows;
+//      MMA (1 thread): 5 passes x 38 tcgen05.mma.kind::tf32 (M=128, N=192, K=8) into one of two
+//        192-column TMEM accumulator stages;
+//      workers again: per head, tcgen05.ld q/k/v of their own row (thread == token row), +bias, stage
+//        K/V in shared memory, then the 15-head exp-softmax attention of the reference
+//        (e = exp(qk/sqrt(20)), attn = e/(sum e + 1e-8), no max subtraction) entirely in registers with
+//        warp-broadcast shared-memory reads; context rows go to C.
+//  K2  additive_pool_kernel<S,SPT>: C (TMA, rounded to TF32 by the TFLOAT32 tensor map) x W_a^T on
+//      tcgen05 (N=208), epilogue tanh -> . q -> stable softmax over the sequence -> weighted row sum.
+#include <cuda.h>
 #include "tc_common.cuh"
 #include "tc_api.cuh"
 
 namespace nrms {
+using namespace tc;
 
-size_t tc_fused_workspace_bytes(int64_t, int) { return (size_t)-1; }
+int make_tmap_k_major(CUtensorMap* out, const float* base, int64_t rows, int cols, int64_t ld, int box_rows);
 
-int tc_news_encoder_fused(const int64_t*, int64_t, const float*, int64_t, const float*, const float*, const float*,
-                          const float*, const float*, float*, void*, size_t, cudaStream_t) {
-  set_error("fused tcgen05 news encoder not built");
+__device__ __forceinline__ void tma_load_2d_f(uint32_t dst_smem, const CUtensorMap* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_f(uint32_t bar, uint32_t bytes) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+constexpr int KCH = 10;            // K chunks of 32 floats (300 -> 320, tail zero)
+constexpr int HP = 3;              // heads per QKV pass
+constexpr int NPASS = H / HP;      // 5
+constexpr int K1_N = 192;          // UMMA N of a pass: [Q 60 | pad 4 | K 60 | pad 4 | V 60 | pad 4]
+constexpr int K1_BSTAGE = 3 * 64 * 128;   // 24,576 B
+constexpr int K1_THREADS = 192;
+constexpr float LOG2E_OVER_SQRT_DH = 1.4426950408889634f / 4.47213595499957939f;
+
+template <int S, int SPT>
+struct K1 {
+  static constexpr int ROWS = S * SPT;
+  static constexpr int ROWS_ALLOC = (ROWS + 7) / 8 * 8;
+  static constexpr int CH = ROWS_ALLOC * 128;                 // bytes of one A chunk (rows x 128 B)
+  static constexpr int OFF_B = KCH * CH;
+  static constexpr int OFF_KV = OFF_B + 2 * K1_BSTAGE;
+  static constexpr int OFF_BIAS = OFF_KV + ROWS * 40 * 4;
+  static constexpr int OFF_IDX = OFF_BIAS + 3712;
+  static constexpr int OFF_BAR = OFF_IDX + 128 * 8;
+  static constexpr int SMEM = OFF_BAR + 128 + 1024;
+  static_assert(ROWS <= 128, "tile rows");
+  static_assert(CH % 1024 == 0 && OFF_B % 1024 == 0, "swizzle alignment");
+  static_assert(SMEM <= 232448, "shared memory budget");
+};
+
+// idx_kind: 0 = dense rows (row r of src), 1 = int64 ids, 2 = int32 ids
+template <int S, int SPT>
+__global__ void __launch_bounds__(K1_THREADS, 1)
+encoder_attn_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ src,
+                    const void* __restrict__ idx, int idx_kind, int64_t n_seq, const float* __restrict__ bqkv,
+                    float* __restrict__ C) {
+  using Cfg = K1<S, SPT>;
+  constexpr int ROWS = Cfg::ROWS;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  float* kv = reinterpret_cast<float*>(sm + Cfg::OFF_KV);
+  float* bias_s = reinterpret_cast<float*>(sm + Cfg::OFF_BIAS);
+  int64_t* rowid = reinterpret_cast<int64_t*>(sm + Cfg::OFF_IDX);
+  const uint32_t bars = base + Cfg::OFF_BAR;
+  const uint32_t full_bar = bars, empty_bar = bars + 16, a_full = bars + 32, a_free = bars + 40;
+  const uint32_t acc_full = bars + 48, acc_empty = bars + 64;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sm + Cfg::OFF_BAR + 96);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n_tiles = (n_seq + SPT - 1) / SPT;
+
+  if (tid == 0) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+      mbar_init(acc_full + 8 * s, 1);
+      mbar_init(acc_empty + 8 * s, 4);
+    }
+    mbar_init(a_full, 128);
+    mbar_init(a_free, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_ptr_smem), 512);
+  for (int i = tid; i < D3; i += K1_THREADS) bias_s[i] = bqkv[i];
+  // K tail of the A tile (floats 300..303 = 16-byte chunk 3 of K chunk 9) is zero for good
+  for (int r = tid; r < Cfg::ROWS_ALLOC; r += K1_THREADS)
+    *reinterpret_cast<float4*>(sm + 9 * Cfg::CH + r * 128 + ((3 ^ (r & 7)) << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer: W_Q / W_K / W_V boxes ----------------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int p = 0; p < NPASS; ++p) {
+          for (int kc = 0; kc < KCH; ++kc, ++it) {
+            const int s = it & 1;
+            mbar_wait(empty_bar + 8 * s, ((it >> 1) & 1) ^ 1);
+            mbar_expect_tx_f(full_bar + 8 * s, K1_BSTAGE);
+            const uint32_t sb = base + Cfg::OFF_B + s * K1_BSTAGE;
+            tma_load_2d_f(sb, &tmap_w, kc * 32, 60 * p, full_bar + 8 * s);
+            tma_load_2d_f(sb + 8192, &tmap_w, kc * 32, D + 60 * p, full_bar + 8 * s);
+            tma_load_2d_f(sb + 16384, &tmap_w, kc * 32, 2 * D + 60 * p, full_bar + 8 * s);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------------------------
+    const uint32_t idesc = umma_idesc_tf32(128, K1_N);
+    uint32_t it = 0, pass_it = 0, tile_it = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
+      mbar_wait(a_full, tile_it & 1);           // the workers finished writing this tile's A rows
+      tc_fence_after();
+      for (int p = 0; p < NPASS; ++p, ++pass_it) {
+        const uint32_t as = pass_it & 1;
+        mbar_wait(acc_empty + 8 * as, ((pass_it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * K1_N;
+        for (int kc = 0; kc < KCH; ++kc, ++it) {
+          const int s = it & 1;
+          mbar_wait(full_bar + 8 * s, (it >> 1) & 1);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t sa = base + kc * Cfg::CH;
+            const uint32_t sb = base + Cfg::OFF_B + s * K1_BSTAGE;
+            const int ksteps = (kc == KCH - 1) ? 2 : 4;     // K = 300 -> 37.5 steps of 8, padded to 38
+            for (int ks = 0; ks < ksteps; ++ks)
+              umma_tf32_ss(d_tmem, umma_desc_k_sw128(sa + ks * 32), umma_desc_k_sw128(sb + ks * 32), idesc,
+                           (kc | ks) ? 1u : 0u);
+            umma_commit(empty_bar + 8 * s);
+            if (kc == KCH - 1) {
+              umma_commit(acc_full + 8 * as);
+              if (p == NPASS - 1) umma_commit(a_free);      // A tile may be overwritten after these MMAs
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ------------------------------ workers (warps 2..5) ----------------------------------------
+    const int q4 = warp & 3;
+    const int wt = (warp - 2) * 32 + lane;       // 0..127 worker-thread index (gather work split)
+    const int row = q4 * 32 + lane;              // tile row == TMEM lane owned by this thread
+    const bool row_ok = row < ROWS;
+    const int sq = row_ok ? row / S : 0;
+    uint32_t pass_it = 0, tile_it = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
+      const int64_t seq0 = t * SPT;
+      // ---- row ids of this tile ----
+      if (wt < ROWS) {
+        const int64_t seq = seq0 + wt / S;
+        int64_t id = 0;
+        if (seq < n_seq) {
+          const int64_t e = seq * S + (wt % S);
+          id = idx_kind == 0 ? e : (idx_kind == 1 ? reinterpret_cast<const int64_t*>(idx)[e]
+                                                  : (int64_t) reinterpret_cast<const int32_t*>(idx)[e]);
+        }
+        rowid[wt] = id;
+      }
+      mbar_wait(a_free, (tile_it & 1) ^ 1);      // previous tile's MMAs no longer read the A tile
+      worker_bar();
+      // ---- gather + TF32 rounding into the swizzled A tile: ROWS x 75 float4 ----
+      constexpr int TOTAL4 = ROWS * DV4;
+#pragma unroll 1
+      for (int f0 = 0; f0 < TOTAL4; f0 += 128 * 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int f = f0 + u * 128 + wt;
+          if (f < TOTAL4) {
+            const int r = f / DV4, c4 = f - r * DV4;
+            v[u] = __ldg(reinterpret_cast<const float4*>(src + rowid[r] * D) + c4);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int f = f0 + u * 128 + wt;
+          if (f < TOTAL4) {
+            const int r = f / DV4, c4 = f - r * DV4;
+            *reinterpret_cast<float4*>(sm + (c4 >> 3) * Cfg::CH + r * 128 + (((c4 & 7) ^ (r & 7)) << 4)) = to_tf32(v[u]);
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(a_full);
+      // ---- per pass: attention for heads 3p .. 3p+2 ----
+      for (int p = 0; p < NPASS; ++p, ++pass_it) {
+        const uint32_t as = pass_it & 1;
+        mbar_wait(acc_full + 8 * as, (pass_it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + as * K1_N + ((uint32_t)(q4 * 32) << 16);
+#pragma unroll 1
+        for (int hh = 0; hh < HP; ++hh) {
+          const int h = p * HP + hh;
+          float qv[DH], kk[DH], vv[DH];
+          tmem_ld16(trow + hh * DH, qv);            tmem_ld4(trow + hh * DH + 16, qv + 16);
+          tmem_ld16(trow + 64 + hh * DH, kk);       tmem_ld4(trow + 64 + hh * DH + 16, kk + 16);
+          tmem_ld16(trow + 128 + hh * DH, vv);      tmem_ld4(trow + 128 + hh * DH + 16, vv + 16);
+          if (hh == HP - 1) {                        // last TMEM read of this accumulator stage
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty + 8 * as);
+          }
+#pragma unroll
+          for (int d = 0; d < DH; ++d) {
+            qv[d] += bias_s[h * DH + d];
+            kk[d] += bias_s[D + h * DH + d];
+            vv[d] += bias_s[2 * D + h * DH + d];
+          }
+          if (row_ok) {
+            float4* kp = reinterpret_cast<float4*>(kv + row * 40);
+#pragma unroll
+            for (int c = 0; c < 5; ++c) {
+              kp[c] = make_float4(kk[4 * c], kk[4 * c + 1], kk[4 * c + 2], kk[4 * c + 3]);
+              kp[5 + c] = make_float4(vv[4 * c], vv[4 * c + 1], vv[4 * c + 2], vv[4 * c + 3]);
+            }
+          }
+          worker_bar();
+          if (row_ok) {
+            float acc[DH];
+#pragma unroll
+            for (int d = 0; d < DH; ++d) acc[d] = 0.f;
+            float Z = 0.f;
+            const float4* base_kv = reinterpret_cast<const float4*>(kv + sq * S * 40);
+#pragma unroll 2
+            for (int j = 0; j < S; ++j) {
+              const float4* kp = base_kv + j * 10;
+              float s = 0.f;
+#pragma unroll
+              for (int c = 0; c < 5; ++c) {
+                const float4 k4 = kp[c];
+                s = fmaf(qv[4 * c], k4.x, s); s = fmaf(qv[4 * c + 1], k4.y, s);
+                s = fmaf(qv[4 * c + 2], k4.z, s); s = fmaf(qv[4 * c + 3], k4.w, s);
+              }
+              const float e = exp2f(s * LOG2E_OVER_SQRT_DH);
+              Z += e;
+#pragma unroll
+              for (int c = 0; c < 5; ++c) {
+                const float4 v4 = kp[5 + c];
+                acc[4 * c] = fmaf(e, v4.x, acc[4 * c]); acc[4 * c + 1] = fmaf(e, v4.y, acc[4 * c + 1]);
+                acc[4 * c + 2] = fmaf(e, v4.z, acc[4 * c + 2]); acc[4 * c + 3] = fmaf(e, v4.w, acc[4 * c + 3]);
+              }
+            }
+            const float inv = 1.f / (Z + 1e-8f);
+            if (seq0 + sq < n_seq) {
+              float4* op = reinterpret_cast<float4*>(C + (seq0 * S + row) * D + h * DH);
+#pragma unroll
+              for (int c = 0; c < 5; ++c)
+                op[c] = make_float4(acc[4 * c] * inv, acc[4 * c + 1] * inv, acc[4 * c + 2] * inv, acc[4 * c + 3] * inv);
+            }
+          }
+          worker_bar();       // K/V staging is reused by the next head
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2: additive attention pooling.  Streaming GEMM (A = C rows, B = W_a) + fused epilogue.
+// ---------------------------------------------------------------------------------------------------
+constexpr int K2_STAGES = 4;
+constexpr int K2_A_SLOT = 16384;           // up to 128 rows x 128 B
+constexpr int K2_B_SLOT = 26624;           // 200 rows x 128 B = 25,600 -> padded to a 1024 multiple
+constexpr int K2_STAGE = K2_A_SLOT + K2_B_SLOT;
+constexpr int K2_N = 208;
+constexpr int K2_THREADS = 192;
+constexpr int K2_OFF_MISC = K2_STAGES * K2_STAGE;       // sc[128] | wv[128] | ba[200] | qa[200] | barriers
+constexpr int K2_SMEM = K2_OFF_MISC + 4096 + 1024;
+
+__device__ __forceinline__ float fast_tanh(float x) {
+  // tanh(x) = 1 - 2/(exp(2x)+1); abs error ~1e-7 (ex2.approx + div.approx), saturates cleanly at +-1
+  const float e = exp2f(x * 2.885390081777927f);
+  return 1.f - __fdividef(2.f, e + 1.f);
+}
+
+template <int S, int SPT>
+__global__ void __launch_bounds__(K2_THREADS, 1)
+additive_pool_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_wa,
+                     const float* __restrict__ C, const float* __restrict__ ba, const float* __restrict__ qa,
+                     float* __restrict__ out, int64_t n_seq, uint32_t stage_tx_bytes) {
+  constexpr int ROWS = S * SPT;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  float* sc = reinterpret_cast<float*>(sm + K2_OFF_MISC);
+  float* wv = sc + 128;
+  float* ba_s = wv + 128;
+  float* qa_s = ba_s + 208;
+  const uint32_t bars = base + K2_OFF_MISC + 3072;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * K2_STAGES, tfull_bar = bars + 16 * K2_STAGES,
+                 tempty_bar = tfull_bar + 16;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sm + K2_OFF_MISC + 3072 + 16 * K2_STAGES + 32);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n_tiles = (n_seq + SPT - 1) / SPT;
+
+  if (tid == 0) {
+    for (int s = 0; s < K2_STAGES; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar + 8 * a, 1);
+      mbar_init(tempty_bar + 8 * a, 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_ptr_smem), 512);
+  for (int i = tid; i < 208; i += K2_THREADS) {
+    ba_s[i] = i < QD ? ba[i] : 0.f;
+    qa_s[i] = i < QD ? qa[i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int r0 = (int)(t * ROWS);
+        for (int kc = 0; kc < KCH; ++kc, ++it) {
+          const int s = it % K2_STAGES;
+          mbar_wait(empty_bar + 8 * s, ((it / K2_STAGES) & 1) ^ 1);
+          mbar_expect_tx_f(full_bar + 8 * s, stage_tx_bytes);
+          const uint32_t sa = base + s * K2_STAGE;
+          tma_load_2d_f(sa, &tmap_c, kc * 32, r0, full_bar + 8 * s);
+          tma_load_2d_f(sa + K2_A_SLOT, &tmap_wa, kc * 32, 0, full_bar + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = umma_idesc_tf32(128, K2_N);
+    uint32_t it = 0, tile_it = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
+      const uint32_t as = tile_it & 1;
+      mbar_wait(tempty_bar + 8 * as, ((tile_it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * 256;
+      for (int kc = 0; kc < KCH; ++kc, ++it) {
+        const int s = it % K2_STAGES;
+        mbar_wait(full_bar + 8 * s, (it / K2_STAGES) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = base + s * K2_STAGE;
+          const uint32_t sb = sa + K2_A_SLOT;
+          const int ksteps = (kc == KCH - 1) ? 2 : 4;
+          for (int ks = 0; ks < ksteps; ++ks)
+            umma_tf32_ss(d_tmem, umma_desc_k_sw128(sa + ks * 32), umma_desc_k_sw128(sb + ks * 32), idesc,
+                         (kc | ks) ? 1u : 0u);
+          umma_commit(empty_bar + 8 * s);
+          if (kc == KCH - 1) umma_commit(tfull_bar + 8 * as);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    const int q4 = warp & 3;
+    const int wt = (warp - 2) * 32 + lane;
+    const int row = q4 * 32 + lane;
+    const bool row_ok = row < ROWS;
+    uint32_t tile_it = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
+      const int64_t seq0 = t * SPT;
+      const uint32_t as = tile_it & 1;
+      mbar_wait(tfull_bar + 8 * as, (tile_it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + as * 256 + ((uint32_t)(q4 * 32) << 16);
+      float s = 0.f;
+#pragma unroll 1
+      for (int col = 0; col < K2_N; col += 16) {
+        float v[16];
+        tmem_ld16(trow + col, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s = fmaf(fast_tanh(v[j] + ba_s[col + j]), qa_s[col + j], s);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * as);
+      sc[row] = s;
+      worker_bar();
+      if (row_ok) {
+        const int sq = row / S;
+        float m = -INFINITY;
+        for (int j = 0; j < S; ++j) m = fmaxf(m, sc[sq * S + j]);
+        float sum = 0.f;
+        for (int j = 0; j < S; ++j) sum += __expf(sc[sq * S + j] - m);
+        wv[row] = __fdividef(__expf(s - m), sum);
+      }
+      worker_bar();
+      // pooled[seq, d] = sum_i w_i C[seq*S + i, d]   (C rows are L2-hot: K1 just wrote them)
+      for (int o = wt; o < SPT * DV4; o += 128) {
+        const int sq = o / DV4, l = o - sq * DV4;
+        if (seq0 + sq < n_seq) {
+          const float4* cp = reinterpret_cast<const float4*>(C + (seq0 + sq) * S * D) + l;
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 5
+          for (int i = 0; i < S; ++i) {
+            const float4 c4 = __ldg(cp + i * DV4);
+            const float w = wv[sq * S + i];
+            acc.x = fmaf(w, c4.x, acc.x); acc.y = fmaf(w, c4.y, acc.y);
+            acc.z = fmaf(w, c4.z, acc.z); acc.w = fmaf(w, c4.w, acc.w);
+          }
+          reinterpret_cast<float4*>(out + (seq0 + sq) * D)[l] = acc;
+        }
+      }
+      worker_bar();     // sc / wv are reused by the next tile
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------------
+template <int S, int SPT>
+static int64_t fused_chunk_seq() { return (int64_t)num_sms() * SPT * 4; }   // 4 full waves of tiles per launch
+
+template <int S, int SPT>
+static int run_fused(const float* src, const void* idx, int idx_kind, int64_t n_seq, const float* wqkv,
+                     const float* bqkv, const float* wa, const float* ba, const float* qa, float* out,
+                     void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  using Cfg = K1<S, SPT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(encoder_attn_kernel<S, SPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(encoder_attn_kernel)");
+    e = cudaFuncSetAttribute(additive_pool_kernel<S, SPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(additive_pool_kernel)");
+    configured = true;
+  }
+  const int64_t chunk = fused_chunk_seq<S, SPT>();
+  const int64_t first = n_seq < chunk ? n_seq : chunk;
+  const size_t need = (size_t)first * S * D * sizeof(float);
+  NRMS_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= need, NRMS_E_WORKSPACE,
+                 "workspace too small: need %zu bytes", need);
+  float* Cbuf = reinterpret_cast<float*>(workspace);
+  alignas(64) CUtensorMap tw, twa, tc_;
+  if (int rc = make_tmap_k_major(&tw, wqkv, D3, D, D, 64)) return rc;
+  if (int rc = make_tmap_k_major(&twa, wa, QD, D, D, QD)) return rc;
+  const size_t idx_elem = idx_kind == 1 ? 8 : 4;
+  for (int64_t s0 = 0; s0 < n_seq; s0 += chunk) {
+    const int64_t n = (n_seq - s0 < chunk) ? (n_seq - s0) : chunk;
+    const int64_t tiles = (n + SPT - 1) / SPT;
+    int grid = num_sms();
+    if (tiles < grid) grid = (int)tiles;
+    const float* src_c = idx_kind == 0 ? src + s0 * S * D : src;
+    const void* idx_c = idx_kind == 0 ? nullptr : (const void*)((const char*)idx + (size_t)s0 * S * idx_elem);
+    encoder_attn_kernel<S, SPT><<<grid, K1_THREADS, Cfg::SMEM, st>>>(tw, src_c, idx_c, idx_kind, n, bqkv, Cbuf);
+    NRMS_LAUNCH_CHECK("encoder_attn_kernel");
+    const int box_c = (int)((n * S < Cfg::ROWS) ? n * S : Cfg::ROWS);
+    if (int rc = make_tmap_k_major(&tc_, Cbuf, n * S, D, D, box_c)) return rc;
+    additive_pool_kernel<S, SPT><<<grid, K2_THREADS, K2_SMEM, st>>>(tc_, twa, Cbuf, ba, qa, out + s0 * D, n,
+                                                                    (uint32_t)(box_c + QD) * 128u);
+    NRMS_LAUNCH_CHECK("additive_pool_kernel");
+  }
+  return NRMS_OK;
+}
+
+size_t tc_fused_workspace_bytes(int64_t n_seq, int S) {
+  if (n_seq <= 0) return (size_t)-1;
+  int64_t chunk;
+  if (S == 20) chunk = fused_chunk_seq<20, 6>();
+  else if (S == 50) chunk = fused_chunk_seq<50, 2>();
+  else return (size_t)-1;
+  const int64_t first = n_seq < chunk ? n_seq : chunk;
+  return (size_t)first * S * D * sizeof(float);
+}
+
+int tc_encoder_fused(const float* src, const void* idx, int idx_kind, int64_t n_seq, int S, const float* wqkv,
+                     const float* bqkv, const float* wa, const float* ba, const float* qa, float* out,
+                     void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (S == 20) return run_fused<20, 6>(src, idx, idx_kind, n_seq, wqkv, bqkv, wa, ba, qa, out, workspace, workspace_bytes, st);
+  if (S == 50) return run_fused<50, 2>(src, idx, idx_kind, n_seq, wqkv, bqkv, wa, ba, qa, out, workspace, workspace_bytes, st);
+  set_error("fused encoder compiled for S = 20 or 50, got %d", S);
   return NRMS_E_UNSUPPORTED;
 }
 

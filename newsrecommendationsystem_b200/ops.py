@@ -40,7 +40,7 @@ class _NewsEncoderFn(torch.autograd.Function):
     """NewsEncoder.forward (reference src/model/NRMS/news_encoder.py:27-48)."""
 
     @staticmethod
-    def forward(ctx, tokens, emb, wqkv, bqkv, wa, ba, qa, dropout_p, seed, offset, mode):
+    def forward(ctx, tokens, emb, wqkv, bqkv, wa, ba, qa, dropout_p, seed, offset, mode, track_grad):
         lib = _lib.load()
         _require_cuda(tokens, emb, wqkv, bqkv, wa, ba, qa)
         tokens = tokens.contiguous()
@@ -50,7 +50,7 @@ class _NewsEncoderFn(torch.autograd.Function):
         dev = emb.device
         emb_c, wqkv_c, bqkv_c, wa_c, ba_c, qa_c = map(_f32c, (emb, wqkv, bqkv, wa, ba, qa))
         out = torch.empty((n, D), dtype=torch.float32, device=dev)
-        needs_grad = any(ctx.needs_input_grad)
+        needs_grad = track_grad and any(ctx.needs_input_grad)   # grad mode is always off inside forward()
         stash = None
         if needs_grad:
             stash = _bytes(lib.nrms_encoder_stash_bytes(n, L), dev)
@@ -83,14 +83,14 @@ class _NewsEncoderFn(torch.autograd.Function):
                                         ptr(d_emb), ptr(d_wqkv), ptr(d_bqkv), ptr(d_wa), ptr(d_ba), ptr(d_qa),
                                         ptr(ws), ws.numel(), p, seed, offset, mode, stream_ptr(dev)),
               "nrms_news_encoder_bwd")
-        return None, d_emb, d_wqkv, d_bqkv, d_wa, d_ba, d_qa, None, None, None, None
+        return None, d_emb, d_wqkv, d_bqkv, d_wa, d_ba, d_qa, None, None, None, None, None
 
 
 class _UserEncoderFn(torch.autograd.Function):
     """UserEncoder.forward (reference src/model/NRMS/user_encoder.py:15-26), dense input."""
 
     @staticmethod
-    def forward(ctx, x, wqkv, bqkv, wa, ba, qa, mode):
+    def forward(ctx, x, wqkv, bqkv, wa, ba, qa, mode, track_grad):
         lib = _lib.load()
         _require_cuda(x, wqkv, bqkv, wa, ba, qa)
         n, S, d = x.shape
@@ -99,7 +99,7 @@ class _UserEncoderFn(torch.autograd.Function):
         dev = x.device
         x_c, wqkv_c, bqkv_c, wa_c, ba_c, qa_c = map(_f32c, (x, wqkv, bqkv, wa, ba, qa))
         out = torch.empty((n, D), dtype=torch.float32, device=dev)
-        needs_grad = any(ctx.needs_input_grad)
+        needs_grad = track_grad and any(ctx.needs_input_grad)
         stash = _bytes(lib.nrms_encoder_stash_bytes(n, S), dev) if needs_grad else None
         ws = _bytes(lib.nrms_encoder_fwd_workspace_bytes(n, S, mode, 1 if needs_grad else 0), dev)
         check(lib.nrms_user_encoder_fwd(ptr(x_c), None, n, S, ptr(wqkv_c), ptr(bqkv_c), ptr(wa_c), ptr(ba_c),
@@ -128,7 +128,7 @@ class _UserEncoderFn(torch.autograd.Function):
                                         ptr(d_wqkv), ptr(d_bqkv), ptr(d_wa), ptr(d_ba), ptr(d_qa), ptr(ws),
                                         ws.numel(), mode, stream_ptr(dev)),
               "nrms_user_encoder_bwd")
-        return d_x, d_wqkv, d_bqkv, d_wa, d_ba, d_qa, None
+        return d_x, d_wqkv, d_bqkv, d_wa, d_ba, d_qa, None, None
 
 
 class _ScoreFn(torch.autograd.Function):
@@ -183,11 +183,12 @@ class _CrossEntropyLabel0Fn(torch.autograd.Function):
 
 # ---- functional API ---------------------------------------------------------------------------
 def news_encoder(tokens, emb, wqkv, bqkv, wa, ba, qa, dropout_p=0.0, seed=0, offset=0, mode=_lib.MODE_TF32):
-    return _NewsEncoderFn.apply(tokens, emb, wqkv, bqkv, wa, ba, qa, dropout_p, seed, offset, mode)
+    return _NewsEncoderFn.apply(tokens, emb, wqkv, bqkv, wa, ba, qa, dropout_p, seed, offset, mode,
+                                torch.is_grad_enabled())
 
 
 def user_encoder(x, wqkv, bqkv, wa, ba, qa, mode=_lib.MODE_TF32):
-    return _UserEncoderFn.apply(x, wqkv, bqkv, wa, ba, qa, mode)
+    return _UserEncoderFn.apply(x, wqkv, bqkv, wa, ba, qa, mode, torch.is_grad_enabled())
 
 
 @torch.no_grad()
