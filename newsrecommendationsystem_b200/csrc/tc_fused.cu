@@ -1,15 +1,16 @@
 // Fused tensor-core encoder forward (inference) for sm_100a.  Two persistent kernels per chunk of
 // sequences; the only intermediate that leaves the SM is the attention context C (L2-resident chunk).
 //
-//  K1  encoder_attn_kernel<S,SPT>:  tile = SPT sequences (S*SPT <= 128 rows: 6 titles or 2 users)
-//      workers (4 warps): gather the tile's input rows (embedding rows by token id, news-vector rows by
+//  K1  encoder_attn_kernel<S,SPT>:  tile = SPT sequences (100 rows: 5 titles or 2 users)
+//      workers (8 warps): gather the tile's input rows (embedding rows by token id, news-vector rows by
 //        int32 index, or dense rows) with coalesced float4 loads, round to TF32 and store them into the
 //        resident A tile in the UMMA SWIZZLE_128B K-major layout (10 chunks of 32 floats);
-//      producer (1 thread): streams W_Q/W_K/W_V through a 2-stage TMA ring, three 64-row boxes per K
-//        chunk (heads 3p..3p+2 of Q, K and V) -> B tile of 192 rows;
-//      MMA (1 thread): 5 passes x 38 tcgen05.mma.kind::tf32 (M=128, N=192, K=8) into one of two
-//        192-column TMEM accumulator stages;
-//      workers again: per head, tcgen05.ld q/k/v of their own row (thread == token row), +bias, stage
+//      producer (1 thread): streams W_Q/W_K/W_V through a 2-stage TMA ring, three 80-row boxes per K
+//        chunk (heads 4p..4p+3 of Q, K and V) -> B tile of 240 rows;
+//      MMA (1 thread): 4 passes x 38 tcgen05.mma.kind::tf32 (M=128, N=240, K=8) into one of two
+//        240-column TMEM accumulator stages;
+//      workers again (two groups of 4 warps, one head each at a time): per head, tcgen05.ld q/k/v of
+//        their own row (thread == token row), +bias, stage
 //        K/V in shared memory, then the 15-head exp-softmax attention of the reference
 //        (e = exp(qk/sqrt(20)), attn = e/(sum e + 1e-8), no max subtraction) entirely in registers with
 //        warp-broadcast shared-memory reads; context rows go to C.
@@ -37,11 +38,20 @@ __device__ __forceinline__ void mbar_expect_tx_f(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 constexpr int KCH = 10;            // K chunks of 32 floats (300 -> 320, tail zero)
-constexpr int HP = 3;              // heads per QKV pass
-constexpr int NPASS = H / HP;      // 5
-constexpr int K1_N = 192;          // UMMA N of a pass: [Q 60 | pad 4 | K 60 | pad 4 | V 60 | pad 4]
-constexpr int K1_BSTAGE = 3 * 64 * 128;   // 24,576 B
-constexpr int K1_THREADS = 192;
+constexpr int HP = 4;              // heads per QKV pass (the 16th "head" of the last pass is a dummy)
+constexpr int NPASS = 4;
+constexpr int K1_BOX = HP * DH;    // 80 weight rows per Q/K/V box (80 x 128 B = 10 KB, 1024-aligned)
+constexpr int K1_N = 3 * K1_BOX;   // UMMA N of a pass = 240: [Q 80 | K 80 | V 80]
+constexpr int K1_BSTAGE = K1_N * 128;     // 30,720 B
+constexpr int K1_WORKERS = 256;    // 8 worker warps = 2 groups of 4 (one group per head, two heads in flight)
+constexpr int K1_THREADS = 64 + K1_WORKERS;
+__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); }
+__device__ __forceinline__ void workers_bar() { asm volatile("bar.sync 3, 256;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 constexpr float LOG2E_OVER_SQRT_DH = 1.4426950408889634f / 4.47213595499957939f;
 
 template <int S, int SPT>
@@ -51,7 +61,8 @@ struct K1 {
   static constexpr int CH = ROWS_ALLOC * 128;                 // bytes of one A chunk (rows x 128 B)
   static constexpr int OFF_B = KCH * CH;
   static constexpr int OFF_KV = OFF_B + 2 * K1_BSTAGE;
-  static constexpr int OFF_BIAS = OFF_KV + ROWS * 40 * 4;
+  static constexpr int KV_BYTES = ROWS * 40 * 4;              // one group's K/V staging (one head)
+  static constexpr int OFF_BIAS = OFF_KV + 2 * KV_BYTES;
   static constexpr int OFF_IDX = OFF_BIAS + 3712;
   static constexpr int OFF_BAR = OFF_IDX + 128 * 8;
   static constexpr int SMEM = OFF_BAR + 128 + 1024;
@@ -88,9 +99,9 @@ encoder_attn_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __r
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
       mbar_init(acc_full + 8 * s, 1);
-      mbar_init(acc_empty + 8 * s, 4);
+      mbar_init(acc_empty + 8 * s, 8);
     }
-    mbar_init(a_full, 128);
+    mbar_init(a_full, K1_WORKERS);
     mbar_init(a_free, 1);
     mbar_fence_init();
   }
@@ -115,9 +126,9 @@ encoder_attn_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __r
             mbar_wait(empty_bar + 8 * s, ((it >> 1) & 1) ^ 1);
             mbar_expect_tx_f(full_bar + 8 * s, K1_BSTAGE);
             const uint32_t sb = base + Cfg::OFF_B + s * K1_BSTAGE;
-            tma_load_2d_f(sb, &tmap_w, kc * 32, 60 * p, full_bar + 8 * s);
-            tma_load_2d_f(sb + 8192, &tmap_w, kc * 32, D + 60 * p, full_bar + 8 * s);
-            tma_load_2d_f(sb + 16384, &tmap_w, kc * 32, 2 * D + 60 * p, full_bar + 8 * s);
+            tma_load_2d_f(sb, &tmap_w, kc * 32, K1_BOX * p, full_bar + 8 * s);
+            tma_load_2d_f(sb + K1_BOX * 128, &tmap_w, kc * 32, D + K1_BOX * p, full_bar + 8 * s);
+            tma_load_2d_f(sb + 2 * K1_BOX * 128, &tmap_w, kc * 32, 2 * D + K1_BOX * p, full_bar + 8 * s);
           }
         }
       }
@@ -156,12 +167,14 @@ encoder_attn_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __r
       }
     }
   } else {
-    // ------------------------------ workers (warps 2..5) ----------------------------------------
-    const int q4 = warp & 3;
-    const int wt = (warp - 2) * 32 + lane;       // 0..127 worker-thread index (gather work split)
+    // ------------------------------ workers (warps 2..9) ----------------------------------------
+    const int g = (warp - 2) >> 2;               // group: handles heads hh = g, g+2 of every pass
+    const int q4 = warp & 3;                     // TMEM lane quarter this warp may access
+    const int wt = (warp - 2) * 32 + lane;       // 0..255 worker-thread index (gather work split)
     const int row = q4 * 32 + lane;              // tile row == TMEM lane owned by this thread
     const bool row_ok = row < ROWS;
     const int sq = row_ok ? row / S : 0;
+    float* kvg = kv + g * (Cfg::KV_BYTES / 4);
     uint32_t pass_it = 0, tile_it = 0;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
       const int64_t seq0 = t * SPT;
@@ -177,15 +190,15 @@ encoder_attn_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __r
         rowid[wt] = id;
       }
       mbar_wait(a_free, (tile_it & 1) ^ 1);      // previous tile's MMAs no longer read the A tile
-      worker_bar();
+      workers_bar();
       // ---- gather + TF32 rounding into the swizzled A tile: ROWS x 75 float4 ----
       constexpr int TOTAL4 = ROWS * DV4;
 #pragma unroll 1
-      for (int f0 = 0; f0 < TOTAL4; f0 += 128 * 8) {
+      for (int f0 = 0; f0 < TOTAL4; f0 += K1_WORKERS * 8) {
         float4 v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const int f = f0 + u * 128 + wt;
+          const int f = f0 + u * K1_WORKERS + wt;
           if (f < TOTAL4) {
             const int r = f / DV4, c4 = f - r * DV4;
             v[u] = __ldg(reinterpret_cast<const float4*>(src + rowid[r] * D) + c4);
@@ -193,7 +206,7 @@ encoder_attn_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __r
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const int f = f0 + u * 128 + wt;
+          const int f = f0 + u * K1_WORKERS + wt;
           if (f < TOTAL4) {
             const int r = f / DV4, c4 = f - r * DV4;
             *reinterpret_cast<float4*>(sm + (c4 >> 3) * Cfg::CH + r * 128 + (((c4 & 7) ^ (r & 7)) << 4)) = to_tf32(v[u]);
@@ -202,56 +215,59 @@ encoder_attn_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __r
       }
       fence_proxy_async_smem();
       mbar_arrive(a_full);
-      // ---- per pass: attention for heads 3p .. 3p+2 ----
+      // ---- per pass: this group's heads 4p+g and 4p+g+2 ----
       for (int p = 0; p < NPASS; ++p, ++pass_it) {
         const uint32_t as = pass_it & 1;
         mbar_wait(acc_full + 8 * as, (pass_it >> 1) & 1);
         tc_fence_after();
         const uint32_t trow = tmem_base + as * K1_N + ((uint32_t)(q4 * 32) << 16);
 #pragma unroll 1
-        for (int hh = 0; hh < HP; ++hh) {
+        for (int u = 0; u < 2; ++u) {
+          const int hh = g + 2 * u;
           const int h = p * HP + hh;
+          if (h >= H) break;                         // dummy 16th head (last pass, group 1)
+          const bool last_read = (u == 1) || (h + 2 >= H);
           float qv[DH], kk[DH], vv[DH];
-          tmem_ld16(trow + hh * DH, qv);            tmem_ld4(trow + hh * DH + 16, qv + 16);
-          tmem_ld16(trow + 64 + hh * DH, kk);       tmem_ld4(trow + 64 + hh * DH + 16, kk + 16);
-          tmem_ld16(trow + 128 + hh * DH, vv);      tmem_ld4(trow + 128 + hh * DH + 16, vv + 16);
-          if (hh == HP - 1) {                        // last TMEM read of this accumulator stage
+          tmem_ld16(trow + hh * DH, qv);                  tmem_ld4(trow + hh * DH + 16, qv + 16);
+          tmem_ld16(trow + K1_BOX + hh * DH, kk);         tmem_ld4(trow + K1_BOX + hh * DH + 16, kk + 16);
+          tmem_ld16(trow + 2 * K1_BOX + hh * DH, vv);     tmem_ld4(trow + 2 * K1_BOX + hh * DH + 16, vv + 16);
+          if (last_read) {                           // this warp is done with the accumulator stage
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty + 8 * as);
           }
 #pragma unroll
           for (int d = 0; d < DH; ++d) {
-            qv[d] += bias_s[h * DH + d];
+            qv[d] = (qv[d] + bias_s[h * DH + d]) * LOG2E_OVER_SQRT_DH;   // fold 1/sqrt(d) and log2(e) into q
             kk[d] += bias_s[D + h * DH + d];
             vv[d] += bias_s[2 * D + h * DH + d];
           }
           if (row_ok) {
-            float4* kp = reinterpret_cast<float4*>(kv + row * 40);
+            float4* kp = reinterpret_cast<float4*>(kvg + row * 40);
 #pragma unroll
             for (int c = 0; c < 5; ++c) {
               kp[c] = make_float4(kk[4 * c], kk[4 * c + 1], kk[4 * c + 2], kk[4 * c + 3]);
               kp[5 + c] = make_float4(vv[4 * c], vv[4 * c + 1], vv[4 * c + 2], vv[4 * c + 3]);
             }
           }
-          worker_bar();
+          group_bar(g);
           if (row_ok) {
             float acc[DH];
 #pragma unroll
             for (int d = 0; d < DH; ++d) acc[d] = 0.f;
             float Z = 0.f;
-            const float4* base_kv = reinterpret_cast<const float4*>(kv + sq * S * 40);
+            const float4* base_kv = reinterpret_cast<const float4*>(kvg + sq * S * 40);
 #pragma unroll 2
             for (int j = 0; j < S; ++j) {
               const float4* kp = base_kv + j * 10;
-              float s = 0.f;
+              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;     // 4 independent chains
 #pragma unroll
               for (int c = 0; c < 5; ++c) {
                 const float4 k4 = kp[c];
-                s = fmaf(qv[4 * c], k4.x, s); s = fmaf(qv[4 * c + 1], k4.y, s);
-                s = fmaf(qv[4 * c + 2], k4.z, s); s = fmaf(qv[4 * c + 3], k4.w, s);
+                s0 = fmaf(qv[4 * c], k4.x, s0); s1 = fmaf(qv[4 * c + 1], k4.y, s1);
+                s2 = fmaf(qv[4 * c + 2], k4.z, s2); s3 = fmaf(qv[4 * c + 3], k4.w, s3);
               }
-              const float e = exp2f(s * LOG2E_OVER_SQRT_DH);
+              const float e = ex2_approx((s0 + s1) + (s2 + s3));   // exp(q.k / sqrt(20)), no max subtraction
               Z += e;
 #pragma unroll
               for (int c = 0; c < 5; ++c) {
@@ -268,7 +284,7 @@ encoder_attn_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __r
                 op[c] = make_float4(acc[4 * c] * inv, acc[4 * c + 1] * inv, acc[4 * c + 2] * inv, acc[4 * c + 3] * inv);
             }
           }
-          worker_bar();       // K/V staging is reused by the next head
+          group_bar(g);       // this group's K/V staging is reused by its next head
         }
       }
     }
@@ -393,11 +409,18 @@ additive_pool_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
       const uint32_t trow = tmem_base + as * 256 + ((uint32_t)(q4 * 32) << 16);
       float s = 0.f;
 #pragma unroll 1
-      for (int col = 0; col < K2_N; col += 16) {
+      for (int col = 0; col < 192; col += 16) {
         float v[16];
         tmem_ld16(trow + col, v);
 #pragma unroll
         for (int j = 0; j < 16; ++j) s = fmaf(fast_tanh(v[j] + ba_s[col + j]), qa_s[col + j], s);
+      }
+      {   // columns 192..199; accumulator columns 200..207 come from unwritten smem rows and are never read
+        float v[8];
+        tmem_ld4(trow + 192, v);
+        tmem_ld4(trow + 196, v + 4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s = fmaf(fast_tanh(v[j] + ba_s[192 + j]), qa_s[192 + j], s);
       }
       tc_fence_before();
       __syncwarp();
@@ -413,18 +436,24 @@ additive_pool_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
         wv[row] = __fdividef(__expf(s - m), sum);
       }
       worker_bar();
-      // pooled[seq, d] = sum_i w_i C[seq*S + i, d]   (C rows are L2-hot: K1 just wrote them)
+      // pooled[seq, d] = sum_i w_i C[seq*S + i, d]   (C rows are L2-hot: K1 just wrote them);
+      // 10 independent 16-byte loads in flight per thread
       for (int o = wt; o < SPT * DV4; o += 128) {
         const int sq = o / DV4, l = o - sq * DV4;
         if (seq0 + sq < n_seq) {
           const float4* cp = reinterpret_cast<const float4*>(C + (seq0 + sq) * S * D) + l;
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 5
-          for (int i = 0; i < S; ++i) {
-            const float4 c4 = __ldg(cp + i * DV4);
-            const float w = wv[sq * S + i];
-            acc.x = fmaf(w, c4.x, acc.x); acc.y = fmaf(w, c4.y, acc.y);
-            acc.z = fmaf(w, c4.z, acc.z); acc.w = fmaf(w, c4.w, acc.w);
+#pragma unroll 1
+          for (int i0 = 0; i0 < S; i0 += 10) {
+            float4 c4[10];
+#pragma unroll
+            for (int i = 0; i < 10; ++i) c4[i] = __ldg(cp + (i0 + i) * DV4);
+#pragma unroll
+            for (int i = 0; i < 10; ++i) {
+              const float w = wv[sq * S + i0 + i];
+              acc.x = fmaf(w, c4[i].x, acc.x); acc.y = fmaf(w, c4[i].y, acc.y);
+              acc.z = fmaf(w, c4[i].z, acc.z); acc.w = fmaf(w, c4[i].w, acc.w);
+            }
           }
           reinterpret_cast<float4*>(out + (seq0 + sq) * D)[l] = acc;
         }
@@ -463,7 +492,7 @@ static int run_fused(const float* src, const void* idx, int idx_kind, int64_t n_
                  "workspace too small: need %zu bytes", need);
   float* Cbuf = reinterpret_cast<float*>(workspace);
   alignas(64) CUtensorMap tw, twa, tc_;
-  if (int rc = make_tmap_k_major(&tw, wqkv, D3, D, D, 64)) return rc;
+  if (int rc = make_tmap_k_major(&tw, wqkv, D3, D, D, K1_BOX)) return rc;
   if (int rc = make_tmap_k_major(&twa, wa, QD, D, D, QD)) return rc;
   const size_t idx_elem = idx_kind == 1 ? 8 : 4;
   for (int64_t s0 = 0; s0 < n_seq; s0 += chunk) {
@@ -487,7 +516,7 @@ static int run_fused(const float* src, const void* idx, int idx_kind, int64_t n_
 size_t tc_fused_workspace_bytes(int64_t n_seq, int S) {
   if (n_seq <= 0) return (size_t)-1;
   int64_t chunk;
-  if (S == 20) chunk = fused_chunk_seq<20, 6>();
+  if (S == 20) chunk = fused_chunk_seq<20, 5>();
   else if (S == 50) chunk = fused_chunk_seq<50, 2>();
   else return (size_t)-1;
   const int64_t first = n_seq < chunk ? n_seq : chunk;
@@ -497,7 +526,7 @@ size_t tc_fused_workspace_bytes(int64_t n_seq, int S) {
 int tc_encoder_fused(const float* src, const void* idx, int idx_kind, int64_t n_seq, int S, const float* wqkv,
                      const float* bqkv, const float* wa, const float* ba, const float* qa, float* out,
                      void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  if (S == 20) return run_fused<20, 6>(src, idx, idx_kind, n_seq, wqkv, bqkv, wa, ba, qa, out, workspace, workspace_bytes, st);
+  if (S == 20) return run_fused<20, 5>(src, idx, idx_kind, n_seq, wqkv, bqkv, wa, ba, qa, out, workspace, workspace_bytes, st);
   if (S == 50) return run_fused<50, 2>(src, idx, idx_kind, n_seq, wqkv, bqkv, wa, ba, qa, out, workspace, workspace_bytes, st);
   set_error("fused encoder compiled for S = 20 or 50, got %d", S);
   return NRMS_E_UNSUPPORTED;
