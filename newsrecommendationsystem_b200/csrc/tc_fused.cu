@@ -3,11 +3,12 @@
 //
 //  K1  encoder_attn_kernel<S,SPT>:  tile = SPT sequences (100 rows: 5 titles or 2 users)
 //      workers (8 warps): gather the tile's input rows (embedding rows by token id, news-vector rows by
-//        int32 index, or dense rows) with coalesced float4 loads, round to TF32 and store them into the
-//        resident A tile in the UMMA SWIZZLE_128B K-major layout (10 chunks of 32 floats);
-//      producer (1 thread): streams W_Q/W_K/W_V through a 2-stage TMA ring, three 80-row boxes per K
+//        int32 index, or dense rows) with coalesced float4 loads, round to FP16 (11-bit significand, the
+//        same as TF32, at half the operand bytes) and store them into the resident A tile in the UMMA
+//        SWIZZLE_128B K-major layout (5 chunks of 64 halfs);
+//      producer (1 thread): streams an fp16 copy of W_Q/W_K/W_V through a 4-stage TMA ring, three 80-row boxes per K
 //        chunk (heads 4p..4p+3 of Q, K and V) -> B tile of 240 rows;
-//      MMA (1 thread): 4 passes x 38 tcgen05.mma.kind::tf32 (M=128, N=240, K=8) into one of two
+//      MMA (1 thread): 4 passes x 19 tcgen05.mma.kind::f16 (M=128, N=240, K=16, fp32 accumulate) into one of two
 //        240-column TMEM accumulator stages;
 //      workers again (two groups of 4 warps, one head each at a time): per head, tcgen05.ld q/k/v of
 //        their own row (thread == token row), +bias, stage
@@ -17,6 +18,7 @@
 //  K2  additive_pool_kernel<S,SPT>: C (TMA, rounded to TF32 by the TFLOAT32 tensor map) x W_a^T on
 //      tcgen05 (N=208), epilogue tanh -> . q -> stable softmax over the sequence -> weighted row sum.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include "tc_common.cuh"
 #include "tc_api.cuh"
 
@@ -24,6 +26,7 @@ namespace nrms {
 using namespace tc;
 
 int make_tmap_k_major(CUtensorMap* out, const float* base, int64_t rows, int cols, int64_t ld, int box_rows);
+int make_tmap_k_major_f16(CUtensorMap* out, const void* base, int64_t rows, int cols, int64_t ld, int box_rows);
 
 __device__ __forceinline__ void tma_load_2d_f(uint32_t dst_smem, const CUtensorMap* tmap, int c0, int c1, uint32_t bar) {
   asm volatile(
@@ -37,7 +40,10 @@ __device__ __forceinline__ void mbar_expect_tx_f(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-constexpr int KCH = 10;            // K chunks of 32 floats (300 -> 320, tail zero)
+constexpr int KCH = 10;            // K2: K chunks of 32 floats (300 -> 320, tail zero)
+constexpr int KCH16 = 5;           // K1: K chunks of 64 halfs (128 B), 300 -> 320 with a zero tail
+constexpr int K1_STAGES = 4;
+constexpr int W16_LD = 320;        // fp16 copy of [W_Q;W_K;W_V]: [900][320] halfs, K zero-padded
 constexpr int HP = 4;              // heads per QKV pass (the 16th "head" of the last pass is a dummy)
 constexpr int NPASS = 4;
 constexpr int K1_BOX = HP * DH;    // 80 weight rows per Q/K/V box (80 x 128 B = 10 KB, 1024-aligned)
@@ -59,13 +65,13 @@ struct K1 {
   static constexpr int ROWS = S * SPT;
   static constexpr int ROWS_ALLOC = (ROWS + 7) / 8 * 8;
   static constexpr int CH = ROWS_ALLOC * 128;                 // bytes of one A chunk (rows x 128 B)
-  static constexpr int OFF_B = KCH * CH;
-  static constexpr int OFF_KV = OFF_B + 2 * K1_BSTAGE;
+  static constexpr int OFF_B = KCH16 * CH;
+  static constexpr int OFF_KV = OFF_B + K1_STAGES * K1_BSTAGE;
   static constexpr int KV_BYTES = ROWS * 40 * 4;              // one group's K/V staging (one head)
   static constexpr int OFF_BIAS = OFF_KV + 2 * KV_BYTES;
   static constexpr int OFF_IDX = OFF_BIAS + 3712;
   static constexpr int OFF_BAR = OFF_IDX + 128 * 8;
-  static constexpr int SMEM = OFF_BAR + 128 + 1024;
+  static constexpr int SMEM = OFF_BAR + 256 + 1024;
   static_assert(ROWS <= 128, "tile rows");
   static_assert(CH % 1024 == 0 && OFF_B % 1024 == 0, "swizzle alignment");
   static_assert(SMEM <= 232448, "shared memory budget");
@@ -87,17 +93,19 @@ encoder_attn_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __r
   float* bias_s = reinterpret_cast<float*>(sm + Cfg::OFF_BIAS);
   int64_t* rowid = reinterpret_cast<int64_t*>(sm + Cfg::OFF_IDX);
   const uint32_t bars = base + Cfg::OFF_BAR;
-  const uint32_t full_bar = bars, empty_bar = bars + 16, a_full = bars + 32, a_free = bars + 40;
-  const uint32_t acc_full = bars + 48, acc_empty = bars + 64;
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sm + Cfg::OFF_BAR + 96);
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * K1_STAGES, a_full = bars + 16 * K1_STAGES,
+                 a_free = a_full + 8, acc_full = a_full + 16, acc_empty = a_full + 32;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sm + Cfg::OFF_BAR + 16 * K1_STAGES + 64);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_tiles = (n_seq + SPT - 1) / SPT;
 
   if (tid == 0) {
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < K1_STAGES; ++s) {
       mbar_init(full_bar + 8 * s, 1);
       mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(acc_full + 8 * s, 1);
       mbar_init(acc_empty + 8 * s, 8);
     }
@@ -107,9 +115,13 @@ encoder_attn_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __r
   }
   if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_ptr_smem), 512);
   for (int i = tid; i < D3; i += K1_THREADS) bias_s[i] = bqkv[i];
-  // K tail of the A tile (floats 300..303 = 16-byte chunk 3 of K chunk 9) is zero for good
-  for (int r = tid; r < Cfg::ROWS_ALLOC; r += K1_THREADS)
-    *reinterpret_cast<float4*>(sm + 9 * Cfg::CH + r * 128 + ((3 ^ (r & 7)) << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+  // K tail of the A tile (halfs 300..319 of every row: K chunk 4, bytes 88..127) is zero for good
+  for (int r = tid; r < Cfg::ROWS_ALLOC; r += K1_THREADS) {
+    uint8_t* rowp = sm + 4 * Cfg::CH + r * 128;
+    *reinterpret_cast<uint2*>(rowp + ((5 ^ (r & 7)) << 4) + 8) = make_uint2(0u, 0u);
+    *reinterpret_cast<uint4*>(rowp + ((6 ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(rowp + ((7 ^ (r & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -121,21 +133,21 @@ encoder_attn_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __r
       uint32_t it = 0;
       for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         for (int p = 0; p < NPASS; ++p) {
-          for (int kc = 0; kc < KCH; ++kc, ++it) {
-            const int s = it & 1;
-            mbar_wait(empty_bar + 8 * s, ((it >> 1) & 1) ^ 1);
+          for (int kc = 0; kc < KCH16; ++kc, ++it) {
+            const int s = it % K1_STAGES;
+            mbar_wait(empty_bar + 8 * s, ((it / K1_STAGES) & 1) ^ 1);
             mbar_expect_tx_f(full_bar + 8 * s, K1_BSTAGE);
             const uint32_t sb = base + Cfg::OFF_B + s * K1_BSTAGE;
-            tma_load_2d_f(sb, &tmap_w, kc * 32, K1_BOX * p, full_bar + 8 * s);
-            tma_load_2d_f(sb + K1_BOX * 128, &tmap_w, kc * 32, D + K1_BOX * p, full_bar + 8 * s);
-            tma_load_2d_f(sb + 2 * K1_BOX * 128, &tmap_w, kc * 32, 2 * D + K1_BOX * p, full_bar + 8 * s);
+            tma_load_2d_f(sb, &tmap_w, kc * 64, K1_BOX * p, full_bar + 8 * s);
+            tma_load_2d_f(sb + K1_BOX * 128, &tmap_w, kc * 64, D + K1_BOX * p, full_bar + 8 * s);
+            tma_load_2d_f(sb + 2 * K1_BOX * 128, &tmap_w, kc * 64, 2 * D + K1_BOX * p, full_bar + 8 * s);
           }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------------------------
-    const uint32_t idesc = umma_idesc_tf32(128, K1_N);
+    const uint32_t idesc = umma_idesc_f16(128, K1_N);
     uint32_t it = 0, pass_it = 0, tile_it = 0;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
       mbar_wait(a_full, tile_it & 1);           // the workers finished writing this tile's A rows
@@ -145,19 +157,19 @@ encoder_attn_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __r
         mbar_wait(acc_empty + 8 * as, ((pass_it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * K1_N;
-        for (int kc = 0; kc < KCH; ++kc, ++it) {
-          const int s = it & 1;
-          mbar_wait(full_bar + 8 * s, (it >> 1) & 1);
+        for (int kc = 0; kc < KCH16; ++kc, ++it) {
+          const int s = it % K1_STAGES;
+          mbar_wait(full_bar + 8 * s, (it / K1_STAGES) & 1);
           tc_fence_after();
           if (lane == 0) {
             const uint32_t sa = base + kc * Cfg::CH;
             const uint32_t sb = base + Cfg::OFF_B + s * K1_BSTAGE;
-            const int ksteps = (kc == KCH - 1) ? 2 : 4;     // K = 300 -> 37.5 steps of 8, padded to 38
+            const int ksteps = (kc == KCH16 - 1) ? 3 : 4;   // K = 300 -> 18.75 steps of 16, padded to 19
             for (int ks = 0; ks < ksteps; ++ks)
-              umma_tf32_ss(d_tmem, umma_desc_k_sw128(sa + ks * 32), umma_desc_k_sw128(sb + ks * 32), idesc,
-                           (kc | ks) ? 1u : 0u);
+              umma_f16_ss(d_tmem, umma_desc_k_sw128(sa + ks * 32), umma_desc_k_sw128(sb + ks * 32), idesc,
+                          (kc | ks) ? 1u : 0u);
             umma_commit(empty_bar + 8 * s);
-            if (kc == KCH - 1) {
+            if (kc == KCH16 - 1) {
               umma_commit(acc_full + 8 * as);
               if (p == NPASS - 1) umma_commit(a_free);      // A tile may be overwritten after these MMAs
             }
@@ -209,7 +221,13 @@ encoder_attn_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __r
           const int f = f0 + u * K1_WORKERS + wt;
           if (f < TOTAL4) {
             const int r = f / DV4, c4 = f - r * DV4;
-            *reinterpret_cast<float4*>(sm + (c4 >> 3) * Cfg::CH + r * 128 + (((c4 & 7) ^ (r & 7)) << 4)) = to_tf32(v[u]);
+            // 4 floats -> 4 halfs (round-to-nearest: same 11-bit significand as TF32) = 8 bytes
+            const __half2 lo = __floats2half2_rn(v[u].x, v[u].y), hi = __floats2half2_rn(v[u].z, v[u].w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(sm + (c4 >> 4) * Cfg::CH + r * 128 + ((((c4 & 15) >> 1) ^ (r & 7)) << 4) +
+                                      ((c4 & 1) << 3)) = pk;
           }
         }
       }
@@ -466,6 +484,16 @@ additive_pool_kernel(const __grid_constant__ CUtensorMap tmap_c, const __grid_co
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// fp16 copy of the packed projection weights for K1's B operand: [900][320] halfs, K tail zero
+__global__ void __launch_bounds__(256) wqkv_to_f16_kernel(const float* __restrict__ w, __half* __restrict__ out) {
+  const int n = D3 * W16_LD;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int r = i / W16_LD, k = i - r * W16_LD;
+    out[i] = __float2half_rn(k < D ? w[r * D + k] : 0.f);
+  }
+}
+constexpr size_t W16_BYTES = (size_t)D3 * W16_LD * 2;   // 576,000 (a multiple of 256)
+
 // ---------------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------------
@@ -487,12 +515,15 @@ static int run_fused(const float* src, const void* idx, int idx_kind, int64_t n_
   }
   const int64_t chunk = fused_chunk_seq<S, SPT>();
   const int64_t first = n_seq < chunk ? n_seq : chunk;
-  const size_t need = (size_t)first * S * D * sizeof(float);
+  const size_t need = W16_BYTES + (size_t)first * S * D * sizeof(float);
   NRMS_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= need, NRMS_E_WORKSPACE,
                  "workspace too small: need %zu bytes", need);
-  float* Cbuf = reinterpret_cast<float*>(workspace);
+  __half* w16 = reinterpret_cast<__half*>(workspace);
+  float* Cbuf = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + W16_BYTES);
+  wqkv_to_f16_kernel<<<148, 256, 0, st>>>(wqkv, w16);
+  NRMS_LAUNCH_CHECK("wqkv_to_f16_kernel");
   alignas(64) CUtensorMap tw, twa, tc_;
-  if (int rc = make_tmap_k_major(&tw, wqkv, D3, D, D, K1_BOX)) return rc;
+  if (int rc = make_tmap_k_major_f16(&tw, w16, D3, W16_LD, W16_LD, K1_BOX)) return rc;
   if (int rc = make_tmap_k_major(&twa, wa, QD, D, D, QD)) return rc;
   const size_t idx_elem = idx_kind == 1 ? 8 : 4;
   for (int64_t s0 = 0; s0 < n_seq; s0 += chunk) {
@@ -520,7 +551,7 @@ size_t tc_fused_workspace_bytes(int64_t n_seq, int S) {
   else if (S == 50) chunk = fused_chunk_seq<50, 2>();
   else return (size_t)-1;
   const int64_t first = n_seq < chunk ? n_seq : chunk;
-  return (size_t)first * S * D * sizeof(float);
+  return W16_BYTES + (size_t)first * S * D * sizeof(float);
 }
 
 int tc_encoder_fused(const float* src, const void* idx, int idx_kind, int64_t n_seq, int S, const float* wqkv,
