@@ -19,6 +19,7 @@
 //      tcgen05 (N=208), epilogue tanh -> . q -> stable softmax over the sequence -> weighted row sum.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 #include "tc_common.cuh"
 #include "tc_api.cuh"
 
@@ -27,6 +28,21 @@ using namespace tc;
 
 int make_tmap_k_major(CUtensorMap* out, const float* base, int64_t rows, int cols, int64_t ld, int box_rows);
 int make_tmap_k_major_f16(CUtensorMap* out, const void* base, int64_t rows, int cols, int64_t ld, int box_rows);
+// K1 v2 (tc_fused2.cu): projections AND attention on tcgen05
+size_t k1v2_w16_bytes();
+int k1v2_prepare(const float* wqkv, void* w16, CUtensorMap* tw, cudaStream_t st);
+int k1v2_run(int S, const CUtensorMap& tw, const float* src, const void* idx, int idx_kind, int64_t n,
+             const float* bqkv, float* Cbuf, cudaStream_t st);
+// NRMS_K1_VARIANT=1 selects the first-generation K1 (CUDA-core attention); default 2 (tensor-core attention)
+static int k1_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("NRMS_K1_VARIANT");
+    v = (e && e[0] == '1') ? 1 : 2;
+  }
+  return v;
+}
+constexpr size_t W16_SLOT_BYTES = 614400;   // >= both variants' fp16 weight copies
 
 __device__ __forceinline__ void tma_load_2d_f(uint32_t dst_smem, const CUtensorMap* tmap, int c0, int c1, uint32_t bar) {
   asm volatile(
@@ -513,17 +529,23 @@ static int run_fused(const float* src, const void* idx, int idx_kind, int64_t n_
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(additive_pool_kernel)");
     configured = true;
   }
+  const int variant = k1_variant();
+  // variant 2 tiles: 5 titles / 2 users as well, so the chunking (4 waves of tiles) is shared
   const int64_t chunk = fused_chunk_seq<S, SPT>();
   const int64_t first = n_seq < chunk ? n_seq : chunk;
-  const size_t need = W16_BYTES + (size_t)first * S * D * sizeof(float);
+  const size_t need = W16_SLOT_BYTES + (size_t)first * S * D * sizeof(float);
   NRMS_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= need, NRMS_E_WORKSPACE,
                  "workspace too small: need %zu bytes", need);
   __half* w16 = reinterpret_cast<__half*>(workspace);
-  float* Cbuf = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + W16_BYTES);
-  wqkv_to_f16_kernel<<<148, 256, 0, st>>>(wqkv, w16);
-  NRMS_LAUNCH_CHECK("wqkv_to_f16_kernel");
+  float* Cbuf = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + W16_SLOT_BYTES);
   alignas(64) CUtensorMap tw, twa, tc_;
-  if (int rc = make_tmap_k_major_f16(&tw, w16, D3, W16_LD, W16_LD, K1_BOX)) return rc;
+  if (variant == 2) {
+    if (int rc = k1v2_prepare(wqkv, w16, &tw, st)) return rc;
+  } else {
+    wqkv_to_f16_kernel<<<148, 256, 0, st>>>(wqkv, w16);
+    NRMS_LAUNCH_CHECK("wqkv_to_f16_kernel");
+    if (int rc = make_tmap_k_major_f16(&tw, w16, D3, W16_LD, W16_LD, K1_BOX)) return rc;
+  }
   if (int rc = make_tmap_k_major(&twa, wa, QD, D, D, QD)) return rc;
   const size_t idx_elem = idx_kind == 1 ? 8 : 4;
   for (int64_t s0 = 0; s0 < n_seq; s0 += chunk) {
@@ -533,8 +555,12 @@ static int run_fused(const float* src, const void* idx, int idx_kind, int64_t n_
     if (tiles < grid) grid = (int)tiles;
     const float* src_c = idx_kind == 0 ? src + s0 * S * D : src;
     const void* idx_c = idx_kind == 0 ? nullptr : (const void*)((const char*)idx + (size_t)s0 * S * idx_elem);
-    encoder_attn_kernel<S, SPT><<<grid, K1_THREADS, Cfg::SMEM, st>>>(tw, src_c, idx_c, idx_kind, n, bqkv, Cbuf);
-    NRMS_LAUNCH_CHECK("encoder_attn_kernel");
+    if (variant == 2) {
+      if (int rc = k1v2_run(S, tw, src_c, idx_c, idx_kind, n, bqkv, Cbuf, st)) return rc;
+    } else {
+      encoder_attn_kernel<S, SPT><<<grid, K1_THREADS, Cfg::SMEM, st>>>(tw, src_c, idx_c, idx_kind, n, bqkv, Cbuf);
+      NRMS_LAUNCH_CHECK("encoder_attn_kernel");
+    }
     const int box_c = (int)((n * S < Cfg::ROWS) ? n * S : Cfg::ROWS);
     if (int rc = make_tmap_k_major(&tc_, Cbuf, n * S, D, D, box_c)) return rc;
     additive_pool_kernel<S, SPT><<<grid, K2_THREADS, K2_SMEM, st>>>(tc_, twa, Cbuf, ba, qa, out + s0 * D, n,
@@ -551,7 +577,7 @@ size_t tc_fused_workspace_bytes(int64_t n_seq, int S) {
   else if (S == 50) chunk = fused_chunk_seq<50, 2>();
   else return (size_t)-1;
   const int64_t first = n_seq < chunk ? n_seq : chunk;
-  return W16_BYTES + (size_t)first * S * D * sizeof(float);
+  return W16_SLOT_BYTES + (size_t)first * S * D * sizeof(float);
 }
 
 int tc_encoder_fused(const float* src, const void* idx, int idx_kind, int64_t n_seq, int S, const float* wqkv,

@@ -1,0 +1,440 @@
+// K1 v2 -- encoder_attn_tc_kernel: fused gather -> QKV projection -> multi-head attention, with BOTH the
+// projections and the attention contractions (Q K^T and P V) on tcgen05 (kind::f16, fp32 accumulate).
+//
+// Tile = SPT sequences laid out in SLOT-row slots (news: 5 titles x 24-row slots, users: 2 histories x 64-row
+// slots; rows >= S inside a slot are zero padding and masked out of the softmax), so a sequence never
+// shares an 8-key swizzle piece with another one and (users) never straddles a warp.
+//
+//   warp 0  TMA producer: fp16 weight copy re-ordered per head ([Q_h;K_h;V_h] = 60 contiguous rows), one
+//           192-row x 64-K box per chunk (3 heads per pass, 5 passes, 5 chunks each) through an smem ring.
+//   warp 1  MMA issuer (one thread).  Static schedule per tile: projection pass 0, then per head
+//           S = Q_h K_h^T (128x128x32)  ->  [one projection chunk of the next pass]  ->
+//           O = P V_h (128x32x128)      ->  [one projection chunk of the next pass].
+//   warps 2-5  workers, thread == tile row == TMEM lane:
+//           W1  tcgen05.ld q/k/v (+bias, q pre-scaled by log2(e)/sqrt(20)) -> fp16 -> Q and K operand tiles
+//               (SWIZZLE_128B K-major) and V^T (keys along K) in shared memory;
+//           W2  tcgen05.ld the row's own score block, e = 2^s for the valid keys (the reference's
+//               exp(s)/(sum+1e-8) without max-subtraction), row sum in fp32, P (fp16, unnormalised) into
+//               the block-diagonal A tile (off-block columns stay zero from kernel start);
+//           W3  tcgen05.ld O (20 columns), scale by 1/(Z+1e-8), store the context row to C.
+// TMEM: two 192-column projection accumulators + one 128-column S/O region (O aliases S) = 512 columns.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include "tc_common.cuh"
+#include "tc_api.cuh"
+
+namespace nrms {
+using namespace tc;
+
+int make_tmap_k_major_f16(CUtensorMap* out, const void* base, int64_t rows, int cols, int64_t ld, int box_rows);
+
+namespace k1v2 {
+
+constexpr int HP = 3, NPASS = 5, KCH = 5;       // heads per pass, passes, 64-half K chunks
+constexpr int PN = 192;                         // projection UMMA N (180 real columns)
+constexpr int NST = 2;                          // weight ring stages
+constexpr int B_STAGE = PN * 128;               // 24,576
+constexpr int W16_ROWS = 960, W16_LD = 320;
+constexpr int THREADS = 192;
+constexpr int OFF_A = 0;                        // 5 x [128 rows x 128 B]
+constexpr int OFF_B = 5 * 16384;                // 81,920
+constexpr int OFF_Q = OFF_B + NST * B_STAGE;    // 131,072
+constexpr int OFF_K = OFF_Q + 16384;
+constexpr int OFF_VT = OFF_K + 16384;           // 2 x [32 rows x 128 B]
+constexpr int OFF_P = OFF_VT + 8192;            // 2 x [128 rows x 128 B]
+constexpr int OFF_BIAS = OFF_P + 32768;         // 204,800
+constexpr int OFF_IDX = OFF_BIAS + 3712;
+constexpr int OFF_BAR = OFF_IDX + 1024;
+constexpr int SMEM = OFF_BAR + 256 + 1024;
+static_assert(SMEM <= 232448, "shared memory budget");
+constexpr int TM_S = 2 * PN;                    // TMEM column of the S / O region (384)
+constexpr float QSCALE = 1.4426950408889634f / 4.47213595499957939f;   // log2(e) / sqrt(20)
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void workers_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// S = sequence length, SLOT = padded slot, SPT = sequences per tile
+template <int S, int SLOT, int SPT>
+__global__ void __launch_bounds__(THREADS, 1)
+encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ src,
+                       const void* __restrict__ idx, int idx_kind, int64_t n_seq, const float* __restrict__ bqkv,
+                       float* __restrict__ C) {
+  static_assert(SLOT % 8 == 0 && SLOT >= S && SPT * SLOT <= 128, "slot layout");
+  constexpr int NPAIR = SPT * S;                 // real rows per tile
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  float* bias_s = reinterpret_cast<float*>(sm + OFF_BIAS);
+  int64_t* rowid = reinterpret_cast<int64_t*>(sm + OFF_IDX);
+  const uint32_t bars = base + OFF_BAR;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * NST;
+  const uint32_t a_full = bars + 16 * NST, a_free = a_full + 8, acc_full = a_full + 16, acc_empty = a_full + 32;
+  const uint32_t qk_ready = a_full + 48, s_ready = a_full + 56, p_ready = a_full + 64, o_ready = a_full + 72;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sm + OFF_BAR + 16 * NST + 96);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t n_tiles = (n_seq + SPT - 1) / SPT;
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc_full + 8 * s, 1);
+      mbar_init(acc_empty + 8 * s, 4);
+    }
+    mbar_init(a_full, 128);
+    mbar_init(a_free, 1);
+    mbar_init(qk_ready, 128);
+    mbar_init(s_ready, 1);
+    mbar_init(p_ready, 128);
+    mbar_init(o_ready, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_ptr_smem), 512);
+  for (int i = tid; i < D3; i += THREADS) bias_s[i] = bqkv[i];
+  // zero the A tile (padding rows / K tail stay zero) and all attention operand tiles (K padding of Q/K,
+  // padded keys of V^T, off-block columns of P)
+  for (int i = tid; i < OFF_B / 16; i += THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < (OFF_BIAS - OFF_Q) / 16; i += THREADS)
+    reinterpret_cast<uint4*>(sm + OFF_Q)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer --------------------------------------------
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int p = 0; p < NPASS; ++p) {
+          for (int kc = 0; kc < KCH; ++kc, ++it) {
+            const int s = it % NST;
+            mbar_wait(empty_bar + 8 * s, ((it / NST) & 1) ^ 1);
+            expect_tx(full_bar + 8 * s, B_STAGE);
+            tma_load_2d(base + OFF_B + s * B_STAGE, &tmap_w, kc * 64, 60 * HP * p, full_bar + 8 * s);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------------------------
+    const uint32_t idesc_proj = umma_idesc_f16(128, PN);
+    const uint32_t idesc_s = umma_idesc_f16(128, 128);
+    const uint32_t idesc_o = umma_idesc_f16(128, 32);
+    uint32_t ring_it = 0, pass_it = 0, head_it = 0, tile_it = 0;
+    // one projection chunk (4 or 3 k-steps of 16) of the pass whose accumulator stage is `as`
+    auto proj_chunk = [&](int kc, uint32_t as, bool last_pass_of_tile) {
+      const int s = ring_it % NST;
+      mbar_wait(full_bar + 8 * s, (ring_it / NST) & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = base + OFF_A + kc * 16384;
+        const uint32_t sb = base + OFF_B + s * B_STAGE;
+        const int ksteps = (kc == KCH - 1) ? 3 : 4;
+        for (int ks = 0; ks < ksteps; ++ks)
+          umma_f16_ss(tmem_base + as * PN, umma_desc_k_sw128(sa + ks * 32), umma_desc_k_sw128(sb + ks * 32),
+                      idesc_proj, (kc | ks) ? 1u : 0u);
+        umma_commit(empty_bar + 8 * s);
+        if (kc == KCH - 1) {
+          umma_commit(acc_full + 8 * as);
+          if (last_pass_of_tile) umma_commit(a_free);
+        }
+      }
+      __syncwarp();
+      ++ring_it;
+    };
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
+      mbar_wait(a_full, tile_it & 1);
+      tc_fence_after();
+      {   // projection pass 0 of this tile
+        const uint32_t as = pass_it & 1;
+        mbar_wait(acc_empty + 8 * as, ((pass_it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        for (int kc = 0; kc < KCH; ++kc) proj_chunk(kc, as, false);
+      }
+      for (int p = 0; p < NPASS; ++p, ++pass_it) {
+        const uint32_t as_next = (pass_it + 1) & 1;
+        const bool has_next = p + 1 < NPASS;
+        for (int hh = 0; hh < HP; ++hh, ++head_it) {
+          const uint32_t hp = head_it & 1;
+          // ---- S = Q K^T ----
+          mbar_wait(qk_ready, hp);
+          tc_fence_after();
+          if (lane == 0) {
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks)
+              umma_f16_ss(tmem_base + TM_S, umma_desc_k_sw128(base + OFF_Q + ks * 32),
+                          umma_desc_k_sw128(base + OFF_K + ks * 32), idesc_s, ks ? 1u : 0u);
+            umma_commit(s_ready);
+          }
+          __syncwarp();
+          if (has_next) {
+            if (hh == 0) {
+              mbar_wait(acc_empty + 8 * as_next, (((pass_it + 1) >> 1) & 1) ^ 1);
+              tc_fence_after();
+            }
+            proj_chunk(2 * hh, as_next, p + 1 == NPASS - 1);
+          }
+          // ---- O = P V ----
+          mbar_wait(p_ready, hp);
+          tc_fence_after();
+          if (lane == 0) {
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma_f16_ss(tmem_base + TM_S, umma_desc_k_sw128(base + OFF_P + (ks >> 2) * 16384 + (ks & 3) * 32),
+                          umma_desc_k_sw128(base + OFF_VT + (ks >> 2) * 4096 + (ks & 3) * 32), idesc_o, ks ? 1u : 0u);
+            umma_commit(o_ready);
+          }
+          __syncwarp();
+          if (has_next && 2 * hh + 1 < KCH) proj_chunk(2 * hh + 1, as_next, p + 1 == NPASS - 1);
+        }
+      }
+    }
+  } else {
+    // ------------------------------ workers (warps 2..5) --------------------------------------
+    const int q4 = warp & 3;
+    const int wt = (warp - 2) * 32 + lane;       // 0..127
+    const int row = q4 * 32 + lane;              // tile row == TMEM lane == key index
+    const int sq = row / SLOT, pos = row - sq * SLOT;
+    const bool row_valid = (sq < SPT) && (pos < S);
+    // warp-uniform first slot of this warp (a 32-row warp spans at most two 24-row slots, one 64-row slot)
+    const int sq_lo = (q4 * 32) / SLOT;
+    const int own = sq - sq_lo;                  // 0 or 1 (SLOT = 24), always 0 (SLOT = 64)
+    constexpr int NLD = (SLOT >= 32) ? SLOT : 2 * SLOT;   // score columns loaded per warp (64 or 48)
+    const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+    uint32_t pass_it = 0, head_it = 0, tile_it = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
+      const int64_t seq0 = t * SPT;
+      if (wt < NPAIR) {
+        const int64_t seq = seq0 + wt / S;
+        int64_t id = 0;
+        if (seq < n_seq) {
+          const int64_t e = seq * S + (wt % S);
+          id = idx_kind == 0 ? e : (idx_kind == 1 ? reinterpret_cast<const int64_t*>(idx)[e]
+                                                  : (int64_t) reinterpret_cast<const int32_t*>(idx)[e]);
+        }
+        rowid[wt] = id;
+      }
+      mbar_wait(a_free, (tile_it & 1) ^ 1);
+      workers_bar();
+      // ---- gather: NPAIR real rows x 75 float4 -> fp16 -> swizzled A tile (slot layout) ----
+      constexpr int TOTAL4 = NPAIR * DV4;
+#pragma unroll 1
+      for (int f0 = 0; f0 < TOTAL4; f0 += 128 * 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int f = f0 + u * 128 + wt;
+          if (f < TOTAL4) {
+            const int pr = f / DV4, c4 = f - pr * DV4;
+            v[u] = __ldg(reinterpret_cast<const float4*>(src + rowid[pr] * D) + c4);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int f = f0 + u * 128 + wt;
+          if (f < TOTAL4) {
+            const int pr = f / DV4, c4 = f - pr * DV4;
+            const int r = (pr / S) * SLOT + (pr % S);
+            uint2 pk;
+            pk.x = pack_h2(v[u].x, v[u].y);
+            pk.y = pack_h2(v[u].z, v[u].w);
+            *reinterpret_cast<uint2*>(sm + OFF_A + (c4 >> 4) * 16384 + r * 128 + ((((c4 & 15) >> 1) ^ (r & 7)) << 4) +
+                                      ((c4 & 1) << 3)) = pk;
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(a_full);
+
+      for (int p = 0; p < NPASS; ++p, ++pass_it) {
+        const uint32_t as = pass_it & 1;
+        mbar_wait(acc_full + 8 * as, (pass_it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + as * PN + lane_addr;
+#pragma unroll 1
+        for (int hh = 0; hh < HP; ++hh, ++head_it) {
+          const int h = p * HP + hh;
+          const uint32_t hp = head_it & 1;
+          // ================= W1: q/k/v of this row -> fp16 operand tiles =================
+          {
+            float qv[DH], kk[DH], vv[DH];
+            tmem_ld16(tacc + 60 * hh, qv);            tmem_ld4(tacc + 60 * hh + 16, qv + 16);
+            tmem_ld16(tacc + 60 * hh + 20, kk);       tmem_ld4(tacc + 60 * hh + 36, kk + 16);
+            tmem_ld16(tacc + 60 * hh + 40, vv);       tmem_ld4(tacc + 60 * hh + 56, vv + 16);
+            if (hh == HP - 1) {                       // accumulator stage fully drained by this warp
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(acc_empty + 8 * as);
+            }
+            uint32_t qp[10], kp[10];
+#pragma unroll
+            for (int d = 0; d < DH; d += 2) {
+              qp[d >> 1] = pack_h2((qv[d] + bias_s[h * DH + d]) * QSCALE, (qv[d + 1] + bias_s[h * DH + d + 1]) * QSCALE);
+              kp[d >> 1] = pack_h2(kk[d] + bias_s[D + h * DH + d], kk[d + 1] + bias_s[D + h * DH + d + 1]);
+            }
+            uint8_t* qrow = sm + OFF_Q + row * 128;
+            uint8_t* krow = sm + OFF_K + row * 128;
+            const int sw = row & 7;
+            *reinterpret_cast<uint4*>(qrow + ((0 ^ sw) << 4)) = make_uint4(qp[0], qp[1], qp[2], qp[3]);
+            *reinterpret_cast<uint4*>(qrow + ((1 ^ sw) << 4)) = make_uint4(qp[4], qp[5], qp[6], qp[7]);
+            *reinterpret_cast<uint2*>(qrow + ((2 ^ sw) << 4)) = make_uint2(qp[8], qp[9]);
+            *reinterpret_cast<uint4*>(krow + ((0 ^ sw) << 4)) = make_uint4(kp[0], kp[1], kp[2], kp[3]);
+            *reinterpret_cast<uint4*>(krow + ((1 ^ sw) << 4)) = make_uint4(kp[4], kp[5], kp[6], kp[7]);
+            *reinterpret_cast<uint2*>(krow + ((2 ^ sw) << 4)) = make_uint2(kp[8], kp[9]);
+            // V^T: element (d, key=row); padded / invalid keys contribute exact zeros
+            uint8_t* vt = sm + OFF_VT + (row >> 6) * 4096 + ((row & 7) << 1);
+            const int piece = (row & 63) >> 3;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) {
+              const float x = row_valid ? vv[d] + bias_s[2 * D + h * DH + d] : 0.f;
+              *reinterpret_cast<__half*>(vt + d * 128 + ((piece ^ (d & 7)) << 4)) = __float2half_rn(x);
+            }
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(qk_ready);
+          // ================= W2: scores -> unnormalised probabilities =================
+          mbar_wait(s_ready, hp);
+          tc_fence_after();
+          float Z = 0.f;
+          {
+            float sv[NLD];
+            if constexpr (SLOT >= 32) {
+#pragma unroll
+              for (int c = 0; c < NLD; c += 16) tmem_ld16(tmem_base + TM_S + lane_addr + sq_lo * SLOT + c, sv + c);
+            } else {          // SLOT == 24: the warp's (up to) two slots, each 16 + 8 columns; never past key 119
+#pragma unroll
+              for (int b = 0; b < 2; ++b) {
+                if (sq_lo + b < SPT) {
+                  tmem_ld16(tmem_base + TM_S + lane_addr + (sq_lo + b) * SLOT, sv + b * SLOT);
+                  tmem_ld8(tmem_base + TM_S + lane_addr + (sq_lo + b) * SLOT + 16, sv + b * SLOT + 16);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < SLOT; ++j) sv[b * SLOT + j] = 0.f;
+                }
+              }
+            }
+            tc_fence_before();
+            float e[SLOT];
+#pragma unroll
+            for (int j = 0; j < SLOT; ++j) {
+              float x = sv[j];
+              if (SLOT < 32) x = own ? sv[SLOT + j] : sv[j];
+              e[j] = (j < S) ? ex2(x) : 0.f;
+              Z += e[j];
+            }
+            // own block = pieces [sq*SLOT/8, +SLOT/8) of this row of P
+            uint8_t* prow = sm + OFF_P + row * 128;
+            const int g0 = sq * (SLOT / 8);
+#pragma unroll
+            for (int m = 0; m < SLOT / 8; ++m) {
+              const int g = g0 + m;
+              const uint4 pk = make_uint4(pack_h2(e[8 * m], e[8 * m + 1]), pack_h2(e[8 * m + 2], e[8 * m + 3]),
+                                          pack_h2(e[8 * m + 4], e[8 * m + 5]), pack_h2(e[8 * m + 6], e[8 * m + 7]));
+              if (sq < SPT) *reinterpret_cast<uint4*>(prow + (g >> 3) * 16384 + (((g & 7) ^ (row & 7)) << 4)) = pk;
+            }
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(p_ready);
+          // ================= W3: context row =================
+          mbar_wait(o_ready, hp);
+          tc_fence_after();
+          {
+            float o[DH];
+            tmem_ld16(tmem_base + TM_S + lane_addr, o);
+            tmem_ld4(tmem_base + TM_S + lane_addr + 16, o + 16);
+            tc_fence_before();
+            const float inv = 1.f / (Z + 1e-8f);
+            if (row_valid && seq0 + sq < n_seq) {
+              float4* op = reinterpret_cast<float4*>(C + ((seq0 + sq) * S + pos) * D + h * DH);
+#pragma unroll
+              for (int c = 0; c < 5; ++c)
+                op[c] = make_float4(o[4 * c] * inv, o[4 * c + 1] * inv, o[4 * c + 2] * inv, o[4 * c + 3] * inv);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// fp16 weight copy, re-ordered per head: row 60*h + {0..19 | 20..39 | 40..59} = {W_Q, W_K, W_V}[20*h + ..]
+__global__ void __launch_bounds__(256) pack_w16_kernel(const float* __restrict__ w, __half* __restrict__ out) {
+  const int n = W16_ROWS * W16_LD;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int r = i / W16_LD, k = i - r * W16_LD;
+    float x = 0.f;
+    if (r < 3 * D && k < D) {
+      const int h = r / 60, j = r - 60 * h;
+      const int src_row = (j / DH) * D + h * DH + (j % DH);
+      x = w[src_row * D + k];
+    }
+    out[i] = __float2half_rn(x);
+  }
+}
+constexpr size_t W16_BYTES = (size_t)W16_ROWS * W16_LD * 2;   // 614,400
+
+}  // namespace k1v2
+
+size_t k1v2_w16_bytes() { return k1v2::W16_BYTES; }
+
+template <int S, int SLOT, int SPT>
+static int launch_k1v2(const CUtensorMap& tw, const float* src, const void* idx, int idx_kind, int64_t n,
+                       const float* bqkv, float* Cbuf, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k1v2::encoder_attn_tc_kernel<S, SLOT, SPT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, k1v2::SMEM);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(encoder_attn_tc_kernel)");
+    configured = true;
+  }
+  const int64_t tiles = (n + SPT - 1) / SPT;
+  int grid = num_sms();
+  if (tiles < grid) grid = (int)tiles;
+  k1v2::encoder_attn_tc_kernel<S, SLOT, SPT><<<grid, k1v2::THREADS, k1v2::SMEM, st>>>(tw, src, idx, idx_kind, n, bqkv, Cbuf);
+  NRMS_LAUNCH_CHECK("encoder_attn_tc_kernel");
+  return NRMS_OK;
+}
+
+// prepares the fp16 weight copy (once per encoder call) and returns its tensor map
+int k1v2_prepare(const float* wqkv, void* w16, CUtensorMap* tw, cudaStream_t st) {
+  k1v2::pack_w16_kernel<<<148, 256, 0, st>>>(wqkv, reinterpret_cast<__half*>(w16));
+  NRMS_LAUNCH_CHECK("pack_w16_kernel");
+  return make_tmap_k_major_f16(tw, w16, k1v2::W16_ROWS, k1v2::W16_LD, k1v2::W16_LD, k1v2::PN);
+}
+
+int k1v2_run(int S, const CUtensorMap& tw, const float* src, const void* idx, int idx_kind, int64_t n,
+             const float* bqkv, float* Cbuf, cudaStream_t st) {
+  if (S == 20) return launch_k1v2<20, 24, 5>(tw, src, idx, idx_kind, n, bqkv, Cbuf, st);
+  if (S == 50) return launch_k1v2<50, 64, 2>(tw, src, idx, idx_kind, n, bqkv, Cbuf, st);
+  set_error("encoder_attn_tc_kernel compiled for S = 20 or 50, got %d", S);
+  return NRMS_E_UNSUPPORTED;
+}
+
+}  // namespace nrms
