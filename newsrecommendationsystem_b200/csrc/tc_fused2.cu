@@ -7,9 +7,8 @@
 //
 //   warp 0  TMA producer: fp16 weight copy re-ordered per head ([Q_h;K_h;V_h] = 60 contiguous rows), one
 //           192-row x 64-K box per chunk (3 heads per pass, 5 passes, 5 chunks each) through an smem ring.
-//   warp 1  MMA issuer (one thread).  Static schedule per tile: projection pass 0, then per head
-//           S = Q_h K_h^T (128x128x32)  ->  [one projection chunk of the next pass]  ->
-//           O = P V_h (128x32x128)      ->  [one projection chunk of the next pass].
+//   warp 6  projection MMA issuer (one thread): 5 passes x 19 tcgen05.mma (128x192x16) per tile.
+//   warp 1  attention MMA issuer (one thread): per head S = Q_h K_h^T (128x128x32), then O = P V_h (128x32x128).
 //   warps 2-5  workers, thread == tile row == TMEM lane:
 //           W1  tcgen05.ld q/k/v (+bias, q pre-scaled by log2(e)/sqrt(20)) -> fp16 -> Q and K operand tiles
 //               (SWIZZLE_128B K-major) and V^T (keys along K) in shared memory;
@@ -30,12 +29,22 @@ int make_tmap_k_major_f16(CUtensorMap* out, const void* base, int64_t rows, int 
 
 namespace k1v2 {
 
+// debug trace (clock64 stamps of worker thread 0 / block 0): read back with nrms_debug_read_trace
+__device__ long long g_trace[2048];
+__device__ int g_trace_n;
+#define TRACE(tag)                                                         \
+  do {                                                                     \
+    if (blockIdx.x == 0 && wt == 0 && g_trace_n < 2040) {                  \
+      g_trace[g_trace_n++] = ((long long)(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFLL); \
+    }                                                                      \
+  } while (0)
+
 constexpr int HP = 3, NPASS = 5, KCH = 5;       // heads per pass, passes, 64-half K chunks
 constexpr int PN = 192;                         // projection UMMA N (180 real columns)
 constexpr int NST = 2;                          // weight ring stages
 constexpr int B_STAGE = PN * 128;               // 24,576
 constexpr int W16_ROWS = 960, W16_LD = 320;
-constexpr int THREADS = 192;
+constexpr int THREADS = 224;             // warps: 0 TMA, 1 attention MMA, 2-5 workers, 6 projection MMA
 constexpr int OFF_A = 0;                        // 5 x [128 rows x 128 B]
 constexpr int OFF_B = 5 * 16384;                // 81,920
 constexpr int OFF_Q = OFF_B + NST * B_STAGE;    // 131,072
@@ -139,81 +148,73 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* 
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------ MMA issuer ------------------------------------------------
+  } else if (warp == 6) {
+    // ------------------------------ projection MMA issuer (one thread) ----------------------------
+    // Independent of the attention MMAs (different TMEM columns / smem), so it gets its own issuing
+    // thread: the latency-critical S / PV MMAs never wait behind descriptor building or a TMA wait.
     const uint32_t idesc_proj = umma_idesc_f16(128, PN);
-    const uint32_t idesc_s = umma_idesc_f16(128, 128);
-    const uint32_t idesc_o = umma_idesc_f16(128, 32);
-    uint32_t ring_it = 0, pass_it = 0, head_it = 0, tile_it = 0;
-    // one projection chunk (4 or 3 k-steps of 16) of the pass whose accumulator stage is `as`
-    auto proj_chunk = [&](int kc, uint32_t as, bool last_pass_of_tile) {
-      const int s = ring_it % NST;
-      mbar_wait(full_bar + 8 * s, (ring_it / NST) & 1);
-      tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sa = base + OFF_A + kc * 16384;
-        const uint32_t sb = base + OFF_B + s * B_STAGE;
-        const int ksteps = (kc == KCH - 1) ? 3 : 4;
-        for (int ks = 0; ks < ksteps; ++ks)
-          umma_f16_ss(tmem_base + as * PN, umma_desc_k_sw128(sa + ks * 32), umma_desc_k_sw128(sb + ks * 32),
-                      idesc_proj, (kc | ks) ? 1u : 0u);
-        umma_commit(empty_bar + 8 * s);
-        if (kc == KCH - 1) {
-          umma_commit(acc_full + 8 * as);
-          if (last_pass_of_tile) umma_commit(a_free);
-        }
-      }
-      __syncwarp();
-      ++ring_it;
-    };
+    const uint64_t desc0 = umma_desc_k_sw128(0);
+    uint32_t ring_it = 0, pass_it = 0, tile_it = 0;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
       mbar_wait(a_full, tile_it & 1);
-      tc_fence_after();
-      {   // projection pass 0 of this tile
+      for (int p = 0; p < NPASS; ++p, ++pass_it) {
         const uint32_t as = pass_it & 1;
         mbar_wait(acc_empty + 8 * as, ((pass_it >> 1) & 1) ^ 1);
-        tc_fence_after();
-        for (int kc = 0; kc < KCH; ++kc) proj_chunk(kc, as, false);
-      }
-      for (int p = 0; p < NPASS; ++p, ++pass_it) {
-        const uint32_t as_next = (pass_it + 1) & 1;
-        const bool has_next = p + 1 < NPASS;
-        for (int hh = 0; hh < HP; ++hh, ++head_it) {
-          const uint32_t hp = head_it & 1;
-          // ---- S = Q K^T ----
-          mbar_wait(qk_ready, hp);
+        for (int kc = 0; kc < KCH; ++kc, ++ring_it) {
+          const int s = ring_it % NST;
+          mbar_wait(full_bar + 8 * s, (ring_it / NST) & 1);
           tc_fence_after();
           if (lane == 0) {
-#pragma unroll
-            for (int ks = 0; ks < 2; ++ks)
-              umma_f16_ss(tmem_base + TM_S, umma_desc_k_sw128(base + OFF_Q + ks * 32),
-                          umma_desc_k_sw128(base + OFF_K + ks * 32), idesc_s, ks ? 1u : 0u);
-            umma_commit(s_ready);
-          }
-          __syncwarp();
-          if (has_next) {
-            if (hh == 0) {
-              mbar_wait(acc_empty + 8 * as_next, (((pass_it + 1) >> 1) & 1) ^ 1);
-              tc_fence_after();
+            const uint32_t sa = (base + OFF_A + kc * 16384) >> 4;
+            const uint32_t sb = (base + OFF_B + s * B_STAGE) >> 4;
+            const int ksteps = (kc == KCH - 1) ? 3 : 4;
+            for (int ks = 0; ks < ksteps; ++ks)
+              umma_f16_ss(tmem_base + as * PN, desc0 | (uint64_t)((sa + 2 * ks) & 0x3FFF),
+                          desc0 | (uint64_t)((sb + 2 * ks) & 0x3FFF), idesc_proj, (kc | ks) ? 1u : 0u);
+            umma_commit(empty_bar + 8 * s);
+            if (kc == KCH - 1) {
+              umma_commit(acc_full + 8 * as);
+              if (p == NPASS - 1) umma_commit(a_free);
             }
-            proj_chunk(2 * hh, as_next, p + 1 == NPASS - 1);
-          }
-          // ---- O = P V ----
-          mbar_wait(p_ready, hp);
-          tc_fence_after();
-          if (lane == 0) {
-#pragma unroll
-            for (int ks = 0; ks < 8; ++ks)
-              umma_f16_ss(tmem_base + TM_S, umma_desc_k_sw128(base + OFF_P + (ks >> 2) * 16384 + (ks & 3) * 32),
-                          umma_desc_k_sw128(base + OFF_VT + (ks >> 2) * 4096 + (ks & 3) * 32), idesc_o, ks ? 1u : 0u);
-            umma_commit(o_ready);
           }
           __syncwarp();
-          if (has_next && 2 * hh + 1 < KCH) proj_chunk(2 * hh + 1, as_next, p + 1 == NPASS - 1);
         }
       }
     }
-  } else {
+  } else if (warp == 1) {
+    // ------------------------------ attention MMA issuer (one thread) -----------------------------
+    const uint32_t idesc_s = umma_idesc_f16(128, 128);
+    const uint32_t idesc_o = umma_idesc_f16(128, 32);
+    const uint64_t desc0 = umma_desc_k_sw128(0);
+    const uint32_t q_a = (base + OFF_Q) >> 4, k_a = (base + OFF_K) >> 4;
+    const uint32_t p_a = (base + OFF_P) >> 4, v_a = (base + OFF_VT) >> 4;
+    uint32_t head_it = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int hd = 0; hd < H; ++hd, ++head_it) {
+        const uint32_t hp = head_it & 1;
+        mbar_wait(qk_ready, hp);                 // S = Q K^T
+        tc_fence_after();
+        if (lane == 0) {
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks)
+            umma_f16_ss(tmem_base + TM_S, desc0 | (uint64_t)((q_a + 2 * ks) & 0x3FFF),
+                        desc0 | (uint64_t)((k_a + 2 * ks) & 0x3FFF), idesc_s, ks ? 1u : 0u);
+          umma_commit(s_ready);
+        }
+        __syncwarp();
+        mbar_wait(p_ready, hp);                  // O = P V
+        tc_fence_after();
+        if (lane == 0) {
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_f16_ss(tmem_base + TM_S, desc0 | (uint64_t)((p_a + (ks >> 2) * 1024 + (ks & 3) * 2) & 0x3FFF),
+                        desc0 | (uint64_t)((v_a + (ks >> 2) * 256 + (ks & 3) * 2) & 0x3FFF), idesc_o, ks ? 1u : 0u);
+          umma_commit(o_ready);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 2 && warp <= 5) {
     // ------------------------------ workers (warps 2..5) --------------------------------------
     const int q4 = warp & 3;
     const int wt = (warp - 2) * 32 + lane;       // 0..127
@@ -238,6 +239,7 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* 
         }
         rowid[wt] = id;
       }
+      TRACE(6);
       mbar_wait(a_free, (tile_it & 1) ^ 1);
       workers_bar();
       // ---- gather: NPAIR real rows x 75 float4 -> fp16 -> swizzled A tile (slot layout) ----
@@ -269,22 +271,31 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* 
       }
       fence_proxy_async_smem();
       mbar_arrive(a_full);
+      TRACE(7);
 
       for (int p = 0; p < NPASS; ++p, ++pass_it) {
         const uint32_t as = pass_it & 1;
         mbar_wait(acc_full + 8 * as, (pass_it >> 1) & 1);
         tc_fence_after();
+        TRACE(8);
         const uint32_t tacc = tmem_base + as * PN + lane_addr;
 #pragma unroll 1
         for (int hh = 0; hh < HP; ++hh, ++head_it) {
           const int h = p * HP + hh;
           const uint32_t hp = head_it & 1;
           // ================= W1: q/k/v of this row -> fp16 operand tiles =================
+          TRACE(1);
           {
             float qv[DH], kk[DH], vv[DH];
-            tmem_ld16(tacc + 60 * hh, qv);            tmem_ld4(tacc + 60 * hh + 16, qv + 16);
-            tmem_ld16(tacc + 60 * hh + 20, kk);       tmem_ld4(tacc + 60 * hh + 36, kk + 16);
-            tmem_ld16(tacc + 60 * hh + 40, vv);       tmem_ld4(tacc + 60 * hh + 56, vv + 16);
+            {
+              uint32_t* qi = reinterpret_cast<uint32_t*>(qv);
+              uint32_t* ki = reinterpret_cast<uint32_t*>(kk);
+              uint32_t* vi = reinterpret_cast<uint32_t*>(vv);
+              tmem_ld16_nw(tacc + 60 * hh, qi);            tmem_ld4_nw(tacc + 60 * hh + 16, qi + 16);
+              tmem_ld16_nw(tacc + 60 * hh + 20, ki);       tmem_ld4_nw(tacc + 60 * hh + 36, ki + 16);
+              tmem_ld16_nw(tacc + 60 * hh + 40, vi);       tmem_ld4_nw(tacc + 60 * hh + 56, vi + 16);
+              tmem_ld_wait();
+            }
             if (hh == HP - 1) {                       // accumulator stage fully drained by this warp
               tc_fence_before();
               __syncwarp();
@@ -316,27 +327,31 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* 
           }
           fence_proxy_async_smem();
           mbar_arrive(qk_ready);
+          TRACE(2);
           // ================= W2: scores -> unnormalised probabilities =================
           mbar_wait(s_ready, hp);
           tc_fence_after();
+          TRACE(3);
           float Z = 0.f;
           {
             float sv[NLD];
+            uint32_t* svi = reinterpret_cast<uint32_t*>(sv);
             if constexpr (SLOT >= 32) {
 #pragma unroll
-              for (int c = 0; c < NLD; c += 16) tmem_ld16(tmem_base + TM_S + lane_addr + sq_lo * SLOT + c, sv + c);
+              for (int c = 0; c < NLD; c += 16) tmem_ld16_nw(tmem_base + TM_S + lane_addr + sq_lo * SLOT + c, svi + c);
             } else {          // SLOT == 24: the warp's (up to) two slots, each 16 + 8 columns; never past key 119
 #pragma unroll
               for (int b = 0; b < 2; ++b) {
                 if (sq_lo + b < SPT) {
-                  tmem_ld16(tmem_base + TM_S + lane_addr + (sq_lo + b) * SLOT, sv + b * SLOT);
-                  tmem_ld8(tmem_base + TM_S + lane_addr + (sq_lo + b) * SLOT + 16, sv + b * SLOT + 16);
+                  tmem_ld16_nw(tmem_base + TM_S + lane_addr + (sq_lo + b) * SLOT, svi + b * SLOT);
+                  tmem_ld8_nw(tmem_base + TM_S + lane_addr + (sq_lo + b) * SLOT + 16, svi + b * SLOT + 16);
                 } else {
 #pragma unroll
                   for (int j = 0; j < SLOT; ++j) sv[b * SLOT + j] = 0.f;
                 }
               }
             }
+            tmem_ld_wait();
             tc_fence_before();
             float e[SLOT];
 #pragma unroll
@@ -359,13 +374,16 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* 
           }
           fence_proxy_async_smem();
           mbar_arrive(p_ready);
+          TRACE(4);
           // ================= W3: context row =================
           mbar_wait(o_ready, hp);
           tc_fence_after();
+          TRACE(5);
           {
             float o[DH];
-            tmem_ld16(tmem_base + TM_S + lane_addr, o);
-            tmem_ld4(tmem_base + TM_S + lane_addr + 16, o + 16);
+            tmem_ld16_nw(tmem_base + TM_S + lane_addr, reinterpret_cast<uint32_t*>(o));
+            tmem_ld4_nw(tmem_base + TM_S + lane_addr + 16, reinterpret_cast<uint32_t*>(o) + 16);
+            tmem_ld_wait();
             tc_fence_before();
             const float inv = 1.f / (Z + 1e-8f);
             if (row_valid && seq0 + sq < n_seq) {
@@ -403,6 +421,16 @@ constexpr size_t W16_BYTES = (size_t)W16_ROWS * W16_LD * 2;   // 614,400
 }  // namespace k1v2
 
 size_t k1v2_w16_bytes() { return k1v2::W16_BYTES; }
+
+extern "C" int nrms_debug_read_trace(long long* host, int max_n) {
+  int n = 0;
+  cudaMemcpyFromSymbol(&n, k1v2::g_trace_n, sizeof(int));
+  if (n > max_n) n = max_n;
+  cudaMemcpyFromSymbol(host, k1v2::g_trace, n * sizeof(long long));
+  int zero = 0;
+  cudaMemcpyToSymbol(k1v2::g_trace_n, &zero, sizeof(int));
+  return n;
+}
 
 template <int S, int SLOT, int SPT>
 static int launch_k1v2(const CUtensorMap& tw, const float* src, const void* idx, int idx_kind, int64_t n,
