@@ -31,6 +31,8 @@ def build(force=False, verbose=False):
         return OUT
     os.makedirs(OBJ, exist_ok=True)
     extra = ["-Xptxas", "-v"] if verbose else []
+    if os.environ.get("NRMS_K1_TRACE"):
+        extra.append("-DNRMS_K1_TRACE")
 
     def cc(src):
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))

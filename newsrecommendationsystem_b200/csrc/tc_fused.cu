@@ -514,7 +514,7 @@ constexpr size_t W16_BYTES = (size_t)D3 * W16_LD * 2;   // 576,000 (a multiple o
 // host
 // ---------------------------------------------------------------------------------------------------
 template <int S, int SPT>
-static int64_t fused_chunk_seq() { return (int64_t)num_sms() * SPT * 4; }   // 4 full waves of tiles per launch
+static int64_t fused_chunk_seq() { return (int64_t)num_sms() * SPT * 8; }   // 8 full waves of tiles per launch
 
 template <int S, int SPT>
 static int run_fused(const float* src, const void* idx, int idx_kind, int64_t n_seq, const float* wqkv,

@@ -9,7 +9,8 @@
 //           192-row x 64-K box per chunk (3 heads per pass, 5 passes, 5 chunks each) through an smem ring.
 //   warp 6  projection MMA issuer (one thread): 5 passes x 19 tcgen05.mma (128x192x16) per tile.
 //   warp 1  attention MMA issuer (one thread): per head S = Q_h K_h^T (128x128x32), then O = P V_h (128x32x128).
-//   warps 2-5  workers, thread == tile row == TMEM lane:
+//   warps 11-12  gather: fill the A tile of the next tile as soon as a_free fires (overlaps the attention).
+//   warps 2-9  workers, thread == tile row == TMEM lane, two warps (roles) per lane quarter:
 //           W1  tcgen05.ld q/k/v (+bias, q pre-scaled by log2(e)/sqrt(20)) -> fp16 -> Q and K operand tiles
 //               (SWIZZLE_128B K-major) and V^T (keys along K) in shared memory;
 //           W2  tcgen05.ld the row's own score block, e = 2^s for the valid keys (the reference's
@@ -19,6 +20,7 @@
 // TMEM: two 192-column projection accumulators + one 128-column S/O region (O aliases S) = 512 columns.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <type_traits>
 #include "tc_common.cuh"
 #include "tc_api.cuh"
 
@@ -32,19 +34,25 @@ namespace k1v2 {
 // debug trace (clock64 stamps of worker thread 0 / block 0): read back with nrms_debug_read_trace
 __device__ long long g_trace[2048];
 __device__ int g_trace_n;
-#define TRACE(tag)                                                         \
-  do {                                                                     \
-    if (blockIdx.x == 0 && wt == 0 && g_trace_n < 2040) {                  \
-      g_trace[g_trace_n++] = ((long long)(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFLL); \
-    }                                                                      \
+#ifdef NRMS_K1_TRACE
+// cheap trace: stamps go to shared memory (per traced thread), dumped to g_trace at kernel end
+#define TRACE(tag)                                                                  \
+  do {                                                                              \
+    if (blockIdx.x == 0 && (wt == 0 || wt == 128) && trace_n < 250) {               \
+      trace_buf[(wt ? 250 : 0) + trace_n++] =                                       \
+          ((long long)((tag) + (wt ? 100 : 0)) << 48) | (clock64() & 0xFFFFFFFFFFFFLL); \
+    }                                                                               \
   } while (0)
+#else
+#define TRACE(tag) do { } while (0)
+#endif
 
 constexpr int HP = 3, NPASS = 5, KCH = 5;       // heads per pass, passes, 64-half K chunks
 constexpr int PN = 192;                         // projection UMMA N (180 real columns)
 constexpr int NST = 2;                          // weight ring stages
 constexpr int B_STAGE = PN * 128;               // 24,576
 constexpr int W16_ROWS = 960, W16_LD = 320;
-constexpr int THREADS = 224;             // warps: 0 TMA, 1 attention MMA, 2-5 workers, 6 projection MMA
+constexpr int THREADS = 480;             // warps: 0 TMA, 1 attention MMA, 2-9 workers, 10 projection MMA, 11-14 gather
 constexpr int OFF_A = 0;                        // 5 x [128 rows x 128 B]
 constexpr int OFF_B = 5 * 16384;                // 81,920
 constexpr int OFF_Q = OFF_B + NST * B_STAGE;    // 131,072
@@ -53,8 +61,14 @@ constexpr int OFF_VT = OFF_K + 16384;           // 2 x [32 rows x 128 B]
 constexpr int OFF_P = OFF_VT + 8192;            // 2 x [128 rows x 128 B]
 constexpr int OFF_BIAS = OFF_P + 32768;         // 204,800
 constexpr int OFF_IDX = OFF_BIAS + 3712;
-constexpr int OFF_BAR = OFF_IDX + 1024;
+constexpr int OFF_Z = OFF_IDX + 1024;         // partial row sums [2 roles][128 rows]
+constexpr int OFF_BAR = OFF_Z + 1024;
+constexpr int OFF_TRACE = OFF_BAR + 256;     // 500 x 8 B (debug builds only)
+#ifdef NRMS_K1_TRACE
+constexpr int SMEM = OFF_TRACE + 4096 + 1024;
+#else
 constexpr int SMEM = OFF_BAR + 256 + 1024;
+#endif
 static_assert(SMEM <= 232448, "shared memory budget");
 constexpr int TM_S = 2 * PN;                    // TMEM column of the S / O region (384)
 constexpr float QSCALE = 1.4426950408889634f / 4.47213595499957939f;   // log2(e) / sqrt(20)
@@ -110,13 +124,13 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(acc_full + 8 * s, 1);
-      mbar_init(acc_empty + 8 * s, 4);
+      mbar_init(acc_empty + 8 * s, 8);
     }
     mbar_init(a_full, 128);
     mbar_init(a_free, 1);
-    mbar_init(qk_ready, 128);
+    mbar_init(qk_ready, 256);
     mbar_init(s_ready, 1);
-    mbar_init(p_ready, 128);
+    mbar_init(p_ready, 256);
     mbar_init(o_ready, 1);
     mbar_fence_init();
   }
@@ -148,7 +162,7 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* 
         }
       }
     }
-  } else if (warp == 6) {
+  } else if (warp == 10) {
     // ------------------------------ projection MMA issuer (one thread) ----------------------------
     // Independent of the attention MMAs (different TMEM columns / smem), so it gets its own issuing
     // thread: the latency-critical S / PV MMAs never wait behind descriptor building or a TMA wait.
@@ -214,50 +228,42 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* 
         __syncwarp();
       }
     }
-  } else if (warp >= 2 && warp <= 5) {
-    // ------------------------------ workers (warps 2..5) --------------------------------------
-    const int q4 = warp & 3;
-    const int wt = (warp - 2) * 32 + lane;       // 0..127
-    const int row = q4 * 32 + lane;              // tile row == TMEM lane == key index
-    const int sq = row / SLOT, pos = row - sq * SLOT;
-    const bool row_valid = (sq < SPT) && (pos < S);
-    // warp-uniform first slot of this warp (a 32-row warp spans at most two 24-row slots, one 64-row slot)
-    const int sq_lo = (q4 * 32) / SLOT;
-    const int own = sq - sq_lo;                  // 0 or 1 (SLOT = 24), always 0 (SLOT = 64)
-    constexpr int NLD = (SLOT >= 32) ? SLOT : 2 * SLOT;   // score columns loaded per warp (64 or 48)
-    const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
-    uint32_t pass_it = 0, head_it = 0, tile_it = 0;
+  } else if (warp >= 11) {
+    // ------------------------------ gather warps (11..14) --------------------------------------
+    // Fill the A tile of the NEXT tile as soon as the projections of the current one have retired
+    // (a_free), i.e. while the workers are still busy with its attention: NPAIR real rows x 75 float4,
+    // 16 independent 16-byte loads in flight per thread, fp32 -> fp16, swizzled slot layout.
+    const int gt = (warp - 11) * 32 + lane;      // 0..127
+    uint32_t tile_it = 0;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
       const int64_t seq0 = t * SPT;
-      if (wt < NPAIR) {
-        const int64_t seq = seq0 + wt / S;
+      for (int pr = gt; pr < NPAIR; pr += 128) {
+        const int64_t seq = seq0 + pr / S;
         int64_t id = 0;
         if (seq < n_seq) {
-          const int64_t e = seq * S + (wt % S);
+          const int64_t e = seq * S + (pr % S);
           id = idx_kind == 0 ? e : (idx_kind == 1 ? reinterpret_cast<const int64_t*>(idx)[e]
                                                   : (int64_t) reinterpret_cast<const int32_t*>(idx)[e]);
         }
-        rowid[wt] = id;
+        rowid[pr] = id;
       }
-      TRACE(6);
-      mbar_wait(a_free, (tile_it & 1) ^ 1);
-      workers_bar();
-      // ---- gather: NPAIR real rows x 75 float4 -> fp16 -> swizzled A tile (slot layout) ----
+      mbar_wait(a_free, (tile_it & 1) ^ 1);      // previous tile's projection MMAs no longer read A
+      asm volatile("bar.sync 2, 128;" ::: "memory");
       constexpr int TOTAL4 = NPAIR * DV4;
 #pragma unroll 1
-      for (int f0 = 0; f0 < TOTAL4; f0 += 128 * 8) {
-        float4 v[8];
+      for (int f0 = 0; f0 < TOTAL4; f0 += 128 * 16) {
+        float4 v[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int f = f0 + u * 128 + wt;
+        for (int u = 0; u < 16; ++u) {
+          const int f = f0 + u * 128 + gt;
           if (f < TOTAL4) {
             const int pr = f / DV4, c4 = f - pr * DV4;
             v[u] = __ldg(reinterpret_cast<const float4*>(src + rowid[pr] * D) + c4);
           }
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int f = f0 + u * 128 + wt;
+        for (int u = 0; u < 16; ++u) {
+          const int f = f0 + u * 128 + gt;
           if (f < TOTAL4) {
             const int pr = f / DV4, c4 = f - pr * DV4;
             const int r = (pr / S) * SLOT + (pr % S);
@@ -271,8 +277,45 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* 
       }
       fence_proxy_async_smem();
       mbar_arrive(a_full);
-      TRACE(7);
-
+      asm volatile("bar.sync 2, 128;" ::: "memory");  // rowid is rewritten for the next tile
+    }
+  } else if (warp >= 2 && warp <= 9) {
+    // ------------------------------ workers (warps 2..9) ----------------------------------------
+    // Two warps share every TMEM lane quarter (thread == tile row == key): role 0 (warps 2-5) handles q, k,
+    // the first half of the row's score block and context columns 0..11; role 1 (warps 6-9) handles v, the
+    // second half of the score block and context columns 12..19.
+    const int role = (warp - 2) >> 2;
+    const int q4 = warp & 3;
+    const int wt = ((warp - 2) & 3) * 32 + lane + role * 128;   // trace id (0 = warp 2 lane 0)
+    const int row = q4 * 32 + lane;
+    const int sq = row / SLOT, pos = row - sq * SLOT;
+    const bool row_valid = (sq < SPT) && (pos < S);
+    const int sq_lo = (q4 * 32) / SLOT;          // warp-uniform first slot of this warp
+    const int own = sq - sq_lo;                  // 0 or 1 (SLOT = 24), always 0 (SLOT = 64)
+    const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+    // score-block split between the roles (whole 8-key pieces): role 0 gets [0, C0), role 1 [C0, SLOT)
+    constexpr int C0 = (SLOT >= 32) ? SLOT / 2 : 16;
+    float* zpart = reinterpret_cast<float*>(sm + OFF_Z);
+    // row-constant shared-memory addresses (swizzle XOR hoisted out of the head loop)
+    const int sw = row & 7;
+    uint8_t* const qrow = sm + OFF_Q + row * 128;
+    uint8_t* const krow = sm + OFF_K + row * 128;
+    const int o0 = (0 ^ sw) << 4, o1 = (1 ^ sw) << 4, o2 = (2 ^ sw) << 4;
+    uint8_t* const vt_base = sm + OFF_VT + (row >> 6) * 4096 + ((row & 7) << 1);
+    int vt_off[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) vt_off[i] = ((((row & 63) >> 3) ^ i) << 4);
+    uint8_t* const prow = sm + OFF_P + row * 128;
+#ifdef NRMS_K1_TRACE
+    long long* trace_buf = reinterpret_cast<long long*>(sm + OFF_TRACE);
+    int trace_n = 0;
+#endif
+    uint32_t pass_it = 0, head_it = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int64_t seq0 = t * SPT;
+      const bool st_ok = row_valid && (seq0 + sq < n_seq);
+      float* const crow0 = C + ((seq0 + sq) * S + pos) * D + (role ? 12 : 0);
+      TRACE(6);
       for (int p = 0; p < NPASS; ++p, ++pass_it) {
         const uint32_t as = pass_it & 1;
         mbar_wait(acc_full + 8 * as, (pass_it >> 1) & 1);
@@ -283,20 +326,15 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* 
         for (int hh = 0; hh < HP; ++hh, ++head_it) {
           const int h = p * HP + hh;
           const uint32_t hp = head_it & 1;
-          // ================= W1: q/k/v of this row -> fp16 operand tiles =================
+          // ================= W1: q,k (role 0) / v (role 1) of this row -> fp16 operand tiles =========
           TRACE(1);
-          {
-            float qv[DH], kk[DH], vv[DH];
-            {
-              uint32_t* qi = reinterpret_cast<uint32_t*>(qv);
-              uint32_t* ki = reinterpret_cast<uint32_t*>(kk);
-              uint32_t* vi = reinterpret_cast<uint32_t*>(vv);
-              tmem_ld16_nw(tacc + 60 * hh, qi);            tmem_ld4_nw(tacc + 60 * hh + 16, qi + 16);
-              tmem_ld16_nw(tacc + 60 * hh + 20, ki);       tmem_ld4_nw(tacc + 60 * hh + 36, ki + 16);
-              tmem_ld16_nw(tacc + 60 * hh + 40, vi);       tmem_ld4_nw(tacc + 60 * hh + 56, vi + 16);
-              tmem_ld_wait();
-            }
-            if (hh == HP - 1) {                       // accumulator stage fully drained by this warp
+          if (role == 0) {
+            uint32_t qk[40];
+            tmem_ld16_nw(tacc + 60 * hh, qk);
+            tmem_ld16_nw(tacc + 60 * hh + 16, qk + 16);
+            tmem_ld8_nw(tacc + 60 * hh + 32, qk + 32);
+            tmem_ld_wait();
+            if (hh == HP - 1) {
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(acc_empty + 8 * as);
@@ -304,98 +342,140 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* 
             uint32_t qp[10], kp[10];
 #pragma unroll
             for (int d = 0; d < DH; d += 2) {
-              qp[d >> 1] = pack_h2((qv[d] + bias_s[h * DH + d]) * QSCALE, (qv[d + 1] + bias_s[h * DH + d + 1]) * QSCALE);
-              kp[d >> 1] = pack_h2(kk[d] + bias_s[D + h * DH + d], kk[d + 1] + bias_s[D + h * DH + d + 1]);
+              qp[d >> 1] = pack_h2((__uint_as_float(qk[d]) + bias_s[h * DH + d]) * QSCALE,
+                                   (__uint_as_float(qk[d + 1]) + bias_s[h * DH + d + 1]) * QSCALE);
+              kp[d >> 1] = pack_h2(__uint_as_float(qk[DH + d]) + bias_s[D + h * DH + d],
+                                   __uint_as_float(qk[DH + d + 1]) + bias_s[D + h * DH + d + 1]);
             }
-            uint8_t* qrow = sm + OFF_Q + row * 128;
-            uint8_t* krow = sm + OFF_K + row * 128;
-            const int sw = row & 7;
-            *reinterpret_cast<uint4*>(qrow + ((0 ^ sw) << 4)) = make_uint4(qp[0], qp[1], qp[2], qp[3]);
-            *reinterpret_cast<uint4*>(qrow + ((1 ^ sw) << 4)) = make_uint4(qp[4], qp[5], qp[6], qp[7]);
-            *reinterpret_cast<uint2*>(qrow + ((2 ^ sw) << 4)) = make_uint2(qp[8], qp[9]);
-            *reinterpret_cast<uint4*>(krow + ((0 ^ sw) << 4)) = make_uint4(kp[0], kp[1], kp[2], kp[3]);
-            *reinterpret_cast<uint4*>(krow + ((1 ^ sw) << 4)) = make_uint4(kp[4], kp[5], kp[6], kp[7]);
-            *reinterpret_cast<uint2*>(krow + ((2 ^ sw) << 4)) = make_uint2(kp[8], kp[9]);
+            *reinterpret_cast<uint4*>(qrow + o0) = make_uint4(qp[0], qp[1], qp[2], qp[3]);
+            *reinterpret_cast<uint4*>(qrow + o1) = make_uint4(qp[4], qp[5], qp[6], qp[7]);
+            *reinterpret_cast<uint2*>(qrow + o2) = make_uint2(qp[8], qp[9]);
+            *reinterpret_cast<uint4*>(krow + o0) = make_uint4(kp[0], kp[1], kp[2], kp[3]);
+            *reinterpret_cast<uint4*>(krow + o1) = make_uint4(kp[4], kp[5], kp[6], kp[7]);
+            *reinterpret_cast<uint2*>(krow + o2) = make_uint2(kp[8], kp[9]);
+          } else {
+            uint32_t vi[DH];
+            tmem_ld16_nw(tacc + 60 * hh + 40, vi);
+            tmem_ld4_nw(tacc + 60 * hh + 56, vi + 16);
+            tmem_ld_wait();
+            TRACE(11);
+            if (hh == HP - 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(acc_empty + 8 * as);
+            }
             // V^T: element (d, key=row); padded / invalid keys contribute exact zeros
-            uint8_t* vt = sm + OFF_VT + (row >> 6) * 4096 + ((row & 7) << 1);
-            const int piece = (row & 63) >> 3;
+            const float vmask = row_valid ? 1.f : 0.f;
+            // all bias loads first: the compiler must keep shared-memory loads behind earlier (possibly
+            // aliasing) shared-memory stores, which would serialise load->convert->store per element
+            __half hv[DH];
 #pragma unroll
-            for (int d = 0; d < DH; ++d) {
-              const float x = row_valid ? vv[d] + bias_s[2 * D + h * DH + d] : 0.f;
-              *reinterpret_cast<__half*>(vt + d * 128 + ((piece ^ (d & 7)) << 4)) = __float2half_rn(x);
-            }
+            for (int d = 0; d < DH; ++d)
+              hv[d] = __float2half_rn((__uint_as_float(vi[d]) + bias_s[2 * D + h * DH + d]) * vmask);
+#pragma unroll
+            for (int d = 0; d < DH; ++d) *reinterpret_cast<__half*>(vt_base + d * 128 + vt_off[d & 7]) = hv[d];
+            TRACE(12);
           }
           fence_proxy_async_smem();
           mbar_arrive(qk_ready);
           TRACE(2);
-          // ================= W2: scores -> unnormalised probabilities =================
+          // ================= W2: this role's half of the score block -> unnormalised probabilities =====
           mbar_wait(s_ready, hp);
           tc_fence_after();
           TRACE(3);
-          float Z = 0.f;
           {
-            float sv[NLD];
-            uint32_t* svi = reinterpret_cast<uint32_t*>(sv);
-            if constexpr (SLOT >= 32) {
+            const int g0 = sq * (SLOT / 8);
+            float Z = 0.f;
+            auto half_block = [&](auto lo_c, auto n_c) {
+              constexpr int LO = decltype(lo_c)::value, NC = decltype(n_c)::value;   // columns [LO, LO+NC) of the block
+              uint32_t sv[(SLOT >= 32) ? NC : 2 * NC];
+              if constexpr (SLOT >= 32) {
 #pragma unroll
-              for (int c = 0; c < NLD; c += 16) tmem_ld16_nw(tmem_base + TM_S + lane_addr + sq_lo * SLOT + c, svi + c);
-            } else {          // SLOT == 24: the warp's (up to) two slots, each 16 + 8 columns; never past key 119
+                for (int c = 0; c < NC; c += 16) tmem_ld16_nw(tmem_base + TM_S + lane_addr + sq_lo * SLOT + LO + c, sv + c);
+              } else {
 #pragma unroll
-              for (int b = 0; b < 2; ++b) {
-                if (sq_lo + b < SPT) {
-                  tmem_ld16_nw(tmem_base + TM_S + lane_addr + (sq_lo + b) * SLOT, svi + b * SLOT);
-                  tmem_ld8_nw(tmem_base + TM_S + lane_addr + (sq_lo + b) * SLOT + 16, svi + b * SLOT + 16);
-                } else {
+                for (int b = 0; b < 2; ++b) {
+                  if (sq_lo + b < SPT) {
+                    if constexpr (NC == 16) tmem_ld16_nw(tmem_base + TM_S + lane_addr + (sq_lo + b) * SLOT + LO, sv + b * NC);
+                    else tmem_ld8_nw(tmem_base + TM_S + lane_addr + (sq_lo + b) * SLOT + LO, sv + b * NC);
+                  } else {
 #pragma unroll
-                  for (int j = 0; j < SLOT; ++j) sv[b * SLOT + j] = 0.f;
+                    for (int j = 0; j < NC; ++j) sv[b * NC + j] = 0u;
+                  }
                 }
               }
-            }
-            tmem_ld_wait();
-            tc_fence_before();
-            float e[SLOT];
+              tmem_ld_wait();
+              tc_fence_before();
+              float e[NC];
 #pragma unroll
-            for (int j = 0; j < SLOT; ++j) {
-              float x = sv[j];
-              if (SLOT < 32) x = own ? sv[SLOT + j] : sv[j];
-              e[j] = (j < S) ? ex2(x) : 0.f;
-              Z += e[j];
-            }
-            // own block = pieces [sq*SLOT/8, +SLOT/8) of this row of P
-            uint8_t* prow = sm + OFF_P + row * 128;
-            const int g0 = sq * (SLOT / 8);
+              for (int j = 0; j < NC; ++j) {
+                uint32_t x = sv[j];
+                if (SLOT < 32) x = own ? sv[NC + j] : sv[j];
+                e[j] = (LO + j < S) ? ex2(__uint_as_float(x)) : 0.f;
+                Z += e[j];
+              }
 #pragma unroll
-            for (int m = 0; m < SLOT / 8; ++m) {
-              const int g = g0 + m;
-              const uint4 pk = make_uint4(pack_h2(e[8 * m], e[8 * m + 1]), pack_h2(e[8 * m + 2], e[8 * m + 3]),
-                                          pack_h2(e[8 * m + 4], e[8 * m + 5]), pack_h2(e[8 * m + 6], e[8 * m + 7]));
-              if (sq < SPT) *reinterpret_cast<uint4*>(prow + (g >> 3) * 16384 + (((g & 7) ^ (row & 7)) << 4)) = pk;
-            }
+              for (int m = 0; m < NC / 8; ++m) {
+                const int g = g0 + LO / 8 + m;
+                const uint4 pk = make_uint4(pack_h2(e[8 * m], e[8 * m + 1]), pack_h2(e[8 * m + 2], e[8 * m + 3]),
+                                            pack_h2(e[8 * m + 4], e[8 * m + 5]), pack_h2(e[8 * m + 6], e[8 * m + 7]));
+                if (sq < SPT) *reinterpret_cast<uint4*>(prow + (g >> 3) * 16384 + (((g & 7) ^ (row & 7)) << 4)) = pk;
+              }
+            };
+            if (role == 0) half_block(std::integral_constant<int, 0>{}, std::integral_constant<int, C0>{});
+            else half_block(std::integral_constant<int, C0>{}, std::integral_constant<int, SLOT - C0>{});
+            zpart[role * 128 + row] = Z;
           }
           fence_proxy_async_smem();
           mbar_arrive(p_ready);
           TRACE(4);
-          // ================= W3: context row =================
+          // ================= W3: context row (columns 0..11 role 0, 12..19 role 1) =================
           mbar_wait(o_ready, hp);
           tc_fence_after();
           TRACE(5);
           {
-            float o[DH];
-            tmem_ld16_nw(tmem_base + TM_S + lane_addr, reinterpret_cast<uint32_t*>(o));
-            tmem_ld4_nw(tmem_base + TM_S + lane_addr + 16, reinterpret_cast<uint32_t*>(o) + 16);
-            tmem_ld_wait();
-            tc_fence_before();
-            const float inv = 1.f / (Z + 1e-8f);
-            if (row_valid && seq0 + sq < n_seq) {
-              float4* op = reinterpret_cast<float4*>(C + ((seq0 + sq) * S + pos) * D + h * DH);
+            const float inv = 1.f / (zpart[row] + zpart[128 + row] + 1e-8f);
+            TRACE(13);
+            const bool st = st_ok;
+            float* crow = crow0 + h * DH;
+            if (role == 0) {
+              uint32_t o[12];
+              tmem_ld8_nw(tmem_base + TM_S + lane_addr, o);
+              tmem_ld4_nw(tmem_base + TM_S + lane_addr + 8, o + 8);
+              tmem_ld_wait();
+              TRACE(14);
+              tc_fence_before();
+              if (st) {
 #pragma unroll
-              for (int c = 0; c < 5; ++c)
-                op[c] = make_float4(o[4 * c] * inv, o[4 * c + 1] * inv, o[4 * c + 2] * inv, o[4 * c + 3] * inv);
+                for (int c = 0; c < 3; ++c)
+                  reinterpret_cast<float4*>(crow)[c] =
+                      make_float4(__uint_as_float(o[4 * c]) * inv, __uint_as_float(o[4 * c + 1]) * inv,
+                                  __uint_as_float(o[4 * c + 2]) * inv, __uint_as_float(o[4 * c + 3]) * inv);
+              }
+              TRACE(15);
+            } else {
+              uint32_t o[8];
+              tmem_ld8_nw(tmem_base + TM_S + lane_addr + 12, o);
+              tmem_ld_wait();
+              tc_fence_before();
+              if (st) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                  reinterpret_cast<float4*>(crow)[c] =
+                      make_float4(__uint_as_float(o[4 * c]) * inv, __uint_as_float(o[4 * c + 1]) * inv,
+                                  __uint_as_float(o[4 * c + 2]) * inv, __uint_as_float(o[4 * c + 3]) * inv);
+              }
             }
           }
         }
       }
     }
+#ifdef NRMS_K1_TRACE
+    if (blockIdx.x == 0 && (wt == 0 || wt == 128)) {
+      for (int i = 0; i < trace_n; ++i) g_trace[(wt ? 250 : 0) + i] = trace_buf[(wt ? 250 : 0) + i];
+      if (wt == 0) g_trace_n = trace_n; 
+    }
+#endif
   }
   tc_fence_before();
   __syncthreads();
@@ -422,13 +502,12 @@ constexpr size_t W16_BYTES = (size_t)W16_ROWS * W16_LD * 2;   // 614,400
 
 size_t k1v2_w16_bytes() { return k1v2::W16_BYTES; }
 
+// debug builds (-DNRMS_K1_TRACE): host[0..250) = role-0 stamps, host[250..500) = role-1 stamps; returns count per role
 extern "C" int nrms_debug_read_trace(long long* host, int max_n) {
   int n = 0;
   cudaMemcpyFromSymbol(&n, k1v2::g_trace_n, sizeof(int));
-  if (n > max_n) n = max_n;
-  cudaMemcpyFromSymbol(host, k1v2::g_trace, n * sizeof(long long));
-  int zero = 0;
-  cudaMemcpyToSymbol(k1v2::g_trace_n, &zero, sizeof(int));
+  if (max_n < 500) return -1;
+  cudaMemcpyFromSymbol(host, k1v2::g_trace, 500 * sizeof(long long));
   return n;
 }
 

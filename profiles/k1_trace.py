@@ -9,7 +9,7 @@ sd = synthetic.init_state_dict(num_words=5001, seed=0)
 class Cfg(NRMSConfig): num_words = 5001
 m = NRMS(Cfg); m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}); m.to(dev).eval()
 lib = _lib.load()
-buf = (ctypes.c_longlong * 2048)()
+buf = (ctypes.c_longlong * 2048)()  # build with NRMS_K1_TRACE=1 python newsrecommendationsystem_b200/csrc/build.py --force
 with torch.no_grad():
     if S == 50:
         x = torch.randn(1184, 50, 300, device=dev) * 0.3
@@ -23,17 +23,14 @@ with torch.no_grad():
     else: m.get_news_vector({"title": toks})
     torch.cuda.synchronize()
 n = lib.nrms_debug_read_trace(buf, 2048)
-ev = [(buf[i] >> 48, buf[i] & 0xFFFFFFFFFFFF) for i in range(n)]
-names = {1: "W1 start", 2: "qk arrived", 3: "s_ready", 4: "p arrived", 5: "o_ready", 6: "tile start", 7: "gather done", 8: "acc_full"}
-t0 = ev[0][1]
-prev = t0
-for tag, t in ev[:90]:
-    print(f"{names.get(tag, tag):12s} t={t - t0:8d} d={t - prev:6d}")
-    prev = t
-# per-phase averages
+ev = [(buf[i] >> 48, buf[i] & 0xFFFFFFFFFFFF) for i in list(range(n)) + list(range(250, 250 + n))]
+names = {11: "ld done", 12: "stores done", 13: "inv", 14: "O ld done", 15: "O stored", 1: "W1 start", 2: "qk arrived", 3: "s_ready", 4: "p arrived", 5: "o_ready", 6: "tile start", 7: "gather done", 8: "acc_full"}
 import collections
-d = collections.defaultdict(list)
-for (a, ta), (b, tb) in zip(ev[:-1], ev[1:]):
-    d[(a, b)].append(tb - ta)
-for k, v in sorted(d.items()):
-    print(names.get(k[0]), "->", names.get(k[1]), "n", len(v), "mean", int(np.mean(v)), "min", min(v), "max", max(v))
+for role in (0, 1):
+    evr = sorted([(tag - 100 * role, t) for tag, t in ev if (tag >= 100) == bool(role)], key=lambda x: x[1])
+    print("=== role", role, "events", len(evr))
+    d = collections.defaultdict(list)
+    for (a, ta), (b, tb) in zip(evr[:-1], evr[1:]):
+        d[(a, b)].append(tb - ta)
+    for k, v in sorted(d.items()):
+        print(names.get(k[0], k[0]), "->", names.get(k[1], k[1]), "n", len(v), "mean", int(np.mean(v)), "min", min(v), "max", max(v))
