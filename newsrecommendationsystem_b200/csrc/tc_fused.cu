@@ -32,7 +32,12 @@ int make_tmap_k_major_f16(CUtensorMap* out, const void* base, int64_t rows, int 
 size_t k1v2_w16_bytes();
 int k1v2_prepare(const float* wqkv, void* w16, CUtensorMap* tw, cudaStream_t st);
 int k1v2_run(int S, const CUtensorMap& tw, const float* src, const void* idx, int idx_kind, int64_t n,
-             const float* bqkv, float* Cbuf, cudaStream_t st);
+             const float* bqkv, void* Cbuf, cudaStream_t st);
+// K2 v2 (tc_fused3.cu): fp16 additive pooling with W_a resident in shared memory
+int k2v2_prepare(const float* wa, void* wa16, CUtensorMap* twa, cudaStream_t st);
+int k2v2_run(int S, const CUtensorMap& twa, const void* Cbuf, int64_t n, const float* ba, const float* qa, float* out,
+             cudaStream_t st);
+constexpr size_t WA16_SLOT_BYTES = 131072;  // fp16 copy of W_a [200][320]
 // NRMS_K1_VARIANT=1 selects the first-generation K1 (CUDA-core attention); default 2 (tensor-core attention)
 static int k1_variant() {
   static int v = -1;
@@ -533,20 +538,24 @@ static int run_fused(const float* src, const void* idx, int idx_kind, int64_t n_
   // variant 2 tiles: 5 titles / 2 users as well, so the chunking (4 waves of tiles) is shared
   const int64_t chunk = fused_chunk_seq<S, SPT>();
   const int64_t first = n_seq < chunk ? n_seq : chunk;
-  const size_t need = W16_SLOT_BYTES + (size_t)first * S * D * sizeof(float);
+  const size_t need = W16_SLOT_BYTES + WA16_SLOT_BYTES + (size_t)first * S * D * sizeof(float);
   NRMS_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= need, NRMS_E_WORKSPACE,
                  "workspace too small: need %zu bytes", need);
   __half* w16 = reinterpret_cast<__half*>(workspace);
-  float* Cbuf = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + W16_SLOT_BYTES);
+  void* wa16 = reinterpret_cast<char*>(workspace) + W16_SLOT_BYTES;
+  float* Cbuf = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + W16_SLOT_BYTES + WA16_SLOT_BYTES);
   alignas(64) CUtensorMap tw, twa, tc_;
   if (variant == 2) {
     if (int rc = k1v2_prepare(wqkv, w16, &tw, st)) return rc;
+    if (int rc = k2v2_prepare(wa, wa16, &twa, st)) return rc;
   } else {
     wqkv_to_f16_kernel<<<148, 256, 0, st>>>(wqkv, w16);
     NRMS_LAUNCH_CHECK("wqkv_to_f16_kernel");
     if (int rc = make_tmap_k_major_f16(&tw, w16, D3, W16_LD, W16_LD, K1_BOX)) return rc;
   }
-  if (int rc = make_tmap_k_major(&twa, wa, QD, D, D, QD)) return rc;
+  if (variant != 2) {
+    if (int rc = make_tmap_k_major(&twa, wa, QD, D, D, QD)) return rc;
+  }
   const size_t idx_elem = idx_kind == 1 ? 8 : 4;
   for (int64_t s0 = 0; s0 < n_seq; s0 += chunk) {
     const int64_t n = (n_seq - s0 < chunk) ? (n_seq - s0) : chunk;
@@ -557,6 +566,8 @@ static int run_fused(const float* src, const void* idx, int idx_kind, int64_t n_
     const void* idx_c = idx_kind == 0 ? nullptr : (const void*)((const char*)idx + (size_t)s0 * S * idx_elem);
     if (variant == 2) {
       if (int rc = k1v2_run(S, tw, src_c, idx_c, idx_kind, n, bqkv, Cbuf, st)) return rc;
+      if (int rc = k2v2_run(S, twa, Cbuf, n, ba, qa, out + s0 * D, st)) return rc;
+      continue;
     } else {
       encoder_attn_kernel<S, SPT><<<grid, K1_THREADS, Cfg::SMEM, st>>>(tw, src_c, idx_c, idx_kind, n, bqkv, Cbuf);
       NRMS_LAUNCH_CHECK("encoder_attn_kernel");
@@ -577,7 +588,7 @@ size_t tc_fused_workspace_bytes(int64_t n_seq, int S) {
   else if (S == 50) chunk = fused_chunk_seq<50, 2>();
   else return (size_t)-1;
   const int64_t first = n_seq < chunk ? n_seq : chunk;
-  return W16_SLOT_BYTES + (size_t)first * S * D * sizeof(float);
+  return W16_SLOT_BYTES + WA16_SLOT_BYTES + (size_t)first * S * D * sizeof(float);
 }
 
 int tc_encoder_fused(const float* src, const void* idx, int idx_kind, int64_t n_seq, int S, const float* wqkv,

@@ -16,7 +16,8 @@
 //           W2  tcgen05.ld the row's own score block, e = 2^s for the valid keys (the reference's
 //               exp(s)/(sum+1e-8) without max-subtraction), row sum in fp32, P (fp16, unnormalised) into
 //               the block-diagonal A tile (off-block columns stay zero from kernel start);
-//           W3  tcgen05.ld O (20 columns), scale by 1/(Z+1e-8), store the context row to C.
+//           W3  tcgen05.ld O (20 columns), scale by 1/(Z+1e-8), store the context row to C as fp16
+//               (pitch 320 halfs; K2 v2 consumes it as the fp16 A operand and for the pooling).
 // TMEM: two 192-column projection accumulators + one 128-column S/O region (O aliases S) = 512 columns.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -52,6 +53,7 @@ constexpr int PN = 192;                         // projection UMMA N (180 real c
 constexpr int NST = 2;                          // weight ring stages
 constexpr int B_STAGE = PN * 128;               // 24,576
 constexpr int W16_ROWS = 960, W16_LD = 320;
+constexpr int CP = 320;                        // pitch (halfs) of the fp16 context rows handed to K2
 constexpr int THREADS = 480;             // warps: 0 TMA, 1 attention MMA, 2-9 workers, 10 projection MMA, 11-14 gather
 constexpr int OFF_A = 0;                        // 5 x [128 rows x 128 B]
 constexpr int OFF_B = 5 * 16384;                // 81,920
@@ -99,7 +101,7 @@ template <int S, int SLOT, int SPT>
 __global__ void __launch_bounds__(THREADS, 1)
 encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ src,
                        const void* __restrict__ idx, int idx_kind, int64_t n_seq, const float* __restrict__ bqkv,
-                       float* __restrict__ C) {
+                       __half* __restrict__ C) {
   static_assert(SLOT % 8 == 0 && SLOT >= S && SPT * SLOT <= 128, "slot layout");
   constexpr int NPAIR = SPT * S;                 // real rows per tile
   extern __shared__ uint8_t smem_raw[];
@@ -314,7 +316,7 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* 
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int64_t seq0 = t * SPT;
       const bool st_ok = row_valid && (seq0 + sq < n_seq);
-      float* const crow0 = C + ((seq0 + sq) * S + pos) * D + (role ? 12 : 0);
+      __half* const crow0 = C + ((seq0 + sq) * S + pos) * CP + (role ? 12 : 0);
       TRACE(6);
       for (int p = 0; p < NPASS; ++p, ++pass_it) {
         const uint32_t as = pass_it & 1;
@@ -437,7 +439,7 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* 
             const float inv = 1.f / (zpart[row] + zpart[128 + row] + 1e-8f);
             TRACE(13);
             const bool st = st_ok;
-            float* crow = crow0 + h * DH;
+            __half* crow = crow0 + h * DH;
             if (role == 0) {
               uint32_t o[12];
               tmem_ld8_nw(tmem_base + TM_S + lane_addr, o);
@@ -448,9 +450,9 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* 
               if (st) {
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
-                  reinterpret_cast<float4*>(crow)[c] =
-                      make_float4(__uint_as_float(o[4 * c]) * inv, __uint_as_float(o[4 * c + 1]) * inv,
-                                  __uint_as_float(o[4 * c + 2]) * inv, __uint_as_float(o[4 * c + 3]) * inv);
+                  reinterpret_cast<uint2*>(crow)[c] =
+                      make_uint2(pack_h2(__uint_as_float(o[4 * c]) * inv, __uint_as_float(o[4 * c + 1]) * inv),
+                                 pack_h2(__uint_as_float(o[4 * c + 2]) * inv, __uint_as_float(o[4 * c + 3]) * inv));
               }
               TRACE(15);
             } else {
@@ -461,9 +463,13 @@ encoder_attn_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* 
               if (st) {
 #pragma unroll
                 for (int c = 0; c < 2; ++c)
-                  reinterpret_cast<float4*>(crow)[c] =
-                      make_float4(__uint_as_float(o[4 * c]) * inv, __uint_as_float(o[4 * c + 1]) * inv,
-                                  __uint_as_float(o[4 * c + 2]) * inv, __uint_as_float(o[4 * c + 3]) * inv);
+                  reinterpret_cast<uint2*>(crow)[c] =
+                      make_uint2(pack_h2(__uint_as_float(o[4 * c]) * inv, __uint_as_float(o[4 * c + 1]) * inv),
+                                 pack_h2(__uint_as_float(o[4 * c + 2]) * inv, __uint_as_float(o[4 * c + 3]) * inv));
+                if (h == H - 1) {          // zero the K padding (columns 300..319) of this context row once
+#pragma unroll
+                  for (int c = 0; c < 5; ++c) reinterpret_cast<uint2*>(crow0 - 12 + D)[c] = make_uint2(0u, 0u);
+                }
               }
             }
           }
@@ -513,7 +519,7 @@ extern "C" int nrms_debug_read_trace(long long* host, int max_n) {
 
 template <int S, int SLOT, int SPT>
 static int launch_k1v2(const CUtensorMap& tw, const float* src, const void* idx, int idx_kind, int64_t n,
-                       const float* bqkv, float* Cbuf, cudaStream_t st) {
+                       const float* bqkv, void* Cbuf, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k1v2::encoder_attn_tc_kernel<S, SLOT, SPT>,
@@ -524,7 +530,8 @@ static int launch_k1v2(const CUtensorMap& tw, const float* src, const void* idx,
   const int64_t tiles = (n + SPT - 1) / SPT;
   int grid = num_sms();
   if (tiles < grid) grid = (int)tiles;
-  k1v2::encoder_attn_tc_kernel<S, SLOT, SPT><<<grid, k1v2::THREADS, k1v2::SMEM, st>>>(tw, src, idx, idx_kind, n, bqkv, Cbuf);
+  k1v2::encoder_attn_tc_kernel<S, SLOT, SPT><<<grid, k1v2::THREADS, k1v2::SMEM, st>>>(
+      tw, src, idx, idx_kind, n, bqkv, reinterpret_cast<__half*>(Cbuf));
   NRMS_LAUNCH_CHECK("encoder_attn_tc_kernel");
   return NRMS_OK;
 }
@@ -537,7 +544,7 @@ int k1v2_prepare(const float* wqkv, void* w16, CUtensorMap* tw, cudaStream_t st)
 }
 
 int k1v2_run(int S, const CUtensorMap& tw, const float* src, const void* idx, int idx_kind, int64_t n,
-             const float* bqkv, float* Cbuf, cudaStream_t st) {
+             const float* bqkv, void* Cbuf, cudaStream_t st) {
   if (S == 20) return launch_k1v2<20, 24, 5>(tw, src, idx, idx_kind, n, bqkv, Cbuf, st);
   if (S == 50) return launch_k1v2<50, 64, 2>(tw, src, idx, idx_kind, n, bqkv, Cbuf, st);
   set_error("encoder_attn_tc_kernel compiled for S = 20 or 50, got %d", S);
