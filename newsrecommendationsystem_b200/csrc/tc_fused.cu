@@ -38,16 +38,22 @@ int k2v2_prepare(const float* wa, void* wa16, CUtensorMap* twa, cudaStream_t st)
 int k2v2_run(int S, const CUtensorMap& twa, const void* Cbuf, int64_t n, const float* ba, const float* qa, float* out,
              cudaStream_t st);
 constexpr size_t WA16_SLOT_BYTES = 131072;  // fp16 copy of W_a [200][320]
-// NRMS_K1_VARIANT=1 selects the first-generation K1 (CUDA-core attention); default 2 (tensor-core attention)
+// K1 v3 (tc_fused4.cu): v2 with two heads in flight and P in tensor memory (TS-form MMA)
+int k1v3_prepare(const float* wqkv, void* w16, CUtensorMap* tw, cudaStream_t st);
+int k1v3_run(int S, const CUtensorMap& tw, const float* src, const void* idx, int idx_kind, int64_t n,
+             const float* bqkv, void* Cbuf, cudaStream_t st);
+// NRMS_K1_VARIANT: 1 = first-generation K1 (CUDA-core attention, fp32 C, TF32 K2); 2 (default) = tensor-core
+// attention; 3 = tensor-core attention with two heads in flight and P in tensor memory (TS-form MMA) -- measured
+// within 5 % of variant 2 this round (profiles/), kept selectable for the next round's pipelining work
 static int k1_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("NRMS_K1_VARIANT");
-    v = (e && e[0] == '1') ? 1 : 2;
+    v = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 2;
   }
   return v;
 }
-constexpr size_t W16_SLOT_BYTES = 614400;   // >= both variants' fp16 weight copies
+constexpr size_t W16_SLOT_BYTES = 655360;   // >= every variant's fp16 weight copy
 
 __device__ __forceinline__ void tma_load_2d_f(uint32_t dst_smem, const CUtensorMap* tmap, int c0, int c1, uint32_t bar) {
   asm volatile(
@@ -545,15 +551,15 @@ static int run_fused(const float* src, const void* idx, int idx_kind, int64_t n_
   void* wa16 = reinterpret_cast<char*>(workspace) + W16_SLOT_BYTES;
   float* Cbuf = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + W16_SLOT_BYTES + WA16_SLOT_BYTES);
   alignas(64) CUtensorMap tw, twa, tc_;
-  if (variant == 2) {
-    if (int rc = k1v2_prepare(wqkv, w16, &tw, st)) return rc;
+  if (variant >= 2) {
+    if (int rc = (variant == 3 ? k1v3_prepare(wqkv, w16, &tw, st) : k1v2_prepare(wqkv, w16, &tw, st))) return rc;
     if (int rc = k2v2_prepare(wa, wa16, &twa, st)) return rc;
   } else {
     wqkv_to_f16_kernel<<<148, 256, 0, st>>>(wqkv, w16);
     NRMS_LAUNCH_CHECK("wqkv_to_f16_kernel");
     if (int rc = make_tmap_k_major_f16(&tw, w16, D3, W16_LD, W16_LD, K1_BOX)) return rc;
   }
-  if (variant != 2) {
+  if (variant < 2) {
     if (int rc = make_tmap_k_major(&twa, wa, QD, D, D, QD)) return rc;
   }
   const size_t idx_elem = idx_kind == 1 ? 8 : 4;
@@ -564,8 +570,9 @@ static int run_fused(const float* src, const void* idx, int idx_kind, int64_t n_
     if (tiles < grid) grid = (int)tiles;
     const float* src_c = idx_kind == 0 ? src + s0 * S * D : src;
     const void* idx_c = idx_kind == 0 ? nullptr : (const void*)((const char*)idx + (size_t)s0 * S * idx_elem);
-    if (variant == 2) {
-      if (int rc = k1v2_run(S, tw, src_c, idx_c, idx_kind, n, bqkv, Cbuf, st)) return rc;
+    if (variant >= 2) {
+      if (int rc = (variant == 3 ? k1v3_run(S, tw, src_c, idx_c, idx_kind, n, bqkv, Cbuf, st)
+                                 : k1v2_run(S, tw, src_c, idx_c, idx_kind, n, bqkv, Cbuf, st))) return rc;
       if (int rc = k2v2_run(S, twa, Cbuf, n, ba, qa, out + s0 * D, st)) return rc;
       continue;
     } else {

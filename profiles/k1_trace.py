@@ -18,13 +18,13 @@ with torch.no_grad():
         toks = torch.from_numpy(synthetic.make_news(2960, num_words=5001)).to(dev)
         for _ in range(2): m.get_news_vector({"title": toks})
     torch.cuda.synchronize()
-    lib.nrms_debug_read_trace(buf, 2048)
     if S == 50: m.get_user_vector(x)
     else: m.get_news_vector({"title": toks})
     torch.cuda.synchronize()
-n = lib.nrms_debug_read_trace(buf, 2048)
+fn = getattr(lib, 'nrms_debug_read_trace3', None) or lib.nrms_debug_read_trace
+n = fn(buf, 2048)
 ev = [(buf[i] >> 48, buf[i] & 0xFFFFFFFFFFFF) for i in list(range(n)) + list(range(250, 250 + n))]
-names = {11: "ld done", 12: "stores done", 13: "inv", 14: "O ld done", 15: "O stored", 1: "W1 start", 2: "qk arrived", 3: "s_ready", 4: "p arrived", 5: "o_ready", 6: "tile start", 7: "gather done", 8: "acc_full"}
+names = {20: "pass start", 21: "acc_full", 22: "W1a done", 23: "W1b done", 24: "s_ready a", 25: "s_ready b", 26: "W2a done", 27: "W2b done", 28: "o_ready a", 29: "o_ready b", 30: "W3a done", 31: "W3b done", 11: "ld done", 12: "stores done", 13: "inv", 14: "O ld done", 15: "O stored", 1: "W1 start", 2: "qk arrived", 3: "s_ready", 4: "p arrived", 5: "o_ready", 6: "tile start", 7: "gather done", 8: "acc_full"}
 import collections
 for role in (0, 1):
     evr = sorted([(tag - 100 * role, t) for tag, t in ev if (tag >= 100) == bool(role)], key=lambda x: x[1])
