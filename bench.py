@@ -245,6 +245,7 @@ def main():
         timed_eval(inputs)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    lib.nrms_set_option(b"time_k1", 1)     # CUDA events around every user-encoder K1 launch of the timed region
     l0 = lib.nrms_launch_count()
     times = []
     means = None
@@ -252,6 +253,9 @@ def main():
         ms, means = timed_eval(inputs, record_stages=True)
         times.append(ms)
     launches = int(lib.nrms_launch_count() - l0)
+    k1_ms, k1_n, k1_seq = (lib.nrms_get_stat(b"k1_ms"), lib.nrms_get_stat(b"k1_launches"),
+                           lib.nrms_get_stat(b"k1_sequences"))
+    lib.nrms_set_option(b"time_k1", 0)
     barrier()
     e2e_times = []
     for i in range(args.steps + 1):
@@ -279,17 +283,28 @@ def main():
     n_imp_rank = n_imp_total / world
     cand_rank = n_cand_total / world
     stage_flops = {"news": n_news_rank * FLOP_PER_TITLE, "users": n_imp_rank * FLOP_PER_USER}
-    dominant = max(st, key=st.get) if st else "news"
-    if dominant in stage_flops:
-        ach = stage_flops[dominant] / (st[dominant] / 1e3) / 1e12
-        roof = dict(bound="tensor", kernel=f"{dominant} encoder stage", achieved=ach, peak=peaks["bf16_tflops"],
-                    unit="TFLOP/s", frac=ach / peaks["bf16_tflops"], traffic=None,
-                    peak_source=f"{peaks['source']} bf16 burst (TF32 nominal peak is half of bf16)")
+    # dominant kernel = the fused user-encoder kernel K1 (gather -> QKV tcgen05 -> attention tcgen05); its average
+    # launch duration is measured live (CUDA events on the launching stream, nrms_set_option("time_k1")).
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("encoder_attn_tc_kernel<50,64,2>")
+    if k1_n > 0 and k1_ms > 0:
+        us_per_launch = 1e3 * k1_ms / k1_n
+        users_per_launch = k1_seq / k1_n
+        # K1 owns everything of the user encoder except the additive projection/pooling (K2): 30.05 of 36.05 MFLOP
+        flop_per_launch = users_per_launch * (FLOP_PER_USER - 6_000_000 - 50_000)
+        ach = flop_per_launch / (us_per_launch * 1e-6) / 1e12
+        roof = dict(bound="tensor", kernel="k1v2::encoder_attn_tc_kernel<50,64,2> (user encoder: gather+QKV+attention)",
+                    achieved=ach, peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=ach / peaks["bf16_tflops"],
+                    traffic=traffic, us_per_launch=us_per_launch, launches=int(k1_n), users_per_launch=users_per_launch,
+                    algorithmic_flop_per_user=FLOP_PER_USER - 6_050_000,
+                    peak_source=f"{peaks['source']} dense bf16/fp16 burst (operands are fp16, fp32 accumulate)")
     else:
-        byt = cand_rank * BYTES_PER_CANDIDATE + n_imp_rank * BYTES_PER_IMPRESSION
-        ach = byt / (st[dominant] / 1e3) / 1e9
-        roof = dict(bound="hbm", kernel=f"{dominant} stage", achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s",
-                    frac=ach / peaks["hbm_gbs"], traffic=None, peak_source=peaks["source"])
+        dominant = max(st, key=st.get) if st else "news"
+        ach = stage_flops.get(dominant, 0.0) / (st[dominant] / 1e3) / 1e12
+        roof = dict(bound="tensor", kernel=f"{dominant} encoder stage", achieved=ach, peak=peaks["bf16_tflops"],
+                    unit="TFLOP/s", frac=ach / peaks["bf16_tflops"], traffic=traffic, peak_source=peaks["source"])
     score_bytes = cand_rank * BYTES_PER_CANDIDATE + n_imp_rank * BYTES_PER_IMPRESSION
     extras = dict(
         stage_ms=st,
@@ -333,7 +348,8 @@ def main():
     if rank == 0:
         line = dict(metric="evaluate impressions/s", value=value, unit="impressions/s", n_gpus=world, steps=args.steps,
                     warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True, scaling="weak",
-                    vs_baseline=None, dtype="tf32" if args.precision == "tf32" else "f32", data="synthetic",
+                    vs_baseline=None, dtype="f16xf16->f32 (tcgen05 kind::f16; TF32-equivalent 11-bit significand)"
+                    if args.precision == "tf32" else "f32", data="synthetic",
                     config=workload_config(world, args.precision), clocks=clocks,
                     e2e=dict(value=e2e_value, unit="impressions/s", h2d_bytes_per_step=host.nbytes(),
                              d2h_bytes_per_step=64, ms_per_step=e2e_ms / args.steps),

@@ -62,6 +62,14 @@ int nrms_abi_version(void);
 /* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t nrms_launch_count(void);
 
+/* Tuning / A-B switches.  "k1_variant": fused tensor-mode encoder kernel generation
+ * (1 = CUDA-core attention, 2 = tcgen05 attention [default], 3 = tcgen05 attention, two heads in flight). */
+int nrms_set_option(const char* key, int value);
+/* "time_k1" = 1 brackets every user-encoder K1 launch with CUDA events on the launching stream (clears the
+ * previous record); nrms_get_stat("k1_ms" | "k1_launches" | "k1_sequences") reads the totals back (syncs on
+ * the recorded events).  Used by bench.py for the roofline of the dominant kernel.  Unknown key: -1. */
+double nrms_get_stat(const char* key);
+
 /* ---- sizes ------------------------------------------------------------------------- */
 /* Bytes of the saved-for-backward stash of one encoder call over n_seq sequences of length S
  * (X, QKV, C, T, w).  The same stash is written by *_fwd (when non-NULL) and read by *_bwd. */

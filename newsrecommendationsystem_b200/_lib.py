@@ -22,6 +22,8 @@ SIGNATURES = {
     "nrms_last_error": (C.c_char_p, []),
     "nrms_abi_version": (_i32, []),
     "nrms_launch_count": (_i64, []),
+    "nrms_set_option": (_i32, [C.c_char_p, _i32]),
+    "nrms_get_stat": (C.c_double, [C.c_char_p]),
     "nrms_encoder_stash_bytes": (_sz, [_i64, _i32]),
     "nrms_encoder_fwd_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
     "nrms_encoder_bwd_workspace_bytes": (_sz, [_i64, _i32, _i32]),

@@ -1,5 +1,6 @@
 // Host side of the encoder entry points (C-ABI): argument checks, stash/workspace carving and
 // the launch sequence.  Kernels live in encoder_kernels.cuh / sgemm.cuh / tc_gemm.cuh.
+#include <string.h>
 #include "common.cuh"
 #include "encoder_kernels.cuh"
 #include "sgemm.cuh"
@@ -343,6 +344,28 @@ int nrms_user_encoder_bwd(const float* d_out, int64_t n_users, int S, const floa
   BwdWs w = carve_bwd(workspace, rows, false);
   return encoder_core_bwd(s, w, d_out, n_users, S, wqkv, wa, qa, d_x, d_wqkv, d_bqkv, d_wa, d_ba, d_qa, 0.f, 0, 0, mode,
                           st);
+}
+
+int nrms_set_option(const char* key, int value) {
+  NRMS_CHECK_ARG(key != nullptr, NRMS_E_INVALID, "null option key");
+  if (strcmp(key, "k1_variant") == 0) {
+    NRMS_CHECK_ARG(set_k1_variant(value) == NRMS_OK, NRMS_E_INVALID, "k1_variant must be 1, 2 or 3");
+    return NRMS_OK;
+  }
+  if (strcmp(key, "time_k1") == 0) {
+    set_time_k1(value != 0);
+    return NRMS_OK;
+  }
+  set_error("unknown option '%s'", key);
+  return NRMS_E_INVALID;
+}
+
+double nrms_get_stat(const char* key) {
+  if (!key) return -1.0;
+  if (strcmp(key, "k1_ms") == 0) return get_k1_stat(0);
+  if (strcmp(key, "k1_launches") == 0) return get_k1_stat(1);
+  if (strcmp(key, "k1_sequences") == 0) return get_k1_stat(2);
+  return -1.0;
 }
 
 int nrms_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,

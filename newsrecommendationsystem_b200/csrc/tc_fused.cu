@@ -20,6 +20,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <utility>
+#include <vector>
 #include "tc_common.cuh"
 #include "tc_api.cuh"
 
@@ -45,13 +47,47 @@ int k1v3_run(int S, const CUtensorMap& tw, const float* src, const void* idx, in
 // NRMS_K1_VARIANT: 1 = first-generation K1 (CUDA-core attention, fp32 C, TF32 K2); 2 (default) = tensor-core
 // attention; 3 = tensor-core attention with two heads in flight and P in tensor memory (TS-form MMA) -- measured
 // within 5 % of variant 2 this round (profiles/), kept selectable for the next round's pipelining work
+static int g_k1_variant = -1;
 static int k1_variant() {
-  static int v = -1;
-  if (v < 0) {
+  if (g_k1_variant < 0) {
     const char* e = getenv("NRMS_K1_VARIANT");
-    v = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 2;
+    g_k1_variant = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 2;
   }
-  return v;
+  return g_k1_variant;
+}
+// ---- optional live timing of the dominant kernel (bench.py's roofline): CUDA events around every K1 launch ----
+static bool g_time_k1 = false;
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_k1_events;
+static std::vector<int64_t> g_k1_seqs;
+void set_time_k1(bool on) {
+  g_time_k1 = on;
+  for (auto& e : g_k1_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  g_k1_events.clear();
+  g_k1_seqs.clear();
+}
+// key: 0 = total ms of the timed K1 launches, 1 = number of launches, 2 = sequences processed by them
+double get_k1_stat(int key) {
+  if (key == 1) return (double)g_k1_events.size();
+  if (key == 2) { double s = 0; for (auto v : g_k1_seqs) s += (double)v; return s; }
+  double total = 0;
+  for (auto& e : g_k1_events) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(e.second) == cudaSuccess && cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess) total += ms;
+  }
+  return total;
+}
+struct K1Timer {
+  cudaStream_t st; bool on; cudaEvent_t a, b;
+  K1Timer(cudaStream_t s, int64_t n, bool enable) : st(s), on(enable && g_time_k1 && g_k1_events.size() < 4096) {
+    if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); g_k1_seqs.push_back(n); }
+  }
+  ~K1Timer() { if (on) { cudaEventRecord(b, st); g_k1_events.emplace_back(a, b); } }
+};
+
+int set_k1_variant(int v) {
+  if (v < 1 || v > 3) return NRMS_E_INVALID;
+  g_k1_variant = v;
+  return NRMS_OK;
 }
 constexpr size_t W16_SLOT_BYTES = 655360;   // >= every variant's fp16 weight copy
 
@@ -571,8 +607,11 @@ static int run_fused(const float* src, const void* idx, int idx_kind, int64_t n_
     const float* src_c = idx_kind == 0 ? src + s0 * S * D : src;
     const void* idx_c = idx_kind == 0 ? nullptr : (const void*)((const char*)idx + (size_t)s0 * S * idx_elem);
     if (variant >= 2) {
-      if (int rc = (variant == 3 ? k1v3_run(S, tw, src_c, idx_c, idx_kind, n, bqkv, Cbuf, st)
-                                 : k1v2_run(S, tw, src_c, idx_c, idx_kind, n, bqkv, Cbuf, st))) return rc;
+      {
+        K1Timer timer(st, n, S == 50);    // only the user-encoder launches (the dominant kernel) are timed
+        if (int rc = (variant == 3 ? k1v3_run(S, tw, src_c, idx_c, idx_kind, n, bqkv, Cbuf, st)
+                                   : k1v2_run(S, tw, src_c, idx_c, idx_kind, n, bqkv, Cbuf, st))) return rc;
+      }
       if (int rc = k2v2_run(S, twa, Cbuf, n, ba, qa, out + s0 * D, st)) return rc;
       continue;
     } else {

@@ -375,3 +375,28 @@ def test_unsupported_shape_and_cpu_inputs_fail_loudly(dev, golden_sd):
         m.get_news_vector({"title": torch.zeros(4, 21, dtype=torch.long)})     # title length 21 not compiled
     with pytest.raises(RuntimeError):
         ops.click_score(torch.zeros(2, 3, 300), torch.zeros(2, 300))           # CPU tensors: no fallback
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_fused_kernel_generations_agree_with_oracle(dev, lib, golden_sd, variant):
+    """All three generations of the fused tensor-mode encoder kernel (CUDA-core attention; tcgen05 attention;
+    two heads in flight with P in tensor memory) stay inside the 1e-3 tolerance, news and users."""
+    from newsrecommendationsystem_b200 import synthetic
+    assert lib.nrms_set_option(b"k1_variant", variant) == 0
+    try:
+        m = make_model(golden_sd, dev, "tf32")
+        toks = synthetic.make_news(777, num_words=Cfg.num_words, seed=500 + variant)
+        toks[11] = 0
+        ref_n, _ = O.news_encoder_forward(golden_sd, toks)
+        rng = np.random.default_rng(variant)
+        ux = (rng.standard_normal((93, 50, 300)) * 0.4).astype(np.float32)
+        ux[5, :40] = 0
+        ref_u, _ = O.user_encoder_forward(golden_sd, ux)
+        with torch.no_grad():
+            nv = m.get_news_vector({"title": torch.from_numpy(toks)})
+            uv = m.get_user_vector(t(ux, dev))
+        assert rel_l2_rows(nv.cpu().numpy(), ref_n) < TOL_VEC["tf32"]
+        assert rel_l2_rows(uv.cpu().numpy(), ref_u) < TOL_VEC["tf32"]
+    finally:
+        lib.nrms_set_option(b"k1_variant", 2)
+    assert lib.nrms_set_option(b"k1_variant", 9) == 1 and lib.nrms_set_option(b"nope", 1) == 1
