@@ -124,6 +124,16 @@ int nrms_user_encoder_bwd(const float* d_out, int64_t n_users, int S,
                           void* workspace, size_t workspace_bytes,
                           int mode, void* stream);
 
+/* Standalone L0 blocks (inference only; inside the encoders they are fused):
+ *   nrms_mhsa_fwd      MultiHeadSelfAttention.forward(Q) with K=V=Q, length=None   multihead_self.py:46-76
+ *                      x [n_seq,S,300] -> ctx [n_seq,S,300]; workspace >= n_seq*S*900*4 bytes
+ *   nrms_additive_fwd  AdditiveAttention.forward                                   additive.py:27-53
+ *                      c [n_seq,S,300] -> out [n_seq,300];   workspace >= n_seq*S*(200+1)*4 + 256 bytes */
+int nrms_mhsa_fwd(const float* x, int64_t n_seq, int S, const float* wqkv, const float* bqkv, float* ctx,
+                  void* workspace, size_t workspace_bytes, int mode, void* stream);
+int nrms_additive_fwd(const float* c, int64_t n_seq, int S, const float* wa, const float* ba, const float* qa,
+                      float* out, void* workspace, size_t workspace_bytes, int mode, void* stream);
+
 /* ---- click predictor --------------------------------------------------------------- */
 /* scores[b,c] = cand[b,c,:] . user[b,:]     cand [B,C,X], user [B,X] */
 int nrms_score_fwd(const float* cand, const float* user, int64_t B, int C, int X,

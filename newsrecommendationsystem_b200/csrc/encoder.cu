@@ -346,6 +346,52 @@ int nrms_user_encoder_bwd(const float* d_out, int64_t n_users, int S, const floa
                           st);
 }
 
+// ---- standalone L0 blocks (inference): MultiHeadSelfAttention.forward / AdditiveAttention.forward ----
+int nrms_mhsa_fwd(const float* x, int64_t n_seq, int S, const float* wqkv, const float* bqkv, float* ctx,
+                  void* workspace, size_t workspace_bytes, int mode, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (int rc = check_common(S, mode)) return rc;
+  NRMS_CHECK_ARG(n_seq >= 0, NRMS_E_INVALID, "bad sizes");
+  if (n_seq == 0) return NRMS_OK;
+  NRMS_CHECK_ARG(x && wqkv && bqkv && ctx, NRMS_E_INVALID, "null pointer");
+  NRMS_CHECK_ARG(aligned16(x) && aligned16(wqkv) && aligned16(bqkv) && aligned16(ctx), NRMS_E_INVALID,
+                 "pointers must be 16-byte aligned");
+  const int64_t rows = n_seq * S;
+  const size_t need = (size_t)rows * D3 * sizeof(float);
+  NRMS_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= need, NRMS_E_WORKSPACE,
+                 "workspace too small: need %zu bytes", need);
+  float* qkv = reinterpret_cast<float*>(workspace);
+  if (int rc = gemm_nt_bias(x, D, wqkv, D, bqkv, qkv, D3, rows, D3, D, mode, st)) return rc;
+  cudaError_t e = (S == 20) ? launch_attention_fwd<20, 15>(qkv, ctx, n_seq, 0.f, 0, 0, st)
+                            : launch_attention_fwd<50, 5>(qkv, ctx, n_seq, 0.f, 0, 0, st);
+  if (e != cudaSuccess) return cuda_fail(e, "attention_fwd");
+  return NRMS_OK;
+}
+
+int nrms_additive_fwd(const float* c, int64_t n_seq, int S, const float* wa, const float* ba, const float* qa,
+                      float* out, void* workspace, size_t workspace_bytes, int mode, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (int rc = check_common(S, mode)) return rc;
+  NRMS_CHECK_ARG(n_seq >= 0, NRMS_E_INVALID, "bad sizes");
+  if (n_seq == 0) return NRMS_OK;
+  NRMS_CHECK_ARG(c && wa && ba && qa && out, NRMS_E_INVALID, "null pointer");
+  NRMS_CHECK_ARG(aligned16(c) && aligned16(wa) && aligned16(ba) && aligned16(out), NRMS_E_INVALID,
+                 "pointers must be 16-byte aligned");
+  const int64_t rows = n_seq * S;
+  const size_t t_bytes = align_up((size_t)rows * QD * sizeof(float), 256);
+  const size_t need = t_bytes + (size_t)rows * sizeof(float);
+  NRMS_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= need, NRMS_E_WORKSPACE,
+                 "workspace too small: need %zu bytes", need);
+  float* t = reinterpret_cast<float*>(workspace);
+  float* w = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + t_bytes);
+  if (int rc = gemm_nt_bias(c, D, wa, D, ba, t, QD, rows, QD, D, mode, st)) return rc;
+  int64_t gx = n_seq < (int64_t)num_sms() * 8 ? n_seq : (int64_t)num_sms() * 8;
+  if (S == 20) additive_fwd_kernel<20><<<(unsigned)gx, 256, 0, st>>>(c, t, qa, w, out, n_seq);
+  else additive_fwd_kernel<50><<<(unsigned)gx, 256, 0, st>>>(c, t, qa, w, out, n_seq);
+  NRMS_LAUNCH_CHECK("additive_fwd");
+  return NRMS_OK;
+}
+
 int nrms_set_option(const char* key, int value) {
   NRMS_CHECK_ARG(key != nullptr, NRMS_E_INVALID, "null option key");
   if (strcmp(key, "k1_variant") == 0) {

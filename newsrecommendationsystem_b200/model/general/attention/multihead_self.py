@@ -33,7 +33,16 @@ class MultiHeadSelfAttention(nn.Module):
                 torch.cat([self.W_Q.bias, self.W_K.bias, self.W_V.bias], dim=0))
 
     def forward(self, Q, K=None, V=None, length=None):
-        raise NotImplementedError(
-            "MultiHeadSelfAttention is fused into the encoder kernels of libnrms_b200; call the owning "
-            "NewsEncoder / UserEncoder (the reference never calls this block on its own in NRMS, and never "
-            "passes K, V or length: src/model/NRMS/news_encoder.py:41, user_encoder.py:23)")
+        """Standalone use (inference).  Inside NewsEncoder / UserEncoder this block is fused into the encoder
+        kernels; NRMS never passes K, V or length (src/model/NRMS/news_encoder.py:41, user_encoder.py:23), so
+        only the self-attention, unmasked form is compiled -- anything else fails loudly."""
+        if (K is not None and K is not Q) or (V is not None and V is not Q) or length is not None:
+            raise NotImplementedError("libnrms_b200 compiles MultiHeadSelfAttention for K = V = Q and length=None "
+                                      "(the only form NRMS uses)")
+        if torch.is_grad_enabled() and (Q.requires_grad or self.W_Q.weight.requires_grad):
+            raise NotImplementedError("standalone MultiHeadSelfAttention.forward is inference-only; training goes "
+                                      "through NewsEncoder / UserEncoder (use torch.no_grad() here)")
+        from .... import ops
+        from ....config import resolve_mode
+        wqkv, bqkv = self.packed()
+        return ops.mhsa_forward(Q.to(self.W_Q.weight.device), wqkv, bqkv, mode=resolve_mode(None, getattr(self, "precision", None)))

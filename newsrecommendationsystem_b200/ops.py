@@ -274,3 +274,35 @@ def gemm_nt(a, b, bias=None, mode=_lib.MODE_TF32):
     check(lib.nrms_gemm_nt(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(bias), ptr(c), c.stride(0), M, N, K, mode,
                            stream_ptr(a.device)), "nrms_gemm_nt")
     return c
+
+
+@torch.no_grad()
+def mhsa_forward(x, wqkv, bqkv, mode=_lib.MODE_TF32):
+    """Standalone MultiHeadSelfAttention.forward(Q) (K=V=Q, no mask), inference only."""
+    lib = _lib.load()
+    _require_cuda(x, wqkv, bqkv)
+    n, S, d = x.shape
+    if d != D:
+        raise RuntimeError(f"compiled for d_model {D}, got {d}")
+    x_c, w_c, b_c = map(_f32c, (x, wqkv, bqkv))
+    ctx = torch.empty_like(x_c)
+    ws = _bytes(n * S * 3 * D * 4, x.device)
+    check(lib.nrms_mhsa_fwd(ptr(x_c), n, S, ptr(w_c), ptr(b_c), ptr(ctx), ptr(ws), ws.numel(), mode,
+                            stream_ptr(x.device)), "nrms_mhsa_fwd")
+    return ctx
+
+
+@torch.no_grad()
+def additive_forward(c, wa, ba, qa, mode=_lib.MODE_TF32):
+    """Standalone AdditiveAttention.forward, inference only."""
+    lib = _lib.load()
+    _require_cuda(c, wa, ba, qa)
+    n, S, d = c.shape
+    if d != D or wa.shape[0] != QD:
+        raise RuntimeError(f"compiled for candidate dim {D} / query dim {QD}")
+    c_c, wa_c, ba_c, qa_c = map(_f32c, (c, wa, ba, qa))
+    out = torch.empty((n, D), dtype=torch.float32, device=c.device)
+    ws = _bytes(n * S * (QD + 1) * 4 + 512, c.device)
+    check(lib.nrms_additive_fwd(ptr(c_c), n, S, ptr(wa_c), ptr(ba_c), ptr(qa_c), ptr(out), ptr(ws), ws.numel(), mode,
+                                stream_ptr(c.device)), "nrms_additive_fwd")
+    return out

@@ -400,3 +400,25 @@ def test_fused_kernel_generations_agree_with_oracle(dev, lib, golden_sd, variant
     finally:
         lib.nrms_set_option(b"k1_variant", 2)
     assert lib.nrms_set_option(b"k1_variant", 9) == 1 and lib.nrms_set_option(b"nope", 1) == 1
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_standalone_l0_blocks(dev, golden_sd, precision):
+    """MultiHeadSelfAttention.forward / AdditiveAttention.forward called on their own (reference L0 API)."""
+    m = make_model(golden_sd, dev, precision)
+    rng = np.random.default_rng(12)
+    x = (rng.standard_normal((7, 20, 300)) * 0.5).astype(np.float32)
+    p_ = O.enc_params(golden_sd, "news_encoder")
+    ref_c, _ = O.mhsa_forward(x, p_, 15)
+    ref_o, _ = O.additive_forward(ref_c, p_)
+    att, add = m.news_encoder.multihead_self_attention, m.news_encoder.additive_attention
+    att.precision = add.precision = precision
+    with torch.no_grad():
+        c = att(t(x, dev))
+        o = add(t(ref_c, dev))
+    tol = 2e-5 if precision == "fp32" else 1e-3
+    assert rel_l2_rows(c.cpu().numpy(), ref_c) < tol
+    assert rel_l2_rows(o.cpu().numpy(), ref_o) < tol
+    with pytest.raises(NotImplementedError):
+        with torch.no_grad():
+            att(t(x, dev), length=torch.tensor([3] * 7))
