@@ -63,7 +63,8 @@ int nrms_abi_version(void);
 int64_t nrms_launch_count(void);
 
 /* Tuning / A-B switches.  "k1_variant": fused tensor-mode encoder kernel generation
- * (1 = CUDA-core attention, 2 = tcgen05 attention [default], 3 = tcgen05 attention, two heads in flight). */
+ * (1 = CUDA-core attention, 2 = tcgen05 attention, 3 = tcgen05 attention with two heads in flight,
+ *  4 [default] = 3 + TMA-gathered fp16 source rows, bias/scale folded into the GEMM, q read from tensor memory). */
 int nrms_set_option(const char* key, int value);
 /* "time_k1" = 1 brackets every user-encoder K1 launch with CUDA events on the launching stream (clears the
  * previous record); nrms_get_stat("k1_ms" | "k1_launches" | "k1_sequences") reads the totals back (syncs on
@@ -74,8 +75,10 @@ double nrms_get_stat(const char* key);
 /* Bytes of the saved-for-backward stash of one encoder call over n_seq sequences of length S
  * (X, QKV, C, T, w).  The same stash is written by *_fwd (when non-NULL) and read by *_bwd. */
 size_t nrms_encoder_stash_bytes(int64_t n_seq, int S);
-/* Scratch bytes for one encoder fwd / bwd call (mode-dependent). */
-size_t nrms_encoder_fwd_workspace_bytes(int64_t n_seq, int S, int mode, int training);
+/* Scratch bytes for one encoder fwd / bwd call (mode-dependent).  n_src_rows: rows of the gather source of the
+ * call (num_words for the news encoder, n_rows of the table for the indexed user encoder, 0 for dense input) --
+ * the tensor-mode inference path keeps an fp16 copy of that source in the workspace. */
+size_t nrms_encoder_fwd_workspace_bytes(int64_t n_seq, int S, int mode, int training, int64_t n_src_rows);
 size_t nrms_encoder_bwd_workspace_bytes(int64_t n_seq, int S, int mode);
 
 /* ---- encoders ---------------------------------------------------------------------- */
@@ -104,10 +107,10 @@ int nrms_news_encoder_bwd(const float* d_out, const int64_t* tokens, int64_t n_t
                           float dropout_p, uint64_t seed, uint64_t offset,
                           int mode, void* stream);
 
-/* User encoder forward.  Input rows are either dense x [n_users, S, 300] (rows == NULL) or
- * gathered from a table: x = table [n_rows,300], rows int32 [n_users, S] (evaluate.py:220-224;
- * the PADDED_NEWS zero vector is a zero row of the table). */
-int nrms_user_encoder_fwd(const float* x, const int32_t* rows, int64_t n_users, int S,
+/* User encoder forward.  Input rows are either dense x [n_users, S, 300] (rows == NULL, n_rows ignored) or
+ * gathered from a table: x = table [n_rows,300], rows int32 [n_users, S] with values in [0, n_rows)
+ * (evaluate.py:220-224; the PADDED_NEWS zero vector is a zero row of the table). */
+int nrms_user_encoder_fwd(const float* x, int64_t n_rows, const int32_t* rows, int64_t n_users, int S,
                           const float* wqkv, const float* bqkv,
                           const float* wa, const float* ba, const float* qa,
                           float* out, void* stash,

@@ -25,13 +25,13 @@ SIGNATURES = {
     "nrms_set_option": (_i32, [C.c_char_p, _i32]),
     "nrms_get_stat": (C.c_double, [C.c_char_p]),
     "nrms_encoder_stash_bytes": (_sz, [_i64, _i32]),
-    "nrms_encoder_fwd_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32]),
+    "nrms_encoder_fwd_workspace_bytes": (_sz, [_i64, _i32, _i32, _i32, _i64]),
     "nrms_encoder_bwd_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "nrms_news_encoder_fwd": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                      _f32, _u64, _u64, _i32, _vp]),
     "nrms_news_encoder_bwd": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                      _vp, _sz, _f32, _u64, _u64, _i32, _vp]),
-    "nrms_user_encoder_fwd": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),
+    "nrms_user_encoder_fwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),
     "nrms_user_encoder_bwd": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                      _i32, _vp]),
     "nrms_mhsa_fwd": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),

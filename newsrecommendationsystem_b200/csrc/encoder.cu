@@ -186,11 +186,11 @@ size_t nrms_encoder_stash_bytes(int64_t n_seq, int S) {
   return carve_stash(nullptr, n_seq * S).bytes;
 }
 
-size_t nrms_encoder_fwd_workspace_bytes(int64_t n_seq, int S, int mode, int training) {
+size_t nrms_encoder_fwd_workspace_bytes(int64_t n_seq, int S, int mode, int training, int64_t n_src_rows) {
   if (n_seq <= 0 || S <= 0) return 0;
   if (training) return 256;
   if (mode == NRMS_MODE_TF32) {
-    size_t fused = tc_fused_workspace_bytes(n_seq, S);
+    size_t fused = tc_fused_workspace_bytes(n_seq, S, n_src_rows);
     if (fused != (size_t)-1) return fused + 256;
   }
   int64_t chunk_seq = INFER_CHUNK_ROWS / S;
@@ -230,8 +230,9 @@ int nrms_news_encoder_fwd(const int64_t* tokens, int64_t n_titles, int L, const 
     return encoder_core_fwd(s, n_titles, L, wqkv, bqkv, wa, ba, qa, out, dropout_p, seed, offset, 0, mode, st);
   }
   // inference
-  if (mode == NRMS_MODE_TF32 && dropout_p == 0.f && tc_fused_workspace_bytes(n_titles, L) != (size_t)-1) {
-    return tc_encoder_fused(emb, tokens, 1, n_titles, L, wqkv, bqkv, wa, ba, qa, out, workspace, workspace_bytes, st);
+  if (mode == NRMS_MODE_TF32 && dropout_p == 0.f && tc_fused_workspace_bytes(n_titles, L, num_words) != (size_t)-1) {
+    return tc_encoder_fused(emb, num_words, tokens, 1, n_titles, L, wqkv, bqkv, wa, ba, qa, out, workspace,
+                            workspace_bytes, st);
   }
   const int64_t chunk_seq = INFER_CHUNK_ROWS / L;
   const int64_t first = n_titles < chunk_seq ? n_titles : chunk_seq;
@@ -283,7 +284,7 @@ int nrms_news_encoder_bwd(const float* d_out, const int64_t* tokens, int64_t n_t
   return NRMS_OK;
 }
 
-int nrms_user_encoder_fwd(const float* x, const int32_t* rows_idx, int64_t n_users, int S, const float* wqkv,
+int nrms_user_encoder_fwd(const float* x, int64_t n_rows, const int32_t* rows_idx, int64_t n_users, int S, const float* wqkv,
                           const float* bqkv, const float* wa, const float* ba, const float* qa, float* out,
                           void* stash, void* workspace, size_t workspace_bytes, int mode, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -300,9 +301,10 @@ int nrms_user_encoder_fwd(const float* x, const int32_t* rows_idx, int64_t n_use
     NRMS_CUDA(cudaMemcpyAsync(s.x, x, (size_t)n_users * S * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return encoder_core_fwd(s, n_users, S, wqkv, bqkv, wa, ba, qa, out, 0.f, 0, 0, 0, mode, st);
   }
-  if (mode == NRMS_MODE_TF32 && tc_fused_workspace_bytes(n_users, S) != (size_t)-1) {
-    return tc_encoder_fused(x, rows_idx, rows_idx ? 2 : 0, n_users, S, wqkv, bqkv, wa, ba, qa, out, workspace,
-                            workspace_bytes, st);
+  NRMS_CHECK_ARG(rows_idx == nullptr || n_rows > 0, NRMS_E_INVALID, "indexed input needs n_rows (rows of the table)");
+  if (mode == NRMS_MODE_TF32 && tc_fused_workspace_bytes(n_users, S, rows_idx ? n_rows : 0) != (size_t)-1) {
+    return tc_encoder_fused(x, rows_idx ? n_rows : 0, rows_idx, rows_idx ? 2 : 0, n_users, S, wqkv, bqkv, wa, ba, qa, out,
+                            workspace, workspace_bytes, st);
   }
   const int64_t chunk_seq = INFER_CHUNK_ROWS / S;
   const int64_t first = n_users < chunk_seq ? n_users : chunk_seq;
@@ -395,7 +397,7 @@ int nrms_additive_fwd(const float* c, int64_t n_seq, int S, const float* wa, con
 int nrms_set_option(const char* key, int value) {
   NRMS_CHECK_ARG(key != nullptr, NRMS_E_INVALID, "null option key");
   if (strcmp(key, "k1_variant") == 0) {
-    NRMS_CHECK_ARG(set_k1_variant(value) == NRMS_OK, NRMS_E_INVALID, "k1_variant must be 1, 2 or 3");
+    NRMS_CHECK_ARG(set_k1_variant(value) == NRMS_OK, NRMS_E_INVALID, "k1_variant must be 1..4");
     return NRMS_OK;
   }
   if (strcmp(key, "time_k1") == 0) {

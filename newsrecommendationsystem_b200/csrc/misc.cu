@@ -281,7 +281,7 @@ using namespace nrms;
 extern "C" {
 
 const char* nrms_last_error(void) { return g_err; }
-int nrms_abi_version(void) { return 1; }
+int nrms_abi_version(void) { return 2; }
 int64_t nrms_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 int nrms_score_fwd(const float* cand, const float* user, int64_t B, int C, int X, float* scores, void* stream) {

@@ -13,12 +13,13 @@ int tc_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, const f
 // additive GEMM (tcgen05) -> tanh/softmax/pool (K2).  Input rows come from `src` [*,300]:
 //   idx_kind 0: dense rows (sequence s, position i -> row s*S+i), 1: int64 ids, 2: int32 ids.
 // tc_fused_workspace_bytes returns (size_t)-1 when the fused path does not apply (S not 20/50).
-size_t tc_fused_workspace_bytes(int64_t n_seq, int S);
-int tc_encoder_fused(const float* src, const void* idx, int idx_kind, int64_t n_seq, int S, const float* wqkv,
-                     const float* bqkv, const float* wa, const float* ba, const float* qa, float* out,
+// n_src_rows = rows of `src` when it is a gather source (idx_kind 1/2), 0 for dense input.
+size_t tc_fused_workspace_bytes(int64_t n_seq, int S, int64_t n_src_rows);
+int tc_encoder_fused(const float* src, int64_t n_src_rows, const void* idx, int idx_kind, int64_t n_seq, int S,
+                     const float* wqkv, const float* bqkv, const float* wa, const float* ba, const float* qa, float* out,
                      void* workspace, size_t workspace_bytes, cudaStream_t st);
 
-int set_k1_variant(int v);   // 1..3, see tc_fused.cu
+int set_k1_variant(int v);   // 1..4, see tc_fused.cu
 void set_time_k1(bool on);   // CUDA-event timing of the user-encoder K1 launches (bench.py roofline)
 double get_k1_stat(int key); // 0 total ms, 1 launches, 2 sequences
 

@@ -47,11 +47,17 @@ int k1v3_run(int S, const CUtensorMap& tw, const float* src, const void* idx, in
 // NRMS_K1_VARIANT: 1 = first-generation K1 (CUDA-core attention, fp32 C, TF32 K2); 2 (default) = tensor-core
 // attention; 3 = tensor-core attention with two heads in flight and P in tensor memory (TS-form MMA) -- measured
 // within 5 % of variant 2 this round (profiles/), kept selectable for the next round's pipelining work
+// K1 v4 (tc_fused5.cu): TMA-gathered fp16 source rows, bias/scale folded into the GEMM, q consumed from tensor memory
+size_t k1v4_src16_bytes(int64_t n_rows);
+int k1v4_prepare(const float* wqkv, const float* bqkv, void* w16, CUtensorMap* tw, cudaStream_t st);
+int k1v4_pack_src(const float* src, int64_t n_rows, void* src16, CUtensorMap* ts, cudaStream_t st);
+int k1v4_run(int S, const CUtensorMap& tw, const CUtensorMap& ts, const void* idx, int idx_kind, int64_t n,
+             int null_row, void* Cbuf, cudaStream_t st);
 static int g_k1_variant = -1;
 static int k1_variant() {
   if (g_k1_variant < 0) {
     const char* e = getenv("NRMS_K1_VARIANT");
-    g_k1_variant = (e && e[0] >= '1' && e[0] <= '3') ? (e[0] - '0') : 2;
+    g_k1_variant = (e && e[0] >= '1' && e[0] <= '4') ? (e[0] - '0') : 4;
   }
   return g_k1_variant;
 }
@@ -85,7 +91,7 @@ struct K1Timer {
 };
 
 int set_k1_variant(int v) {
-  if (v < 1 || v > 3) return NRMS_E_INVALID;
+  if (v < 1 || v > 4) return NRMS_E_INVALID;
   g_k1_variant = v;
   return NRMS_OK;
 }
@@ -563,9 +569,14 @@ constexpr size_t W16_BYTES = (size_t)D3 * W16_LD * 2;   // 576,000 (a multiple o
 template <int S, int SPT>
 static int64_t fused_chunk_seq() { return (int64_t)num_sms() * SPT * 8; }   // 8 full waves of tiles per launch
 
+// workspace: [fp16 W_qkv copy][fp16 W_a copy][fp16 gather source (variant 4)][context rows C of one chunk]
+static size_t fused_src16_bytes(int idx_kind_dense, int64_t n_src_rows, int64_t chunk_rows) {
+  return align_up(k1v4_src16_bytes(idx_kind_dense ? chunk_rows : n_src_rows), 1024);
+}
+
 template <int S, int SPT>
-static int run_fused(const float* src, const void* idx, int idx_kind, int64_t n_seq, const float* wqkv,
-                     const float* bqkv, const float* wa, const float* ba, const float* qa, float* out,
+static int run_fused(const float* src, int64_t n_src_rows, const void* idx, int idx_kind, int64_t n_seq,
+                     const float* wqkv, const float* bqkv, const float* wa, const float* ba, const float* qa, float* out,
                      void* workspace, size_t workspace_bytes, cudaStream_t st) {
   using Cfg = K1<S, SPT>;
   static bool configured = false;
@@ -577,19 +588,27 @@ static int run_fused(const float* src, const void* idx, int idx_kind, int64_t n_
     configured = true;
   }
   const int variant = k1_variant();
-  // variant 2 tiles: 5 titles / 2 users as well, so the chunking (4 waves of tiles) is shared
+  // every variant tiles 5 titles / 2 users, so the chunking (8 waves of tiles) is shared
   const int64_t chunk = fused_chunk_seq<S, SPT>();
   const int64_t first = n_seq < chunk ? n_seq : chunk;
-  const size_t need = W16_SLOT_BYTES + WA16_SLOT_BYTES + (size_t)first * S * D * sizeof(float);
+  const size_t src16_bytes = fused_src16_bytes(idx_kind == 0, n_src_rows, first * S);
+  const size_t need = W16_SLOT_BYTES + WA16_SLOT_BYTES + src16_bytes + (size_t)first * S * D * sizeof(float);
   NRMS_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= need, NRMS_E_WORKSPACE,
                  "workspace too small: need %zu bytes", need);
   __half* w16 = reinterpret_cast<__half*>(workspace);
   void* wa16 = reinterpret_cast<char*>(workspace) + W16_SLOT_BYTES;
-  float* Cbuf = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + W16_SLOT_BYTES + WA16_SLOT_BYTES);
-  alignas(64) CUtensorMap tw, twa, tc_;
+  void* src16 = reinterpret_cast<char*>(workspace) + W16_SLOT_BYTES + WA16_SLOT_BYTES;
+  float* Cbuf = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + W16_SLOT_BYTES + WA16_SLOT_BYTES + src16_bytes);
+  alignas(64) CUtensorMap tw, twa, tc_, ts;
   if (variant >= 2) {
-    if (int rc = (variant == 3 ? k1v3_prepare(wqkv, w16, &tw, st) : k1v2_prepare(wqkv, w16, &tw, st))) return rc;
-    if (int rc = k2v2_prepare(wa, wa16, &twa, st)) return rc;
+    int rc = variant == 4 ? k1v4_prepare(wqkv, bqkv, w16, &tw, st)
+                          : (variant == 3 ? k1v3_prepare(wqkv, w16, &tw, st) : k1v2_prepare(wqkv, w16, &tw, st));
+    if (rc) return rc;
+    if (int rc2 = k2v2_prepare(wa, wa16, &twa, st)) return rc2;
+    if (variant == 4 && idx_kind != 0) {
+      NRMS_CHECK_ARG(n_src_rows > 0, NRMS_E_INVALID, "indexed input needs the row count of its source table");
+      if (int rc3 = k1v4_pack_src(src, n_src_rows, src16, &ts, st)) return rc3;
+    }
   } else {
     wqkv_to_f16_kernel<<<148, 256, 0, st>>>(wqkv, w16);
     NRMS_LAUNCH_CHECK("wqkv_to_f16_kernel");
@@ -607,10 +626,18 @@ static int run_fused(const float* src, const void* idx, int idx_kind, int64_t n_
     const float* src_c = idx_kind == 0 ? src + s0 * S * D : src;
     const void* idx_c = idx_kind == 0 ? nullptr : (const void*)((const char*)idx + (size_t)s0 * S * idx_elem);
     if (variant >= 2) {
+      if (variant == 4 && idx_kind == 0) {   // dense rows: this chunk's rows become the fp16 gather source
+        if (int rc = k1v4_pack_src(src_c, n * S, src16, &ts, st)) return rc;
+      }
       {
         K1Timer timer(st, n, S == 50);    // only the user-encoder launches (the dominant kernel) are timed
-        if (int rc = (variant == 3 ? k1v3_run(S, tw, src_c, idx_c, idx_kind, n, bqkv, Cbuf, st)
-                                   : k1v2_run(S, tw, src_c, idx_c, idx_kind, n, bqkv, Cbuf, st))) return rc;
+        int rc;
+        if (variant == 4)
+          rc = k1v4_run(S, tw, ts, idx_c, idx_kind, n, (int)(idx_kind == 0 ? n * S : n_src_rows), Cbuf, st);
+        else
+          rc = variant == 3 ? k1v3_run(S, tw, src_c, idx_c, idx_kind, n, bqkv, Cbuf, st)
+                            : k1v2_run(S, tw, src_c, idx_c, idx_kind, n, bqkv, Cbuf, st);
+        if (rc) return rc;
       }
       if (int rc = k2v2_run(S, twa, Cbuf, n, ba, qa, out + s0 * D, st)) return rc;
       continue;
@@ -627,21 +654,23 @@ static int run_fused(const float* src, const void* idx, int idx_kind, int64_t n_
   return NRMS_OK;
 }
 
-size_t tc_fused_workspace_bytes(int64_t n_seq, int S) {
+// n_src_rows: rows of the gather source (vocabulary / news-vector table); 0 for dense input
+size_t tc_fused_workspace_bytes(int64_t n_seq, int S, int64_t n_src_rows) {
   if (n_seq <= 0) return (size_t)-1;
   int64_t chunk;
   if (S == 20) chunk = fused_chunk_seq<20, 5>();
   else if (S == 50) chunk = fused_chunk_seq<50, 2>();
   else return (size_t)-1;
   const int64_t first = n_seq < chunk ? n_seq : chunk;
-  return W16_SLOT_BYTES + WA16_SLOT_BYTES + (size_t)first * S * D * sizeof(float);
+  return W16_SLOT_BYTES + WA16_SLOT_BYTES + fused_src16_bytes(n_src_rows <= 0, n_src_rows, first * S) +
+         (size_t)first * S * D * sizeof(float);
 }
 
-int tc_encoder_fused(const float* src, const void* idx, int idx_kind, int64_t n_seq, int S, const float* wqkv,
-                     const float* bqkv, const float* wa, const float* ba, const float* qa, float* out,
+int tc_encoder_fused(const float* src, int64_t n_src_rows, const void* idx, int idx_kind, int64_t n_seq, int S,
+                     const float* wqkv, const float* bqkv, const float* wa, const float* ba, const float* qa, float* out,
                      void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  if (S == 20) return run_fused<20, 5>(src, idx, idx_kind, n_seq, wqkv, bqkv, wa, ba, qa, out, workspace, workspace_bytes, st);
-  if (S == 50) return run_fused<50, 2>(src, idx, idx_kind, n_seq, wqkv, bqkv, wa, ba, qa, out, workspace, workspace_bytes, st);
+  if (S == 20) return run_fused<20, 5>(src, n_src_rows, idx, idx_kind, n_seq, wqkv, bqkv, wa, ba, qa, out, workspace, workspace_bytes, st);
+  if (S == 50) return run_fused<50, 2>(src, n_src_rows, idx, idx_kind, n_seq, wqkv, bqkv, wa, ba, qa, out, workspace, workspace_bytes, st);
   set_error("fused encoder compiled for S = 20 or 50, got %d", S);
   return NRMS_E_UNSUPPORTED;
 }

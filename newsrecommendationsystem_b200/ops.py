@@ -54,7 +54,7 @@ class _NewsEncoderFn(torch.autograd.Function):
         stash = None
         if needs_grad:
             stash = _bytes(lib.nrms_encoder_stash_bytes(n, L), dev)
-        ws_bytes = lib.nrms_encoder_fwd_workspace_bytes(n, L, mode, 1 if needs_grad else 0)
+        ws_bytes = lib.nrms_encoder_fwd_workspace_bytes(n, L, mode, 1 if needs_grad else 0, emb_c.shape[0])
         ws = _bytes(ws_bytes, dev)
         check(lib.nrms_news_encoder_fwd(ptr(tokens), n, L, ptr(emb_c), emb_c.shape[0], ptr(wqkv_c), ptr(bqkv_c),
                                         ptr(wa_c), ptr(ba_c), ptr(qa_c), ptr(out), ptr(stash), ptr(ws), ws.numel(),
@@ -101,8 +101,8 @@ class _UserEncoderFn(torch.autograd.Function):
         out = torch.empty((n, D), dtype=torch.float32, device=dev)
         needs_grad = track_grad and any(ctx.needs_input_grad)
         stash = _bytes(lib.nrms_encoder_stash_bytes(n, S), dev) if needs_grad else None
-        ws = _bytes(lib.nrms_encoder_fwd_workspace_bytes(n, S, mode, 1 if needs_grad else 0), dev)
-        check(lib.nrms_user_encoder_fwd(ptr(x_c), None, n, S, ptr(wqkv_c), ptr(bqkv_c), ptr(wa_c), ptr(ba_c),
+        ws = _bytes(lib.nrms_encoder_fwd_workspace_bytes(n, S, mode, 1 if needs_grad else 0, 0), dev)
+        check(lib.nrms_user_encoder_fwd(ptr(x_c), 0, None, n, S, ptr(wqkv_c), ptr(bqkv_c), ptr(wa_c), ptr(ba_c),
                                         ptr(qa_c), ptr(out), ptr(stash), ptr(ws), ws.numel(), mode, stream_ptr(dev)),
               "nrms_user_encoder_fwd")
         if needs_grad:
@@ -203,9 +203,9 @@ def user_encoder_indexed(table, rows, wqkv, bqkv, wa, ba, qa, mode=_lib.MODE_TF3
     n, S = rows.shape
     dev = table.device
     out = torch.empty((n, D), dtype=torch.float32, device=dev)
-    ws = _bytes(lib.nrms_encoder_fwd_workspace_bytes(n, S, mode, 0), dev)
+    ws = _bytes(lib.nrms_encoder_fwd_workspace_bytes(n, S, mode, 0, table.shape[0]), dev)
     args = [_f32c(t) for t in (table, wqkv, bqkv, wa, ba, qa)]
-    check(lib.nrms_user_encoder_fwd(ptr(args[0]), ptr(rows), n, S, ptr(args[1]), ptr(args[2]), ptr(args[3]),
+    check(lib.nrms_user_encoder_fwd(ptr(args[0]), args[0].shape[0], ptr(rows), n, S, ptr(args[1]), ptr(args[2]), ptr(args[3]),
                                     ptr(args[4]), ptr(args[5]), ptr(out), None, ptr(ws), ws.numel(), mode,
                                     stream_ptr(dev)), "nrms_user_encoder_fwd(indexed)")
     return out

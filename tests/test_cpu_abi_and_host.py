@@ -48,7 +48,7 @@ def test_argument_count_matches_header():
 
 
 def test_version_and_error_paths_without_gpu(lib):
-    assert lib.nrms_abi_version() == 1
+    assert lib.nrms_abi_version() == 2
     # invalid arguments are rejected before any CUDA call; message is retrievable
     rc = lib.nrms_score_fwd(None, None, 4, 0, 300, None, None)
     assert rc == 1 and b"bad sizes" in lib.nrms_last_error()

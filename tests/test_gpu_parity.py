@@ -55,7 +55,7 @@ def t(a, dev):
 
 # ---------------------------------------------------------------------------------------------
 def test_library_loaded_and_versioned(lib):
-    assert lib.nrms_abi_version() == 1
+    assert lib.nrms_abi_version() == 2
 
 
 @pytest.mark.parametrize("mode", ["fp32", "tf32"])
@@ -87,7 +87,7 @@ def test_gather_bit_exact(dev, lib, golden, golden_sd):
     wqkv = torch.cat([sd[p["Wq"]], sd[p["Wk"]], sd[p["Wv"]]]).contiguous()
     bqkv = torch.cat([sd[p["bq"]], sd[p["bk"]], sd[p["bv"]]]).contiguous()
     stash = torch.zeros(lib.nrms_encoder_stash_bytes(n, L), dtype=torch.uint8, device=dev)
-    ws = torch.zeros(max(256, lib.nrms_encoder_fwd_workspace_bytes(n, L, MODE_FP32, 1)), dtype=torch.uint8, device=dev)
+    ws = torch.zeros(max(256, lib.nrms_encoder_fwd_workspace_bytes(n, L, MODE_FP32, 1, 0)), dtype=torch.uint8, device=dev)
     out = torch.empty(n, 300, device=dev)
     check(lib.nrms_news_encoder_fwd(ptr(toks), n, L, ptr(sd[O.EMB_KEY]), sd[O.EMB_KEY].shape[0], ptr(wqkv), ptr(bqkv),
                                     ptr(sd[p["Wa"]]), ptr(sd[p["ba"]]), ptr(sd[p["qa"]]), ptr(out), ptr(stash),
@@ -377,10 +377,11 @@ def test_unsupported_shape_and_cpu_inputs_fail_loudly(dev, golden_sd):
         ops.click_score(torch.zeros(2, 3, 300), torch.zeros(2, 300))           # CPU tensors: no fallback
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_fused_kernel_generations_agree_with_oracle(dev, lib, golden_sd, variant):
-    """All three generations of the fused tensor-mode encoder kernel (CUDA-core attention; tcgen05 attention;
-    two heads in flight with P in tensor memory) stay inside the 1e-3 tolerance, news and users."""
+    """All generations of the fused tensor-mode encoder kernel (CUDA-core attention; tcgen05 attention; two heads
+    in flight with P in tensor memory; TMA-gathered fp16 rows with the bias folded into the GEMM) stay inside the
+    1e-3 tolerance, news and users."""
     from newsrecommendationsystem_b200 import synthetic
     assert lib.nrms_set_option(b"k1_variant", variant) == 0
     try:
@@ -398,7 +399,7 @@ def test_fused_kernel_generations_agree_with_oracle(dev, lib, golden_sd, variant
         assert rel_l2_rows(nv.cpu().numpy(), ref_n) < TOL_VEC["tf32"]
         assert rel_l2_rows(uv.cpu().numpy(), ref_u) < TOL_VEC["tf32"]
     finally:
-        lib.nrms_set_option(b"k1_variant", 2)
+        lib.nrms_set_option(b"k1_variant", 4)
     assert lib.nrms_set_option(b"k1_variant", 9) == 1 and lib.nrms_set_option(b"nope", 1) == 1
 
 
