@@ -33,6 +33,8 @@ def build(force=False, verbose=False):
     extra = ["-Xptxas", "-v"] if verbose else []
     if os.environ.get("NRMS_K1_TRACE"):
         extra.append("-DNRMS_K1_TRACE")
+    for d in os.environ.get("NRMS_DEFINES", "").split():
+        extra.append("-D" + d)
 
     def cc(src):
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))

@@ -21,20 +21,28 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(bar) : "memory");
 }
-// Bounded wait: a protocol bug traps (~2 s) instead of hanging the GPU box.
+// Bounded wait: a protocol bug traps (after 2^28 polls, > 1 s) instead of hanging the GPU box.  Kept to a handful of
+// instructions with no clock reads, printf or calls: the wait is inlined dozens of times in the fused kernels, whose
+// code has to stay inside the instruction caches, and a call in the MMA-issue loops makes ptxas park the operand
+// descriptors in vector registers and pay two R2UR (~40 cycles each) per tcgen05.mma (measured: ~160 and ~100
+// cycles per MMA instead of the 64-cycle pipe floor).  -DNRMS_MBAR_DEBUG restores the printf report.
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
-  const long long t0 = clock64();
-  while (true) {
-    asm volatile(
-        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (clock64() - t0 > 4000000000LL) {
+  uint32_t polls = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++polls == (1u << 28)) {
+#ifdef NRMS_MBAR_DEBUG
       printf("nrms: mbarrier wait timeout (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
              (int)threadIdx.x, bar, parity);
+#endif
       __trap();
     }
   }
@@ -47,13 +55,14 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ bool elect_one() {
+__device__ __forceinline__ uint32_t elect_one_u32() {
   uint32_t pred = 0;
   asm volatile(
       "{ .reg .b32 r; .reg .pred p; elect.sync r|p, 0xffffffff; selp.u32 %0, 1, 0, p; }"
       : "=r"(pred)::"memory");
-  return pred != 0;
+  return pred;
 }
+__device__ __forceinline__ bool elect_one() { return elect_one_u32() != 0; }
 
 // ---- TMEM ---------------------------------------------------------------------------------
 // Whole-warp instructions.  ncols: power of two in [32, 512].
@@ -121,6 +130,55 @@ __device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, u
 // arrive on an mbarrier when all previously issued MMAs of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// ---- warp-converged issue ---------------------------------------------------------------------------------------
+// The *_p forms are executed by ALL lanes of a converged warp and take the elect.sync result as an operand: the
+// instruction itself is predicated inside the asm block.  Wrapped in `if (lane == 0)` / `if (elect_one())` ptxas
+// lowers every tcgen05.mma / commit to an ELECT + BRA.U.ANY "waterfall" (6-10 instructions, measured 60-160 cycles
+// per MMA from the issuing warp of K1); predicated in converged code it emits bare back-to-back UTCHMMA with the
+// descriptors in uniform registers.  The warp index feeding the role branch must be __shfl_sync-uniform.
+__device__ __forceinline__ void umma_f16_ss_p(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate, uint32_t elected) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, pe;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 pe, %5, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts_p(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate, uint32_t elected) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, pe;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 pe, %5, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts_p(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate, uint32_t elected) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, pe;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 pe, %5, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_p(uint32_t bar, uint32_t elected) {
+  asm volatile(
+      "{ .reg .pred pe; setp.ne.b32 pe, %1, 0;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0]; }" ::"r"(bar), "r"(elected)
+      : "memory");
 }
 
 // ---- TMEM -> registers: this thread's lane (row), 16 consecutive fp32 columns -----------------

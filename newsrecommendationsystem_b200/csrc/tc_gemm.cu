@@ -223,6 +223,21 @@ int make_tmap_k_major_f16(CUtensorMap* out, const void* base, int64_t rows, int 
   return NRMS_OK;
 }
 
+// fp16 row-major [rows, cols], un-swizzled box of box_rows x box_cols halfs (box_cols*2 % 16 == 0): TMA stores
+int make_tmap_store_f16(CUtensorMap* out, const void* base, int64_t rows, int cols, int64_t ld, int box_cols, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  NRMS_CHECK_ARG(fn != nullptr, NRMS_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NRMS_CHECK_ARG(r == CUDA_SUCCESS, NRMS_E_CUDA, "cuTensorMapEncodeTiled(store f16) failed with CUresult %d", (int)r);
+  return NRMS_OK;
+}
+
 int tc_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
                int64_t M, int N, int K, cudaStream_t st) {
   if (M <= 0) return NRMS_OK;
