@@ -53,11 +53,14 @@ int k1v4_prepare(const float* wqkv, const float* bqkv, void* w16, CUtensorMap* t
 int k1v4_pack_src(const float* src, int64_t n_rows, void* src16, CUtensorMap* ts, cudaStream_t st);
 int k1v4_run(int S, const CUtensorMap& tw, const CUtensorMap& ts, const void* idx, int idx_kind, int64_t n,
              int null_row, void* Cbuf, cudaStream_t st);
+// K1 v5 (tc_fused6.cu): v4 with two projection accumulators and P kept in place over the scores (default)
+int k1v5_run(int S, const CUtensorMap& tw, const CUtensorMap& ts, const void* idx, int idx_kind, int64_t n,
+             int null_row, void* Cbuf, cudaStream_t st);
 static int g_k1_variant = -1;
 static int k1_variant() {
   if (g_k1_variant < 0) {
     const char* e = getenv("NRMS_K1_VARIANT");
-    g_k1_variant = (e && e[0] >= '1' && e[0] <= '4') ? (e[0] - '0') : 4;
+    g_k1_variant = (e && e[0] >= '1' && e[0] <= '5') ? (e[0] - '0') : 5;
   }
   return g_k1_variant;
 }
@@ -91,7 +94,7 @@ struct K1Timer {
 };
 
 int set_k1_variant(int v) {
-  if (v < 1 || v > 4) return NRMS_E_INVALID;
+  if (v < 1 || v > 5) return NRMS_E_INVALID;
   g_k1_variant = v;
   return NRMS_OK;
 }
@@ -601,11 +604,11 @@ static int run_fused(const float* src, int64_t n_src_rows, const void* idx, int 
   float* Cbuf = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + W16_SLOT_BYTES + WA16_SLOT_BYTES + src16_bytes);
   alignas(64) CUtensorMap tw, twa, tc_, ts;
   if (variant >= 2) {
-    int rc = variant == 4 ? k1v4_prepare(wqkv, bqkv, w16, &tw, st)
+    int rc = variant >= 4 ? k1v4_prepare(wqkv, bqkv, w16, &tw, st)
                           : (variant == 3 ? k1v3_prepare(wqkv, w16, &tw, st) : k1v2_prepare(wqkv, w16, &tw, st));
     if (rc) return rc;
     if (int rc2 = k2v2_prepare(wa, wa16, &twa, st)) return rc2;
-    if (variant == 4 && idx_kind != 0) {
+    if (variant >= 4 && idx_kind != 0) {
       NRMS_CHECK_ARG(n_src_rows > 0, NRMS_E_INVALID, "indexed input needs the row count of its source table");
       if (int rc3 = k1v4_pack_src(src, n_src_rows, src16, &ts, st)) return rc3;
     }
@@ -626,13 +629,15 @@ static int run_fused(const float* src, int64_t n_src_rows, const void* idx, int 
     const float* src_c = idx_kind == 0 ? src + s0 * S * D : src;
     const void* idx_c = idx_kind == 0 ? nullptr : (const void*)((const char*)idx + (size_t)s0 * S * idx_elem);
     if (variant >= 2) {
-      if (variant == 4 && idx_kind == 0) {   // dense rows: this chunk's rows become the fp16 gather source
+      if (variant >= 4 && idx_kind == 0) {   // dense rows: this chunk's rows become the fp16 gather source
         if (int rc = k1v4_pack_src(src_c, n * S, src16, &ts, st)) return rc;
       }
       {
         K1Timer timer(st, n, S == 50);    // only the user-encoder launches (the dominant kernel) are timed
         int rc;
-        if (variant == 4)
+        if (variant == 5)
+          rc = k1v5_run(S, tw, ts, idx_c, idx_kind, n, (int)(idx_kind == 0 ? n * S : n_src_rows), Cbuf, st);
+        else if (variant == 4)
           rc = k1v4_run(S, tw, ts, idx_c, idx_kind, n, (int)(idx_kind == 0 ? n * S : n_src_rows), Cbuf, st);
         else
           rc = variant == 3 ? k1v3_run(S, tw, src_c, idx_c, idx_kind, n, bqkv, Cbuf, st)

@@ -1,4 +1,4 @@
-"""Debug: clock64 phase trace of K1 v4, block 0 (build with NRMS_K1_TRACE=1 python .../csrc/build.py --force).
+"""Debug: clock64 phase trace of K1 v5 (NRMS_K1_VARIANT=4: v4), block 0 (build with NRMS_K1_TRACE=1 python .../csrc/build.py --force).
 Tracers: 0 worker role 0 (warp 2), 1 worker role 1 (warp 6), 2 projection MMA issuer, 3 attention MMA issuer."""
 import ctypes, os, sys, collections
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -20,8 +20,8 @@ with torch.no_grad():
     for _ in range(3): f()
     torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 4096)(); cnt = (ctypes.c_int * 4)()
-lib.nrms_debug_read_trace4(buf, cnt)
-names = {20: "pass start", 21: "acc_full", 22: "W1a done", 23: "W1b done", 24: "s_ready a", 25: "s_ready b", 26: "W2a done",
+(lib.nrms_debug_read_trace5 if os.environ.get('NRMS_K1_VARIANT', '5') == '5' else lib.nrms_debug_read_trace4)(buf, cnt)
+names = {20: "pass start", 21: "acc_full", 22: "W1 done", 23: "W3fin done", 24: "s_ready a", 25: "s_ready b", 26: "W2a done",
          27: "W2b done", 28: "o_ready a", 29: "o_ready b", 30: "W3 done", 31: "staged",
          40: "P pass start", 41: "P acc_empty", 42: "P kc0", 43: "P kc1", 44: "P kc2", 45: "P kc3", 46: "P kc4",
          47: "P wait", 48: "P issued", 55: "A S issued", 56: "A O issued", 50: "A pass start", 51: "A kv a", 52: "A kv b", 53: "A p a", 54: "A p b"}

@@ -377,7 +377,7 @@ def test_unsupported_shape_and_cpu_inputs_fail_loudly(dev, golden_sd):
         ops.click_score(torch.zeros(2, 3, 300), torch.zeros(2, 300))           # CPU tensors: no fallback
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
 def test_fused_kernel_generations_agree_with_oracle(dev, lib, golden_sd, variant):
     """All generations of the fused tensor-mode encoder kernel (CUDA-core attention; tcgen05 attention; two heads
     in flight with P in tensor memory; TMA-gathered fp16 rows with the bias folded into the GEMM) stay inside the
@@ -399,7 +399,7 @@ def test_fused_kernel_generations_agree_with_oracle(dev, lib, golden_sd, variant
         assert rel_l2_rows(nv.cpu().numpy(), ref_n) < TOL_VEC["tf32"]
         assert rel_l2_rows(uv.cpu().numpy(), ref_u) < TOL_VEC["tf32"]
     finally:
-        lib.nrms_set_option(b"k1_variant", 4)
+        lib.nrms_set_option(b"k1_variant", 5)
     assert lib.nrms_set_option(b"k1_variant", 9) == 1 and lib.nrms_set_option(b"nope", 1) == 1
 
 
