@@ -34,11 +34,14 @@ static Stash carve_stash(void* base, int64_t rows) {
 constexpr int64_t INFER_CHUNK_ROWS = 2048 * 20;  // rows processed per pass in inference (reference batch 2048 titles)
 constexpr int REDUCE_BLOCKS = 296;
 
+// Tensor mode adds the transposed operand copies of the weight-gradient GEMMs (see encoder_core_bwd):
+// t1 [900, ldr] | t2 [300, ldr] (ldr = rows rounded up to 4) | wt [300, 900].
 struct BwdWs {
-  float *d_c, *d_u, *d_qkv, *d_x, *partial;
+  float *d_c, *d_u, *d_qkv, *d_x, *partial, *t1, *t2, *wt;
+  int64_t ldr;
   size_t bytes;
 };
-static BwdWs carve_bwd(void* base, int64_t rows, bool need_dx) {
+static BwdWs carve_bwd(void* base, int64_t rows, bool need_dx, int mode) {
   BwdWs s;
   char* p = reinterpret_cast<char*>(base);
   size_t off = 0;
@@ -52,6 +55,13 @@ static BwdWs carve_bwd(void* base, int64_t rows, bool need_dx) {
   s.d_qkv = take((size_t)rows * D3);
   s.d_x = need_dx ? take((size_t)rows * D) : nullptr;
   s.partial = take((size_t)REDUCE_BLOCKS * D3);
+  s.ldr = (rows + 3) / 4 * 4;
+  s.t1 = s.t2 = s.wt = nullptr;
+  if (mode == NRMS_MODE_TF32) {
+    s.t1 = take((size_t)s.ldr * D3);
+    s.t2 = take((size_t)s.ldr * D);
+    s.wt = take((size_t)D3 * D);
+  }
   s.bytes = off;
   return s;
 }
@@ -129,7 +139,15 @@ static int encoder_core_bwd(const Stash& s, const BwdWs& w, const float* d_out, 
                             const float* wqkv, const float* wa, const float* qa, float* d_x, float* d_wqkv,
                             float* d_bqkv, float* d_wa, float* d_ba, float* d_qa, float p2, uint64_t seed,
                             uint64_t offset, int mode, cudaStream_t st) {
-  (void)mode;  // backward contractions run in fp32 on the CUDA cores
+  // FP32 mode: every contraction on the CUDA cores (reference-exact up to summation order).  Tensor mode: the four
+  // GEMMs run on tcgen05 (TF32 operands rounded by the TMA unit, fp32 accumulation) through the K-major NT kernel:
+  //   dC  += dU   Wa        = NT(dU   [rows,200], Wa^T   [300,200])
+  //   dX   = dQKV Wqkv      = NT(dQKV [rows,900], Wqkv^T [300,900])
+  //   dWa   += dU^T   C     = NT(dU^T   [200,rows], C^T [300,rows])      split along K = rows, atomic epilogue
+  //   dWqkv += dQKV^T X     = NT(dQKV^T [900,rows], X^T [300,rows])
+  // so the row-major activations are transposed once per use (1.2 KB/row of extra traffic, a fraction of what the
+  // fp32 SGEMMs cost: measured 6.3 ms -> see profiles/).
+  const bool tc = (mode == NRMS_MODE_TF32);
   const int64_t rows = n_seq * S;
   int nb = (int)(n_seq < REDUCE_BLOCKS ? n_seq : REDUCE_BLOCKS);
   if (S == 20) additive_bwd_kernel<20><<<nb, 256, 0, st>>>(d_out, s.c, s.t, s.w, qa, w.d_c, w.d_u, w.partial, n_seq);
@@ -143,14 +161,26 @@ static int encoder_core_bwd(const Stash& s, const BwdWs& w, const float* d_out, 
   NRMS_LAUNCH_CHECK("colsum_du");
   partial_reduce_accum_kernel<<<1, 256, 0, st>>>(w.partial, cb, QD, d_ba);
   NRMS_LAUNCH_CHECK("dba_reduce");
-  // d_wa[200,300] += dU^T C   (reduction over rows, split-K + fp32 atomics)
   int splits = (int)((rows + 4095) / 4096);
   if (splits > 64) splits = 64;
-  cudaError_t e = sgemm_launch<1, 1, EPI_ATOMIC>(w.d_u, QD, s.c, D, nullptr, d_wa, D, QD, D, rows, splits, st);
-  if (e != cudaSuccess) return cuda_fail(e, "sgemm dWa");
-  // d_c += dU * Wa   ([rows,200] x [200,300])
-  e = sgemm_launch<0, 1, EPI_ACCUM>(w.d_u, QD, wa, D, nullptr, w.d_c, D, rows, D, QD, 1, st);
-  if (e != cudaSuccess) return cuda_fail(e, "sgemm dC");
+  cudaError_t e;
+  if (tc) {
+    // d_wa[200,300] += dU^T C
+    if (int rc = transpose_f32(w.d_u, QD, w.t1, w.ldr, rows, QD, st)) return rc;
+    if (int rc = transpose_f32(s.c, D, w.t2, w.ldr, rows, D, st)) return rc;
+    if (int rc = tc_gemm_nt_ex(w.t1, w.ldr, w.t2, w.ldr, nullptr, d_wa, D, QD, D, (int)rows,
+                               tc_gemm_auto_splits(QD, D, (int)rows), TC_EPI_ATOMIC, st)) return rc;
+    // d_c += dU * Wa
+    if (int rc = transpose_f32(wa, D, w.wt, QD, QD, D, st)) return rc;
+    if (int rc = tc_gemm_nt_ex(w.d_u, QD, w.wt, QD, nullptr, w.d_c, D, rows, D, QD, 1, TC_EPI_ACCUM, st)) return rc;
+  } else {
+    // d_wa[200,300] += dU^T C   (reduction over rows, split-K + fp32 atomics)
+    e = sgemm_launch<1, 1, EPI_ATOMIC>(w.d_u, QD, s.c, D, nullptr, d_wa, D, QD, D, rows, splits, st);
+    if (e != cudaSuccess) return cuda_fail(e, "sgemm dWa");
+    // d_c += dU * Wa   ([rows,200] x [200,300])
+    e = sgemm_launch<0, 1, EPI_ACCUM>(w.d_u, QD, wa, D, nullptr, w.d_c, D, rows, D, QD, 1, st);
+    if (e != cudaSuccess) return cuda_fail(e, "sgemm dC");
+  }
   // attention backward (applies the dropout-2 mask to d_c on load)
   if (S == 20) e = launch_attention_bwd<20, 15>(s.qkv, w.d_c, w.d_qkv, n_seq, p2, seed, offset, st);
   else e = launch_attention_bwd<50, 5>(s.qkv, w.d_c, w.d_qkv, n_seq, p2, seed, offset, st);
@@ -160,12 +190,23 @@ static int encoder_core_bwd(const Stash& s, const BwdWs& w, const float* d_out, 
   NRMS_LAUNCH_CHECK("colsum_dqkv");
   partial_reduce_accum_kernel<<<(D3 + 255) / 256, 256, 0, st>>>(w.partial, cb, D3, d_bqkv);
   NRMS_LAUNCH_CHECK("dbqkv_reduce");
-  // d_wqkv[900,300] += dQKV^T X
-  e = sgemm_launch<1, 1, EPI_ATOMIC>(w.d_qkv, D3, s.x, D, nullptr, d_wqkv, D, D3, D, rows, splits, st);
-  if (e != cudaSuccess) return cuda_fail(e, "sgemm dWqkv");
-  // d_x = dQKV * Wqkv   ([rows,900] x [900,300])
-  e = sgemm_launch<0, 1, EPI_STORE>(w.d_qkv, D3, wqkv, D, nullptr, d_x, D, rows, D, D3, 1, st);
-  if (e != cudaSuccess) return cuda_fail(e, "sgemm dX");
+  if (tc) {
+    // d_wqkv[900,300] += dQKV^T X
+    if (int rc = transpose_f32(w.d_qkv, D3, w.t1, w.ldr, rows, D3, st)) return rc;
+    if (int rc = transpose_f32(s.x, D, w.t2, w.ldr, rows, D, st)) return rc;
+    if (int rc = tc_gemm_nt_ex(w.t1, w.ldr, w.t2, w.ldr, nullptr, d_wqkv, D, D3, D, (int)rows,
+                               tc_gemm_auto_splits(D3, D, (int)rows), TC_EPI_ATOMIC, st)) return rc;
+    // d_x = dQKV * Wqkv
+    if (int rc = transpose_f32(wqkv, D, w.wt, D3, D3, D, st)) return rc;
+    if (int rc = tc_gemm_nt_ex(w.d_qkv, D3, w.wt, D3, nullptr, d_x, D, rows, D, D3, 1, TC_EPI_STORE, st)) return rc;
+  } else {
+    // d_wqkv[900,300] += dQKV^T X
+    e = sgemm_launch<1, 1, EPI_ATOMIC>(w.d_qkv, D3, s.x, D, nullptr, d_wqkv, D, D3, D, rows, splits, st);
+    if (e != cudaSuccess) return cuda_fail(e, "sgemm dWqkv");
+    // d_x = dQKV * Wqkv   ([rows,900] x [900,300])
+    e = sgemm_launch<0, 1, EPI_STORE>(w.d_qkv, D3, wqkv, D, nullptr, d_x, D, rows, D, D3, 1, st);
+    if (e != cudaSuccess) return cuda_fail(e, "sgemm dX");
+  }
   return NRMS_OK;
 }
 
@@ -199,9 +240,8 @@ size_t nrms_encoder_fwd_workspace_bytes(int64_t n_seq, int S, int mode, int trai
 }
 
 size_t nrms_encoder_bwd_workspace_bytes(int64_t n_seq, int S, int mode) {
-  (void)mode;
   if (n_seq <= 0 || S <= 0) return 0;
-  return carve_bwd(nullptr, n_seq * S, true).bytes + 256;
+  return carve_bwd(nullptr, n_seq * S, true, mode).bytes + 256;
 }
 
 int nrms_news_encoder_fwd(const int64_t* tokens, int64_t n_titles, int L, const float* emb, int64_t num_words,
@@ -269,10 +309,10 @@ int nrms_news_encoder_bwd(const float* d_out, const int64_t* tokens, int64_t n_t
   NRMS_CHECK_ARG(aligned16(d_out) && aligned16(stash) && aligned16(d_emb) && aligned16(d_wqkv) && aligned16(d_wa),
                  NRMS_E_INVALID, "pointers must be 16-byte aligned");
   const int64_t rows = n_titles * L;
-  NRMS_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= carve_bwd(nullptr, rows, true).bytes,
-                 NRMS_E_WORKSPACE, "workspace too small: need %zu bytes", carve_bwd(nullptr, rows, true).bytes);
+  NRMS_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= carve_bwd(nullptr, rows, true, mode).bytes,
+                 NRMS_E_WORKSPACE, "workspace too small: need %zu bytes", carve_bwd(nullptr, rows, true, mode).bytes);
   Stash s = carve_stash(const_cast<void*>(stash), rows);
-  BwdWs w = carve_bwd(workspace, rows, true);
+  BwdWs w = carve_bwd(workspace, rows, true, mode);
   int rc = encoder_core_bwd(s, w, d_out, n_titles, L, wqkv, wa, qa, w.d_x, d_wqkv, d_bqkv, d_wa, d_ba, d_qa,
                             dropout_p, seed, offset, mode, st);
   if (rc) return rc;
@@ -340,10 +380,10 @@ int nrms_user_encoder_bwd(const float* d_out, int64_t n_users, int S, const floa
   NRMS_CHECK_ARG(aligned16(d_out) && aligned16(stash) && aligned16(d_x) && aligned16(d_wqkv) && aligned16(d_wa),
                  NRMS_E_INVALID, "pointers must be 16-byte aligned");
   const int64_t rows = n_users * S;
-  NRMS_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= carve_bwd(nullptr, rows, false).bytes,
-                 NRMS_E_WORKSPACE, "workspace too small: need %zu bytes", carve_bwd(nullptr, rows, false).bytes);
+  NRMS_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= carve_bwd(nullptr, rows, false, mode).bytes,
+                 NRMS_E_WORKSPACE, "workspace too small: need %zu bytes", carve_bwd(nullptr, rows, false, mode).bytes);
   Stash s = carve_stash(const_cast<void*>(stash), rows);
-  BwdWs w = carve_bwd(workspace, rows, false);
+  BwdWs w = carve_bwd(workspace, rows, false, mode);
   return encoder_core_bwd(s, w, d_out, n_users, S, wqkv, wa, qa, d_x, d_wqkv, d_bqkv, d_wa, d_ba, d_qa, 0.f, 0, 0, mode,
                           st);
 }

@@ -8,6 +8,13 @@ namespace nrms {
 // memory, fp32 accumulation in TMEM.  Same layout contract as sgemm (multiples of 4, 16B aligned).
 int tc_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
                int64_t M, int N, int K, cudaStream_t st);
+// Same contraction with an epilogue mode (store / C += / atomic C +=) and an optional split along K (atomic only).
+enum { TC_EPI_STORE = 0, TC_EPI_ACCUM = 1, TC_EPI_ATOMIC = 2 };
+int tc_gemm_nt_ex(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
+                  int64_t M, int N, int K, int k_splits, int epi, cudaStream_t st);
+int tc_gemm_auto_splits(int64_t M, int N, int K);
+// dst[c][r] = src[r][c]: the K-major (NT) tensor-core GEMM sees A^T B and A B contractions through transposed copies
+int transpose_f32(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int64_t R, int C, cudaStream_t st);
 
 // Fused tensor-core encoder forward (inference): gather -> QKV (tcgen05) -> attention (K1), then
 // additive GEMM (tcgen05) -> tanh/softmax/pool (K2).  Input rows come from `src` [*,300]:

@@ -150,6 +150,18 @@ __device__ __forceinline__ void umma_f16_ss_p(uint32_t d_tmem, uint64_t a_desc, 
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(elected)
       : "memory");
 }
+__device__ __forceinline__ void umma_tf32_ss_p(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate, uint32_t elected) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, pe;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 pe, %5, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
 __device__ __forceinline__ void umma_f16_ts_p(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                               uint32_t accumulate, uint32_t elected) {
   asm volatile(

@@ -570,7 +570,11 @@ constexpr size_t W16_BYTES = (size_t)D3 * W16_LD * 2;   // 576,000 (a multiple o
 // host
 // ---------------------------------------------------------------------------------------------------
 template <int S, int SPT>
-static int64_t fused_chunk_seq() { return (int64_t)num_sms() * SPT * 8; }   // 8 full waves of tiles per launch
+static int64_t fused_chunk_seq() {          // full waves of tiles per launch (default 8 -- 16 and 32 measured the same; NRMS_FUSED_WAVES to experiment)
+  static int waves = 0;
+  if (!waves) { const char* e = getenv("NRMS_FUSED_WAVES"); waves = e ? atoi(e) : 8; if (waves < 1) waves = 8; }
+  return (int64_t)num_sms() * SPT * waves;
+}
 
 // workspace: [fp16 W_qkv copy][fp16 W_a copy][fp16 gather source (variant 4)][context rows C of one chunk]
 static size_t fused_src16_bytes(int idx_kind_dense, int64_t n_src_rows, int64_t chunk_rows) {
@@ -591,7 +595,7 @@ static int run_fused(const float* src, int64_t n_src_rows, const void* idx, int 
     configured = true;
   }
   const int variant = k1_variant();
-  // every variant tiles 5 titles / 2 users, so the chunking (8 waves of tiles) is shared
+  // every variant tiles 5 titles / 2 users, so the chunking (whole waves of tiles) is shared
   const int64_t chunk = fused_chunk_seq<S, SPT>();
   const int64_t first = n_seq < chunk ? n_seq : chunk;
   const size_t src16_bytes = fused_src16_bytes(idx_kind == 0, n_src_rows, first * S);

@@ -39,9 +39,13 @@ __device__ __forceinline__ void expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(bytes)
                : "memory");
 }
+// One MUFU operation per element (tanh.approx.f32, max relative error 2^-11 -- the precision of the fp16 operands
+// of the GEMM that feeds it) instead of ex2 + rcp: the 200 tanh per context row make the score warps MUFU-bound
+// (16 operations per clock per SM, profiles/tmem_ld_probe.cu).
 __device__ __forceinline__ float fast_tanh(float x) {
-  const float e = exp2f(x * 2.885390081777927f);   // tanh(x) = 1 - 2/(exp(2x)+1)
-  return 1.f - __fdividef(2.f, e + 1.f);
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 template <int S, int SPT>
@@ -63,7 +67,8 @@ additive_pool_f16_kernel(const __grid_constant__ CUtensorMap tmap_c, const __gri
   const uint32_t b_full = tfull_bar + 32, wv_ready = tfull_bar + 40, wv_free = tfull_bar + 56;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sm + OFF_MISC + 3840 + 16 * NSTA + 80);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler (converged MMA issue)
   const int64_t n_tiles = (n_seq + SPT - 1) / SPT;
 
   if (tid == 0) {
@@ -114,6 +119,7 @@ additive_pool_f16_kernel(const __grid_constant__ CUtensorMap tmap_c, const __gri
   } else if (warp == 1) {
     const uint32_t idesc = umma_idesc_f16(128, BN);
     const uint64_t desc0 = umma_desc_k_sw128(0);
+    const uint32_t el = elect_one_u32();     // whole warp converged: see tc_common.cuh umma_*_p
     mbar_wait(b_full, 0);
     uint32_t it = 0, tile_it = 0;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
@@ -125,17 +131,16 @@ additive_pool_f16_kernel(const __grid_constant__ CUtensorMap tmap_c, const __gri
         const int s = it % NSTA;
         mbar_wait(full_bar + 8 * s, (it / NSTA) & 1);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = (base + OFF_A + s * A_SLOT) >> 4;
-          const uint32_t sb = (base + OFF_B + kc * B_CHUNK) >> 4;
-          const int ksteps = (kc == KCH - 1) ? 3 : 4;
-          for (int ks = 0; ks < ksteps; ++ks)
-            umma_f16_ss(d_tmem, desc0 | (uint64_t)((sa + 2 * ks) & 0x3FFF), desc0 | (uint64_t)((sb + 2 * ks) & 0x3FFF),
-                        idesc, (kc | ks) ? 1u : 0u);
-          umma_commit(empty_bar + 8 * s);
-          if (kc == KCH - 1) umma_commit(tfull_bar + 8 * as);
-        }
-        __syncwarp();
+        const uint32_t sa = (base + OFF_A + s * A_SLOT) >> 4;
+        const uint32_t sb = (base + OFF_B + kc * B_CHUNK) >> 4;
+        const int ksteps = (kc == KCH - 1) ? 3 : 4;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          if (ks < ksteps)
+            umma_f16_ss_p(d_tmem, desc0 | (uint64_t)((sa + 2 * ks) & 0x3FFF), desc0 | (uint64_t)((sb + 2 * ks) & 0x3FFF),
+                          idesc, (kc | ks) ? 1u : 0u, el);
+        umma_commit_p(empty_bar + 8 * s, el);
+        if (kc == KCH - 1) umma_commit_p(tfull_bar + 8 * as, el);
       }
     }
   } else if (warp <= 5) {

@@ -1,4 +1,6 @@
-// Generic TF32 tensor-core GEMM for sm_100a:  C[M,N] = A[M,K] * B[N,K]^T (+ bias).
+// Generic TF32 tensor-core GEMM for sm_100a:  C[M,N] (=, +=, atomic +=) A[M,K] * B[N,K]^T (+ bias), optionally
+// split along K (one work item = output tile x K range; the training backward's weight gradients reduce over
+// 10^5 rows into a handful of tiles).
 //
 // Persistent, warp-specialised, TMA-fed:
 //   warp 0     : TMA producer.  One thread issues cp.async.bulk.tensor.2d loads of a 128x32 (A) and a
@@ -41,7 +43,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int64_t M, int N, int K,
-                  uint32_t stage_tx_bytes) {
+                  uint32_t stage_tx_bytes, int k_splits, int chunks_per_split, int epi) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -54,11 +56,18 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   volatile uint32_t* tmem_ptr_smem =
       reinterpret_cast<volatile uint32_t*>(base_ptr + TG_STAGES * TG_STAGE_BYTES + 16 * TG_STAGES + 32);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler (converged MMA issue)
   const int n_tiles = (N + TG_BN - 1) / TG_BN;
   const int64_t m_tiles = (M + TG_BM - 1) / TG_BM;
-  const int64_t total_tiles = m_tiles * n_tiles;
-  const int num_chunks = (K + TG_BK - 1) / TG_BK;
+  const int64_t total_tiles = m_tiles * n_tiles * k_splits;   // work items: K split fastest
+  const int all_chunks = (K + TG_BK - 1) / TG_BK;
+  // chunk range of work item w (the host guarantees every split is non-empty)
+  auto chunk_range = [&](int64_t w, int& c0, int& c1) {
+    c0 = (int)(w % k_splits) * chunks_per_split;
+    c1 = c0 + chunks_per_split;
+    if (c1 > all_chunks) c1 = all_chunks;
+  };
 
   if (tid == 0) {
     for (int s = 0; s < TG_STAGES; ++s) {
@@ -81,10 +90,13 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // ------------------------------ TMA producer ---------------------------------------
     if (lane == 0) {
       uint32_t it = 0;
-      for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int64_t w = blockIdx.x; w < total_tiles; w += gridDim.x) {
+        const int64_t t = w / k_splits;
         const int m0 = (int)(t / n_tiles) * TG_BM;
         const int n0 = (int)(t % n_tiles) * TG_BN;
-        for (int kc = 0; kc < num_chunks; ++kc, ++it) {
+        int c0, c1;
+        chunk_range(w, c0, c1);
+        for (int kc = c0; kc < c1; ++kc, ++it) {
           const int s = it % TG_STAGES;
           const uint32_t ph = (it / TG_STAGES) & 1;
           mbar_wait(empty_bar + 8 * s, ph ^ 1);
@@ -96,46 +108,52 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer -----------------------------------------
+    // ------------------------------ MMA issuer (whole warp converged, see tc_common.cuh umma_*_p) ---
+    const uint32_t el = elect_one_u32();
+    const uint64_t desc0 = umma_desc_k_sw128(0);
     uint32_t it = 0, tile_it = 0;
-    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
+    for (int64_t w = blockIdx.x; w < total_tiles; w += gridDim.x, ++tile_it) {
+      const int64_t t = w / k_splits;
       const int n0 = (int)(t % n_tiles) * TG_BN;
       int n_valid = N - n0;
       if (n_valid > TG_BN) n_valid = TG_BN;
       const int n_mma = (n_valid + 15) & ~15;
       const uint32_t idesc = umma_idesc_tf32(TG_BM, n_mma);
       const uint32_t as = tile_it & 1;
+      int c0, c1;
+      chunk_range(w, c0, c1);
       mbar_wait(tempty_bar + 8 * as, ((tile_it >> 1) & 1) ^ 1);   // epilogue drained this accumulator stage
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * TG_BN;
-      for (int kc = 0; kc < num_chunks; ++kc, ++it) {
+      for (int kc = c0; kc < c1; ++kc, ++it) {
         const int s = it % TG_STAGES;
         const uint32_t ph = (it / TG_STAGES) & 1;
         mbar_wait(full_bar + 8 * s, ph);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = base + s * TG_STAGE_BYTES;
-          const uint32_t sb = sa + TG_A_BYTES;
-          int ksteps = (K - kc * TG_BK + 7) / 8;
-          if (ksteps > 4) ksteps = 4;
-          for (int ks = 0; ks < ksteps; ++ks)
-            umma_tf32_ss(d_tmem, umma_desc_k_sw128(sa + ks * 32), umma_desc_k_sw128(sb + ks * 32), idesc,
-                         (kc | ks) ? 1u : 0u);
-          umma_commit(empty_bar + 8 * s);
-          if (kc == num_chunks - 1) umma_commit(tfull_bar + 8 * as);
-        }
-        __syncwarp();
+        const uint32_t sa = (base + s * TG_STAGE_BYTES) >> 4;
+        const uint32_t sb = sa + (TG_A_BYTES >> 4);
+        int ksteps = (K - kc * TG_BK + 7) / 8;
+        if (ksteps > 4) ksteps = 4;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          if (ks < ksteps)
+            umma_tf32_ss_p(d_tmem, desc0 | (uint64_t)((sa + 2 * ks) & 0x3FFF), desc0 | (uint64_t)((sb + 2 * ks) & 0x3FFF),
+                           idesc, (kc > c0 || ks) ? 1u : 0u, el);
+        umma_commit_p(empty_bar + 8 * s, el);
+        if (kc == c1 - 1) umma_commit_p(tfull_bar + 8 * as, el);
       }
     }
   } else {
     // ------------------------------ epilogue (warps 2..5) ------------------------------
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     uint32_t tile_it = 0;
-    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tile_it) {
+    for (int64_t w = blockIdx.x; w < total_tiles; w += gridDim.x, ++tile_it) {
+      const int64_t t = w / k_splits;
       const int64_t m0 = (t / n_tiles) * TG_BM;
       const int n0 = (int)(t % n_tiles) * TG_BN;
       int n_valid = N - n0;
       if (n_valid > TG_BN) n_valid = TG_BN;
+      const bool add_bias = bias != nullptr && (w % k_splits) == 0;
       const uint32_t as = tile_it & 1;
       mbar_wait(tfull_bar + 8 * as, (tile_it >> 1) & 1);
       tc_fence_after();
@@ -149,10 +167,20 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           for (int j = 0; j < 4; ++j) {
             const int n = n0 + col + 4 * j;
             if (n < N) {
-              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (bias) b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
-              *reinterpret_cast<float4*>(C + m * ldc + n) =
-                  make_float4(v[4 * j] + b4.x, v[4 * j + 1] + b4.y, v[4 * j + 2] + b4.z, v[4 * j + 3] + b4.w);
+              float4 r = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if (add_bias) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+                r = make_float4(r.x + b4.x, r.y + b4.y, r.z + b4.z, r.w + b4.w);
+              }
+              float4* dst = reinterpret_cast<float4*>(C + m * ldc + n);
+              if (epi == TC_EPI_STORE) {
+                *dst = r;
+              } else if (epi == TC_EPI_ACCUM) {
+                const float4 o = *dst;
+                *dst = make_float4(o.x + r.x, o.y + r.y, o.z + r.z, o.w + r.w);
+              } else {
+                atomicAdd(dst, r);
+              }
             }
           }
         }
@@ -238,10 +266,12 @@ int make_tmap_store_f16(CUtensorMap* out, const void* base, int64_t rows, int co
   return NRMS_OK;
 }
 
-int tc_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
-               int64_t M, int N, int K, cudaStream_t st) {
+int tc_gemm_nt_ex(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
+                  int64_t M, int N, int K, int k_splits, int epi, cudaStream_t st) {
   if (M <= 0) return NRMS_OK;
   NRMS_CHECK_ARG(M < (1ll << 31), NRMS_E_UNSUPPORTED, "M too large for one tensor map");
+  NRMS_CHECK_ARG(epi >= TC_EPI_STORE && epi <= TC_EPI_ATOMIC && (k_splits <= 1 || epi == TC_EPI_ATOMIC), NRMS_E_INVALID,
+                 "split-K needs the atomic epilogue");
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM);
@@ -256,10 +286,67 @@ int tc_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, const f
   if (int rc = make_tmap_k_major(&tb, B, N, K, ldb, box_b)) return rc;
   const uint32_t stage_tx = (uint32_t)(box_a + box_b) * TG_BK * 4;
   const int64_t tiles = ((M + TG_BM - 1) / TG_BM) * ((N + TG_BN - 1) / TG_BN);
+  const int chunks = (K + TG_BK - 1) / TG_BK;
+  if (k_splits < 1) k_splits = 1;
+  if (k_splits > chunks) k_splits = chunks;
+  const int cps = (chunks + k_splits - 1) / k_splits;
+  k_splits = (chunks + cps - 1) / cps;            // every split owns at least one chunk
+  const int64_t items = tiles * k_splits;
   int grid = num_sms();
-  if (tiles < grid) grid = (int)tiles;
-  tc_gemm_nt_kernel<<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, bias, C, ldc, M, N, K, stage_tx);
+  if (items < grid) grid = (int)items;
+  tc_gemm_nt_kernel<<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, bias, C, ldc, M, N, K, stage_tx, k_splits, cps, epi);
   NRMS_LAUNCH_CHECK("tc_gemm_nt");
+  return NRMS_OK;
+}
+
+int tc_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
+               int64_t M, int N, int K, cudaStream_t st) {
+  return tc_gemm_nt_ex(A, lda, B, ldb, bias, C, ldc, M, N, K, 1, TC_EPI_STORE, st);
+}
+
+// number of K splits that fills the machine for an [M,N] output (weight gradients: few tiles, very long K)
+int tc_gemm_auto_splits(int64_t M, int N, int K) {
+  const int64_t tiles = ((M + TG_BM - 1) / TG_BM) * ((N + TG_BN - 1) / TG_BN);
+  int64_t s = (num_sms() + tiles - 1) / tiles;
+  const int chunks = (K + TG_BK - 1) / TG_BK;
+  if (s > chunks / 8) s = chunks / 8;             // keep the main loop long enough to amortise the epilogue
+  return s < 1 ? 1 : (int)s;
+}
+
+// dst[c][r] = src[r][c]  (src [R,C] row stride ld_src, dst [C,R] row stride ld_dst); 32x32 tiles through shared memory
+__global__ void __launch_bounds__(256) transpose_f32_kernel(const float* __restrict__ src, int64_t ld_src,
+                                                            float* __restrict__ dst, int64_t ld_dst, int64_t R, int C) {
+  __shared__ float tile[32][33];
+  const int c_tiles = (C + 31) / 32;
+  const int64_t r_tiles = (R + 31) / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+  for (int64_t t = blockIdx.x; t < r_tiles * c_tiles; t += gridDim.x) {
+    const int64_t r0 = (t / c_tiles) * 32;
+    const int c0 = (int)(t % c_tiles) * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const int64_t r = r0 + ty + j;
+      const int c = c0 + tx;
+      tile[ty + j][tx] = (r < R && c < C) ? __ldg(src + r * ld_src + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const int c = c0 + ty + j;
+      const int64_t r = r0 + tx;
+      if (c < C && r < R) dst[(int64_t)c * ld_dst + r] = tile[tx][ty + j];
+    }
+    __syncthreads();
+  }
+}
+
+int transpose_f32(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int64_t R, int C, cudaStream_t st) {
+  if (R <= 0 || C <= 0) return NRMS_OK;
+  const int64_t tiles = ((R + 31) / 32) * ((C + 31) / 32);
+  int64_t grid = (int64_t)num_sms() * 16;
+  if (tiles < grid) grid = tiles;
+  transpose_f32_kernel<<<(unsigned)grid, 256, 0, st>>>(src, ld_src, dst, ld_dst, R, C);
+  NRMS_LAUNCH_CHECK("transpose_f32_kernel");
   return NRMS_OK;
 }
 

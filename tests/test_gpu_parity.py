@@ -199,6 +199,20 @@ def test_train_step_fp32_matches_reference(dev, golden, golden_sd):
             assert (d <= 1e-6).mean() >= 0.8 and d.mean() < 2e-6, (k, d.mean())
 
 
+def test_train_step_tensor_mode_gradients(dev, golden, golden_sd):
+    """Tensor mode: forward projections AND the four backward contractions (dX, dC, dWqkv, dWa: split-K, atomic and
+    accumulate epilogues of the tcgen05 GEMM over transposed operand copies) run with TF32 operands.  Every gradient
+    stays within 3e-3 of the reference's fp32 gradient (relative to the tensor's largest entry), the loss within 2e-3."""
+    m, losses, grads = _train_once(golden, golden_sd, dev, "tf32", steps=1)
+    assert abs(losses[0] - float(golden["train/loss"])) < 2e-3
+    for k, g in grads.items():
+        ref = golden["train/grad/" + k]
+        got = g if "embedding" in k else (g[:48] if g.ndim == 2 else g)
+        scale = np.abs(ref).max() + 1e-12
+        assert np.abs(got - ref).max() < 3e-3 * scale + 1e-8, (k, np.abs(got - ref).max(), scale)
+    assert not grads[O.EMB_KEY][0].any()
+
+
 def test_train_logits_tf32(dev, golden, golden_sd):
     m = make_model(golden_sd, dev, "tf32")
     cand, clicked = golden["train/cand"], golden["train/clicked"]
