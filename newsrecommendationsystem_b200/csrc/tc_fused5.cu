@@ -588,7 +588,8 @@ int k1v4_prepare(const float* wqkv, const float* bqkv, void* w16, CUtensorMap* t
 
 // fp16 gather source of n_rows fp32 rows (+ the null row) and its gather4 tensor map (box = 64 halfs x 1 row)
 int k1v4_pack_src(const float* src, int64_t n_rows, void* src16, CUtensorMap* ts, cudaStream_t st) {
-  NRMS_CHECK_ARG(n_rows + 1 < (1ll << 31), NRMS_E_UNSUPPORTED, "gather source too large for 32-bit TMA coordinates");
+  NRMS_CHECK_ARG((n_rows + 1) * k1v4::SRC_LD * 2 < (1ll << 32), NRMS_E_UNSUPPORTED,
+                 "gather source too large (32-bit byte offsets in the K1 gather)");
   const int64_t total = (n_rows + 1) * 40;
   int64_t gb = (total + 255) / 256;
   if (gb > (int64_t)num_sms() * 16) gb = (int64_t)num_sms() * 16;

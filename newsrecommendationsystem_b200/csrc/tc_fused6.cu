@@ -12,12 +12,15 @@
 //     denominator never leaves its registers.
 //   * 8 worker warps = 2 head sets x 4 TMEM lane quarters.  All exp2 of a row run on one thread, but the unit
 //     is shared by the SM anyway (measured 16 ex2 per clock per SM, profiles/tmem_ld_probe.cu).
+//   * The A tile is gathered with cp.async (16 bytes per lane, coalesced 128-byte row pieces) instead of TMA
+//     gather4: the tile is single-buffered, so the gather latency is exposed once per tile, and gather4 needed
+//     ~6,000 cycles per tile.
 //   * MMA issue, commits and waits follow the rules measured on v4: whole-warp converged issue with the elect.sync
 //     result as a predicate operand (tc_common.cuh umma_*_p), no calls or clock reads in the waits, operand waits
 //     hoisted in front of the accumulator wait.
 //
 // Warps: 0 weight TMA producer, 1 attention MMA issuer (+ TMEM allocator), 2-9 workers (thread == tile row == TMEM
-// lane; warp = (head set, lane quarter)), 10 projection MMA issuer, 11 A-tile gather.
+// lane; warp = (head set, lane quarter)), 10 projection MMA issuer, 11 A-tile gather, 12 context store.
 // TMEM (512 columns): projection accumulators [0,128) and [128,256) | head set s at 256 + 128 s.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -57,7 +60,8 @@ constexpr int NST = 5;                          // weight ring stages (= one who
 static_assert(NST == KCH, "the projection issuer relies on stage == K chunk");
 constexpr int B_STAGE = PN * 128;               // 16,384
 constexpr int CP = 320;                         // pitch (halfs) of the fp16 context rows handed to K2
-constexpr int THREADS = 384;
+constexpr int SRC_LD = 320;                     // pitch (halfs) of the fp16 gather source (k1v4_pack_src)
+constexpr int THREADS = 416;                    // 13 warps
 constexpr int OFF_A = 0;                        // 5 x [128 rows x 128 B]
 constexpr int OFF_B = KCH * 16384;              // 81,920
 constexpr int OFF_SET = OFF_B + NST * B_STAGE;  // 163,840 ; per set: K (tf32) 16 KB | V^T (fp16) 8 KB
@@ -65,7 +69,7 @@ constexpr int SET_BYTES = 16384 + 8192;
 constexpr int OFF_STG = OFF_SET + 2 * SET_BYTES;  // context staging for the TMA store: [128 rows][2 heads x 20 halfs]
 constexpr int STG_BYTES = 128 * 80;             // 10,240
 constexpr int OFF_BAR = OFF_STG + STG_BYTES;
-constexpr int SMEM = OFF_BAR + 512 + 1024;
+constexpr int SMEM = OFF_BAR + 512 + 512 + 1024;   // barriers | source-row ids of the tile | alignment slack
 static_assert(SMEM <= 232448, "shared memory budget");
 constexpr int TM_ACC = 128;                     // columns per projection accumulator
 constexpr int TM_SET0 = 256, TM_SET = 128;      // head sets: S [0,128) -> P [0,64) in place, O [64,96)
@@ -109,6 +113,20 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
   const __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
+// 2^x on the FMA and integer pipes (Cody-Waite split by the 1.5*2^23 trick, degree-4 Taylor polynomial of 2^f on
+// [-0.5, 0.5], relative error < 5e-5 -- an order below the fp16 rounding of P): the MUFU unit delivers 16 ex2 per clock
+// per SM (profiles/tmem_ld_probe.cu) and the softmax of a pass needs 12,800 of them, so every other probability is
+// computed here, in parallel with the MUFU half.
+__device__ __forceinline__ float ex2_fma(float x) {
+  x = fmaxf(x, -100.f);
+  const float t = x + 12582912.f;                    // integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(f, 0.009618129f, 0.05550411f);
+  p = fmaf(f, p, 0.2402265f);
+  p = fmaf(f, p, 0.6931472f);
+  p = fmaf(f, p, 1.f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+}
 // fp32 bits -> tf32 bits, round to nearest, ties away from zero (cvt.rna.tf32.f32 for finite values) on the integer
 // pipe: cvt.rna shares the quarter-rate conversion unit with ex2, which the softmax already saturates
 __device__ __forceinline__ uint32_t rna_tf32(uint32_t x) { return (x + 0x1000u) & 0xFFFFE000u; }
@@ -117,8 +135,8 @@ __device__ __forceinline__ uint32_t rna_tf32(uint32_t x) { return (x + 0x1000u) 
 template <int S, int SLOT, int SPT>
 __global__ void __launch_bounds__(THREADS, 1)
 encoder_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_src,
-                        const __grid_constant__ CUtensorMap tmap_c, const void* __restrict__ idx, int idx_kind,
-                        int64_t n_seq, int null_row) {
+                        const __grid_constant__ CUtensorMap tmap_c, const __half* __restrict__ src16,
+                        const void* __restrict__ idx, int idx_kind, int64_t n_seq, int null_row) {
   static_assert(SLOT % 8 == 0 && SLOT >= S && SPT * SLOT <= 128, "slot layout");
   static_assert(SLOT == 64 || SLOT == 24, "score-block code paths");
   constexpr int GPS = (S + 3) / 4;               // 4-row gather groups per sequence
@@ -132,7 +150,8 @@ encoder_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
   const uint32_t a_full = bars + 16 * NST, a_free = a_full + 8 * KCH;      // [KCH] each
   const uint32_t acc_full = a_free + 8 * KCH, acc_empty = acc_full + 16;   // [2] each (one per accumulator)
   const uint32_t kv_ready = acc_empty + 16, s_ready = kv_ready + 16, p_ready = s_ready + 16, o_ready = p_ready + 16;
-  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sm + OFF_BAR + 16 * NST + 16 * KCH + 112);
+  const uint32_t stg_full = o_ready + 16, stg_free = stg_full + 8;
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sm + OFF_BAR + 16 * NST + 16 * KCH + 128);
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler: role branches stay uniform
@@ -155,6 +174,8 @@ encoder_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
       mbar_init(p_ready + 8 * s, 4);
       mbar_init(o_ready + 8 * s, 1);
     }
+    mbar_init(stg_full, 8);               // one arrival per worker warp
+    mbar_init(stg_free, 1);               // the store warp, once the bulk store has read the staging tile
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_ptr_smem), 512);
@@ -179,6 +200,9 @@ encoder_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
 #pragma unroll 1
           for (int kc = 0; kc < KCH; ++kc) {
             mbar_wait(w_empty + 8 * kc, (pass_it & 1) ^ 1);
+#ifdef NRMS_DBG_NOWLOAD
+            if (pass_it >= 1) { mbar_arrive(w_full + 8 * kc); continue; }     // timing experiment: stale weights
+#endif
             expect_tx(w_full + 8 * kc, B_STAGE);
             tma_load_2d(base + OFF_B + kc * B_STAGE, &tmap_w, kc * 64, PN * p, w_full + 8 * kc);
           }
@@ -186,34 +210,77 @@ encoder_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
       }
     }
   } else if (warp == 11) {
-    // ------------------------------ A-tile gather (TMA gather4, one 4-row group per lane) ------
-    const int sq = lane / GPS, g = lane - sq * GPS;
-    const uint32_t dst0 = base + OFF_A + (uint32_t)(sq * SLOT + 4 * g) * 128u;
+    // ------------------------------ A-tile gather: cp.async, 16 bytes per lane ---------------------
+    // Eight lanes move one 128-byte row piece (coalesced), four rows per instruction, straight into the swizzled
+    // K-major layout; sequences missing from a partial tile are zero-filled (src-size 0).  Measured against the TMA
+    // gather4 form of v4 (one instruction per four rows per chunk): ~6,000 -> ~1,500 cycles from "chunk free" to
+    // "chunk full", which is exposed once per tile because the A tile is single-buffered.
+    (void)tmap_src; (void)null_row;
+    constexpr int NREAL = S * SPT;                   // real rows of a tile (100)
+    constexpr int NIT = (NREAL + 3) / 4;
+    static_assert(NIT <= 32, "validity mask");
+    int* const rowid = reinterpret_cast<int*>(sm + OFF_BAR + 512);     // [NREAL] source row of every real tile row
+    const int g = lane >> 3, c = lane & 7;
+    // one warp issues 5 x 25 copies per tile: everything but the source row is precomputed, so an iteration is an
+    // address add and the cp.async (the first cut recomputed rows and swizzles per copy and was instruction-bound)
+    uint32_t dst_off[NIT];
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+      const int n = 4 * i + g;
+      const int r = (n / S) * SLOT + (n % S);
+      dst_off[i] = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+    }
+    const char* const srcb = reinterpret_cast<const char*>(src16) + c * 16;
     uint32_t tile_it = 0;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
       const int64_t seq0 = t * SPT;
       const int n_here = (n_seq - seq0 < SPT) ? (int)(n_seq - seq0) : SPT;
-      const bool active = sq < n_here;
-      int r[4] = {null_row, null_row, null_row, null_row};
-      if (active) {
-        const int64_t e0 = (seq0 + sq) * S + 4 * g;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (4 * g + j < S) {
-            const int64_t e = e0 + j;
-            r[j] = idx_kind == 0 ? (int)e : (idx_kind == 1 ? (int)reinterpret_cast<const int64_t*>(idx)[e]
-                                                          : reinterpret_cast<const int32_t*>(idx)[e]);
-          }
+      for (int n = lane; n < NREAL; n += 32) {
+        int r = -1;
+        if (n / S < n_here) {
+          const int64_t e = seq0 * S + n;
+          r = idx_kind == 0 ? (int)e : (idx_kind == 1 ? (int)reinterpret_cast<const int64_t*>(idx)[e]
+                                                        : reinterpret_cast<const int32_t*>(idx)[e]);
         }
+        rowid[n] = r;
       }
-      const uint32_t tx = (uint32_t)(n_here * GPS) * 512u;
+      __syncwarp();
+      uint32_t src_off[NIT];
+      uint32_t valid = 0u;
+#pragma unroll
+      for (int i = 0; i < NIT; ++i) {
+        const int n = 4 * i + g;
+        const int sr = (n < NREAL) ? rowid[n] : -1;
+        src_off[i] = sr < 0 ? 0u : (uint32_t)sr * (uint32_t)(SRC_LD * 2);
+        if (sr >= 0) valid |= 1u << i;
+      }
 #pragma unroll 1
       for (int kc = 0; kc < KCH; ++kc) {
         mbar_wait(a_free + 8 * kc, (tile_it & 1) ^ 1);     // the previous tile's last pass is done with this chunk
-        if (lane == 0) expect_tx(a_full + 8 * kc, tx);
-        __syncwarp();
-        if (active) tma_gather4(dst0 + kc * 16384, &tmap_src, kc * 64, r[0], r[1], r[2], r[3], a_full + 8 * kc);
+        const uint32_t dchunk = base + OFF_A + kc * 16384;
+        const char* const schunk = srcb + kc * 128;
+#pragma unroll
+        for (int i = 0; i < NIT; ++i) {
+          if (4 * i + g < NREAL) {
+            const uint32_t nbytes = ((valid >> i) & 1u) ? 16u : 0u;       // 0: zero-fill (sequence not in this tile)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dchunk + dst_off[i]),
+                         "l"(schunk + src_off[i]), "r"(nbytes) : "memory");
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
       }
+#pragma unroll
+      for (int kc = 0; kc < KCH; ++kc) {
+        if (kc == 0) asm volatile("cp.async.wait_group 4;" ::: "memory");
+        else if (kc == 1) asm volatile("cp.async.wait_group 3;" ::: "memory");
+        else if (kc == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else if (kc == 3) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full + 8 * kc);
+      }
+      __syncwarp();                                     // rowid is rewritten for the next tile
     }
   } else if (warp == 10) {
     // ------------------------------ projection MMA issuer (whole warp converged, see umma_*_p) ---
@@ -338,25 +405,20 @@ encoder_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
     float inv = 0.f;
     int64_t pend_seq0 = 0;
     int pend_n = 0, pend_p = -1;
+    uint32_t n_staged = 0;
     auto finish_w3 = [&]() {
-      // the bulk store of the pass before must have read the staging tile before it is overwritten; its issuer
-      // checks that here (long done by now) rather than stalling right after the issue
-      if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      // 40 context columns of the pass (heads 2p, 2p+1; the dummy 16th head gives the zero K padding 300..319) go
+      // to the staging tile [128 rows][80 B]; the store warp sends it off as one 2-D bulk tensor store per sequence
+      mbar_wait(stg_free, (n_staged & 1) ^ 1);           // the previous bulk store has read the tile
       uint2* const srow = reinterpret_cast<uint2*>(sm + OFF_STG + row * 80 + set * 40);
 #pragma unroll
       for (int c = 0; c < 5; ++c)
         srow[c] = make_uint2(pack_h2(__uint_as_float(o[4 * c]) * inv, __uint_as_float(o[4 * c + 1]) * inv),
                              pack_h2(__uint_as_float(o[4 * c + 2]) * inv, __uint_as_float(o[4 * c + 3]) * inv));
       fence_proxy_async_smem();
-      asm volatile("bar.sync 1, 256;" ::: "memory");     // staging tile complete
-      // 40 context columns of the pass (heads 2p, 2p+1; the dummy 16th head gives the zero K padding 300..319),
-      // staged as [128 rows][80 B]: one 2-D bulk tensor store per sequence
-      if (warp == 2 && lane == 0) {
-        for (int uu = 0; uu < pend_n; ++uu)
-          tma_store_2d(base + OFF_STG + uu * SLOT * 80, &tmap_c, 40 * pend_p, (int)((pend_seq0 + uu) * S));
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(stg_full);
+      ++n_staged;
     };
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
       const int64_t seq0 = t * SPT;
@@ -419,8 +481,8 @@ encoder_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
             uint32_t pk[32];
 #pragma unroll
             for (int j = 0; j < 64; j += 2) {
-              const float e0 = (j < S) ? ex2(__uint_as_float(sv[j])) : 0.f;
-              const float e1 = (j + 1 < S) ? ex2(__uint_as_float(sv[j + 1])) : 0.f;
+              const float e0 = (j < S) ? ex2(__uint_as_float(sv[j])) : 0.f;               // MUFU
+              const float e1 = (j + 1 < S) ? ex2_fma(__uint_as_float(sv[j + 1])) : 0.f;   // FMA pipe
               Z += e0 + e1;
               pk[j >> 1] = (j < S) ? pack_h2(e0, e1) : 0u;
             }
@@ -450,7 +512,7 @@ encoder_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
               const float s0 = __uint_as_float(own ? sv[1][j] : sv[0][j]);
               const float s1 = __uint_as_float(own ? sv[1][j + 1] : sv[0][j + 1]);
               const float e0 = (j < S) ? ex2(s0) : 0.f;
-              const float e1 = (j + 1 < S) ? ex2(s1) : 0.f;
+              const float e1 = (j + 1 < S) ? ex2_fma(s1) : 0.f;
               Z += e0 + e1;
               pk[j >> 1] = pack_h2(e0, e1);
             }
@@ -499,10 +561,29 @@ encoder_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
       }
     }
     if (pend_p >= 0) finish_w3();
-    if (warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 #ifdef NRMS_K1_TRACE
     if (tracer) TRACE_END(set);
 #endif
+  }
+  else if (warp == 12) {
+    // ------------------------------ context store: staging tile -> global (bulk tensor stores) ----
+    if (lane == 0) {
+      uint32_t k = 0;
+      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int64_t seq0 = t * SPT;
+        const int n_here = (n_seq - seq0 < SPT) ? (int)(n_seq - seq0) : SPT;
+#pragma unroll 1
+        for (int p = 0; p < NPASS; ++p, ++k) {
+          mbar_wait(stg_full, k & 1);
+          for (int uu = 0; uu < n_here; ++uu)
+            tma_store_2d(base + OFF_STG + uu * SLOT * 80, &tmap_c, 40 * p, (int)((seq0 + uu) * S));
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_arrive(stg_free);
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -519,8 +600,8 @@ extern "C" int nrms_debug_read_trace5(long long* host, int* counts) {
 }
 
 template <int S, int SLOT, int SPT>
-static int launch_k1v5(const CUtensorMap& tw, const CUtensorMap& ts, const void* idx, int idx_kind, int64_t n,
-                       int null_row, void* Cbuf, cudaStream_t st) {
+static int launch_k1v5(const CUtensorMap& tw, const CUtensorMap& ts, const void* src16, const void* idx, int idx_kind,
+                       int64_t n, int null_row, void* Cbuf, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k1v5::encoder_attn_tc5_kernel<S, SLOT, SPT>,
@@ -534,16 +615,16 @@ static int launch_k1v5(const CUtensorMap& tw, const CUtensorMap& ts, const void*
   alignas(64) CUtensorMap tc_;     // context rows [n*S][320] halfs, store box = S rows x 40 halfs (one sequence, one pass)
   if (int rc = make_tmap_store_f16(&tc_, Cbuf, n * S, k1v5::CP, k1v5::CP, 40, S)) return rc;
   k1v5::encoder_attn_tc5_kernel<S, SLOT, SPT><<<grid, k1v5::THREADS, k1v5::SMEM, st>>>(
-      tw, ts, tc_, idx, idx_kind, n, null_row);
+      tw, ts, tc_, reinterpret_cast<const __half*>(src16), idx, idx_kind, n, null_row);
   NRMS_LAUNCH_CHECK("encoder_attn_tc5_kernel");
   return NRMS_OK;
 }
 
 // Same operands as k1v4_run (the fp16 weight copy and gather source of k1v4_prepare / k1v4_pack_src).
-int k1v5_run(int S, const CUtensorMap& tw, const CUtensorMap& ts, const void* idx, int idx_kind, int64_t n,
-             int null_row, void* Cbuf, cudaStream_t st) {
-  if (S == 20) return launch_k1v5<20, 24, 5>(tw, ts, idx, idx_kind, n, null_row, Cbuf, st);
-  if (S == 50) return launch_k1v5<50, 64, 2>(tw, ts, idx, idx_kind, n, null_row, Cbuf, st);
+int k1v5_run(int S, const CUtensorMap& tw, const CUtensorMap& ts, const void* src16, const void* idx, int idx_kind,
+             int64_t n, int null_row, void* Cbuf, cudaStream_t st) {
+  if (S == 20) return launch_k1v5<20, 24, 5>(tw, ts, src16, idx, idx_kind, n, null_row, Cbuf, st);
+  if (S == 50) return launch_k1v5<50, 64, 2>(tw, ts, src16, idx, idx_kind, n, null_row, Cbuf, st);
   set_error("encoder_attn_tc5_kernel compiled for S = 20 or 50, got %d", S);
   return NRMS_E_UNSUPPORTED;
 }
