@@ -54,7 +54,7 @@ class ClockSampler:
         self.p = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             pass
@@ -70,10 +70,10 @@ class ClockSampler:
         self.f.flush()
         rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
         os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for r in rows:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
             except (ValueError, IndexError):
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
@@ -81,8 +81,8 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": float(max(mx)),
+                "power_w_max": float(max(pw)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def make_data(world):
@@ -288,14 +288,14 @@ def main():
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("encoder_attn_tc_kernel<50,64,2>")
+        traffic = json.load(open(tpath)).get("encoder_attn_tc5_kernel<50,64,2>")
     if k1_n > 0 and k1_ms > 0:
         us_per_launch = 1e3 * k1_ms / k1_n
         users_per_launch = k1_seq / k1_n
         # K1 owns everything of the user encoder except the additive projection/pooling (K2): 30.05 of 36.05 MFLOP
         flop_per_launch = users_per_launch * (FLOP_PER_USER - 6_000_000 - 50_000)
         ach = flop_per_launch / (us_per_launch * 1e-6) / 1e12
-        roof = dict(bound="tensor", kernel="k1v2::encoder_attn_tc_kernel<50,64,2> (user encoder: gather+QKV+attention)",
+        roof = dict(bound="tensor", kernel="k1v5::encoder_attn_tc5_kernel<50,64,2> (user encoder: gather+QKV+attention)",
                     achieved=ach, peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=ach / peaks["bf16_tflops"],
                     traffic=traffic, us_per_launch=us_per_launch, launches=int(k1_n), users_per_launch=users_per_launch,
                     algorithmic_flop_per_user=FLOP_PER_USER - 6_050_000,
@@ -338,7 +338,8 @@ def main():
         torch.cuda.synchronize()
         tms = max_over_ranks(e0.elapsed_time(e1))
         train = dict(samples_per_s=128 * world * n_train / (tms / 1e3), ms_per_step=tms / n_train, batch_per_gpu=128,
-                     k_neg=4, dropout=0.2, loss=loss_val, forward_precision=args.precision, backward_precision="fp32")
+                     k_neg=4, dropout=0.2, loss=loss_val, forward_precision=args.precision,
+                     backward_precision=args.precision)
         model.eval()
 
     cpu = None
