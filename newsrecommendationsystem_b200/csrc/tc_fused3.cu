@@ -3,7 +3,7 @@
 //   T = C W_a^T on tcgen05 (kind::f16, fp32 accumulate, 128 x 208 x 16) with W_a (fp16, 128 KB) RESIDENT in
 //   shared memory for the whole kernel -- only the context rows stream (4-stage TMA ring) -- then
 //   s_i = tanh(T_i + b_a) . q_a, stable softmax over the sequence, out = sum_i w_i C_i.
-//   warp 0 TMA, warp 1 MMA, warps 2-5 "score" (TMEM -> tanh.q -> softmax weights), warps 6-9 "pool"
+//   warp 0 TMA, warp 1 MMA, warps 2-5 "score" (TMEM -> tanh.q -> softmax weights), warps 6-13 "pool"
 //   (weighted row sum of the previous tile, read back from L2), double-buffered through mbarriers.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -27,7 +27,8 @@ constexpr int OFF_B = 0;
 constexpr int OFF_A = KCH * B_CHUNK;       // 133,120
 constexpr int OFF_MISC = OFF_A + NSTA * A_SLOT;   // 198,656: sc[2][128] wv[2][128] ba[208] qa[208] | barriers
 constexpr int SMEM = OFF_MISC + 4096 + 1024;
-constexpr int THREADS = 320;
+constexpr int POOL_THREADS = 256;          // 8 pool warps: one output float4 per thread and tile for S = 50
+constexpr int THREADS = 192 + POOL_THREADS;
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* tmap, int c0, int c1, uint32_t bar) {
   asm volatile(
@@ -80,7 +81,7 @@ additive_pool_f16_kernel(const __grid_constant__ CUtensorMap tmap_c, const __gri
       mbar_init(tfull_bar + 8 * a, 1);
       mbar_init(tempty_bar + 8 * a, 4);
       mbar_init(wv_ready + 8 * a, 128);
-      mbar_init(wv_free + 8 * a, 128);
+      mbar_init(wv_free + 8 * a, POOL_THREADS);
     }
     mbar_init(b_full, 1);
     mbar_fence_init();
@@ -190,7 +191,7 @@ additive_pool_f16_kernel(const __grid_constant__ CUtensorMap tmap_c, const __gri
     }
   } else {
     // ------------------------------ pool warps --------------------------------------------------
-    const int pt = (warp - 6) * 32 + lane;     // 0..127
+    const int pt = (warp - 6) * 32 + lane;     // 0..POOL_THREADS-1
     uint32_t tile_it = 0;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
       const int64_t seq0 = t * SPT;
@@ -198,18 +199,21 @@ additive_pool_f16_kernel(const __grid_constant__ CUtensorMap tmap_c, const __gri
       mbar_wait(wv_ready + 8 * as, (tile_it >> 1) & 1);
       const float* w = wv + as * 128;
       // pooled[seq, 4l..4l+3] = sum_i w_i C[seq*S+i, 4l..4l+3]; rows are L2-hot (K1 just wrote them)
-      for (int o = pt; o < SPT * DV4; o += 128) {
+      for (int o = pt; o < SPT * DV4; o += POOL_THREADS) {
         const int sq = o / DV4, l = o - sq * DV4;
         if (seq0 + sq < n_seq) {
           const uint2* cp = reinterpret_cast<const uint2*>(C + (seq0 + sq) * S * CP) + l;
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          // the rows come back from L2 (~800 cycles under load): keep 25 (S = 50) / 20 (S = 20) loads in flight
+          constexpr int PB = (S % 25 == 0) ? 25 : 20;
+          static_assert(S % PB == 0, "pool batch");
 #pragma unroll 1
-          for (int i0 = 0; i0 < S; i0 += 10) {
-            uint2 c4[10];
+          for (int i0 = 0; i0 < S; i0 += PB) {
+            uint2 c4[PB];
 #pragma unroll
-            for (int i = 0; i < 10; ++i) c4[i] = __ldg(cp + (i0 + i) * (CP / 4));
+            for (int i = 0; i < PB; ++i) c4[i] = __ldg(cp + (i0 + i) * (CP / 4));
 #pragma unroll
-            for (int i = 0; i < 10; ++i) {
+            for (int i = 0; i < PB; ++i) {
               const float wi = w[sq * S + i0 + i];
               const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&c4[i].x));
               const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&c4[i].y));
