@@ -12,15 +12,15 @@
 //     denominator never leaves its registers.
 //   * 8 worker warps = 2 head sets x 4 TMEM lane quarters.  All exp2 of a row run on one thread, but the unit
 //     is shared by the SM anyway (measured 16 ex2 per clock per SM, profiles/tmem_ld_probe.cu).
-//   * The A tile is gathered with cp.async (16 bytes per lane, coalesced 128-byte row pieces) instead of TMA
-//     gather4: the tile is single-buffered, so the gather latency is exposed once per tile, and gather4 needed
-//     ~6,000 cycles per tile.
+//   * The A tile is gathered by four warps with cp.async (16 bytes per lane, coalesced 128-byte row pieces), the
+//     rows of the next tile prefetched into L2 a tile ahead, instead of TMA gather4: the tile is single-buffered,
+//     so the refill latency is exposed once per tile, and gather4 needed ~8,000 cycles per tile.
 //   * MMA issue, commits and waits follow the rules measured on v4: whole-warp converged issue with the elect.sync
 //     result as a predicate operand (tc_common.cuh umma_*_p), no calls or clock reads in the waits, operand waits
 //     hoisted in front of the accumulator wait.
 //
 // Warps: 0 weight TMA producer, 1 attention MMA issuer (+ TMEM allocator), 2-9 workers (thread == tile row == TMEM
-// lane; warp = (head set, lane quarter)), 10 projection MMA issuer, 11 A-tile gather, 12 context store.
+// lane; warp = (head set, lane quarter)), 10 projection MMA issuer, 11 context store, 12-15 A-tile gather.
 // TMEM (512 columns): projection accumulators [0,128) and [128,256) | head set s at 256 + 128 s.
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -38,8 +38,8 @@ namespace k1v5 {
 
 // debug trace (-DNRMS_K1_TRACE): clock64 stamps of lane 0 of four warps of block 0 (0 worker set 0, 1 worker
 // set 1, 2 projection issuer, 3 attention issuer), written straight to global memory; nrms_debug_read_trace5
-__device__ long long g_trace[4][1024];
-__device__ int g_trace_n[4];
+__device__ long long g_trace[5][1024];     // 4 = A-tile gather warp
+__device__ int g_trace_n[5];
 #ifdef NRMS_K1_TRACE
 #define TRACE(who, tag)                                                                         \
   do {                                                                                          \
@@ -61,7 +61,8 @@ static_assert(NST == KCH, "the projection issuer relies on stage == K chunk");
 constexpr int B_STAGE = PN * 128;               // 16,384
 constexpr int CP = 320;                         // pitch (halfs) of the fp16 context rows handed to K2
 constexpr int SRC_LD = 320;                     // pitch (halfs) of the fp16 gather source (k1v4_pack_src)
-constexpr int THREADS = 416;                    // 13 warps
+constexpr int THREADS = 512;                    // 16 warps
+constexpr int NGW = 4;                          // A-tile gather warps (12..15)
 constexpr int OFF_A = 0;                        // 5 x [128 rows x 128 B]
 constexpr int OFF_B = KCH * 16384;              // 81,920
 constexpr int OFF_SET = OFF_B + NST * B_STAGE;  // 163,840 ; per set: K (tf32) 16 KB | V^T (fp16) 8 KB
@@ -69,7 +70,7 @@ constexpr int SET_BYTES = 16384 + 8192;
 constexpr int OFF_STG = OFF_SET + 2 * SET_BYTES;  // context staging for the TMA store: [128 rows][2 heads x 20 halfs]
 constexpr int STG_BYTES = 128 * 80;             // 10,240
 constexpr int OFF_BAR = OFF_STG + STG_BYTES;
-constexpr int SMEM = OFF_BAR + 512 + 512 + 1024;   // barriers | source-row ids of the tile | alignment slack
+constexpr int SMEM = OFF_BAR + 512 + 1024;        // barriers | alignment slack
 static_assert(SMEM <= 232448, "shared memory budget");
 constexpr int TM_ACC = 128;                     // columns per projection accumulator
 constexpr int TM_SET0 = 256, TM_SET = 128;      // head sets: S [0,128) -> P [0,64) in place, O [64,96)
@@ -163,7 +164,7 @@ encoder_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
       mbar_init(w_empty + 8 * s, 1);
     }
     for (int k = 0; k < KCH; ++k) {
-      mbar_init(a_full + 8 * k, 1);
+      mbar_init(a_full + 8 * k, NGW);     // one arrival per gather warp
       mbar_init(a_free + 8 * k, 1);
     }
     for (int s = 0; s < 2; ++s) {
@@ -209,62 +210,73 @@ encoder_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
         }
       }
     }
-  } else if (warp == 11) {
-    // ------------------------------ A-tile gather: cp.async, 16 bytes per lane ---------------------
+  } else if (warp >= 12) {
+    // ------------------------------ A-tile gather: 4 warps, cp.async + L2 prefetch of the next tile ---
     // Eight lanes move one 128-byte row piece (coalesced), four rows per instruction, straight into the swizzled
-    // K-major layout; sequences missing from a partial tile are zero-filled (src-size 0).  Measured against the TMA
-    // gather4 form of v4 (one instruction per four rows per chunk): ~6,000 -> ~1,500 cycles from "chunk free" to
-    // "chunk full", which is exposed once per tile because the A tile is single-buffered.
+    // K-major layout; sequences missing from a partial tile are zero-filled (src-size 0).  The tile is
+    // single-buffered, so the time from "chunk free" (last projection pass done with it) to "chunk full" is exposed
+    // once per tile: TMA gather4 (v4) needed ~8,000 cycles, cp.async ~5,500 (profiles/r1_k1v5_trace_*.txt).
     (void)tmap_src; (void)null_row;
     constexpr int NREAL = S * SPT;                   // real rows of a tile (100)
-    constexpr int NIT = (NREAL + 3) / 4;
-    static_assert(NIT <= 32, "validity mask");
-    int* const rowid = reinterpret_cast<int*>(sm + OFF_BAR + 512);     // [NREAL] source row of every real tile row
+    constexpr int NIT = (NREAL + 3) / 4;             // 4-row copy instructions per chunk (25)
+    constexpr int NMINE = (NIT + NGW - 1) / NGW;     // ... per gather warp (7)
+    const int gw = warp - 12;
     const int g = lane >> 3, c = lane & 7;
-    // one warp issues 5 x 25 copies per tile: everything but the source row is precomputed, so an iteration is an
-    // address add and the cp.async (the first cut recomputed rows and swizzles per copy and was instruction-bound)
-    uint32_t dst_off[NIT];
+    // everything but the source row is precomputed: a copy is an address add and the cp.async
+    uint32_t dst_off[NMINE];
 #pragma unroll
-    for (int i = 0; i < NIT; ++i) {
-      const int n = 4 * i + g;
+    for (int k = 0; k < NMINE; ++k) {
+      const int n = 4 * (gw + NGW * k) + g;
       const int r = (n / S) * SLOT + (n % S);
-      dst_off[i] = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+      dst_off[k] = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
     }
     const char* const srcb = reinterpret_cast<const char*>(src16) + c * 16;
     uint32_t tile_it = 0;
-    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
+    TRACE_DECL;
+    // cp.async straight into the swizzled layout.  A third of the gathered rows miss L2 (ncu: 27 MB of DRAM reads per
+    // launch for 75 MB gathered), and the copies can only start once the chunk is free, so every lane first pulls
+    // the NEXT tile's row pieces into L2 (prefetch.global.L2, fire and forget) while the current tile computes.
+    uint32_t src_off[NMINE];
+    uint32_t valid = 0u;
+    auto load_rows = [&](int64_t t) {
       const int64_t seq0 = t * SPT;
       const int n_here = (n_seq - seq0 < SPT) ? (int)(n_seq - seq0) : SPT;
-      for (int n = lane; n < NREAL; n += 32) {
-        int r = -1;
-        if (n / S < n_here) {
-          const int64_t e = seq0 * S + n;
-          r = idx_kind == 0 ? (int)e : (idx_kind == 1 ? (int)reinterpret_cast<const int64_t*>(idx)[e]
-                                                        : reinterpret_cast<const int32_t*>(idx)[e]);
-        }
-        rowid[n] = r;
-      }
-      __syncwarp();
-      uint32_t src_off[NIT];
-      uint32_t valid = 0u;
+      valid = 0u;
 #pragma unroll
-      for (int i = 0; i < NIT; ++i) {
-        const int n = 4 * i + g;
-        const int sr = (n < NREAL) ? rowid[n] : -1;
-        src_off[i] = sr < 0 ? 0u : (uint32_t)sr * (uint32_t)(SRC_LD * 2);
-        if (sr >= 0) valid |= 1u << i;
+      for (int k = 0; k < NMINE; ++k) {
+        const int n = 4 * (gw + NGW * k) + g;
+        int sr = -1;
+        if (n < NREAL && n / S < n_here) {
+          const int64_t e = seq0 * S + n;
+          sr = idx_kind == 0 ? (int)e : (idx_kind == 1 ? (int)__ldg(reinterpret_cast<const int64_t*>(idx) + e)
+                                                         : __ldg(reinterpret_cast<const int32_t*>(idx) + e));
+        }
+        src_off[k] = sr < 0 ? 0u : (uint32_t)sr * (uint32_t)(SRC_LD * 2);
+        if (sr >= 0) valid |= 1u << k;
       }
+    };
+    auto prefetch_rows = [&]() {        // lanes c = 0..4 of a row group cover the five 128-byte pieces of the row
+      if (c < KCH) {
+#pragma unroll
+        for (int k = 0; k < NMINE; ++k)
+          if ((valid >> k) & 1u)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(src16) + src_off[k] + c * 128));
+      }
+    };
+    if ((int64_t)blockIdx.x < n_tiles) load_rows(blockIdx.x);
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
 #pragma unroll 1
       for (int kc = 0; kc < KCH; ++kc) {
         mbar_wait(a_free + 8 * kc, (tile_it & 1) ^ 1);     // the previous tile's last pass is done with this chunk
+        if (gw == 0) TRACE(4, 60 + kc);
         const uint32_t dchunk = base + OFF_A + kc * 16384;
         const char* const schunk = srcb + kc * 128;
 #pragma unroll
-        for (int i = 0; i < NIT; ++i) {
-          if (4 * i + g < NREAL) {
-            const uint32_t nbytes = ((valid >> i) & 1u) ? 16u : 0u;       // 0: zero-fill (sequence not in this tile)
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dchunk + dst_off[i]),
-                         "l"(schunk + src_off[i]), "r"(nbytes) : "memory");
+        for (int k = 0; k < NMINE; ++k) {
+          if (4 * (gw + NGW * k) + g < NREAL) {
+            const uint32_t nbytes = ((valid >> k) & 1u) ? 16u : 0u;       // 0: zero-fill (sequence not in this tile)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dchunk + dst_off[k]),
+                         "l"(schunk + src_off[k]), "r"(nbytes) : "memory");
           }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
@@ -279,9 +291,14 @@ encoder_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(a_full + 8 * kc);
+        if (gw == 0) TRACE(4, 70 + kc);
       }
-      __syncwarp();                                     // rowid is rewritten for the next tile
+      if (t + gridDim.x < n_tiles) {
+        load_rows(t + gridDim.x);
+        prefetch_rows();
+      }
     }
+    if (gw == 0) TRACE_END(4);
   } else if (warp == 10) {
     // ------------------------------ projection MMA issuer (whole warp converged, see umma_*_p) ---
     const uint32_t idesc_proj = umma_idesc_f16(128, PN);
@@ -296,10 +313,7 @@ encoder_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
         TRACE(2, 40);
         // NST == KCH: chunk kc of every pass lives in ring stage kc; operand waits first, accumulator wait last
 #pragma unroll
-        for (int kc = 0; kc < KCH; ++kc) {
-          if (p == 0) mbar_wait(a_full + 8 * kc, tile_it & 1);
-          mbar_wait(w_full + 8 * kc, pass_it & 1);
-        }
+        for (int kc = 0; kc < KCH; ++kc) mbar_wait(w_full + 8 * kc, pass_it & 1);
         TRACE(2, 47);
         mbar_wait(acc_empty + 8 * b, (u & 1) ^ 1);     // pass_it - 2: k, v drained and q consumed
         tc_fence_after();
@@ -311,6 +325,10 @@ encoder_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
           // in flight, so a score or context MMA of the attention issuer never waits behind a whole projection pass
           if (kc >= PROJ_AHEAD) mbar_wait(w_empty + 8 * (kc - PROJ_AHEAD), pass_it & 1);
           else if (pass_it > 0) mbar_wait(w_empty + 8 * (kc + KCH - PROJ_AHEAD), (pass_it & 1) ^ 1);
+          if (p == 0) {                                  // first pass of a tile: start as soon as chunk kc has landed
+            mbar_wait(a_full + 8 * kc, tile_it & 1);
+            tc_fence_after();
+          }
           const uint32_t sa = (base + OFF_A + kc * 16384) >> 4;
           const uint32_t sb = (base + OFF_B + kc * B_STAGE) >> 4;
           const int ksteps = (kc == KCH - 1) ? 3 : 4;      // columns 256..303 (the bias column is 300)
@@ -565,7 +583,7 @@ encoder_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
     if (tracer) TRACE_END(set);
 #endif
   }
-  else if (warp == 12) {
+  else if (warp == 11) {
     // ------------------------------ context store: staging tile -> global (bulk tensor stores) ----
     if (lane == 0) {
       uint32_t k = 0;
@@ -592,10 +610,10 @@ encoder_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
 
 }  // namespace k1v5
 
-// debug builds (-DNRMS_K1_TRACE): host[who*1024 ..] = stamps of tracer `who`; counts[4]
+// debug builds (-DNRMS_K1_TRACE): host[who*1024 ..] = stamps of tracer `who`; counts[5]
 extern "C" int nrms_debug_read_trace5(long long* host, int* counts) {
-  cudaMemcpyFromSymbol(counts, k1v5::g_trace_n, 4 * sizeof(int));
-  cudaMemcpyFromSymbol(host, k1v5::g_trace, 4 * 1024 * sizeof(long long));
+  cudaMemcpyFromSymbol(counts, k1v5::g_trace_n, 5 * sizeof(int));
+  cudaMemcpyFromSymbol(host, k1v5::g_trace, 5 * 1024 * sizeof(long long));
   return 0;
 }
 

@@ -19,14 +19,15 @@ with torch.no_grad():
         f = lambda: m.get_news_vector({"title": toks})
     for _ in range(3): f()
     torch.cuda.synchronize()
-buf = (ctypes.c_longlong * 4096)(); cnt = (ctypes.c_int * 4)()
+NT = 5 if os.environ.get('NRMS_K1_VARIANT', '5') == '5' else 4
+buf = (ctypes.c_longlong * (1024 * NT))(); cnt = (ctypes.c_int * NT)()
 (lib.nrms_debug_read_trace5 if os.environ.get('NRMS_K1_VARIANT', '5') == '5' else lib.nrms_debug_read_trace4)(buf, cnt)
 names = {20: "pass start", 21: "acc_full", 22: "W1 done", 23: "W3fin done", 24: "s_ready a", 25: "s_ready b", 26: "W2a done",
          27: "W2b done", 28: "o_ready a", 29: "o_ready b", 30: "W3 done", 31: "staged",
          40: "P pass start", 41: "P acc_empty", 42: "P kc0", 43: "P kc1", 44: "P kc2", 45: "P kc3", 46: "P kc4",
-         47: "P wait", 48: "P issued", 55: "A S issued", 56: "A O issued", 50: "A pass start", 51: "A kv a", 52: "A kv b", 53: "A p a", 54: "A p b"}
+         47: "P wait", 48: "P issued", 55: "A S issued", 56: "A O issued", 60: "G free0", 61: "G free1", 62: "G free2", 63: "G free3", 64: "G free4", 70: "G full0", 71: "G full1", 72: "G full2", 73: "G full3", 74: "G full4", 50: "A pass start", 51: "A kv a", 52: "A kv b", 53: "A p a", 54: "A p b"}
 allev = []
-for who in range(4):
+for who in range(NT):
     ev = [(buf[who * 1024 + i] >> 48, buf[who * 1024 + i] & 0xFFFFFFFFFFFF) for i in range(cnt[who])]
     allev += [(t, who, tag) for tag, t in ev]
     print("=== tracer", who, "events", len(ev))
@@ -40,8 +41,8 @@ allev.sort()
 t0 = allev[0][0]
 starts = [t for t, who, tag in allev if who == 0 and tag == 20]
 if len(starts) > 24:
-    lo, hi = starts[16], starts[19]
-    print("=== merged timeline, passes 16..18 (cycles since pass-16 start)")
+    lo, hi = starts[14], starts[17]
+    print("=== merged timeline, passes 14..16 (cycles since pass-14 start; pass 16 opens a tile)")
     for t, who, tag in allev:
         if lo <= t <= hi:
             print(f"  {t - lo:7d}  tracer {who}  {names.get(tag, tag)}")
