@@ -117,7 +117,14 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // 2^x on the FMA and integer pipes (Cody-Waite split by the 1.5*2^23 trick, degree-4 Taylor polynomial of 2^f on
 // [-0.5, 0.5], relative error < 5e-5 -- an order below the fp16 rounding of P): the MUFU unit delivers 16 ex2 per clock
 // per SM (profiles/tmem_ld_probe.cu) and the softmax of a pass needs 12,800 of them, so every other probability is
-// computed here, in parallel with the MUFU half.
+// computed here, in parallel with the MUFU half.  Measured (A/B on the evaluate bench): the ten extra instructions per
+// element cost more issue slots than the MUFU relief buys back -- every 2nd element here: 129.2 us per launch, none:
+// 124.1 us -- so the default sends one element in EX2_FMA_MOD to this path (0 = none).
+#ifndef NRMS_EX2_FMA_MOD
+#define NRMS_EX2_FMA_MOD 0
+#endif
+constexpr int EX2_FMA_MOD = NRMS_EX2_FMA_MOD;
+__device__ __forceinline__ bool ex2_on_fma(int j) { return EX2_FMA_MOD > 0 && (j % EX2_FMA_MOD) == EX2_FMA_MOD - 1; }
 __device__ __forceinline__ float ex2_fma(float x) {
   x = fmaxf(x, -100.f);
   const float t = x + 12582912.f;                    // integer part lands in the low mantissa bits
@@ -499,8 +506,9 @@ encoder_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
             uint32_t pk[32];
 #pragma unroll
             for (int j = 0; j < 64; j += 2) {
-              const float e0 = (j < S) ? ex2(__uint_as_float(sv[j])) : 0.f;               // MUFU
-              const float e1 = (j + 1 < S) ? ex2_fma(__uint_as_float(sv[j + 1])) : 0.f;   // FMA pipe
+              const float x0 = __uint_as_float(sv[j]), x1 = __uint_as_float(sv[j + 1]);
+              const float e0 = (j < S) ? (ex2_on_fma(j) ? ex2_fma(x0) : ex2(x0)) : 0.f;
+              const float e1 = (j + 1 < S) ? (ex2_on_fma(j + 1) ? ex2_fma(x1) : ex2(x1)) : 0.f;
               Z += e0 + e1;
               pk[j >> 1] = (j < S) ? pack_h2(e0, e1) : 0u;
             }
@@ -529,8 +537,8 @@ encoder_attn_tc5_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
             for (int j = 0; j < 20; j += 2) {
               const float s0 = __uint_as_float(own ? sv[1][j] : sv[0][j]);
               const float s1 = __uint_as_float(own ? sv[1][j + 1] : sv[0][j + 1]);
-              const float e0 = (j < S) ? ex2(s0) : 0.f;
-              const float e1 = (j + 1 < S) ? ex2_fma(s1) : 0.f;
+              const float e0 = (j < S) ? (ex2_on_fma(j) ? ex2_fma(s0) : ex2(s0)) : 0.f;
+              const float e1 = (j + 1 < S) ? (ex2_on_fma(j + 1) ? ex2_fma(s1) : ex2(s1)) : 0.f;
               Z += e0 + e1;
               pk[j >> 1] = pack_h2(e0, e1);
             }
