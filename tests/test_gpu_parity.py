@@ -329,6 +329,39 @@ def test_evaluate_pipeline_golden(dev, golden, golden_sd, precision):
     np.testing.assert_allclose(means, golden["eval/means"], atol=5e-4 if precision == "fp32" else 5e-3)
 
 
+def test_evaluate_full_size_tensor_vs_fp32_mode(dev):
+    """BASELINE configs[1] at FULL size (65,238 news, 73,152 impressions, 2.7 M candidates, 70,976-word vocabulary):
+    the oracle would take minutes here, so the tensor-core pipeline (K1 v5 / K2, every tile shape and the chunked
+    launches) is checked against the library's own FP32 CUDA-core mode -- which the small-size tests tie to the
+    oracle and the reference goldens: every news vector within 1e-3 relative, metric means equal to 3 decimals,
+    scores within 5e-3, and the run is deterministic (two passes are bit-identical)."""
+    import bench
+    from newsrecommendationsystem_b200 import NRMS, NRMSConfig, synthetic
+    from newsrecommendationsystem_b200.evaluate import EvalHost, EvalInputs, evaluate_tensors
+    sd = synthetic.init_state_dict(num_words=bench.NUM_WORDS, seed=0)
+    news, imp = bench.make_data(1)
+    host = EvalHost(news, imp["hist_rows"], imp["cand_offsets"], imp["cand_rows"], imp["labels"])
+    inp = EvalInputs.from_host(host, dev)
+    out = {}
+    for precision in ("fp32", "tf32"):
+        m = NRMS(NRMSConfig)
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+        m.to(dev).eval().set_precision(precision)
+        means, det = evaluate_tensors(m, inp, return_details=True)
+        out[precision] = (np.asarray(means), det["table"].clone(), det["scores"].clone())
+        if precision == "tf32":
+            means2, det2 = evaluate_tensors(m, inp, return_details=True)
+            assert torch.equal(det2["table"], det["table"]) and torch.equal(det2["scores"], det["scores"])
+            assert np.array_equal(np.asarray(means2), np.asarray(means))
+    (m32, t32, s32), (mtc, ttc, stc) = out["fp32"], out["tf32"]
+    n = bench.NEWS_PER_GPU
+    rel = (ttc[:n] - t32[:n]).norm(dim=1) / t32[:n].norm(dim=1)
+    assert float(rel.max()) < 1e-3, float(rel.max())
+    assert float(ttc[n:].abs().max()) == 0.0                      # PADDED_NEWS row stays exactly zero
+    assert float((stc - s32).abs().max()) < 5e-3
+    np.testing.assert_allclose(mtc, m32, atol=5e-4)
+
+
 @pytest.mark.parametrize("precision", ["fp32", "tf32"])
 def test_evaluate_pipeline_vs_oracle_medium(dev, golden_sd, precision):
     """3k news / 2k impressions: metric means agree with the oracle to 3 decimals."""
