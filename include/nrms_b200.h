@@ -177,6 +177,45 @@ int nrms_rank_metrics(const float* scores, const int8_t* labels, const int64_t* 
 int nrms_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias,
                  float* C, int64_t ldc, int64_t M, int N, int K, int mode, void* stream);
 
+/* ---- config-5 variant: LayerNorm(300) between the self-attention context and the additive block ------------
+ * The reference tree has no code for its "+LN +AdamW +cosine" row (README.md:105-112); the definition used here is
+ * builder-defined: c = LayerNorm(dropout(MHSA(x))) with torch semantics (biased variance,
+ * eps 1e-5, affine weight/bias [300]) in BOTH encoders, then AdditiveAttention(c).  Same contracts as the entry
+ * points above; the stash of a training forward is nrms_encoder_ln_stash_bytes bytes.  d_ln_gamma / d_ln_beta are
+ * accumulated into (zero them first), like the other gradient outputs. */
+size_t nrms_encoder_ln_stash_bytes(int64_t n_seq, int S);
+int nrms_news_encoder_ln_fwd(const int64_t* tokens, int64_t n_titles, int L,
+                             const float* emb, int64_t num_words,
+                             const float* wqkv, const float* bqkv,
+                             const float* ln_gamma, const float* ln_beta,
+                             const float* wa, const float* ba, const float* qa,
+                             float* out, void* stash,
+                             void* workspace, size_t workspace_bytes,
+                             float dropout_p, uint64_t seed, uint64_t offset,
+                             int mode, void* stream);
+int nrms_news_encoder_ln_bwd(const float* d_out, const int64_t* tokens, int64_t n_titles, int L, int64_t num_words,
+                             const float* wqkv, const float* ln_gamma, const float* wa, const float* qa,
+                             const void* stash,
+                             float* d_emb, float* d_wqkv, float* d_bqkv, float* d_ln_gamma, float* d_ln_beta,
+                             float* d_wa, float* d_ba, float* d_qa,
+                             void* workspace, size_t workspace_bytes,
+                             float dropout_p, uint64_t seed, uint64_t offset,
+                             int mode, void* stream);
+int nrms_user_encoder_ln_fwd(const float* x, int64_t n_rows, const int32_t* rows_idx, int64_t n_users, int S,
+                             const float* wqkv, const float* bqkv,
+                             const float* ln_gamma, const float* ln_beta,
+                             const float* wa, const float* ba, const float* qa,
+                             float* out, void* stash,
+                             void* workspace, size_t workspace_bytes,
+                             int mode, void* stream);
+int nrms_user_encoder_ln_bwd(const float* d_out, int64_t n_users, int S,
+                             const float* wqkv, const float* ln_gamma, const float* wa, const float* qa,
+                             const void* stash,
+                             float* d_x, float* d_wqkv, float* d_bqkv, float* d_ln_gamma, float* d_ln_beta,
+                             float* d_wa, float* d_ba, float* d_qa,
+                             void* workspace, size_t workspace_bytes,
+                             int mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,9 +5,9 @@ hand-written sm_100a library `libnrms_b200.so` through the C-ABI in `include/nrm
 Importing the package does not load CUDA; the first op call does, and raises if the library
 is missing (there is no CPU fallback).
 """
-from .config import NRMSConfig, BaseConfig  # noqa: F401
+from .config import NRMSConfig, NRMSLNConfig, BaseConfig  # noqa: F401
 
-__all__ = ["NRMSConfig", "BaseConfig", "NRMS", "NewsEncoder", "UserEncoder", "DotProductClickPredictor"]
+__all__ = ["NRMSConfig", "NRMSLNConfig", "BaseConfig", "NRMS", "NewsEncoder", "UserEncoder", "DotProductClickPredictor"]
 
 
 def __getattr__(name):

@@ -3,8 +3,10 @@
 The B200 modules read ONLY attributes the reference modules read (`num_words`,
 `word_embedding_dim`, `num_attention_heads`, `query_vector_dim`, `dropout_probability`,
 `num_words_title`, `num_clicked_news_a_user`), so a reference `NRMSConfig` object can be passed
-unchanged.  One optional extra attribute is honoured when present:
+unchanged.  Two optional extra attributes are honoured when present:
   precision: "tf32" (tcgen05 tensor cores, default) | "fp32" (CUDA-core reference-exact mode)
+  use_layernorm: True adds nn.LayerNorm(300) on the self-attention context of both encoders (the "+LN" of the
+      reference README's config-5 row, which has no code in the tree; builder-defined)
 """
 import os
 
@@ -37,6 +39,12 @@ class BaseConfig:
 class NRMSConfig(BaseConfig):
     dataset_attributes = {"news": ['title'], "record": []}
     num_attention_heads = 15
+
+
+class NRMSLNConfig(NRMSConfig):
+    """BASELINE configs[4]: NRMS + LayerNorm, trained with AdamW + cosine decay (optim.FusedAdam(adamw=True),
+    optim.cosine_lr)."""
+    use_layernorm = True
 
 
 def resolve_mode(config=None, override=None):

@@ -9,11 +9,20 @@
 namespace nrms {
 
 // ---- stash layout: X [rows,300] | QKV [rows,900] | C [rows,300] | T [rows,200] | w [rows] ----
+// LayerNorm variant (config 5): + CN [rows,300] (normalised context, the additive block's input) | stats [rows,2]
 struct Stash {
-  float *x, *qkv, *c, *t, *w;
+  float *x, *qkv, *c, *t, *w, *cn, *stats;
   size_t bytes;
 };
-static Stash carve_stash(void* base, int64_t rows) {
+// optional LayerNorm between the self-attention context and the additive block (nullptr = reference NRMS)
+struct LnArgs {
+  const float* gamma;
+  const float* beta;
+  float* d_gamma;
+  float* d_beta;
+};
+constexpr float LN_EPS = 1e-5f;    // torch.nn.LayerNorm default
+static Stash carve_stash(void* base, int64_t rows, bool ln = false) {
   Stash s;
   char* p = reinterpret_cast<char*>(base);
   size_t off = 0;
@@ -27,6 +36,8 @@ static Stash carve_stash(void* base, int64_t rows) {
   s.c = take((size_t)rows * D);
   s.t = take((size_t)rows * QD);
   s.w = take((size_t)rows);
+  s.cn = ln ? take((size_t)rows * D) : nullptr;
+  s.stats = ln ? take((size_t)rows * 2) : nullptr;
   s.bytes = off;
   return s;
 }
@@ -115,7 +126,8 @@ static int gemm_nt_bias(const float* A, int64_t lda, const float* B, int64_t ldb
 // Forward over `n_seq` sequences whose input rows X are already materialised in st.x.
 static int encoder_core_fwd(const Stash& s, int64_t n_seq, int S, const float* wqkv, const float* bqkv,
                             const float* wa, const float* ba, const float* qa, float* out, float p2,
-                            uint64_t seed, uint64_t offset, int64_t row_base, int mode, cudaStream_t st) {
+                            uint64_t seed, uint64_t offset, int64_t row_base, int mode, cudaStream_t st,
+                            const LnArgs* ln = nullptr) {
   const int64_t rows = n_seq * S;
   int rc = gemm_nt_bias(s.x, D, wqkv, D, bqkv, s.qkv, D3, rows, D3, D, mode, st);
   if (rc) return rc;
@@ -125,11 +137,19 @@ static int encoder_core_fwd(const Stash& s, int64_t n_seq, int S, const float* w
   if (S == 20) e = launch_attention_fwd<20, 15>(s.qkv, s.c, n_seq, p2, seed, off2, st);
   else e = launch_attention_fwd<50, 5>(s.qkv, s.c, n_seq, p2, seed, off2, st);
   if (e != cudaSuccess) return cuda_fail(e, "attention_fwd");
-  rc = gemm_nt_bias(s.c, D, wa, D, ba, s.t, QD, rows, QD, D, mode, st);
+  const float* cin = s.c;
+  if (ln) {
+    int64_t lb = (rows + 7) / 8;
+    if (lb > (int64_t)num_sms() * 8) lb = (int64_t)num_sms() * 8;
+    layernorm_fwd_kernel<<<(unsigned)lb, 256, 0, st>>>(s.c, ln->gamma, ln->beta, s.cn, s.stats, rows, LN_EPS);
+    NRMS_LAUNCH_CHECK("layernorm_fwd");
+    cin = s.cn;
+  }
+  rc = gemm_nt_bias(cin, D, wa, D, ba, s.t, QD, rows, QD, D, mode, st);
   if (rc) return rc;
   int64_t gx = n_seq < (int64_t)num_sms() * 8 ? n_seq : (int64_t)num_sms() * 8;
-  if (S == 20) additive_fwd_kernel<20><<<(unsigned)gx, 256, 0, st>>>(s.c, s.t, qa, s.w, out, n_seq);
-  else additive_fwd_kernel<50><<<(unsigned)gx, 256, 0, st>>>(s.c, s.t, qa, s.w, out, n_seq);
+  if (S == 20) additive_fwd_kernel<20><<<(unsigned)gx, 256, 0, st>>>(cin, s.t, qa, s.w, out, n_seq);
+  else additive_fwd_kernel<50><<<(unsigned)gx, 256, 0, st>>>(cin, s.t, qa, s.w, out, n_seq);
   NRMS_LAUNCH_CHECK("additive_fwd");
   return NRMS_OK;
 }
@@ -138,7 +158,7 @@ static int encoder_core_fwd(const Stash& s, int64_t n_seq, int S, const float* w
 static int encoder_core_bwd(const Stash& s, const BwdWs& w, const float* d_out, int64_t n_seq, int S,
                             const float* wqkv, const float* wa, const float* qa, float* d_x, float* d_wqkv,
                             float* d_bqkv, float* d_wa, float* d_ba, float* d_qa, float p2, uint64_t seed,
-                            uint64_t offset, int mode, cudaStream_t st) {
+                            uint64_t offset, int mode, cudaStream_t st, const LnArgs* ln = nullptr) {
   // FP32 mode: every contraction on the CUDA cores (reference-exact up to summation order).  Tensor mode: the four
   // GEMMs run on tcgen05 (TF32 operands rounded by the TMA unit, fp32 accumulation) through the K-major NT kernel:
   //   dC  += dU   Wa        = NT(dU   [rows,200], Wa^T   [300,200])
@@ -149,9 +169,10 @@ static int encoder_core_bwd(const Stash& s, const BwdWs& w, const float* d_out, 
   // fp32 SGEMMs cost: measured 6.3 ms -> see profiles/).
   const bool tc = (mode == NRMS_MODE_TF32);
   const int64_t rows = n_seq * S;
+  const float* cin = ln ? s.cn : s.c;        // input of the additive block
   int nb = (int)(n_seq < REDUCE_BLOCKS ? n_seq : REDUCE_BLOCKS);
-  if (S == 20) additive_bwd_kernel<20><<<nb, 256, 0, st>>>(d_out, s.c, s.t, s.w, qa, w.d_c, w.d_u, w.partial, n_seq);
-  else additive_bwd_kernel<50><<<nb, 256, 0, st>>>(d_out, s.c, s.t, s.w, qa, w.d_c, w.d_u, w.partial, n_seq);
+  if (S == 20) additive_bwd_kernel<20><<<nb, 256, 0, st>>>(d_out, cin, s.t, s.w, qa, w.d_c, w.d_u, w.partial, n_seq);
+  else additive_bwd_kernel<50><<<nb, 256, 0, st>>>(d_out, cin, s.t, s.w, qa, w.d_c, w.d_u, w.partial, n_seq);
   NRMS_LAUNCH_CHECK("additive_bwd");
   partial_reduce_accum_kernel<<<1, 256, 0, st>>>(w.partial, nb, QD, d_qa);
   NRMS_LAUNCH_CHECK("dqa_reduce");
@@ -167,7 +188,7 @@ static int encoder_core_bwd(const Stash& s, const BwdWs& w, const float* d_out, 
   if (tc) {
     // d_wa[200,300] += dU^T C
     if (int rc = transpose_f32(w.d_u, QD, w.t1, w.ldr, rows, QD, st)) return rc;
-    if (int rc = transpose_f32(s.c, D, w.t2, w.ldr, rows, D, st)) return rc;
+    if (int rc = transpose_f32(cin, D, w.t2, w.ldr, rows, D, st)) return rc;
     if (int rc = tc_gemm_nt_ex(w.t1, w.ldr, w.t2, w.ldr, nullptr, d_wa, D, QD, D, (int)rows,
                                tc_gemm_auto_splits(QD, D, (int)rows), TC_EPI_ATOMIC, st)) return rc;
     // d_c += dU * Wa
@@ -175,11 +196,20 @@ static int encoder_core_bwd(const Stash& s, const BwdWs& w, const float* d_out, 
     if (int rc = tc_gemm_nt_ex(w.d_u, QD, w.wt, QD, nullptr, w.d_c, D, rows, D, QD, 1, TC_EPI_ACCUM, st)) return rc;
   } else {
     // d_wa[200,300] += dU^T C   (reduction over rows, split-K + fp32 atomics)
-    e = sgemm_launch<1, 1, EPI_ATOMIC>(w.d_u, QD, s.c, D, nullptr, d_wa, D, QD, D, rows, splits, st);
+    e = sgemm_launch<1, 1, EPI_ATOMIC>(w.d_u, QD, cin, D, nullptr, d_wa, D, QD, D, rows, splits, st);
     if (e != cudaSuccess) return cuda_fail(e, "sgemm dWa");
     // d_c += dU * Wa   ([rows,200] x [200,300])
     e = sgemm_launch<0, 1, EPI_ACCUM>(w.d_u, QD, wa, D, nullptr, w.d_c, D, rows, D, QD, 1, st);
     if (e != cudaSuccess) return cuda_fail(e, "sgemm dC");
+  }
+  if (ln) {   // d_c holds dL/dCN: through the LayerNorm, in place; d_gamma / d_beta via per-block partial sums
+    int lb = (int)((rows + 7) / 8 < REDUCE_BLOCKS ? (rows + 7) / 8 : REDUCE_BLOCKS);
+    layernorm_bwd_kernel<<<lb, 256, 0, st>>>(w.d_c, s.c, s.stats, ln->gamma, w.partial, rows);
+    NRMS_LAUNCH_CHECK("layernorm_bwd");
+    partial_reduce_accum_strided_kernel<<<(D + 255) / 256, 256, 0, st>>>(w.partial, lb, 2 * D, D, ln->d_gamma);
+    NRMS_LAUNCH_CHECK("dgamma_reduce");
+    partial_reduce_accum_strided_kernel<<<(D + 255) / 256, 256, 0, st>>>(w.partial + D, lb, 2 * D, D, ln->d_beta);
+    NRMS_LAUNCH_CHECK("dbeta_reduce");
   }
   // attention backward (applies the dropout-2 mask to d_c on load)
   if (S == 20) e = launch_attention_bwd<20, 15>(s.qkv, w.d_c, w.d_qkv, n_seq, p2, seed, offset, st);
@@ -227,6 +257,11 @@ size_t nrms_encoder_stash_bytes(int64_t n_seq, int S) {
   return carve_stash(nullptr, n_seq * S).bytes;
 }
 
+size_t nrms_encoder_ln_stash_bytes(int64_t n_seq, int S) {
+  if (n_seq <= 0 || S <= 0) return 0;
+  return carve_stash(nullptr, n_seq * S, true).bytes;
+}
+
 size_t nrms_encoder_fwd_workspace_bytes(int64_t n_seq, int S, int mode, int training, int64_t n_src_rows) {
   if (n_seq <= 0 || S <= 0) return 0;
   if (training) return 256;
@@ -236,7 +271,7 @@ size_t nrms_encoder_fwd_workspace_bytes(int64_t n_seq, int S, int mode, int trai
   }
   int64_t chunk_seq = INFER_CHUNK_ROWS / S;
   if (n_seq < chunk_seq) chunk_seq = n_seq;
-  return carve_stash(nullptr, chunk_seq * S).bytes + 256;
+  return carve_stash(nullptr, chunk_seq * S, true).bytes + 256;     // room for the LayerNorm variant's fields too
 }
 
 size_t nrms_encoder_bwd_workspace_bytes(int64_t n_seq, int S, int mode) {
@@ -244,11 +279,20 @@ size_t nrms_encoder_bwd_workspace_bytes(int64_t n_seq, int S, int mode) {
   return carve_bwd(nullptr, n_seq * S, true, mode).bytes + 256;
 }
 
-int nrms_news_encoder_fwd(const int64_t* tokens, int64_t n_titles, int L, const float* emb, int64_t num_words,
-                          const float* wqkv, const float* bqkv, const float* wa, const float* ba, const float* qa,
-                          float* out, void* stash, void* workspace, size_t workspace_bytes, float dropout_p,
-                          uint64_t seed, uint64_t offset, int mode, void* stream) {
+static int check_ln(const LnArgs* ln, bool bwd) {
+  if (!ln) return NRMS_OK;
+  NRMS_CHECK_ARG(ln->gamma && aligned16(ln->gamma), NRMS_E_INVALID, "LayerNorm weight missing or misaligned");
+  if (bwd) NRMS_CHECK_ARG(ln->d_gamma && ln->d_beta, NRMS_E_INVALID, "LayerNorm gradient pointers missing");
+  else NRMS_CHECK_ARG(ln->beta && aligned16(ln->beta), NRMS_E_INVALID, "LayerNorm bias missing or misaligned");
+  return NRMS_OK;
+}
+
+static int news_encoder_fwd_impl(const int64_t* tokens, int64_t n_titles, int L, const float* emb, int64_t num_words,
+                                 const float* wqkv, const float* bqkv, const float* wa, const float* ba, const float* qa,
+                                 float* out, void* stash, void* workspace, size_t workspace_bytes, float dropout_p,
+                                 uint64_t seed, uint64_t offset, int mode, void* stream, const LnArgs* ln) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (int rc = check_ln(ln, false)) return rc;
   if (int rc = check_common(L, mode)) return rc;
   NRMS_CHECK_ARG(L == 20, NRMS_E_UNSUPPORTED, "news encoder compiled for title length 20, got %d", L);
   NRMS_CHECK_ARG(n_titles >= 0 && num_words > 0, NRMS_E_INVALID, "bad sizes");
@@ -261,26 +305,26 @@ int nrms_news_encoder_fwd(const int64_t* tokens, int64_t n_titles, int L, const 
 
   if (stash) {  // training: everything kept for backward
     NRMS_CHECK_ARG(aligned16(stash), NRMS_E_INVALID, "stash misaligned");
-    Stash s = carve_stash(stash, n_titles * L);
+    Stash s = carve_stash(stash, n_titles * L, ln != nullptr);
     const int64_t rows = n_titles * L;
     int64_t gb = (rows + 7) / 8;
     if (gb > (int64_t)num_sms() * 16) gb = (int64_t)num_sms() * 16;
     gather_embedding_kernel<<<(unsigned)gb, 256, 0, st>>>(tokens, rows, emb, s.x, dropout_p, scale, seed, offset);
     NRMS_LAUNCH_CHECK("gather_embedding");
-    return encoder_core_fwd(s, n_titles, L, wqkv, bqkv, wa, ba, qa, out, dropout_p, seed, offset, 0, mode, st);
+    return encoder_core_fwd(s, n_titles, L, wqkv, bqkv, wa, ba, qa, out, dropout_p, seed, offset, 0, mode, st, ln);
   }
   // inference
   if (mode == NRMS_MODE_TF32 && dropout_p == 0.f && tc_fused_workspace_bytes(n_titles, L, num_words) != (size_t)-1) {
     return tc_encoder_fused(emb, num_words, tokens, 1, n_titles, L, wqkv, bqkv, wa, ba, qa, out, workspace,
-                            workspace_bytes, st);
+                            workspace_bytes, st, ln ? ln->gamma : nullptr, ln ? ln->beta : nullptr);
   }
   const int64_t chunk_seq = INFER_CHUNK_ROWS / L;
   const int64_t first = n_titles < chunk_seq ? n_titles : chunk_seq;
-  NRMS_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= carve_stash(nullptr, first * L).bytes,
-                 NRMS_E_WORKSPACE, "workspace too small: need %zu bytes", carve_stash(nullptr, first * L).bytes);
+  NRMS_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= carve_stash(nullptr, first * L, true).bytes,
+                 NRMS_E_WORKSPACE, "workspace too small: need %zu bytes", carve_stash(nullptr, first * L, true).bytes);
   for (int64_t s0 = 0; s0 < n_titles; s0 += chunk_seq) {
     const int64_t n = (n_titles - s0 < chunk_seq) ? (n_titles - s0) : chunk_seq;
-    Stash s = carve_stash(workspace, n * L);
+    Stash s = carve_stash(workspace, n * L, ln != nullptr);
     const int64_t rows = n * L;
     int64_t gb = (rows + 7) / 8;
     if (gb > (int64_t)num_sms() * 16) gb = (int64_t)num_sms() * 16;
@@ -288,18 +332,38 @@ int nrms_news_encoder_fwd(const int64_t* tokens, int64_t n_titles, int L, const 
     gather_embedding_kernel<<<(unsigned)gb, 256, 0, st>>>(tokens + s0 * L, rows, emb, s.x, dropout_p, scale, seed,
                                                           offset + (uint64_t)s0 * L * D / 4);
     NRMS_LAUNCH_CHECK("gather_embedding");
-    int rc = encoder_core_fwd(s, n, L, wqkv, bqkv, wa, ba, qa, out + s0 * D, dropout_p, seed, offset, s0 * L, mode, st);
+    int rc = encoder_core_fwd(s, n, L, wqkv, bqkv, wa, ba, qa, out + s0 * D, dropout_p, seed, offset, s0 * L, mode, st,
+                              ln);
     if (rc) return rc;
   }
   return NRMS_OK;
 }
 
-int nrms_news_encoder_bwd(const float* d_out, const int64_t* tokens, int64_t n_titles, int L, int64_t num_words,
-                          const float* wqkv, const float* wa, const float* qa, const void* stash, float* d_emb,
-                          float* d_wqkv, float* d_bqkv, float* d_wa, float* d_ba, float* d_qa, void* workspace,
-                          size_t workspace_bytes, float dropout_p, uint64_t seed, uint64_t offset, int mode,
-                          void* stream) {
+int nrms_news_encoder_fwd(const int64_t* tokens, int64_t n_titles, int L, const float* emb, int64_t num_words,
+                          const float* wqkv, const float* bqkv, const float* wa, const float* ba, const float* qa,
+                          float* out, void* stash, void* workspace, size_t workspace_bytes, float dropout_p,
+                          uint64_t seed, uint64_t offset, int mode, void* stream) {
+  return news_encoder_fwd_impl(tokens, n_titles, L, emb, num_words, wqkv, bqkv, wa, ba, qa, out, stash, workspace,
+                               workspace_bytes, dropout_p, seed, offset, mode, stream, nullptr);
+}
+
+int nrms_news_encoder_ln_fwd(const int64_t* tokens, int64_t n_titles, int L, const float* emb, int64_t num_words,
+                             const float* wqkv, const float* bqkv, const float* ln_gamma, const float* ln_beta,
+                             const float* wa, const float* ba, const float* qa, float* out, void* stash, void* workspace,
+                             size_t workspace_bytes, float dropout_p, uint64_t seed, uint64_t offset, int mode,
+                             void* stream) {
+  const LnArgs ln{ln_gamma, ln_beta, nullptr, nullptr};
+  return news_encoder_fwd_impl(tokens, n_titles, L, emb, num_words, wqkv, bqkv, wa, ba, qa, out, stash, workspace,
+                               workspace_bytes, dropout_p, seed, offset, mode, stream, &ln);
+}
+
+static int news_encoder_bwd_impl(const float* d_out, const int64_t* tokens, int64_t n_titles, int L, int64_t num_words,
+                                 const float* wqkv, const float* wa, const float* qa, const void* stash, float* d_emb,
+                                 float* d_wqkv, float* d_bqkv, float* d_wa, float* d_ba, float* d_qa, void* workspace,
+                                 size_t workspace_bytes, float dropout_p, uint64_t seed, uint64_t offset, int mode,
+                                 void* stream, const LnArgs* ln) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (int rc = check_ln(ln, true)) return rc;
   if (int rc = check_common(L, mode)) return rc;
   NRMS_CHECK_ARG(L == 20, NRMS_E_UNSUPPORTED, "news encoder compiled for title length 20, got %d", L);
   if (n_titles == 0) return NRMS_OK;
@@ -311,10 +375,10 @@ int nrms_news_encoder_bwd(const float* d_out, const int64_t* tokens, int64_t n_t
   const int64_t rows = n_titles * L;
   NRMS_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= carve_bwd(nullptr, rows, true, mode).bytes,
                  NRMS_E_WORKSPACE, "workspace too small: need %zu bytes", carve_bwd(nullptr, rows, true, mode).bytes);
-  Stash s = carve_stash(const_cast<void*>(stash), rows);
+  Stash s = carve_stash(const_cast<void*>(stash), rows, ln != nullptr);
   BwdWs w = carve_bwd(workspace, rows, true, mode);
   int rc = encoder_core_bwd(s, w, d_out, n_titles, L, wqkv, wa, qa, w.d_x, d_wqkv, d_bqkv, d_wa, d_ba, d_qa,
-                            dropout_p, seed, offset, mode, st);
+                            dropout_p, seed, offset, mode, st, ln);
   if (rc) return rc;
   const float scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
   int64_t gb = (rows + 7) / 8;
@@ -324,10 +388,32 @@ int nrms_news_encoder_bwd(const float* d_out, const int64_t* tokens, int64_t n_t
   return NRMS_OK;
 }
 
-int nrms_user_encoder_fwd(const float* x, int64_t n_rows, const int32_t* rows_idx, int64_t n_users, int S, const float* wqkv,
-                          const float* bqkv, const float* wa, const float* ba, const float* qa, float* out,
-                          void* stash, void* workspace, size_t workspace_bytes, int mode, void* stream) {
+int nrms_news_encoder_bwd(const float* d_out, const int64_t* tokens, int64_t n_titles, int L, int64_t num_words,
+                          const float* wqkv, const float* wa, const float* qa, const void* stash, float* d_emb,
+                          float* d_wqkv, float* d_bqkv, float* d_wa, float* d_ba, float* d_qa, void* workspace,
+                          size_t workspace_bytes, float dropout_p, uint64_t seed, uint64_t offset, int mode,
+                          void* stream) {
+  return news_encoder_bwd_impl(d_out, tokens, n_titles, L, num_words, wqkv, wa, qa, stash, d_emb, d_wqkv, d_bqkv, d_wa,
+                               d_ba, d_qa, workspace, workspace_bytes, dropout_p, seed, offset, mode, stream, nullptr);
+}
+
+int nrms_news_encoder_ln_bwd(const float* d_out, const int64_t* tokens, int64_t n_titles, int L, int64_t num_words,
+                             const float* wqkv, const float* ln_gamma, const float* wa, const float* qa,
+                             const void* stash, float* d_emb, float* d_wqkv, float* d_bqkv, float* d_ln_gamma,
+                             float* d_ln_beta, float* d_wa, float* d_ba, float* d_qa, void* workspace,
+                             size_t workspace_bytes, float dropout_p, uint64_t seed, uint64_t offset, int mode,
+                             void* stream) {
+  const LnArgs ln{ln_gamma, nullptr, d_ln_gamma, d_ln_beta};
+  return news_encoder_bwd_impl(d_out, tokens, n_titles, L, num_words, wqkv, wa, qa, stash, d_emb, d_wqkv, d_bqkv, d_wa,
+                               d_ba, d_qa, workspace, workspace_bytes, dropout_p, seed, offset, mode, stream, &ln);
+}
+
+static int user_encoder_fwd_impl(const float* x, int64_t n_rows, const int32_t* rows_idx, int64_t n_users, int S,
+                                 const float* wqkv, const float* bqkv, const float* wa, const float* ba, const float* qa,
+                                 float* out, void* stash, void* workspace, size_t workspace_bytes, int mode,
+                                 void* stream, const LnArgs* ln) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (int rc = check_ln(ln, false)) return rc;
   if (int rc = check_common(S, mode)) return rc;
   NRMS_CHECK_ARG(n_users >= 0, NRMS_E_INVALID, "bad sizes");
   if (n_users == 0) return NRMS_OK;
@@ -337,22 +423,22 @@ int nrms_user_encoder_fwd(const float* x, int64_t n_rows, const int32_t* rows_id
   if (stash) {
     NRMS_CHECK_ARG(rows_idx == nullptr, NRMS_E_UNSUPPORTED, "indexed input is inference-only");
     NRMS_CHECK_ARG(aligned16(stash), NRMS_E_INVALID, "stash misaligned");
-    Stash s = carve_stash(stash, n_users * S);
+    Stash s = carve_stash(stash, n_users * S, ln != nullptr);
     NRMS_CUDA(cudaMemcpyAsync(s.x, x, (size_t)n_users * S * D * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    return encoder_core_fwd(s, n_users, S, wqkv, bqkv, wa, ba, qa, out, 0.f, 0, 0, 0, mode, st);
+    return encoder_core_fwd(s, n_users, S, wqkv, bqkv, wa, ba, qa, out, 0.f, 0, 0, 0, mode, st, ln);
   }
   NRMS_CHECK_ARG(rows_idx == nullptr || n_rows > 0, NRMS_E_INVALID, "indexed input needs n_rows (rows of the table)");
   if (mode == NRMS_MODE_TF32 && tc_fused_workspace_bytes(n_users, S, rows_idx ? n_rows : 0) != (size_t)-1) {
     return tc_encoder_fused(x, rows_idx ? n_rows : 0, rows_idx, rows_idx ? 2 : 0, n_users, S, wqkv, bqkv, wa, ba, qa, out,
-                            workspace, workspace_bytes, st);
+                            workspace, workspace_bytes, st, ln ? ln->gamma : nullptr, ln ? ln->beta : nullptr);
   }
   const int64_t chunk_seq = INFER_CHUNK_ROWS / S;
   const int64_t first = n_users < chunk_seq ? n_users : chunk_seq;
-  NRMS_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= carve_stash(nullptr, first * S).bytes,
-                 NRMS_E_WORKSPACE, "workspace too small: need %zu bytes", carve_stash(nullptr, first * S).bytes);
+  NRMS_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= carve_stash(nullptr, first * S, true).bytes,
+                 NRMS_E_WORKSPACE, "workspace too small: need %zu bytes", carve_stash(nullptr, first * S, true).bytes);
   for (int64_t s0 = 0; s0 < n_users; s0 += chunk_seq) {
     const int64_t n = (n_users - s0 < chunk_seq) ? (n_users - s0) : chunk_seq;
-    Stash s = carve_stash(workspace, n * S);
+    Stash s = carve_stash(workspace, n * S, ln != nullptr);
     const int64_t rows = n * S;
     if (rows_idx) {
       int64_t gb = (rows + 7) / 8;
@@ -362,16 +448,34 @@ int nrms_user_encoder_fwd(const float* x, int64_t n_rows, const int32_t* rows_id
     } else {
       s.x = const_cast<float*>(x) + s0 * S * D;  // dense input is read in place
     }
-    int rc = encoder_core_fwd(s, n, S, wqkv, bqkv, wa, ba, qa, out + s0 * D, 0.f, 0, 0, 0, mode, st);
+    int rc = encoder_core_fwd(s, n, S, wqkv, bqkv, wa, ba, qa, out + s0 * D, 0.f, 0, 0, 0, mode, st, ln);
     if (rc) return rc;
   }
   return NRMS_OK;
 }
 
-int nrms_user_encoder_bwd(const float* d_out, int64_t n_users, int S, const float* wqkv, const float* wa,
-                          const float* qa, const void* stash, float* d_x, float* d_wqkv, float* d_bqkv, float* d_wa,
-                          float* d_ba, float* d_qa, void* workspace, size_t workspace_bytes, int mode, void* stream) {
+int nrms_user_encoder_fwd(const float* x, int64_t n_rows, const int32_t* rows_idx, int64_t n_users, int S, const float* wqkv,
+                          const float* bqkv, const float* wa, const float* ba, const float* qa, float* out,
+                          void* stash, void* workspace, size_t workspace_bytes, int mode, void* stream) {
+  return user_encoder_fwd_impl(x, n_rows, rows_idx, n_users, S, wqkv, bqkv, wa, ba, qa, out, stash, workspace,
+                               workspace_bytes, mode, stream, nullptr);
+}
+
+int nrms_user_encoder_ln_fwd(const float* x, int64_t n_rows, const int32_t* rows_idx, int64_t n_users, int S,
+                             const float* wqkv, const float* bqkv, const float* ln_gamma, const float* ln_beta,
+                             const float* wa, const float* ba, const float* qa, float* out, void* stash, void* workspace,
+                             size_t workspace_bytes, int mode, void* stream) {
+  const LnArgs ln{ln_gamma, ln_beta, nullptr, nullptr};
+  return user_encoder_fwd_impl(x, n_rows, rows_idx, n_users, S, wqkv, bqkv, wa, ba, qa, out, stash, workspace,
+                               workspace_bytes, mode, stream, &ln);
+}
+
+static int user_encoder_bwd_impl(const float* d_out, int64_t n_users, int S, const float* wqkv, const float* wa,
+                                 const float* qa, const void* stash, float* d_x, float* d_wqkv, float* d_bqkv,
+                                 float* d_wa, float* d_ba, float* d_qa, void* workspace, size_t workspace_bytes,
+                                 int mode, void* stream, const LnArgs* ln) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (int rc = check_ln(ln, true)) return rc;
   if (int rc = check_common(S, mode)) return rc;
   if (n_users == 0) return NRMS_OK;
   NRMS_CHECK_ARG(n_users > 0, NRMS_E_INVALID, "bad sizes");
@@ -382,10 +486,26 @@ int nrms_user_encoder_bwd(const float* d_out, int64_t n_users, int S, const floa
   const int64_t rows = n_users * S;
   NRMS_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= carve_bwd(nullptr, rows, false, mode).bytes,
                  NRMS_E_WORKSPACE, "workspace too small: need %zu bytes", carve_bwd(nullptr, rows, false, mode).bytes);
-  Stash s = carve_stash(const_cast<void*>(stash), rows);
+  Stash s = carve_stash(const_cast<void*>(stash), rows, ln != nullptr);
   BwdWs w = carve_bwd(workspace, rows, false, mode);
   return encoder_core_bwd(s, w, d_out, n_users, S, wqkv, wa, qa, d_x, d_wqkv, d_bqkv, d_wa, d_ba, d_qa, 0.f, 0, 0, mode,
-                          st);
+                          st, ln);
+}
+
+int nrms_user_encoder_bwd(const float* d_out, int64_t n_users, int S, const float* wqkv, const float* wa,
+                          const float* qa, const void* stash, float* d_x, float* d_wqkv, float* d_bqkv, float* d_wa,
+                          float* d_ba, float* d_qa, void* workspace, size_t workspace_bytes, int mode, void* stream) {
+  return user_encoder_bwd_impl(d_out, n_users, S, wqkv, wa, qa, stash, d_x, d_wqkv, d_bqkv, d_wa, d_ba, d_qa, workspace,
+                               workspace_bytes, mode, stream, nullptr);
+}
+
+int nrms_user_encoder_ln_bwd(const float* d_out, int64_t n_users, int S, const float* wqkv, const float* ln_gamma,
+                             const float* wa, const float* qa, const void* stash, float* d_x, float* d_wqkv,
+                             float* d_bqkv, float* d_ln_gamma, float* d_ln_beta, float* d_wa, float* d_ba, float* d_qa,
+                             void* workspace, size_t workspace_bytes, int mode, void* stream) {
+  const LnArgs ln{ln_gamma, nullptr, d_ln_gamma, d_ln_beta};
+  return user_encoder_bwd_impl(d_out, n_users, S, wqkv, wa, qa, stash, d_x, d_wqkv, d_bqkv, d_wa, d_ba, d_qa, workspace,
+                               workspace_bytes, mode, stream, &ln);
 }
 
 // ---- standalone L0 blocks (inference): MultiHeadSelfAttention.forward / AdditiveAttention.forward ----

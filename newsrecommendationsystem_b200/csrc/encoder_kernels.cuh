@@ -412,4 +412,128 @@ partial_reduce_accum_kernel(const float* __restrict__ partial, int n_blocks, int
   out[col] += acc;
 }
 
+// out[col] += sum_b partial[b * stride + col], col < n_cols
+static __global__ void __launch_bounds__(256)
+partial_reduce_accum_strided_kernel(const float* __restrict__ partial, int n_blocks, int stride, int n_cols,
+                                    float* __restrict__ out) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= n_cols) return;
+  float acc = 0.f;
+  for (int b = 0; b < n_blocks; ++b) acc += partial[(int64_t)b * stride + col];
+  out[col] += acc;
+}
+
+// ----------------------------------------------------------------------------------------
+// LayerNorm(300) over the context rows (config-5 variant, builder-defined: DESIGN.md section 1; torch semantics:
+// biased variance, eps inside the square root).  One warp per row, the row in registers (three float4 per lane).
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ float ln_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+static __global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     float* __restrict__ y, float* __restrict__ stats, int64_t n_rows, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp0; r < n_rows; r += n_warps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + r * D);
+    float4 v[3];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int i = lane + 32 * j;
+      v[j] = (i < DV4) ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += v[j].x + v[j].y + v[j].z + v[j].w;
+    }
+    const float mean = ln_warp_sum(s) * (1.f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (lane + 32 * j < DV4) {
+        const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+        q += a * a + b * b + c * c + d * d;
+      }
+    }
+    const float rstd = rsqrtf(ln_warp_sum(q) * (1.f / D) + eps);
+    float4* yr = reinterpret_cast<float4*>(y + r * D);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int i = lane + 32 * j;
+      if (i < DV4) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + i);
+        yr[i] = make_float4((v[j].x - mean) * rstd * g.x + b.x, (v[j].y - mean) * rstd * g.y + b.y,
+                            (v[j].z - mean) * rstd * g.z + b.z, (v[j].w - mean) * rstd * g.w + b.w);
+      }
+    }
+    if (stats && lane == 0) {
+      stats[2 * r] = mean;
+      stats[2 * r + 1] = rstd;
+    }
+  }
+}
+
+// dy (in) -> dx (in place); per-block partial sums of d_gamma (columns [0,300)) and d_beta ([300,600)) go to
+// partial[blockIdx.x][600], reduced by partial_reduce_accum_kernel.  Block = 8 warps, each warp owns rows.
+static __global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(float* __restrict__ dy_dx, const float* __restrict__ x, const float* __restrict__ stats,
+                     const float* __restrict__ gamma, float* __restrict__ partial, int64_t n_rows) {
+  __shared__ float red[8][2 * D];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t warp0 = (int64_t)blockIdx.x * 8 + warp;
+  const int64_t n_warps = (int64_t)gridDim.x * 8;
+  float4 dg[3], db[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) dg[j] = db[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int64_t r = warp0; r < n_rows; r += n_warps) {
+    const float mean = stats[2 * r], rstd = stats[2 * r + 1];
+    const float4* xr = reinterpret_cast<const float4*>(x + r * D);
+    float4* dr = reinterpret_cast<float4*>(dy_dx + r * D);
+    float4 xh[3], g[3];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int i = lane + 32 * j;
+      xh[j] = g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < DV4) {
+        const float4 xv = xr[i], dyv = dr[i];
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + i);
+        xh[j] = make_float4((xv.x - mean) * rstd, (xv.y - mean) * rstd, (xv.z - mean) * rstd, (xv.w - mean) * rstd);
+        g[j] = make_float4(dyv.x * gm.x, dyv.y * gm.y, dyv.z * gm.z, dyv.w * gm.w);
+        dg[j].x += dyv.x * xh[j].x; dg[j].y += dyv.y * xh[j].y; dg[j].z += dyv.z * xh[j].z; dg[j].w += dyv.w * xh[j].w;
+        db[j].x += dyv.x; db[j].y += dyv.y; db[j].z += dyv.z; db[j].w += dyv.w;
+        s1 += g[j].x + g[j].y + g[j].z + g[j].w;
+        s2 += g[j].x * xh[j].x + g[j].y * xh[j].y + g[j].z * xh[j].z + g[j].w * xh[j].w;
+      }
+    }
+    const float m1 = ln_warp_sum(s1) * (1.f / D), m2 = ln_warp_sum(s2) * (1.f / D);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int i = lane + 32 * j;
+      if (i < DV4)
+        dr[i] = make_float4(rstd * (g[j].x - m1 - xh[j].x * m2), rstd * (g[j].y - m1 - xh[j].y * m2),
+                            rstd * (g[j].z - m1 - xh[j].z * m2), rstd * (g[j].w - m1 - xh[j].w * m2));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const int i = lane + 32 * j;
+    if (i < DV4) {
+      reinterpret_cast<float4*>(red[warp])[i] = dg[j];
+      reinterpret_cast<float4*>(red[warp] + D)[i] = db[j];
+    }
+  }
+  __syncthreads();
+  for (int col = threadIdx.x; col < 2 * D; col += 256) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += red[w][col];
+    partial[(int64_t)blockIdx.x * (2 * D) + col] = a;
+  }
+}
+
 }  // namespace nrms

@@ -22,9 +22,11 @@ int transpose_f32(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, 
 // tc_fused_workspace_bytes returns (size_t)-1 when the fused path does not apply (S not 20/50).
 // n_src_rows = rows of `src` when it is a gather source (idx_kind 1/2), 0 for dense input.
 size_t tc_fused_workspace_bytes(int64_t n_seq, int S, int64_t n_src_rows);
+// ln_gamma / ln_beta (nullable): LayerNorm(300) on the context rows between K1 and K2 (config-5 variant).
 int tc_encoder_fused(const float* src, int64_t n_src_rows, const void* idx, int idx_kind, int64_t n_seq, int S,
                      const float* wqkv, const float* bqkv, const float* wa, const float* ba, const float* qa, float* out,
-                     void* workspace, size_t workspace_bytes, cudaStream_t st);
+                     void* workspace, size_t workspace_bytes, cudaStream_t st, const float* ln_gamma = nullptr,
+                     const float* ln_beta = nullptr);
 
 int set_k1_variant(int v);   // 1..5, see tc_fused.cu
 void set_time_k1(bool on);   // CUDA-event timing of the user-encoder K1 launches (bench.py roofline)

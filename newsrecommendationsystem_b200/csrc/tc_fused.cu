@@ -581,10 +581,50 @@ static size_t fused_src16_bytes(int idx_kind_dense, int64_t n_src_rows, int64_t 
   return align_up(k1v4_src16_bytes(idx_kind_dense ? chunk_rows : n_src_rows), 1024);
 }
 
+// In-place LayerNorm(300) over the fp16 context rows [rows][320] that K1 hands to K2 (columns 300..319 stay zero):
+// one warp per row, five half2 per lane, statistics in fp32.
+__global__ void __launch_bounds__(256) layernorm_f16_rows_kernel(__half* __restrict__ c, const float* __restrict__ gamma,
+                                                                 const float* __restrict__ beta, int64_t n_rows, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp0; r < n_rows; r += n_warps) {
+    __half2* row = reinterpret_cast<__half2*>(c + r * 320);
+    float2 v[5];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int i = lane + 32 * j;
+      v[j] = (i < D / 2) ? __half22float2(row[i]) : make_float2(0.f, 0.f);
+      s += v[j].x + v[j].y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+      if (lane + 32 * j < D / 2) q += (v[j].x - mean) * (v[j].x - mean) + (v[j].y - mean) * (v[j].y - mean);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.f / D) + eps);
+#pragma unroll
+    for (int j = 0; j < 5; ++j) {
+      const int i = lane + 32 * j;
+      if (i < D / 2) {
+        const float2 g = __ldg(reinterpret_cast<const float2*>(gamma) + i);
+        const float2 b = __ldg(reinterpret_cast<const float2*>(beta) + i);
+        row[i] = __floats2half2_rn((v[j].x - mean) * rstd * g.x + b.x, (v[j].y - mean) * rstd * g.y + b.y);
+      }
+    }
+  }
+}
+
 template <int S, int SPT>
 static int run_fused(const float* src, int64_t n_src_rows, const void* idx, int idx_kind, int64_t n_seq,
                      const float* wqkv, const float* bqkv, const float* wa, const float* ba, const float* qa, float* out,
-                     void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                     void* workspace, size_t workspace_bytes, cudaStream_t st, const float* ln_gamma,
+                     const float* ln_beta) {
   using Cfg = K1<S, SPT>;
   static bool configured = false;
   if (!configured) {
@@ -594,7 +634,8 @@ static int run_fused(const float* src, int64_t n_src_rows, const void* idx, int 
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(additive_pool_kernel)");
     configured = true;
   }
-  const int variant = k1_variant();
+  int variant = k1_variant();
+  if (ln_gamma && variant < 2) variant = 5;   // the LayerNorm step works on the fp16 context rows of variants 2..5
   // every variant tiles 5 titles / 2 users, so the chunking (whole waves of tiles) is shared
   const int64_t chunk = fused_chunk_seq<S, SPT>();
   const int64_t first = n_seq < chunk ? n_seq : chunk;
@@ -648,6 +689,13 @@ static int run_fused(const float* src, int64_t n_src_rows, const void* idx, int 
                             : k1v2_run(S, tw, src_c, idx_c, idx_kind, n, bqkv, Cbuf, st);
         if (rc) return rc;
       }
+      if (ln_gamma) {
+        int64_t lb = (n * S + 7) / 8;
+        if (lb > (int64_t)num_sms() * 8) lb = (int64_t)num_sms() * 8;
+        layernorm_f16_rows_kernel<<<(unsigned)lb, 256, 0, st>>>(reinterpret_cast<__half*>(Cbuf), ln_gamma, ln_beta,
+                                                                n * S, 1e-5f);
+        NRMS_LAUNCH_CHECK("layernorm_f16_rows_kernel");
+      }
       if (int rc = k2v2_run(S, twa, Cbuf, n, ba, qa, out + s0 * D, st)) return rc;
       continue;
     } else {
@@ -677,9 +725,10 @@ size_t tc_fused_workspace_bytes(int64_t n_seq, int S, int64_t n_src_rows) {
 
 int tc_encoder_fused(const float* src, int64_t n_src_rows, const void* idx, int idx_kind, int64_t n_seq, int S,
                      const float* wqkv, const float* bqkv, const float* wa, const float* ba, const float* qa, float* out,
-                     void* workspace, size_t workspace_bytes, cudaStream_t st) {
-  if (S == 20) return run_fused<20, 5>(src, n_src_rows, idx, idx_kind, n_seq, wqkv, bqkv, wa, ba, qa, out, workspace, workspace_bytes, st);
-  if (S == 50) return run_fused<50, 2>(src, n_src_rows, idx, idx_kind, n_seq, wqkv, bqkv, wa, ba, qa, out, workspace, workspace_bytes, st);
+                     void* workspace, size_t workspace_bytes, cudaStream_t st, const float* ln_gamma,
+                     const float* ln_beta) {
+  if (S == 20) return run_fused<20, 5>(src, n_src_rows, idx, idx_kind, n_seq, wqkv, bqkv, wa, ba, qa, out, workspace, workspace_bytes, st, ln_gamma, ln_beta);
+  if (S == 50) return run_fused<50, 2>(src, n_src_rows, idx, idx_kind, n_seq, wqkv, bqkv, wa, ba, qa, out, workspace, workspace_bytes, st, ln_gamma, ln_beta);
   set_error("fused encoder compiled for S = 20 or 50, got %d", S);
   return NRMS_E_UNSUPPORTED;
 }

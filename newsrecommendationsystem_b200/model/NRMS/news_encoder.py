@@ -20,6 +20,8 @@ class NewsEncoder(nn.Module):
         self.multihead_self_attention = MultiHeadSelfAttention(config.word_embedding_dim,
                                                                config.num_attention_heads)
         self.additive_attention = AdditiveAttention(config.query_vector_dim, config.word_embedding_dim)
+        # config-5 variant (builder-defined): LayerNorm on the self-attention context
+        self.layer_norm = nn.LayerNorm(config.word_embedding_dim) if getattr(config, "use_layernorm", False) else None
         self.precision = None          # None -> config.precision / $NRMS_B200_PRECISION / "tf32"
         self._dropout_calls = 0
         self.dropout_seed = 0x5EED
@@ -46,7 +48,8 @@ class NewsEncoder(nn.Module):
                                 self.additive_attention.linear.weight, self.additive_attention.linear.bias,
                                 self.additive_attention.attention_query_vector,
                                 dropout_p=p, seed=self.dropout_seed, offset=offset,
-                                mode=resolve_mode(self.config, self.precision))
+                                mode=resolve_mode(self.config, self.precision),
+                                ln=None if self.layer_norm is None else (self.layer_norm.weight, self.layer_norm.bias))
 
     def forward(self, news):
         """news: {"title": batch_size * num_words_title} -> batch_size, word_embedding_dim"""

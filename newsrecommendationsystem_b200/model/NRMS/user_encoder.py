@@ -14,7 +14,12 @@ class UserEncoder(nn.Module):
         self.multihead_self_attention = MultiHeadSelfAttention(config.word_embedding_dim,
                                                                config.num_attention_heads)
         self.additive_attention = AdditiveAttention(config.query_vector_dim, config.word_embedding_dim)
+        # config-5 variant (builder-defined): LayerNorm on the self-attention context
+        self.layer_norm = nn.LayerNorm(config.word_embedding_dim) if getattr(config, "use_layernorm", False) else None
         self.precision = None
+
+    def _ln(self):
+        return None if self.layer_norm is None else (self.layer_norm.weight, self.layer_norm.bias)
 
     def _weights(self):
         wqkv, bqkv = self.multihead_self_attention.packed()
@@ -25,9 +30,9 @@ class UserEncoder(nn.Module):
         """user_vector: batch_size, num_clicked_news_a_user, word_embedding_dim -> batch_size, word_embedding_dim"""
         dev = self.additive_attention.linear.weight.device
         return ops.user_encoder(user_vector.to(dev), *self._weights(),
-                                mode=resolve_mode(self.config, self.precision))
+                                mode=resolve_mode(self.config, self.precision), ln=self._ln())
 
     def forward_indexed(self, table, rows):
         """Inference: history rows gathered from the news-vector table (int32 [B, 50])."""
         return ops.user_encoder_indexed(table, rows, *self._weights(),
-                                        mode=resolve_mode(self.config, self.precision))
+                                        mode=resolve_mode(self.config, self.precision), ln=self._ln())

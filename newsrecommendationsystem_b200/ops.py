@@ -40,9 +40,11 @@ class _NewsEncoderFn(torch.autograd.Function):
     """NewsEncoder.forward (reference src/model/NRMS/news_encoder.py:27-48)."""
 
     @staticmethod
-    def forward(ctx, tokens, emb, wqkv, bqkv, wa, ba, qa, dropout_p, seed, offset, mode, track_grad):
+    def forward(ctx, tokens, emb, wqkv, bqkv, wa, ba, qa, dropout_p, seed, offset, mode, track_grad,
+                ln_w=None, ln_b=None):
         lib = _lib.load()
         _require_cuda(tokens, emb, wqkv, bqkv, wa, ba, qa)
+        ln = ln_w is not None          # config-5 variant: LayerNorm between self-attention and additive attention
         tokens = tokens.contiguous()
         if tokens.dtype != torch.int64:
             tokens = tokens.long()
@@ -53,23 +55,32 @@ class _NewsEncoderFn(torch.autograd.Function):
         needs_grad = track_grad and any(ctx.needs_input_grad)   # grad mode is always off inside forward()
         stash = None
         if needs_grad:
-            stash = _bytes(lib.nrms_encoder_stash_bytes(n, L), dev)
+            stash = _bytes((lib.nrms_encoder_ln_stash_bytes if ln else lib.nrms_encoder_stash_bytes)(n, L), dev)
         ws_bytes = lib.nrms_encoder_fwd_workspace_bytes(n, L, mode, 1 if needs_grad else 0, emb_c.shape[0])
         ws = _bytes(ws_bytes, dev)
-        check(lib.nrms_news_encoder_fwd(ptr(tokens), n, L, ptr(emb_c), emb_c.shape[0], ptr(wqkv_c), ptr(bqkv_c),
-                                        ptr(wa_c), ptr(ba_c), ptr(qa_c), ptr(out), ptr(stash), ptr(ws), ws.numel(),
-                                        float(dropout_p), int(seed), int(offset), mode, stream_ptr(dev)),
-              "nrms_news_encoder_fwd")
+        if ln:
+            _require_cuda(ln_w, ln_b)
+            lnw_c, lnb_c = _f32c(ln_w), _f32c(ln_b)
+            check(lib.nrms_news_encoder_ln_fwd(ptr(tokens), n, L, ptr(emb_c), emb_c.shape[0], ptr(wqkv_c), ptr(bqkv_c),
+                                               ptr(lnw_c), ptr(lnb_c), ptr(wa_c), ptr(ba_c), ptr(qa_c), ptr(out),
+                                               ptr(stash), ptr(ws), ws.numel(), float(dropout_p), int(seed),
+                                               int(offset), mode, stream_ptr(dev)), "nrms_news_encoder_ln_fwd")
+        else:
+            lnw_c = None
+            check(lib.nrms_news_encoder_fwd(ptr(tokens), n, L, ptr(emb_c), emb_c.shape[0], ptr(wqkv_c), ptr(bqkv_c),
+                                            ptr(wa_c), ptr(ba_c), ptr(qa_c), ptr(out), ptr(stash), ptr(ws), ws.numel(),
+                                            float(dropout_p), int(seed), int(offset), mode, stream_ptr(dev)),
+                  "nrms_news_encoder_fwd")
         if needs_grad:
-            ctx.save_for_backward(tokens, wqkv_c, wa_c, qa_c, stash)
-            ctx.meta = (n, L, emb_c.shape[0], float(dropout_p), int(seed), int(offset), mode)
+            ctx.save_for_backward(tokens, wqkv_c, wa_c, qa_c, stash, *([lnw_c] if ln else []))
+            ctx.meta = (n, L, emb_c.shape[0], float(dropout_p), int(seed), int(offset), mode, ln)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         lib = _lib.load()
-        tokens, wqkv, wa, qa, stash = ctx.saved_tensors
-        n, L, V, p, seed, offset, mode = ctx.meta
+        n, L, V, p, seed, offset, mode, ln = ctx.meta
+        tokens, wqkv, wa, qa, stash = ctx.saved_tensors[:5]
         dev = d_out.device
         d_out = d_out.contiguous().float()
         d_emb = torch.zeros((V, D), dtype=torch.float32, device=dev)
@@ -79,20 +90,31 @@ class _NewsEncoderFn(torch.autograd.Function):
         d_ba = torch.zeros((QD,), dtype=torch.float32, device=dev)
         d_qa = torch.zeros((QD,), dtype=torch.float32, device=dev)
         ws = _bytes(lib.nrms_encoder_bwd_workspace_bytes(n, L, mode), dev)
-        check(lib.nrms_news_encoder_bwd(ptr(d_out), ptr(tokens), n, L, V, ptr(wqkv), ptr(wa), ptr(qa), ptr(stash),
-                                        ptr(d_emb), ptr(d_wqkv), ptr(d_bqkv), ptr(d_wa), ptr(d_ba), ptr(d_qa),
-                                        ptr(ws), ws.numel(), p, seed, offset, mode, stream_ptr(dev)),
-              "nrms_news_encoder_bwd")
-        return None, d_emb, d_wqkv, d_bqkv, d_wa, d_ba, d_qa, None, None, None, None, None
+        d_lnw = d_lnb = None
+        if ln:
+            lnw = ctx.saved_tensors[5]
+            d_lnw = torch.zeros((D,), dtype=torch.float32, device=dev)
+            d_lnb = torch.zeros((D,), dtype=torch.float32, device=dev)
+            check(lib.nrms_news_encoder_ln_bwd(ptr(d_out), ptr(tokens), n, L, V, ptr(wqkv), ptr(lnw), ptr(wa), ptr(qa),
+                                               ptr(stash), ptr(d_emb), ptr(d_wqkv), ptr(d_bqkv), ptr(d_lnw), ptr(d_lnb),
+                                               ptr(d_wa), ptr(d_ba), ptr(d_qa), ptr(ws), ws.numel(), p, seed, offset,
+                                               mode, stream_ptr(dev)), "nrms_news_encoder_ln_bwd")
+        else:
+            check(lib.nrms_news_encoder_bwd(ptr(d_out), ptr(tokens), n, L, V, ptr(wqkv), ptr(wa), ptr(qa), ptr(stash),
+                                            ptr(d_emb), ptr(d_wqkv), ptr(d_bqkv), ptr(d_wa), ptr(d_ba), ptr(d_qa),
+                                            ptr(ws), ws.numel(), p, seed, offset, mode, stream_ptr(dev)),
+                  "nrms_news_encoder_bwd")
+        return None, d_emb, d_wqkv, d_bqkv, d_wa, d_ba, d_qa, None, None, None, None, None, d_lnw, d_lnb
 
 
 class _UserEncoderFn(torch.autograd.Function):
     """UserEncoder.forward (reference src/model/NRMS/user_encoder.py:15-26), dense input."""
 
     @staticmethod
-    def forward(ctx, x, wqkv, bqkv, wa, ba, qa, mode, track_grad):
+    def forward(ctx, x, wqkv, bqkv, wa, ba, qa, mode, track_grad, ln_w=None, ln_b=None):
         lib = _lib.load()
         _require_cuda(x, wqkv, bqkv, wa, ba, qa)
+        ln = ln_w is not None
         n, S, d = x.shape
         if d != D:
             raise RuntimeError(f"user encoder compiled for dim {D}, got {d}")
@@ -100,21 +122,30 @@ class _UserEncoderFn(torch.autograd.Function):
         x_c, wqkv_c, bqkv_c, wa_c, ba_c, qa_c = map(_f32c, (x, wqkv, bqkv, wa, ba, qa))
         out = torch.empty((n, D), dtype=torch.float32, device=dev)
         needs_grad = track_grad and any(ctx.needs_input_grad)
-        stash = _bytes(lib.nrms_encoder_stash_bytes(n, S), dev) if needs_grad else None
+        stash = _bytes((lib.nrms_encoder_ln_stash_bytes if ln else lib.nrms_encoder_stash_bytes)(n, S), dev) \
+            if needs_grad else None
         ws = _bytes(lib.nrms_encoder_fwd_workspace_bytes(n, S, mode, 1 if needs_grad else 0, 0), dev)
-        check(lib.nrms_user_encoder_fwd(ptr(x_c), 0, None, n, S, ptr(wqkv_c), ptr(bqkv_c), ptr(wa_c), ptr(ba_c),
-                                        ptr(qa_c), ptr(out), ptr(stash), ptr(ws), ws.numel(), mode, stream_ptr(dev)),
-              "nrms_user_encoder_fwd")
+        if ln:
+            _require_cuda(ln_w, ln_b)
+            lnw_c, lnb_c = _f32c(ln_w), _f32c(ln_b)
+            check(lib.nrms_user_encoder_ln_fwd(ptr(x_c), 0, None, n, S, ptr(wqkv_c), ptr(bqkv_c), ptr(lnw_c), ptr(lnb_c),
+                                               ptr(wa_c), ptr(ba_c), ptr(qa_c), ptr(out), ptr(stash), ptr(ws),
+                                               ws.numel(), mode, stream_ptr(dev)), "nrms_user_encoder_ln_fwd")
+        else:
+            lnw_c = None
+            check(lib.nrms_user_encoder_fwd(ptr(x_c), 0, None, n, S, ptr(wqkv_c), ptr(bqkv_c), ptr(wa_c), ptr(ba_c),
+                                            ptr(qa_c), ptr(out), ptr(stash), ptr(ws), ws.numel(), mode,
+                                            stream_ptr(dev)), "nrms_user_encoder_fwd")
         if needs_grad:
-            ctx.save_for_backward(wqkv_c, wa_c, qa_c, stash)
-            ctx.meta = (n, S, mode)
+            ctx.save_for_backward(wqkv_c, wa_c, qa_c, stash, *([lnw_c] if ln else []))
+            ctx.meta = (n, S, mode, ln)
         return out
 
     @staticmethod
     def backward(ctx, d_out):
         lib = _lib.load()
-        wqkv, wa, qa, stash = ctx.saved_tensors
-        n, S, mode = ctx.meta
+        n, S, mode, ln = ctx.meta
+        wqkv, wa, qa, stash = ctx.saved_tensors[:4]
         dev = d_out.device
         d_out = d_out.contiguous().float()
         d_x = torch.empty((n, S, D), dtype=torch.float32, device=dev)
@@ -124,11 +155,21 @@ class _UserEncoderFn(torch.autograd.Function):
         d_ba = torch.zeros((QD,), dtype=torch.float32, device=dev)
         d_qa = torch.zeros((QD,), dtype=torch.float32, device=dev)
         ws = _bytes(lib.nrms_encoder_bwd_workspace_bytes(n, S, mode), dev)
-        check(lib.nrms_user_encoder_bwd(ptr(d_out), n, S, ptr(wqkv), ptr(wa), ptr(qa), ptr(stash), ptr(d_x),
-                                        ptr(d_wqkv), ptr(d_bqkv), ptr(d_wa), ptr(d_ba), ptr(d_qa), ptr(ws),
-                                        ws.numel(), mode, stream_ptr(dev)),
-              "nrms_user_encoder_bwd")
-        return d_x, d_wqkv, d_bqkv, d_wa, d_ba, d_qa, None, None
+        d_lnw = d_lnb = None
+        if ln:
+            lnw = ctx.saved_tensors[4]
+            d_lnw = torch.zeros((D,), dtype=torch.float32, device=dev)
+            d_lnb = torch.zeros((D,), dtype=torch.float32, device=dev)
+            check(lib.nrms_user_encoder_ln_bwd(ptr(d_out), n, S, ptr(wqkv), ptr(lnw), ptr(wa), ptr(qa), ptr(stash),
+                                               ptr(d_x), ptr(d_wqkv), ptr(d_bqkv), ptr(d_lnw), ptr(d_lnb), ptr(d_wa),
+                                               ptr(d_ba), ptr(d_qa), ptr(ws), ws.numel(), mode, stream_ptr(dev)),
+                  "nrms_user_encoder_ln_bwd")
+        else:
+            check(lib.nrms_user_encoder_bwd(ptr(d_out), n, S, ptr(wqkv), ptr(wa), ptr(qa), ptr(stash), ptr(d_x),
+                                            ptr(d_wqkv), ptr(d_bqkv), ptr(d_wa), ptr(d_ba), ptr(d_qa), ptr(ws),
+                                            ws.numel(), mode, stream_ptr(dev)),
+                  "nrms_user_encoder_bwd")
+        return d_x, d_wqkv, d_bqkv, d_wa, d_ba, d_qa, None, None, d_lnw, d_lnb
 
 
 class _ScoreFn(torch.autograd.Function):
@@ -182,17 +223,21 @@ class _CrossEntropyLabel0Fn(torch.autograd.Function):
 
 
 # ---- functional API ---------------------------------------------------------------------------
-def news_encoder(tokens, emb, wqkv, bqkv, wa, ba, qa, dropout_p=0.0, seed=0, offset=0, mode=_lib.MODE_TF32):
+def news_encoder(tokens, emb, wqkv, bqkv, wa, ba, qa, dropout_p=0.0, seed=0, offset=0, mode=_lib.MODE_TF32,
+                 ln=None):
+    """ln = (weight, bias) of the optional LayerNorm(300) (config-5 variant), None for the reference NRMS."""
+    lw, lb = ln if ln is not None else (None, None)
     return _NewsEncoderFn.apply(tokens, emb, wqkv, bqkv, wa, ba, qa, dropout_p, seed, offset, mode,
-                                torch.is_grad_enabled())
+                                torch.is_grad_enabled(), lw, lb)
 
 
-def user_encoder(x, wqkv, bqkv, wa, ba, qa, mode=_lib.MODE_TF32):
-    return _UserEncoderFn.apply(x, wqkv, bqkv, wa, ba, qa, mode, torch.is_grad_enabled())
+def user_encoder(x, wqkv, bqkv, wa, ba, qa, mode=_lib.MODE_TF32, ln=None):
+    lw, lb = ln if ln is not None else (None, None)
+    return _UserEncoderFn.apply(x, wqkv, bqkv, wa, ba, qa, mode, torch.is_grad_enabled(), lw, lb)
 
 
 @torch.no_grad()
-def user_encoder_indexed(table, rows, wqkv, bqkv, wa, ba, qa, mode=_lib.MODE_TF32):
+def user_encoder_indexed(table, rows, wqkv, bqkv, wa, ba, qa, mode=_lib.MODE_TF32, ln=None):
     """Inference-only user encoder whose input rows are gathered from `table` [n_rows,300] by
     int32 `rows` [n_users,S] (replaces the dict/stack loops of reference src/evaluate.py:220-224)."""
     lib = _lib.load()
@@ -205,6 +250,13 @@ def user_encoder_indexed(table, rows, wqkv, bqkv, wa, ba, qa, mode=_lib.MODE_TF3
     out = torch.empty((n, D), dtype=torch.float32, device=dev)
     ws = _bytes(lib.nrms_encoder_fwd_workspace_bytes(n, S, mode, 0, table.shape[0]), dev)
     args = [_f32c(t) for t in (table, wqkv, bqkv, wa, ba, qa)]
+    if ln is not None:
+        lw, lb = _f32c(ln[0]), _f32c(ln[1])
+        check(lib.nrms_user_encoder_ln_fwd(ptr(args[0]), args[0].shape[0], ptr(rows), n, S, ptr(args[1]), ptr(args[2]),
+                                           ptr(lw), ptr(lb), ptr(args[3]), ptr(args[4]), ptr(args[5]), ptr(out), None,
+                                           ptr(ws), ws.numel(), mode, stream_ptr(dev)),
+              "nrms_user_encoder_ln_fwd(indexed)")
+        return out
     check(lib.nrms_user_encoder_fwd(ptr(args[0]), args[0].shape[0], ptr(rows), n, S, ptr(args[1]), ptr(args[2]), ptr(args[3]),
                                     ptr(args[4]), ptr(args[5]), ptr(out), None, ptr(ws), ws.numel(), mode,
                                     stream_ptr(dev)), "nrms_user_encoder_fwd(indexed)")

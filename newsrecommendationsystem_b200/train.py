@@ -40,6 +40,14 @@ class TrainStep:
         self.steps += 1
         return loss.detach()
 
+    def step_rows(self, token_table, cand_rows, hist_rows):
+        """Index-only minibatch: `token_table` is the pre-tokenised news table int64 [N_news, L]
+        resident on the GPU, `cand_rows` [B, 1+K] and `hist_rows` [B, N] are news-row indices -- 55 x B x 8 bytes of
+        H2D per step instead of the 55 token tensors the reference DataLoader ships (dataset.py:17-85,
+        train.py:118-124).  The token rows are gathered on the device."""
+        rows = torch.cat([cand_rows, hist_rows], dim=1).to(token_table.device, non_blocking=True)
+        return self.step_tokens(token_table[rows], cand_rows.shape[1])
+
     def step(self, candidate_news, clicked_news):
         """Reference minibatch format: lists of {"title": LongTensor[B, L]} (src/train.py:202-203)."""
         titles = torch.stack([x["title"] for x in candidate_news] + [x["title"] for x in clicked_news], dim=1)

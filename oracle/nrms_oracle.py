@@ -47,8 +47,18 @@ def enc_keys(prefix: str):
 EMB_KEY = "news_encoder.word_embedding.weight"
 
 
+def ln_keys(prefix: str):
+    """config-5 variant (builder-defined, no reference code: README.md:105-112): nn.LayerNorm(300) on the
+    self-attention context of an encoder.  Present in `params` only for the variant."""
+    return dict(ln_g=f"{prefix}.layer_norm.weight", ln_b=f"{prefix}.layer_norm.bias")
+
+
 def enc_params(params: dict, prefix: str) -> dict:
-    return {k: params[v] for k, v in enc_keys(prefix).items()}
+    p = {k: params[v] for k, v in enc_keys(prefix).items()}
+    for k, v in ln_keys(prefix).items():
+        if v in params:
+            p[k] = params[v]
+    return p
 
 
 # --------------------------------------------------------------------------------------
@@ -107,8 +117,11 @@ def encoder_forward(x, p, num_heads, mask2=None):
     c, cm = mhsa_forward(x, p, num_heads)
     if mask2 is not None:
         c = c * mask2
+    cl = None
+    if "ln_g" in p:                      # config-5 variant: c = LayerNorm(dropout(MHSA(x)))
+        c, cl = layernorm_forward(c, p["ln_g"], p["ln_b"])
     out, ca = additive_forward(c, p)
-    return out, dict(mhsa=cm, add=ca, mask2=mask2)
+    return out, dict(mhsa=cm, add=ca, mask2=mask2, ln=cl)
 
 
 def news_encoder_forward(params, tokens, num_heads=15, mask1=None, mask2=None):
@@ -212,6 +225,9 @@ def mhsa_backward(dout, cache, p, num_heads):
 
 def encoder_backward(dout, cache, p, num_heads):
     dc, ga = additive_backward(dout, cache["add"], p)
+    if cache.get("ln") is not None:
+        dc, dg, db = layernorm_backward(dc, cache["ln"])
+        ga.update(ln_g=dg, ln_b=db)
     if cache["mask2"] is not None:
         dc = dc * cache["mask2"]
     dx, gm = mhsa_backward(dc, cache["mhsa"], p, num_heads)
@@ -242,6 +258,10 @@ def nrms_backward(dlogits, cache, params, num_heads=15):
         grads[name] = gn[k]
     for k, name in enc_keys(USER).items():
         grads[name] = gu[k]
+    for prefix, g in ((NEWS, gn), (USER, gu)):
+        for k, name in ln_keys(prefix).items():
+            if k in g:
+                grads[name] = g[k]
     return grads
 
 

@@ -470,3 +470,90 @@ def test_standalone_l0_blocks(dev, golden_sd, precision):
     with pytest.raises(NotImplementedError):
         with torch.no_grad():
             att(t(x, dev), length=torch.tensor([3] * 7))
+
+
+# ---------------------------------------------------------------------------------------------
+# config-5 variant: LayerNorm(300) on the self-attention context of both encoders (builder-defined; the oracle's
+# version of it is pinned against torch autograd in tests/test_oracle_golden.py)
+# ---------------------------------------------------------------------------------------------
+class CfgLN(Cfg):
+    use_layernorm = True
+
+
+def _ln_state_dict(golden_sd, seed=11):
+    rng = np.random.default_rng(seed)
+    sd = dict(golden_sd)
+    for prefix in (O.NEWS, O.USER):
+        sd[f"{prefix}.layer_norm.weight"] = (1 + 0.1 * rng.standard_normal(300)).astype(np.float32)
+        sd[f"{prefix}.layer_norm.bias"] = (0.1 * rng.standard_normal(300)).astype(np.float32)
+    return sd
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_layernorm_variant_vectors_and_evaluate(dev, golden_sd, precision):
+    from newsrecommendationsystem_b200 import synthetic
+    from newsrecommendationsystem_b200.evaluate import EvalInputs, evaluate_tensors
+    sd = _ln_state_dict(golden_sd)
+    m = make_model(sd, dev, precision, cfg=CfgLN)
+    assert set(m.state_dict().keys()) == set(sd.keys())
+    toks = synthetic.make_news(1500, num_words=Cfg.num_words, seed=77)
+    toks[3] = 0
+    ref_n, _ = O.news_encoder_forward(sd, toks)
+    rng = np.random.default_rng(5)
+    ux = (rng.standard_normal((131, 50, 300)) * 0.4).astype(np.float32)
+    ux[2, :45] = 0
+    ref_u, _ = O.user_encoder_forward(sd, ux)
+    with torch.no_grad():
+        nv = m.get_news_vector({"title": torch.from_numpy(toks)})
+        uv = m.get_user_vector(t(ux, dev))
+    tol = {"fp32": 3e-5, "tf32": 2e-3}[precision]       # the normalisation divides by the row spread
+    assert rel_l2_rows(nv.cpu().numpy(), ref_n) < tol
+    assert rel_l2_rows(uv.cpu().numpy(), ref_u) < tol
+    imp = synthetic.make_impressions(600, 1500, seed=78, single_class_every=40)
+    ref_means = O.evaluate_pipeline(sd, toks, imp["hist_rows"], imp["cand_offsets"], imp["cand_rows"], imp["labels"])[0]
+    inp = EvalInputs(toks, imp["hist_rows"], imp["cand_offsets"], imp["cand_rows"], imp["labels"], device=dev)
+    means = evaluate_tensors(m, inp)
+    np.testing.assert_allclose(means, ref_means, atol=5e-4 if precision == "fp32" else 5e-3)
+
+
+@pytest.mark.parametrize("precision,gtol", [("fp32", 3e-4), ("tf32", 5e-3)])
+def test_layernorm_variant_train_step_gradients(dev, golden, golden_sd, precision, gtol):
+    from newsrecommendationsystem_b200.train import TrainStep
+    sd = _ln_state_dict(golden_sd)
+    cand, clicked = golden["train/cand"][:16], golden["train/clicked"][:16]
+    loss_ref, _, grads_ref, _, _ = O.train_step(sd, {}, cand, clicked, step=1)
+    m = make_model(sd, dev, precision, cfg=CfgLN)
+    ts = TrainStep(m, lr=1e-4, adamw=True, weight_decay=0.01)
+    titles = torch.from_numpy(np.concatenate([cand, clicked], axis=1))
+    loss = float(ts.step_tokens(titles, cand.shape[1]).item())
+    assert abs(loss - float(loss_ref)) < (1e-5 if precision == "fp32" else 2e-3)
+    grads = {k: p.grad.detach().cpu().numpy() for k, p in m.named_parameters()}
+    assert set(grads) == set(grads_ref)
+    # b_K's gradient is zero in exact arithmetic (a common shift of the scores of a row cancels in the softmax), so
+    # both sides hold rounding noise there: the floor is 1e-6 of the largest gradient entry of the model
+    floor = 1e-6 * max(float(np.abs(v).max()) for v in grads_ref.values())
+    for k, g in grads.items():
+        ref = grads_ref[k]
+        scale = np.abs(ref).max() + 1e-12
+        assert np.abs(g - ref).max() < gtol * scale + floor, (k, np.abs(g - ref).max(), scale)
+
+
+def test_train_step_from_row_indices(dev, golden, golden_sd):
+    """index-only batches over a GPU-resident token table give the same step as token batches."""
+    from newsrecommendationsystem_b200.train import TrainStep
+    rng = np.random.default_rng(3)
+    table = rng.integers(1, Cfg.num_words, size=(500, 20)).astype(np.int64)
+    cand_rows = rng.integers(0, 500, size=(8, 5))
+    hist_rows = rng.integers(0, 500, size=(8, 50))
+    losses = []
+    for mode in ("tokens", "rows"):
+        m = make_model(golden_sd, dev, "fp32")
+        ts = TrainStep(m, lr=1e-4)
+        if mode == "tokens":
+            titles = torch.from_numpy(np.concatenate([table[cand_rows], table[hist_rows]], axis=1))
+            losses.append(float(ts.step_tokens(titles, 5).item()))
+        else:
+            losses.append(float(ts.step_rows(t(table, dev), torch.from_numpy(cand_rows), torch.from_numpy(hist_rows)).item()))
+        w = m.user_encoder.additive_attention.linear.weight.detach().cpu().numpy()
+        losses.append(w)
+    assert losses[0] == losses[2] and np.array_equal(losses[1], losses[3])

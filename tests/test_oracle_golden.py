@@ -179,3 +179,46 @@ def test_torch_port_matches_golden(golden, golden_sd):
     import torch
     s = TP.prediction(torch.from_numpy(golden["fwd/news_vectors"][:23]), torch.from_numpy(golden["fwd/user_vectors"][0]))
     np.testing.assert_allclose(s, golden["fwd/scores_single"], rtol=1e-5, atol=1e-6)
+
+
+def _torch_ln_encoder(x, p, heads=15):
+    """The config-5 encoder composed from stock torch pieces in float64: the reference's MHSA arithmetic
+    (multihead_self.py:15-23,46-76), torch.nn.functional.layer_norm, the reference's additive attention
+    (additive.py:27-53).  Builder-defined variant: the reference tree has no code for its '+LN' row."""
+    import torch
+    B, S, D = x.shape
+    d = D // heads
+    q = x @ p["Wq"].T + p["bq"]
+    k = x @ p["Wk"].T + p["bk"]
+    v = x @ p["Wv"].T + p["bv"]
+    sp = lambda a: a.view(B, S, heads, d).transpose(1, 2)
+    s = sp(q) @ sp(k).transpose(-1, -2) / np.sqrt(d)
+    e = torch.exp(s)
+    attn = e / (e.sum(-1, keepdim=True) + 1e-8)
+    c = (attn @ sp(v)).transpose(1, 2).contiguous().view(B, S, D)
+    c = torch.nn.functional.layer_norm(c, (D,), p["ln_g"], p["ln_b"], 1e-5)
+    tt = torch.tanh(c @ p["Wa"].T + p["ba"])
+    w = torch.softmax(tt @ p["qa"], dim=1)
+    return torch.bmm(w.unsqueeze(1), c).squeeze(1)
+
+
+def test_layernorm_variant_encoder_matches_torch_autograd():
+    import torch
+    rng = np.random.default_rng(7)
+    B, S, D = 3, 20, 300
+    p = dict(Wq=rng.uniform(-.1, .1, (D, D)), bq=rng.uniform(-.05, .05, D), Wk=rng.uniform(-.1, .1, (D, D)),
+             bk=rng.uniform(-.05, .05, D), Wv=rng.uniform(-.1, .1, (D, D)), bv=rng.uniform(-.05, .05, D),
+             Wa=rng.uniform(-.05, .05, (200, D)), ba=rng.uniform(-.05, .05, 200), qa=rng.uniform(-.1, .1, 200),
+             ln_g=1 + 0.1 * rng.standard_normal(D), ln_b=0.1 * rng.standard_normal(D))
+    x = rng.standard_normal((B, S, D))
+    out, cache = O.encoder_forward(x, p, 15)
+    dout = rng.standard_normal(out.shape)
+    dx, g = O.encoder_backward(dout, cache, p, 15)
+    pt = {k: torch.tensor(v, requires_grad=True) for k, v in p.items()}
+    xt = torch.tensor(x, requires_grad=True)
+    yt = _torch_ln_encoder(xt, pt)
+    yt.backward(torch.tensor(dout))
+    np.testing.assert_allclose(out, yt.detach().numpy(), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(dx, xt.grad.numpy(), rtol=0, atol=1e-11)
+    for k in p:
+        np.testing.assert_allclose(g[k], pt[k].grad.numpy(), rtol=0, atol=1e-10, err_msg=k)
