@@ -288,14 +288,14 @@ def main():
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("encoder_attn_tc5_kernel<50,64,2>")
+        traffic = json.load(open(tpath)).get("encoder_attn_tc6_kernel<50,64,2>")
     if k1_n > 0 and k1_ms > 0:
         us_per_launch = 1e3 * k1_ms / k1_n
         users_per_launch = k1_seq / k1_n
         # K1 owns everything of the user encoder except the additive projection/pooling (K2): 30.05 of 36.05 MFLOP
         flop_per_launch = users_per_launch * (FLOP_PER_USER - 6_000_000 - 50_000)
         ach = flop_per_launch / (us_per_launch * 1e-6) / 1e12
-        roof = dict(bound="tensor", kernel="k1v5::encoder_attn_tc5_kernel<50,64,2> (user encoder: gather+QKV+attention)",
+        roof = dict(bound="tensor", kernel="k1v6::encoder_attn_tc6_kernel<50,64,2> (user encoder: gather+QKV+attention)",
                     achieved=ach, peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=ach / peaks["bf16_tflops"],
                     traffic=traffic, us_per_launch=us_per_launch, launches=int(k1_n), users_per_launch=users_per_launch,
                     algorithmic_flop_per_user=FLOP_PER_USER - 6_050_000,

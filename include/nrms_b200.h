@@ -65,7 +65,8 @@ int64_t nrms_launch_count(void);
 /* Tuning / A-B switches.  "k1_variant": fused tensor-mode encoder kernel generation
  * (1 = CUDA-core attention, 2 = tcgen05 attention, 3 = tcgen05 attention with two heads in flight,
  *  4 = 3 + TMA-gathered fp16 source rows, bias/scale folded into the GEMM, q read from tensor memory,
- *  5 [default] = 4 with two projection accumulators and the probabilities kept in place over the scores). */
+ *  5 = 4 with two projection accumulators and the probabilities kept in place over the scores,
+ *  6 [default] = 5 with two worker groups taking alternate passes). */
 int nrms_set_option(const char* key, int value);
 /* "time_k1" = 1 brackets every user-encoder K1 launch with CUDA events on the launching stream (clears the
  * previous record); nrms_get_stat("k1_ms" | "k1_launches" | "k1_sequences") reads the totals back (syncs on

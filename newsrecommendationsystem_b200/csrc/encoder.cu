@@ -557,7 +557,7 @@ int nrms_additive_fwd(const float* c, int64_t n_seq, int S, const float* wa, con
 int nrms_set_option(const char* key, int value) {
   NRMS_CHECK_ARG(key != nullptr, NRMS_E_INVALID, "null option key");
   if (strcmp(key, "k1_variant") == 0) {
-    NRMS_CHECK_ARG(set_k1_variant(value) == NRMS_OK, NRMS_E_INVALID, "k1_variant must be 1..4");
+    NRMS_CHECK_ARG(set_k1_variant(value) == NRMS_OK, NRMS_E_INVALID, "k1_variant must be 1..6");
     return NRMS_OK;
   }
   if (strcmp(key, "time_k1") == 0) {

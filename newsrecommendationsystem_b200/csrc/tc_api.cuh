@@ -28,7 +28,7 @@ int tc_encoder_fused(const float* src, int64_t n_src_rows, const void* idx, int 
                      void* workspace, size_t workspace_bytes, cudaStream_t st, const float* ln_gamma = nullptr,
                      const float* ln_beta = nullptr);
 
-int set_k1_variant(int v);   // 1..5, see tc_fused.cu
+int set_k1_variant(int v);   // 1..6, see tc_fused.cu
 void set_time_k1(bool on);   // CUDA-event timing of the user-encoder K1 launches (bench.py roofline)
 double get_k1_stat(int key); // 0 total ms, 1 launches, 2 sequences
 

@@ -25,7 +25,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // instructions with no clock reads, printf or calls: the wait is inlined dozens of times in the fused kernels, whose
 // code has to stay inside the instruction caches, and a call in the MMA-issue loops makes ptxas park the operand
 // descriptors in vector registers and pay two R2UR (~40 cycles each) per tcgen05.mma (measured: ~160 and ~100
-// cycles per MMA instead of the 64-cycle pipe floor).  -DNRMS_MBAR_DEBUG restores the printf report.
+// cycles per MMA instead of the 64-cycle pipe floor).  -DNRMS_MBAR_DEBUG=<block> makes the stuck waiters of that block report.
 __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   asm volatile(
@@ -38,13 +38,14 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++polls == (1u << 28)) {
 #ifdef NRMS_MBAR_DEBUG
-      printf("nrms: mbarrier wait timeout (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
+    if (++polls == (1u << 22) && blockIdx.x == NRMS_MBAR_DEBUG)     // every stuck waiter of one block reports
+      printf("nrms: mbarrier wait stuck (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x,
              (int)threadIdx.x, bar, parity);
+    if (polls == (1u << 28)) __trap();
+#else
+    if (++polls == (1u << 28)) __trap();
 #endif
-      __trap();
-    }
   }
 }
 

@@ -56,11 +56,15 @@ int k1v4_run(int S, const CUtensorMap& tw, const CUtensorMap& ts, const void* id
 // K1 v5 (tc_fused6.cu): v4 with two projection accumulators and P kept in place over the scores (default)
 int k1v5_run(int S, const CUtensorMap& tw, const CUtensorMap& ts, const void* src16, const void* idx, int idx_kind,
              int64_t n, int null_row, void* Cbuf, cudaStream_t st);
+// K1 v6 (tc_fused7.cu): v5 with two worker groups taking alternate passes
+int k1v6_run(int S, const CUtensorMap& tw, const CUtensorMap& ts, const void* src16, const void* idx, int idx_kind,
+             int64_t n, int null_row, void* Cbuf, cudaStream_t st);
+constexpr int K1_DEFAULT_VARIANT = 6;
 static int g_k1_variant = -1;
 static int k1_variant() {
   if (g_k1_variant < 0) {
     const char* e = getenv("NRMS_K1_VARIANT");
-    g_k1_variant = (e && e[0] >= '1' && e[0] <= '5') ? (e[0] - '0') : 5;
+    g_k1_variant = (e && e[0] >= '1' && e[0] <= '6') ? (e[0] - '0') : K1_DEFAULT_VARIANT;
   }
   return g_k1_variant;
 }
@@ -94,7 +98,7 @@ struct K1Timer {
 };
 
 int set_k1_variant(int v) {
-  if (v < 1 || v > 5) return NRMS_E_INVALID;
+  if (v < 1 || v > 6) return NRMS_E_INVALID;
   g_k1_variant = v;
   return NRMS_OK;
 }
@@ -680,7 +684,9 @@ static int run_fused(const float* src, int64_t n_src_rows, const void* idx, int 
       {
         K1Timer timer(st, n, S == 50);    // only the user-encoder launches (the dominant kernel) are timed
         int rc;
-        if (variant == 5)
+        if (variant == 6)
+          rc = k1v6_run(S, tw, ts, src16, idx_c, idx_kind, n, (int)(idx_kind == 0 ? n * S : n_src_rows), Cbuf, st);
+        else if (variant == 5)
           rc = k1v5_run(S, tw, ts, src16, idx_c, idx_kind, n, (int)(idx_kind == 0 ? n * S : n_src_rows), Cbuf, st);
         else if (variant == 4)
           rc = k1v4_run(S, tw, ts, idx_c, idx_kind, n, (int)(idx_kind == 0 ? n * S : n_src_rows), Cbuf, st);

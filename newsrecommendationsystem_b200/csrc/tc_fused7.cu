@@ -1,0 +1,662 @@
+// K1 v6 -- encoder_attn_tc6_kernel: K1 v5 (tc_fused6.cu) with the worker side split over TWO groups of eight warps
+// that take alternate passes (group g serves the passes with pass_it % 2 == g, i.e. always the same projection
+// accumulator).  In v5 one thread carried the whole per-row chain of a pass -- drain k,v -> (scores) -> exp2/pack ->
+// (context) -> scale/stage -- and the next pass of its head set could not start before it had finished (~3,000
+// cycles per pass, the tensor pipe needs 1,856).  Now the drain of pass i+1 (TMEM loads, rounding, packing) and the
+// context finish of pass i run on the other group while pass i is in its exp2 phase; what stays serial per head
+// set is K/V store -> S MMA -> exp2/pack -> PV MMA.  Two extra hand-offs make that safe with single-buffered K/V tiles
+// and head-set regions: the K/V stores of pass i+1 wait for o_ready(i) (the PV MMA has read V^T), and the S MMA of
+// pass i+1 waits for o_taken(i) (the other group has the context of pass i in registers).
+// Register budget: 22 warps = 704 threads -> 88 registers; the score block is processed in two halves.
+//
+// Warps: 0 weight TMA producer, 1 attention MMA issuer (+ TMEM allocator), 2-17 workers (thread == tile row == TMEM
+// lane; warp = (pass parity, head set, lane quarter)), 18 projection MMA issuer, 19 context store, 20-21 A-tile gather.
+// TMEM (512 columns): projection accumulators [0,128) and [128,256) | head set s at 256 + 128 s.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+#include <type_traits>
+#include "tc_common.cuh"
+#include "tc_api.cuh"
+
+namespace nrms {
+using namespace tc;
+
+int make_tmap_store_f16(CUtensorMap* out, const void* base, int64_t rows, int cols, int64_t ld, int box_cols, int box_rows);
+
+namespace k1v6 {
+
+// debug trace (-DNRMS_K1_TRACE): clock64 stamps of lane 0 of four warps of block 0 (0 worker set 0, 1 worker
+// set 1, 2 projection issuer, 3 attention issuer), written straight to global memory; nrms_debug_read_trace6
+__device__ long long g_trace[5][1024];     // 0/1 = worker groups (set 0), 2 proj, 3 attn, 4 = A-tile gather warp
+__device__ int g_trace_n[5];
+#ifdef NRMS_K1_TRACE
+#define TRACE(who, tag)                                                                         \
+  do {                                                                                          \
+    if (blockIdx.x == 0 && lane == 0 && trace_n < 1024)                                         \
+      g_trace[who][trace_n++] = ((long long)(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFLL);      \
+  } while (0)
+#define TRACE_DECL int trace_n = 0
+#define TRACE_END(who) do { if (blockIdx.x == 0 && lane == 0) g_trace_n[who] = trace_n; } while (0)
+#else
+#define TRACE(who, tag) do { } while (0)
+#define TRACE_DECL do { } while (0)
+#define TRACE_END(who) do { } while (0)
+#endif
+
+constexpr int NPASS = 8, KCH = 5;
+constexpr int PN = 128;                         // projection UMMA N (120 real columns per pass)
+constexpr int NST = 5;                          // weight ring stages (= one whole projection pass)
+static_assert(NST == KCH, "the projection issuer relies on stage == K chunk");
+constexpr int B_STAGE = PN * 128;               // 16,384
+constexpr int CP = 320;                         // pitch (halfs) of the fp16 context rows handed to K2
+constexpr int SRC_LD = 320;                     // pitch (halfs) of the fp16 gather source (k1v4_pack_src)
+constexpr int THREADS = 704;                    // 22 warps
+constexpr int NGW = 2;                          // A-tile gather warps (20, 21)
+constexpr int OFF_A = 0;                        // 5 x [128 rows x 128 B]
+constexpr int OFF_B = KCH * 16384;              // 81,920
+constexpr int OFF_SET = OFF_B + NST * B_STAGE;  // 163,840 ; per set: K (tf32) 16 KB | V^T (fp16) 8 KB
+constexpr int SET_BYTES = 16384 + 8192;
+constexpr int OFF_STG = OFF_SET + 2 * SET_BYTES;  // context staging for the TMA store: [128 rows][2 heads x 20 halfs]
+constexpr int STG_BYTES = 128 * 80;             // 10,240
+constexpr int OFF_BAR = OFF_STG + STG_BYTES;
+constexpr int SMEM = OFF_BAR + 512 + 1024;        // barriers | alignment slack
+static_assert(SMEM <= 232448, "shared memory budget");
+constexpr int TM_ACC = 128;                     // columns per projection accumulator
+constexpr int TM_SET0 = 256, TM_SET = 128;      // head sets: S [0,128) -> P [0,64) in place, O [64,96)
+constexpr int TM_O = 64;
+#ifndef NRMS_PROJ_AHEAD
+#define NRMS_PROJ_AHEAD 2
+#endif
+constexpr int PROJ_AHEAD = NRMS_PROJ_AHEAD;   // projection chunks in flight in the tensor pipe queue
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+// four rows r0..r3 of the 2-D tensor (box = 64 halfs x 1 row) -> four consecutive 128-byte rows at dst_smem
+__device__ __forceinline__ void tma_gather4(uint32_t dst_smem, const CUtensorMap* tmap, int col, int r0, int r1, int r2,
+                                            int r3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
+      : "memory");
+}
+// shared-memory box [rows][40 halfs] -> global tensor at {col, row}; completion tracked by bulk groups
+__device__ __forceinline__ void tma_store_2d(uint32_t src_smem, const CUtensorMap* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(src_smem)
+               : "memory");
+}
+__device__ __forceinline__ void expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// 2^x on the FMA and integer pipes (Cody-Waite split by the 1.5*2^23 trick, degree-4 Taylor polynomial of 2^f on
+// [-0.5, 0.5], relative error < 5e-5 -- an order below the fp16 rounding of P): the MUFU unit delivers 16 ex2 per clock
+// per SM (profiles/tmem_ld_probe.cu) and the softmax of a pass needs 12,800 of them, so every other probability is
+// computed here, in parallel with the MUFU half.  Measured (A/B on the evaluate bench): the ten extra instructions per
+// element cost more issue slots than the MUFU relief buys back -- every 2nd element here: 129.2 us per launch, none:
+// 124.1 us -- so the default sends one element in EX2_FMA_MOD to this path (0 = none).
+#ifndef NRMS_EX2_FMA_MOD
+#define NRMS_EX2_FMA_MOD 0
+#endif
+constexpr int EX2_FMA_MOD = NRMS_EX2_FMA_MOD;
+__device__ __forceinline__ bool ex2_on_fma(int j) { return EX2_FMA_MOD > 0 && (j % EX2_FMA_MOD) == EX2_FMA_MOD - 1; }
+__device__ __forceinline__ float ex2_fma(float x) {
+  x = fmaxf(x, -100.f);
+  const float t = x + 12582912.f;                    // integer part lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(f, 0.009618129f, 0.05550411f);
+  p = fmaf(f, p, 0.2402265f);
+  p = fmaf(f, p, 0.6931472f);
+  p = fmaf(f, p, 1.f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+}
+// fp32 bits -> tf32 bits, round to nearest, ties away from zero (cvt.rna.tf32.f32 for finite values) on the integer
+// pipe: cvt.rna shares the quarter-rate conversion unit with ex2, which the softmax already saturates
+__device__ __forceinline__ uint32_t rna_tf32(uint32_t x) { return (x + 0x1000u) & 0xFFFFE000u; }
+
+// S = sequence length, SLOT = padded slot (rows of the tile per sequence), SPT = sequences per tile
+template <int S, int SLOT, int SPT>
+__global__ void __launch_bounds__(THREADS, 1)
+encoder_attn_tc6_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_src,
+                        const __grid_constant__ CUtensorMap tmap_c, const __half* __restrict__ src16,
+                        const void* __restrict__ idx, int idx_kind, int64_t n_seq, int null_row) {
+  static_assert(SLOT % 8 == 0 && SLOT >= S && SPT * SLOT <= 128, "slot layout");
+  static_assert(SLOT == 64 || SLOT == 24, "score-block code paths");
+  constexpr int GPS = (S + 3) / 4;               // 4-row gather groups per sequence
+  static_assert(GPS * SPT <= 32 && GPS * 4 <= SLOT, "one gather group per lane");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const uint32_t bars = base + OFF_BAR;
+  const uint32_t w_full = bars, w_empty = bars + 8 * NST;                 // [NST] each
+  const uint32_t a_full = bars + 16 * NST, a_free = a_full + 8 * KCH;      // [KCH] each
+  const uint32_t acc_full = a_free + 8 * KCH, acc_empty = acc_full + 16;   // [2] each (one per accumulator)
+  const uint32_t kv_ready = acc_empty + 16, s_ready = kv_ready + 16, p_ready = s_ready + 16, o_ready = p_ready + 16;
+  // stg_full / stg_free: one pair per worker group (pass parity).  A worker only meets every other pass, so a single
+  // parity bit could not tell "the store of pass k-1 is done" from "not even the store of pass k-2 is done".
+  const uint32_t stg_full = o_ready + 16, stg_free = stg_full + 16, o_taken = stg_free + 16;   // [2] each
+  const uint32_t v_ready = o_taken + 16;                                                     // [2]; kv_ready = K only
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sm + OFF_BAR + 16 * NST + 16 * KCH + 192);
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform for the compiler: role branches stay uniform
+  const int64_t n_tiles = (n_seq + SPT - 1) / SPT;
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(w_full + 8 * s, 1);
+      mbar_init(w_empty + 8 * s, 1);
+    }
+    for (int k = 0; k < KCH; ++k) {
+      mbar_init(a_full + 8 * k, NGW);     // one arrival per gather warp
+      mbar_init(a_free + 8 * k, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(acc_full + 8 * s, 1);
+      mbar_init(acc_empty + 8 * s, 9);    // 8 worker warps (k, v drained) + the attention issuer (q consumed by both S MMAs)
+      mbar_init(kv_ready + 8 * s, 4);
+      mbar_init(s_ready + 8 * s, 1);
+      mbar_init(p_ready + 8 * s, 4);
+      mbar_init(o_ready + 8 * s, 1);
+      mbar_init(o_taken + 8 * s, 4);      // the four quarter-warps of the group that loaded the context
+      mbar_init(v_ready + 8 * s, 4);
+    }
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(stg_full + 8 * g, 8);     // one arrival per worker warp of the group
+      mbar_init(stg_free + 8 * g, 1);     // the store warp, once the bulk store of a pass of that parity has read the tile
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32((const void*)tmem_ptr_smem), 512);
+  // zero the A tile (padding rows are never written by the gather) and both operand sets (K columns 20..31,
+  // padded keys of V^T)
+  for (int i = tid; i < OFF_B / 16; i += THREADS) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = tid; i < (2 * SET_BYTES) / 16; i += THREADS)
+    reinterpret_cast<uint4*>(sm + OFF_SET)[i] = make_uint4(0u, 0u, 0u, 0u);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------ weight TMA producer: one 128-row box per K chunk ----------
+    if (lane == 0) {
+      uint32_t pass_it = 0;
+      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+#pragma unroll 1
+        for (int p = 0; p < NPASS; ++p, ++pass_it) {
+#pragma unroll 1
+          for (int kc = 0; kc < KCH; ++kc) {
+            mbar_wait(w_empty + 8 * kc, (pass_it & 1) ^ 1);
+#ifdef NRMS_DBG_NOWLOAD
+            if (pass_it >= 1) { mbar_arrive(w_full + 8 * kc); continue; }     // timing experiment: stale weights
+#endif
+            expect_tx(w_full + 8 * kc, B_STAGE);
+            tma_load_2d(base + OFF_B + kc * B_STAGE, &tmap_w, kc * 64, PN * p, w_full + 8 * kc);
+          }
+        }
+      }
+    }
+  } else if (warp >= 20) {
+    // ------------------------------ A-tile gather: 4 warps, cp.async + L2 prefetch of the next tile ---
+    // Eight lanes move one 128-byte row piece (coalesced), four rows per instruction, straight into the swizzled
+    // K-major layout; sequences missing from a partial tile are zero-filled (src-size 0).  The tile is
+    // single-buffered, so the time from "chunk free" (last projection pass done with it) to "chunk full" is exposed
+    // once per tile: TMA gather4 (v4) needed ~8,000 cycles, cp.async ~5,500 (profiles/r1_k1v5_trace_*.txt).
+    (void)tmap_src; (void)null_row;
+    constexpr int NREAL = S * SPT;                   // real rows of a tile (100)
+    constexpr int NIT = (NREAL + 3) / 4;             // 4-row copy instructions per chunk (25)
+    constexpr int NMINE = (NIT + NGW - 1) / NGW;     // ... per gather warp (7)
+    const int gw = warp - 20;
+    const int g = lane >> 3, c = lane & 7;
+    // everything but the source row is precomputed: a copy is an address add and the cp.async
+    uint32_t dst_off[NMINE];
+#pragma unroll
+    for (int k = 0; k < NMINE; ++k) {
+      const int n = 4 * (gw + NGW * k) + g;
+      const int r = (n / S) * SLOT + (n % S);
+      dst_off[k] = (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
+    }
+    const char* const srcb = reinterpret_cast<const char*>(src16) + c * 16;
+    uint32_t tile_it = 0;
+    TRACE_DECL;
+    // cp.async straight into the swizzled layout.  A third of the gathered rows miss L2 (ncu: 27 MB of DRAM reads per
+    // launch for 75 MB gathered), and the copies can only start once the chunk is free, so every lane first pulls
+    // the NEXT tile's row pieces into L2 (prefetch.global.L2, fire and forget) while the current tile computes.
+    uint32_t src_off[NMINE];
+    uint32_t valid = 0u;
+    auto load_rows = [&](int64_t t) {
+      const int64_t seq0 = t * SPT;
+      const int n_here = (n_seq - seq0 < SPT) ? (int)(n_seq - seq0) : SPT;
+      valid = 0u;
+#pragma unroll
+      for (int k = 0; k < NMINE; ++k) {
+        const int n = 4 * (gw + NGW * k) + g;
+        int sr = -1;
+        if (n < NREAL && n / S < n_here) {
+          const int64_t e = seq0 * S + n;
+          sr = idx_kind == 0 ? (int)e : (idx_kind == 1 ? (int)__ldg(reinterpret_cast<const int64_t*>(idx) + e)
+                                                         : __ldg(reinterpret_cast<const int32_t*>(idx) + e));
+        }
+        src_off[k] = sr < 0 ? 0u : (uint32_t)sr * (uint32_t)(SRC_LD * 2);
+        if (sr >= 0) valid |= 1u << k;
+      }
+    };
+    auto prefetch_rows = [&]() {        // lanes c = 0..4 of a row group cover the five 128-byte pieces of the row
+      if (c < KCH) {
+#pragma unroll
+        for (int k = 0; k < NMINE; ++k)
+          if ((valid >> k) & 1u)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(src16) + src_off[k] + c * 128));
+      }
+    };
+    if ((int64_t)blockIdx.x < n_tiles) load_rows(blockIdx.x);
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
+#pragma unroll 1
+      for (int kc = 0; kc < KCH; ++kc) {
+        mbar_wait(a_free + 8 * kc, (tile_it & 1) ^ 1);     // the previous tile's last pass is done with this chunk
+        if (gw == 0) TRACE(4, 60 + kc);
+        const uint32_t dchunk = base + OFF_A + kc * 16384;
+        const char* const schunk = srcb + kc * 128;
+#pragma unroll
+        for (int k = 0; k < NMINE; ++k) {
+          if (4 * (gw + NGW * k) + g < NREAL) {
+            const uint32_t nbytes = ((valid >> k) & 1u) ? 16u : 0u;       // 0: zero-fill (sequence not in this tile)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dchunk + dst_off[k]),
+                         "l"(schunk + src_off[k]), "r"(nbytes) : "memory");
+          }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+#pragma unroll
+      for (int kc = 0; kc < KCH; ++kc) {
+        if (kc == 0) asm volatile("cp.async.wait_group 4;" ::: "memory");
+        else if (kc == 1) asm volatile("cp.async.wait_group 3;" ::: "memory");
+        else if (kc == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else if (kc == 3) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full + 8 * kc);
+        if (gw == 0) TRACE(4, 70 + kc);
+      }
+      if (t + gridDim.x < n_tiles) {
+        load_rows(t + gridDim.x);
+        prefetch_rows();
+      }
+    }
+    if (gw == 0) TRACE_END(4);
+  } else if (warp == 18) {
+    // ------------------------------ projection MMA issuer (whole warp converged, see umma_*_p) ---
+    const uint32_t idesc_proj = umma_idesc_f16(128, PN);
+    const uint64_t desc0 = umma_desc_k_sw128(0);
+    const uint32_t el = elect_one_u32();
+    uint32_t pass_it = 0, tile_it = 0;
+    TRACE_DECL;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
+#pragma unroll 1
+      for (int p = 0; p < NPASS; ++p, ++pass_it) {
+        const uint32_t b = pass_it & 1, u = pass_it >> 1;
+        TRACE(2, 40);
+        // NST == KCH: chunk kc of every pass lives in ring stage kc; operand waits first, accumulator wait last
+        // (operand waits per chunk, below: the last stage of the ring is refilled ~900 cycles after the previous pass
+        // ends, the first ones long before)
+        TRACE(2, 47);
+        mbar_wait(acc_empty + 8 * b, (u & 1) ^ 1);     // pass_it - 2: k, v drained and q consumed
+        tc_fence_after();
+        TRACE(2, 41);
+        const uint32_t tacc = tmem_base + TM_ACC * b;
+#pragma unroll
+        for (int kc = 0; kc < KCH; ++kc) {
+          // The tensor pipe runs its queue in order: at most PROJ_AHEAD chunks (4 MMAs, ~256 cycles each) are kept
+          // in flight, so a score or context MMA of the attention issuer never waits behind a whole projection pass
+          if (kc >= PROJ_AHEAD) mbar_wait(w_empty + 8 * (kc - PROJ_AHEAD), pass_it & 1);
+          else if (pass_it > 0) mbar_wait(w_empty + 8 * (kc + KCH - PROJ_AHEAD), (pass_it & 1) ^ 1);
+          if (p == 0) mbar_wait(a_full + 8 * kc, tile_it & 1);   // first pass of a tile: chunk kc has landed
+          mbar_wait(w_full + 8 * kc, pass_it & 1);
+          tc_fence_after();
+          const uint32_t sa = (base + OFF_A + kc * 16384) >> 4;
+          const uint32_t sb = (base + OFF_B + kc * B_STAGE) >> 4;
+          const int ksteps = (kc == KCH - 1) ? 3 : 4;      // columns 256..303 (the bias column is 300)
+#pragma unroll
+          for (int ks = 0; ks < ksteps; ++ks)
+            umma_f16_ss_p(tacc, desc0 | (uint64_t)((sa + 2 * ks) & 0x3FFF), desc0 | (uint64_t)((sb + 2 * ks) & 0x3FFF),
+                          idesc_proj, (kc | ks) ? 1u : 0u, el);
+          umma_commit_p(w_empty + 8 * kc, el);
+          if (p == NPASS - 1) umma_commit_p(a_free + 8 * kc, el);
+        }
+        umma_commit_p(acc_full + 8 * b, el);
+        TRACE(2, 48);
+      }
+    }
+    TRACE_END(2);
+  } else if (warp == 1) {
+    // ------------------------------ attention MMA issuer (whole warp converged) ------------------
+    // The workers publish in the fixed order kv(0), kv(1), p(0), p(1) every pass, so a static wait order works.
+    const uint32_t idesc_s = umma_idesc_tf32(128, 128);
+    const uint32_t idesc_o = umma_idesc_f16(128, 32);
+    const uint64_t desc0 = umma_desc_k_sw128(0);
+    const uint32_t el = elect_one_u32();
+    uint32_t pass_it = 0;
+    TRACE_DECL;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+#pragma unroll 1
+      for (int p = 0; p < NPASS; ++p, ++pass_it) {
+        const uint32_t ph = pass_it & 1, b = pass_it & 1;
+        TRACE(3, 50);
+#pragma unroll
+        for (int set = 0; set < 2; ++set) {           // S = Q K^T   (A = q columns of the projection accumulator)
+          mbar_wait(kv_ready + 8 * set, ph);
+          if (pass_it > 0) mbar_wait(o_taken + 8 * set, ph ^ 1);   // context of the previous pass is in registers
+          tc_fence_after();
+          TRACE(3, 51 + set);
+          const uint32_t k_a = (base + OFF_SET + set * SET_BYTES) >> 4;
+#pragma unroll
+          for (int ks = 0; ks < 3; ++ks)
+            umma_tf32_ts_p(tmem_base + TM_SET0 + TM_SET * set, tmem_base + TM_ACC * b + 60 * set + 8 * ks,
+                           desc0 | (uint64_t)((k_a + 2 * ks) & 0x3FFF), idesc_s, ks ? 1u : 0u, el);
+          umma_commit_p(s_ready + 8 * set, el);
+          if (set == 1) umma_commit_p(acc_empty + 8 * b, el);
+          TRACE(3, 55);
+        }
+#pragma unroll
+        for (int set = 0; set < 2; ++set) {           // O = P V   (A = P, in place over the scores)
+          mbar_wait(p_ready + 8 * set, ph);
+          mbar_wait(v_ready + 8 * set, ph);
+          tc_fence_after();
+          TRACE(3, 53 + set);
+          const uint32_t v_a = (base + OFF_SET + set * SET_BYTES + 16384) >> 4;
+          const uint32_t tset = tmem_base + TM_SET0 + TM_SET * set;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_f16_ts_p(tset + TM_O, tset + 8 * ks, desc0 | (uint64_t)((v_a + (ks >> 2) * 256 + (ks & 3) * 2) & 0x3FFF),
+                          idesc_o, ks ? 1u : 0u, el);
+          umma_commit_p(o_ready + 8 * set, el);
+          TRACE(3, 56);
+        }
+      }
+    }
+    TRACE_END(3);
+  } else if (warp >= 2 && warp <= 17) {
+    // ------------------------------ workers (warps 2..17): warp = (pass parity, head set, TMEM lane quarter) ----
+    const int grp = (warp - 2) >> 2;
+    const int set = grp & 1, par = grp >> 1;
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    const int sq = row / SLOT;
+    const int sq_lo = (q4 * 32) / SLOT;                 // first sequence touched by this warp (warp-uniform)
+    const int own = sq - sq_lo;                         // SLOT == 24: which of the warp's two candidate blocks is mine
+    const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+    uint8_t* const setp = sm + OFF_SET + set * SET_BYTES;
+    const uint32_t tS = tmem_base + TM_SET0 + TM_SET * set + lane_addr;
+    const uint32_t tacc = tmem_base + TM_ACC * par + lane_addr + 60 * set;     // this group's accumulator
+    const int sw = row & 7;
+    const int vt_row_off = (row >> 6) * 4096 + ((row & 7) << 1);
+    uint32_t zeros[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) zeros[i] = 0u;
+    uint32_t pass_it = 0;
+#ifdef NRMS_K1_TRACE
+    int trace_n = 0;
+    const bool tracer = (warp == 2 || warp == 10);        // set 0 of either group
+#define WTRACE(tag) do { if (tracer) TRACE(par, tag); } while (0)
+#else
+#define WTRACE(tag) do { } while (0)
+#endif
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+#pragma unroll 1
+      for (int p = 0; p < NPASS; ++p, ++pass_it) {
+        if ((int)(pass_it & 1) != par) continue;            // the other group's pass
+        const uint32_t ph = pass_it & 1, u = pass_it >> 1;
+        WTRACE(20);
+        mbar_wait(acc_full + 8 * par, u & 1);
+        tc_fence_after();
+        WTRACE(21);
+        // ================= W1: k and v of the head -> operand tiles =========
+        {
+          uint32_t xk[DH], xv[DH];
+          tmem_ld16_nw(tacc + 20, xk);
+          tmem_ld4_nw(tacc + 36, xk + 16);
+          tmem_ld16_nw(tacc + 40, xv);
+          tmem_ld4_nw(tacc + 56, xv + 16);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty + 8 * par);
+          uint32_t hv[DH / 2];
+#pragma unroll
+          for (int d = 0; d < DH; ++d) xk[d] = rna_tf32(xk[d]);
+#pragma unroll
+          for (int d = 0; d < DH; d += 2) hv[d >> 1] = pack_h2(__uint_as_float(xv[d]), __uint_as_float(xv[d + 1]));
+          // The K / V^T tiles of the set are single-buffered.  K is only read by the S MMA of the previous pass (done
+          // long ago: s_ready), V^T by its PV MMA (o_ready, late) -- so K goes first with its own barrier and the next
+          // S MMA never waits for the V^T store and its proxy fence (~600 cycles, profiles/).
+          if (pass_it > 0) mbar_wait(s_ready + 8 * set, ph ^ 1);
+          uint8_t* const krow = setp + row * 128;
+#pragma unroll
+          for (int c = 0; c < 5; ++c)
+            *reinterpret_cast<uint4*>(krow + ((c ^ sw) << 4)) = make_uint4(xk[4 * c], xk[4 * c + 1], xk[4 * c + 2], xk[4 * c + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(kv_ready + 8 * set);
+          WTRACE(22);
+          if (pass_it > 0) mbar_wait(o_ready + 8 * set, ph ^ 1);
+          uint8_t* const vt_base = setp + 16384 + vt_row_off;
+#pragma unroll
+          for (int d = 0; d < DH; d += 2) {
+            const uint32_t h2 = hv[d >> 1];
+            *reinterpret_cast<uint16_t*>(vt_base + d * 128 + ((((row & 63) >> 3) ^ (d & 7)) << 4)) = (uint16_t)(h2 & 0xFFFFu);
+            *reinterpret_cast<uint16_t*>(vt_base + (d + 1) * 128 + ((((row & 63) >> 3) ^ ((d + 1) & 7)) << 4)) = (uint16_t)(h2 >> 16);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(v_ready + 8 * set);
+          WTRACE(23);
+        }
+        // ================= W2: score block -> P, in place (two halves: register budget) =================
+        float Z = 0.f;
+        {
+          mbar_wait(s_ready + 8 * set, ph);
+          tc_fence_after();
+          WTRACE(24);
+          if constexpr (SLOT == 64) {
+            // one sequence per warp: keys sq_lo*64 + j, j < S.  P columns: own 32 (values, zero tail), other 32 zero.
+            constexpr int NL = (S + 3) / 4 * 4;           // columns loaded (multiple of 4), 32 < NL <= 64
+            static_assert(NL > 32 && NL <= 64, "two halves");
+            const uint32_t tblk = tS + sq_lo * SLOT;
+            const uint32_t t_own = tS + sq_lo * 32, t_oth = tS + (1 - sq_lo) * 32;
+            uint32_t sv[32], pk[16];
+            tmem_ld16_nw(tblk, sv);
+            tmem_ld16_nw(tblk + 16, sv + 16);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float e0 = ex2(__uint_as_float(sv[j])), e1 = ex2(__uint_as_float(sv[j + 1]));
+              Z += e0 + e1;
+              pk[j >> 1] = pack_h2(e0, e1);
+            }
+            // second half of the loads BEFORE the first stores: columns [32, NL) are still scores until then
+            constexpr int N2 = NL - 32;
+            uint32_t sv2[32];
+#pragma unroll
+            for (int c = 0; c + 16 <= N2; c += 16) tmem_ld16_nw(tblk + 32 + c, sv2 + c);
+            if constexpr (N2 % 16 >= 8) tmem_ld8_nw(tblk + 32 + N2 / 16 * 16, sv2 + N2 / 16 * 16);
+            if constexpr (N2 % 8 >= 4) tmem_ld4_nw(tblk + 32 + N2 / 8 * 8, sv2 + N2 / 8 * 8);
+            tmem_ld_wait();
+            tmem_st16(t_own, pk);
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              const float e0 = (32 + j < S) ? ex2(__uint_as_float(sv2[j])) : 0.f;
+              const float e1 = (32 + j + 1 < S) ? ex2(__uint_as_float(sv2[j + 1])) : 0.f;
+              Z += e0 + e1;
+              pk[j >> 1] = (32 + j < S) ? pack_h2(e0, e1) : 0u;
+            }
+            tmem_st16(t_own + 16, pk);
+            tmem_st16(t_oth, zeros);
+            tmem_st16(t_oth + 16, zeros);
+          } else {
+            // SLOT == 24: the warp's rows belong to sequence sq_lo or sq_lo + 1; each lane reads ITS block (20 keys),
+            // writes its 12 P columns there, zeros in the warp's other candidate block and in every other block
+            uint32_t sv[2][20];
+#pragma unroll
+            for (int bb = 0; bb < 2; ++bb) {
+              if (sq_lo + bb < SPT) {
+                tmem_ld16_nw(tS + (sq_lo + bb) * SLOT, sv[bb]);
+                tmem_ld4_nw(tS + (sq_lo + bb) * SLOT + 16, sv[bb] + 16);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 20; ++j) sv[bb][j] = 0u;
+              }
+            }
+            tmem_ld_wait();
+            uint32_t pk[12];
+#pragma unroll
+            for (int j = 0; j < 20; j += 2) {
+              const float s0 = __uint_as_float(own ? sv[1][j] : sv[0][j]);
+              const float s1 = __uint_as_float(own ? sv[1][j + 1] : sv[0][j + 1]);
+              const float e0 = (j < S) ? ex2(s0) : 0.f;
+              const float e1 = (j + 1 < S) ? ex2(s1) : 0.f;
+              Z += e0 + e1;
+              pk[j >> 1] = pack_h2(e0, e1);
+            }
+            pk[10] = 0u;
+            pk[11] = 0u;
+            uint32_t pz[12];
+#pragma unroll
+            for (int bb = 0; bb < 2; ++bb) {
+              if (sq_lo + bb < SPT) {
+#pragma unroll
+                for (int j = 0; j < 12; ++j) pz[j] = (own == bb) ? pk[j] : 0u;
+                tmem_st8(tS + (sq_lo + bb) * 12, pz);
+                tmem_st4(tS + (sq_lo + bb) * 12 + 8, pz + 8);
+              }
+            }
+#pragma unroll
+            for (int sz = 0; sz < SPT; ++sz) {
+              if (sz != sq_lo && sz != sq_lo + 1) {          // warp-uniform
+                tmem_st8(tS + sz * 12, zeros);
+                tmem_st4(tS + sz * 12 + 8, zeros);
+              }
+            }
+            tmem_st4(tS + SPT * 12, zeros);                  // keys 120..127
+          }
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(p_ready + 8 * set);
+          WTRACE(26);
+        }
+        // ================= W3: context row -> registers -> staging tile =================
+        {
+          mbar_wait(o_ready + 8 * set, ph);
+          tc_fence_after();
+          WTRACE(28);
+          uint32_t o[DH];
+          tmem_ld16_nw(tS + TM_O, o);
+          tmem_ld4_nw(tS + TM_O + 16, o + 16);
+          tmem_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(o_taken + 8 * set);        // the S MMA of the next pass may overwrite the set
+          const float inv = 1.f / (Z + 1e-8f);
+          // 40 context columns of the pass (heads 2p, 2p+1; the dummy 16th head gives the zero K padding 300..319) go
+          // to the staging tile [128 rows][80 B]; the store warp sends it off as one 2-D bulk tensor store per sequence
+          if (pass_it > 0) mbar_wait(stg_free + 8 * (par ^ 1), ((pass_it - 1) >> 1) & 1);   // store of pass_it - 1 has read the tile
+          uint2* const srow = reinterpret_cast<uint2*>(sm + OFF_STG + row * 80 + set * 40);
+#pragma unroll
+          for (int c = 0; c < 5; ++c)
+            srow[c] = make_uint2(pack_h2(__uint_as_float(o[4 * c]) * inv, __uint_as_float(o[4 * c + 1]) * inv),
+                                 pack_h2(__uint_as_float(o[4 * c + 2]) * inv, __uint_as_float(o[4 * c + 3]) * inv));
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(stg_full + 8 * par);
+          WTRACE(30);
+        }
+      }
+    }
+#ifdef NRMS_K1_TRACE
+    if (tracer) TRACE_END(par);
+#endif
+  }
+  else if (warp == 19) {
+    // ------------------------------ context store: staging tile -> global (bulk tensor stores) ----
+    if (lane == 0) {
+      uint32_t k = 0;
+      for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int64_t seq0 = t * SPT;
+        const int n_here = (n_seq - seq0 < SPT) ? (int)(n_seq - seq0) : SPT;
+#pragma unroll 1
+        for (int p = 0; p < NPASS; ++p, ++k) {
+          mbar_wait(stg_full + 8 * (k & 1), (k >> 1) & 1);
+          for (int uu = 0; uu < n_here; ++uu)
+            tma_store_2d(base + OFF_STG + uu * SLOT * 80, &tmap_c, 40 * p, (int)((seq0 + uu) * S));
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          mbar_arrive(stg_free + 8 * (k & 1));
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace k1v6
+
+// debug builds (-DNRMS_K1_TRACE): host[who*1024 ..] = stamps of tracer `who`; counts[5]
+extern "C" int nrms_debug_read_trace6(long long* host, int* counts) {
+  cudaMemcpyFromSymbol(counts, k1v6::g_trace_n, 5 * sizeof(int));
+  cudaMemcpyFromSymbol(host, k1v6::g_trace, 5 * 1024 * sizeof(long long));
+  return 0;
+}
+
+template <int S, int SLOT, int SPT>
+static int launch_k1v6(const CUtensorMap& tw, const CUtensorMap& ts, const void* src16, const void* idx, int idx_kind,
+                       int64_t n, int null_row, void* Cbuf, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k1v6::encoder_attn_tc6_kernel<S, SLOT, SPT>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, k1v6::SMEM);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(encoder_attn_tc6_kernel)");
+    configured = true;
+  }
+  const int64_t tiles = (n + SPT - 1) / SPT;
+  int grid = num_sms();
+  if (tiles < grid) grid = (int)tiles;
+  alignas(64) CUtensorMap tc_;     // context rows [n*S][320] halfs, store box = S rows x 40 halfs (one sequence, one pass)
+  if (int rc = make_tmap_store_f16(&tc_, Cbuf, n * S, k1v6::CP, k1v6::CP, 40, S)) return rc;
+  k1v6::encoder_attn_tc6_kernel<S, SLOT, SPT><<<grid, k1v6::THREADS, k1v6::SMEM, st>>>(
+      tw, ts, tc_, reinterpret_cast<const __half*>(src16), idx, idx_kind, n, null_row);
+  NRMS_LAUNCH_CHECK("encoder_attn_tc6_kernel");
+  return NRMS_OK;
+}
+
+// Same operands as k1v4_run (the fp16 weight copy and gather source of k1v4_prepare / k1v4_pack_src).
+int k1v6_run(int S, const CUtensorMap& tw, const CUtensorMap& ts, const void* src16, const void* idx, int idx_kind,
+             int64_t n, int null_row, void* Cbuf, cudaStream_t st) {
+  if (S == 20) return launch_k1v6<20, 24, 5>(tw, ts, src16, idx, idx_kind, n, null_row, Cbuf, st);
+  if (S == 50) return launch_k1v6<50, 64, 2>(tw, ts, src16, idx, idx_kind, n, null_row, Cbuf, st);
+  set_error("encoder_attn_tc6_kernel compiled for S = 20 or 50, got %d", S);
+  return NRMS_E_UNSUPPORTED;
+}
+
+}  // namespace nrms

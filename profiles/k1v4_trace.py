@@ -19,9 +19,9 @@ with torch.no_grad():
         f = lambda: m.get_news_vector({"title": toks})
     for _ in range(3): f()
     torch.cuda.synchronize()
-NT = 5 if os.environ.get('NRMS_K1_VARIANT', '5') == '5' else 4
+NT = 5 if os.environ.get('NRMS_K1_VARIANT', '6') in ('5', '6') else 4
 buf = (ctypes.c_longlong * (1024 * NT))(); cnt = (ctypes.c_int * NT)()
-(lib.nrms_debug_read_trace5 if os.environ.get('NRMS_K1_VARIANT', '5') == '5' else lib.nrms_debug_read_trace4)(buf, cnt)
+{'6': lib.nrms_debug_read_trace6, '5': lib.nrms_debug_read_trace5}.get(os.environ.get('NRMS_K1_VARIANT', '6'), lib.nrms_debug_read_trace4)(buf, cnt)
 names = {20: "pass start", 21: "acc_full", 22: "W1 done", 23: "W3fin done", 24: "s_ready a", 25: "s_ready b", 26: "W2a done",
          27: "W2b done", 28: "o_ready a", 29: "o_ready b", 30: "W3 done", 31: "staged",
          40: "P pass start", 41: "P acc_empty", 42: "P kc0", 43: "P kc1", 44: "P kc2", 45: "P kc3", 46: "P kc4",

@@ -424,11 +424,12 @@ def test_unsupported_shape_and_cpu_inputs_fail_loudly(dev, golden_sd):
         ops.click_score(torch.zeros(2, 3, 300), torch.zeros(2, 300))           # CPU tensors: no fallback
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
 def test_fused_kernel_generations_agree_with_oracle(dev, lib, golden_sd, variant):
-    """All generations of the fused tensor-mode encoder kernel (CUDA-core attention; tcgen05 attention; two heads
-    in flight with P in tensor memory; TMA-gathered fp16 rows with the bias folded into the GEMM) stay inside the
-    1e-3 tolerance, news and users."""
+    """All generations of the fused tensor-mode encoder kernel (1 CUDA-core attention; 2 tcgen05 attention; 3 two
+    heads in flight with P in tensor memory; 4 TMA-gathered fp16 rows with the bias folded into the GEMM; 5 two
+    projection accumulators, P in place; 6 two worker groups on alternate passes) stay inside the 1e-3 tolerance,
+    news and users."""
     from newsrecommendationsystem_b200 import synthetic
     assert lib.nrms_set_option(b"k1_variant", variant) == 0
     try:
@@ -446,7 +447,7 @@ def test_fused_kernel_generations_agree_with_oracle(dev, lib, golden_sd, variant
         assert rel_l2_rows(nv.cpu().numpy(), ref_n) < TOL_VEC["tf32"]
         assert rel_l2_rows(uv.cpu().numpy(), ref_u) < TOL_VEC["tf32"]
     finally:
-        lib.nrms_set_option(b"k1_variant", 5)
+        lib.nrms_set_option(b"k1_variant", 6)
     assert lib.nrms_set_option(b"k1_variant", 9) == 1 and lib.nrms_set_option(b"nope", 1) == 1
 
 
