@@ -30,7 +30,8 @@ NUM_WORDS = 70976
 # algorithmic work per unit (SURVEY.md 8(d) / DESIGN.md section 5)
 FLOP_PER_TITLE = 13_700_000
 FLOP_PER_USER = 36_050_000
-BYTES_PER_CANDIDATE = 1212
+BYTES_PER_CANDIDATE = 1212          # fp32 news vector + int64 index + fp32 score (FP32 mode)
+BYTES_PER_CANDIDATE_F16 = 652       # tensor mode: the candidate row is read from the fp16 table copy (640 B)
 BYTES_PER_IMPRESSION = 1208
 
 
@@ -305,7 +306,10 @@ def main():
         ach = stage_flops.get(dominant, 0.0) / (st[dominant] / 1e3) / 1e12
         roof = dict(bound="tensor", kernel=f"{dominant} encoder stage", achieved=ach, peak=peaks["bf16_tflops"],
                     unit="TFLOP/s", frac=ach / peaks["bf16_tflops"], traffic=traffic, peak_source=peaks["source"])
-    score_bytes = cand_rank * BYTES_PER_CANDIDATE + n_imp_rank * BYTES_PER_IMPRESSION
+    per_cand = BYTES_PER_CANDIDATE_F16 if args.precision == "tf32" else BYTES_PER_CANDIDATE
+    # + the one-off fp16 copy of the table inside the stage (read fp32, write fp16)
+    pack_bytes = (NEWS_PER_GPU * world + 1) * (1200 + 640) if args.precision == "tf32" else 0
+    score_bytes = cand_rank * per_cand + n_imp_rank * BYTES_PER_IMPRESSION + pack_bytes
     extras = dict(
         stage_ms=st,
         news_per_s=n_news_rank * world / (st.get("news", float("nan")) / 1e3),

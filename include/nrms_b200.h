@@ -150,6 +150,11 @@ int nrms_score_bwd(const float* d_scores, const float* cand, const float* user,
  * scores[k] = table[cand_rows[k], :] . user_vec[i, :]   (X = 300). */
 int nrms_score_csr(const float* table, const int32_t* cand_rows, const int64_t* offsets,
                    const float* user_vec, int64_t n_impressions, float* scores, void* stream);
+/* Tensor-mode scoring: the candidate rows are read from an fp16 copy of the table (half the bytes per candidate, fp32
+ * accumulation).  nrms_pack_rows_f16 writes that copy: dst16 = (n_rows + 1) * 640 bytes, rows of 320 halfs. */
+int nrms_pack_rows_f16(const float* src, int64_t n_rows, void* dst16, void* stream);
+int nrms_score_csr_f16(const void* table16, const int32_t* cand_rows, const int64_t* offsets,
+                       const float* user_vec, int64_t n_impressions, float* scores, void* stream);
 
 /* ---- loss / optimizer --------------------------------------------------------------- */
 /* loss = mean_b( -log_softmax(logits[b,:])[0] ); d_logits = d(loss)/d(logits) * grad_scale. */

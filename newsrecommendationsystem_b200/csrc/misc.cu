@@ -1,11 +1,13 @@
 // Click predictor (dense + CSR), cross-entropy(label 0), fused Adam/AdamW, row gather,
 // ranking metrics, and the error plumbing of the C-ABI.
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "encoder_kernels.cuh"
 #include <math.h>
 #include <atomic>
 
 namespace nrms {
+int k1v4_pack_rows(const float* src, int64_t n_rows, void* src16, cudaStream_t st);   // tc_fused5.cu
 
 static thread_local char g_err[512] = "";
 
@@ -97,6 +99,56 @@ score_csr_kernel(const float* __restrict__ table, const int32_t* __restrict__ ca
         for (int k = 0; k < 10; ++k) {
           acc = fmaf(v[k].x, u[k].x, acc); acc = fmaf(v[k].y, u[k].y, acc);
           acc = fmaf(v[k].z, u[k].z, acc); acc = fmaf(v[k].w, u[k].w, acc);
+        }
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (g == 0 && c < end) scores[c] = acc;
+    }
+  }
+}
+
+// Tensor-mode variant: the candidate rows come from an fp16 copy of the news-vector table ([rows][320] halfs, the
+// same layout the user encoder gathers from: values 0..299, 1.0 at 300, zeros after), fp32 accumulation.  Half the
+// bytes per candidate (640 B); the 42 MB table stays L2-resident.  8 lanes per row, 5 x 16 bytes per lane.
+__global__ void __launch_bounds__(256)
+score_csr_f16_kernel(const __half* __restrict__ table16, const int32_t* __restrict__ cand_rows,
+                     const int64_t* __restrict__ offsets, const float* __restrict__ user_vec, int64_t n_imp,
+                     float* __restrict__ scores) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane & 7, grp = lane >> 3;
+  const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t imp = warp; imp < n_imp; imp += nwarps) {
+    // lane g owns the 8-element chunks g, g+8, ..., g+32 of the 320-wide row (chunks 37.5.. are the 1.0 / zero tail)
+    const float4* up = reinterpret_cast<const float4*>(user_vec + imp * D);
+    float4 u[5][2];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int ch = g + 8 * k;                 // 8 floats = 2 float4 at 2*ch, 2*ch+1 (valid below 75)
+      u[k][0] = (2 * ch < DV4) ? __ldg(up + 2 * ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+      u[k][1] = (2 * ch + 1 < DV4) ? __ldg(up + 2 * ch + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int64_t beg = offsets[imp], end = offsets[imp + 1];
+    for (int64_t c0 = beg; c0 < end; c0 += 4) {
+      const int64_t c = c0 + grp;
+      float acc = 0.f;
+      if (c < end) {
+        const uint4* rp = reinterpret_cast<const uint4*>(table16 + (int64_t)cand_rows[c] * 320);
+        uint4 v[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) v[k] = __ldg(rp + g + 8 * k);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v[k].x));
+          const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v[k].y));
+          const float2 cc = __half22float2(*reinterpret_cast<const __half2*>(&v[k].z));
+          const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&v[k].w));
+          acc = fmaf(a.x, u[k][0].x, acc); acc = fmaf(a.y, u[k][0].y, acc);
+          acc = fmaf(b.x, u[k][0].z, acc); acc = fmaf(b.y, u[k][0].w, acc);
+          acc = fmaf(cc.x, u[k][1].x, acc); acc = fmaf(cc.y, u[k][1].y, acc);
+          acc = fmaf(d.x, u[k][1].z, acc); acc = fmaf(d.y, u[k][1].w, acc);
         }
       }
       acc += __shfl_xor_sync(0xffffffffu, acc, 4);
@@ -320,6 +372,28 @@ int nrms_score_csr(const float* table, const int32_t* cand_rows, const int64_t* 
   if (gb > (int64_t)num_sms() * 8) gb = (int64_t)num_sms() * 8;
   score_csr_kernel<<<(unsigned)gb, 256, 0, st>>>(table, cand_rows, offsets, user_vec, n_impressions, scores);
   NRMS_LAUNCH_CHECK("score_csr");
+  return NRMS_OK;
+}
+
+int nrms_pack_rows_f16(const float* src, int64_t n_rows, void* dst16, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  NRMS_CHECK_ARG(n_rows >= 0, NRMS_E_INVALID, "bad sizes");
+  NRMS_CHECK_ARG(src && dst16 && aligned16(src) && aligned16(dst16), NRMS_E_INVALID, "null/misaligned pointer");
+  return k1v4_pack_rows(src, n_rows, dst16, st);
+}
+
+int nrms_score_csr_f16(const void* table16, const int32_t* cand_rows, const int64_t* offsets, const float* user_vec,
+                       int64_t n_impressions, float* scores, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  NRMS_CHECK_ARG(n_impressions >= 0, NRMS_E_INVALID, "bad sizes");
+  if (n_impressions == 0) return NRMS_OK;
+  NRMS_CHECK_ARG(table16 && cand_rows && offsets && user_vec && scores && aligned16(table16) && aligned16(user_vec),
+                 NRMS_E_INVALID, "null/misaligned pointer");
+  int64_t gb = (n_impressions + 7) / 8;
+  if (gb > (int64_t)num_sms() * 8) gb = (int64_t)num_sms() * 8;
+  score_csr_f16_kernel<<<(unsigned)gb, 256, 0, st>>>(reinterpret_cast<const __half*>(table16), cand_rows, offsets,
+                                                    user_vec, n_impressions, scores);
+  NRMS_LAUNCH_CHECK("score_csr_f16");
   return NRMS_OK;
 }
 

@@ -586,6 +586,16 @@ int k1v4_prepare(const float* wqkv, const float* bqkv, void* w16, CUtensorMap* t
   return make_tmap_k_major_f16(tw, w16, k1v4::W16_ROWS, k1v4::W16_LD, k1v4::W16_LD, k1v4::PN);
 }
 
+// fp16 copy [n_rows + 1][320] of n_rows fp32 rows (1.0 in column 300, zero tail, all-zero last row), no tensor map
+int k1v4_pack_rows(const float* src, int64_t n_rows, void* src16, cudaStream_t st) {
+  const int64_t total = (n_rows + 1) * 40;
+  int64_t gb = (total + 255) / 256;
+  if (gb > (int64_t)num_sms() * 16) gb = (int64_t)num_sms() * 16;
+  k1v4::pack_src16_kernel<<<(unsigned)gb, 256, 0, st>>>(src, n_rows, reinterpret_cast<__half*>(src16));
+  NRMS_LAUNCH_CHECK("pack_src16_kernel");
+  return NRMS_OK;
+}
+
 // fp16 gather source of n_rows fp32 rows (+ the null row) and its gather4 tensor map (box = 64 halfs x 1 row)
 int k1v4_pack_src(const float* src, int64_t n_rows, void* src16, CUtensorMap* ts, cudaStream_t st) {
   NRMS_CHECK_ARG((n_rows + 1) * k1v4::SRC_LD * 2 < (1ll << 32), NRMS_E_UNSUPPORTED,

@@ -149,6 +149,13 @@ def encode_news_table(model, news_tokens: torch.Tensor) -> torch.Tensor:
 
 
 @torch.no_grad()
+def _tensor_mode(model):
+    from . import _lib
+    from .config import resolve_mode
+    ue = model.user_encoder
+    return resolve_mode(ue.config, ue.precision) == _lib.MODE_TF32
+
+
 def evaluate_tensors(model, inputs: EvalInputs, max_count=None, return_details=False, mark=None):
     """evaluate() on resident tensors -> (AUC, MRR, nDCG@5, nDCG@10) as Python floats.
 
@@ -172,7 +179,11 @@ def evaluate_tensors(model, inputs: EvalInputs, max_count=None, return_details=F
         mark("users")
         c0, c1 = int(inputs.cand_offsets_host[lo]), int(inputs.cand_offsets_host[hi])
         offs = (inputs.cand_offsets[lo:hi + 1] - c0).contiguous()
-        scores = ops.score_csr(table, inputs.cand_rows[c0:c1], offs, user_vec)
+        if _tensor_mode(model):
+            # tensor mode: candidates are read from an fp16 copy of the table (half the bytes, fp32 accumulation)
+            scores = ops.score_csr_f16(ops.pack_rows_f16(table), inputs.cand_rows[c0:c1], offs, user_vec)
+        else:
+            scores = ops.score_csr(table, inputs.cand_rows[c0:c1], offs, user_vec)
         mark("score")
         per, sums = ops.rank_metrics(scores, inputs.labels[c0:c1], offs)
         mark("metrics")

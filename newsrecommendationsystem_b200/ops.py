@@ -283,6 +283,28 @@ def score_csr(table, cand_rows, offsets, user_vec):
 
 
 @torch.no_grad()
+def pack_rows_f16(table):
+    """fp16 copy of an fp32 [n,300] table in the layout the tensor-mode kernels read: [n+1, 320] halfs."""
+    lib = _lib.load()
+    _require_cuda(table)
+    t = _f32c(table)
+    out = torch.empty((t.shape[0] + 1, 320), dtype=torch.float16, device=t.device)
+    check(lib.nrms_pack_rows_f16(ptr(t), t.shape[0], ptr(out), stream_ptr(t.device)), "nrms_pack_rows_f16")
+    return out
+
+
+@torch.no_grad()
+def score_csr_f16(table16, cand_rows, offsets, user_vec):
+    lib = _lib.load()
+    _require_cuda(table16, cand_rows, offsets, user_vec)
+    n_imp = offsets.numel() - 1
+    scores = torch.empty((cand_rows.numel(),), dtype=torch.float32, device=table16.device)
+    check(lib.nrms_score_csr_f16(ptr(table16), ptr(cand_rows), ptr(offsets), ptr(user_vec), n_imp, ptr(scores),
+                                 stream_ptr(table16.device)), "nrms_score_csr_f16")
+    return scores
+
+
+@torch.no_grad()
 def rank_metrics(scores, labels, offsets):
     """-> (per_impression [n,4] fp64 with NaN rows for single-class impressions, sums_counts [8] fp64)."""
     lib = _lib.load()

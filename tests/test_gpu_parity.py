@@ -558,3 +558,27 @@ def test_train_step_from_row_indices(dev, golden, golden_sd):
         w = m.user_encoder.additive_attention.linear.weight.detach().cpu().numpy()
         losses.append(w)
     assert losses[0] == losses[2] and np.array_equal(losses[1], losses[3])
+
+
+def test_score_csr_f16_table(dev):
+    """Tensor-mode scoring reads an fp16 copy of the news-vector table: same indexing as the fp32 kernel (bit-exact on
+    fp16-representable rows), fp32 accumulation, rounding error of the copy within 1e-3 of |u||v|."""
+    from newsrecommendationsystem_b200 import ops
+    rng = np.random.default_rng(9)
+    table = (rng.standard_normal((700, 300)) * 0.3).astype(np.float32)
+    table[-1] = 0
+    users = (rng.standard_normal((37, 300)) * 0.3).astype(np.float32)
+    counts = rng.integers(1, 40, size=37)
+    counts[5] = 301
+    offs = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    rows = rng.integers(0, 700, size=offs[-1]).astype(np.int32)
+    tb, ub = t(table, dev), t(users, dev)
+    s32 = ops.score_csr(tb, t(rows, dev), t(offs, dev), ub).cpu().numpy()
+    t16 = ops.pack_rows_f16(tb)
+    assert t16.shape == (701, 320) and float(t16[:700, 300].float().min()) == 1.0 and not t16[700].any()
+    s16 = ops.score_csr_f16(t16, t(rows, dev), t(offs, dev), ub).cpu().numpy()
+    imp = np.repeat(np.arange(37), counts)
+    bound = 1e-3 * np.linalg.norm(users[imp], axis=1) * np.linalg.norm(table[rows], axis=1)
+    assert np.all(np.abs(s16 - s32) <= bound + 1e-6)
+    exact = ops.score_csr(t16[:700, :300].float().contiguous(), t(rows, dev), t(offs, dev), ub).cpu().numpy()
+    np.testing.assert_allclose(s16, exact, rtol=0, atol=2e-5)
