@@ -24,6 +24,9 @@ def _free_port():
 
 
 class _StubUserEncoder:
+    config = None
+    precision = "fp32"          # evaluate_tensors then scores from the fp32 table (ops.score_csr, stubbed below)
+
     def __init__(self, sd):
         self.sd = sd
 
