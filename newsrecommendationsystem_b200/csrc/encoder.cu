@@ -560,6 +560,10 @@ int nrms_set_option(const char* key, int value) {
     NRMS_CHECK_ARG(set_k1_variant(value) == NRMS_OK, NRMS_E_INVALID, "k1_variant must be 1..6");
     return NRMS_OK;
   }
+  if (strcmp(key, "user_table_attn") == 0) {
+    set_table_attn(value != 0);
+    return NRMS_OK;
+  }
   if (strcmp(key, "time_k1") == 0) {
     set_time_k1(value != 0);
     return NRMS_OK;

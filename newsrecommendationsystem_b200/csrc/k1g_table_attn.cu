@@ -1,0 +1,306 @@
+// K1g -- user-encoder self-attention over PRE-PROJECTED news rows (evaluate path, indexed input).
+//
+// The user encoder's Q/K/V projections are row-wise linear maps of the gathered news vectors
+// (reference: src/model/general/attention/multihead_self.py:53-58 applied to the rows stacked at
+// src/evaluate.py:220-224), and every row comes from the same news-vector table.  Projecting the TABLE once
+// (one [n_rows, 900] GEMM, tc_gemm_nt_f16out) and gathering q, k, v per history row gives the same numbers
+// with 1/56 of the projection work at MIND-small shapes (65 k table rows against 3.66 M history rows); what
+// remains per user is 15 heads x (50 x 50 x 20) of attention on gathered rows: an L2 / MUFU-bound kernel,
+// not a tensor-pipe-bound one.
+//
+//   table16 : [n_rows][3 head groups][q | k | v][5 heads][24 halfs] = 2,160 B per row; q pre-scaled by
+//             log2(e)/sqrt(20), bias included, every 20-half head slice padded to 48 B (pad = 0 for q and k,
+//             (1, 0, 0, 0) for v: the context MMA then also returns Z = sum_j P_ij in column 20)
+//   stage   : one (user, head group) = 50 rows x 720 B, copied row by row with cp.async.bulk (one 720-byte bulk
+//             copy per history row, completion on the stage's mbarrier); 6 stages = two users in flight.
+//             The 720-byte pitch keeps every ldmatrix (8 rows x 16 B) bank-conflict free.
+//   warp 15 : producer (history indices -> bulk copies), runs up to six stages ahead
+//   warp w  : head w (w = 0..14; head group w / 5), FA2-style on mma.sync m16n8k16/k8 (fp16 in, fp32
+//             accumulate): K and V fragments of the head stay in registers for its four 16-row query tiles;
+//             S = Q K^T -> P = 2^S (ex2.approx) -> fp16 A fragments in registers -> O = P V -> O / (Z + 1e-8)
+//             (exp without max subtraction and the 1e-8 of multihead_self.py:17-20) -> fp16 context rows
+//             [50][300] (+ 20 zero columns, cleared once by the host), the layout K2 reads.
+//
+// The tensor work here is ~3 MFLOP per user on tiles of 16 x 8: warp-level mma.sync is the right granularity
+// (a 128-row tcgen05 tile would be 61 % padding, see K1 v6), and the kernel is bound by the row gather and
+// the exponentials, not by the MMA rate.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include "tc_common.cuh"
+#include "tc_api.cuh"
+
+namespace nrms {
+namespace k1g {
+
+constexpr int S = 50;              // history length
+constexpr int H = 15;              // heads
+constexpr int HG = 5;              // heads per group (one stage)
+constexpr int SLICE = 48;          // bytes per (row, head) slice: 20 halfs + 4 pad
+constexpr int GROUP = 3 * HG * SLICE;   // 720 B: q | k | v slices of one head group
+constexpr int OFF_K = HG * SLICE;       // 240
+constexpr int OFF_V = 2 * HG * SLICE;   // 480
+constexpr int PITCH = 3 * GROUP;        // 2,160 B: one table16 row
+constexpr int STAGE = S * PITCH;        // 108,000 B: one user
+constexpr int NSTAGE = 2;
+#ifndef K1G_PREFETCH_AHEAD
+#define K1G_PREFETCH_AHEAD 0
+#endif
+constexpr int PREFETCH_AHEAD = K1G_PREFETCH_AHEAD;
+constexpr int ROW_BYTES = PITCH;
+constexpr int OFF_ZERO = NSTAGE * STAGE;   // 64 B of zeros (rows >= 50 of every ldmatrix)
+constexpr int OFF_BAR = OFF_ZERO + 64;     // full[6], empty[6]
+constexpr int SMEM = OFF_BAR + 128;        // 216,192 B
+constexpr int THREADS = 512;
+constexpr int CP = 320;            // pitch (halfs) of the context rows K2 reads
+
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x2_t(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr) : "memory");
+}
+// D += A(16x16, row) * B(16x8, col), fp16 operands, fp32 accumulate
+__device__ __forceinline__ void mma_k16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                        uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// D += A(16x8, row) * B(8x8, col)
+__device__ __forceinline__ void mma_k8(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(b0));
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// 2^x on the FMA / integer pipes (Cody-Waite split by the 1.5*2^23 trick + degree-4 polynomial, relative error < 5e-5,
+// an order below the fp16 rounding of P).  K1G_EX2_FMA = n > 0 sends every n-th exponential of a key tile pair here:
+// the MUFU unit (16 ex2 per clock per SM) is the second-busiest pipe of this kernel after the HMMA pipe.
+#ifndef K1G_EX2_FMA
+#define K1G_EX2_FMA 2
+#endif
+__device__ __forceinline__ float ex2_fma(float x) {
+  x = fmaxf(x, -100.f);
+  const float t = x + 12582912.f;
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(f, 0.009618129f, 0.05550411f);
+  p = fmaf(f, p, 0.2402265f);
+  p = fmaf(f, p, 0.6931472f);
+  p = fmaf(f, p, 1.f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
+}
+template <int J>
+__device__ __forceinline__ float ex2_sel(float x) {
+  if (K1G_EX2_FMA > 0 && (J % K1G_EX2_FMA) == K1G_EX2_FMA - 1) return ex2_fma(x);
+  return ex2f(x);
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// smem byte address of row `row` of a stage (the zero line for rows >= 50), plus a byte offset (a multiple of 16)
+__device__ __forceinline__ uint32_t row_addr(uint32_t stage, uint32_t zero, int row, int off) {
+  return row < S ? stage + (uint32_t)(row * PITCH + off) : zero + (uint32_t)(off & 31);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+table_attn_kernel(const __half* __restrict__ table16, int n_table_rows, const int32_t* __restrict__ hist_rows,
+                  int64_t n_users, __half* __restrict__ ctx) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sbase = tc::smem_u32(smem);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const uint32_t zero = sbase + OFF_ZERO;
+  const uint32_t full_bar = sbase + OFF_BAR, empty_bar = full_bar + 8 * NSTAGE;
+
+  if (tid < 16) reinterpret_cast<uint32_t*>(smem + OFF_ZERO)[tid] = 0u;
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      tc::mbar_init(full_bar + 8 * s, 1);
+      tc::mbar_init(empty_bar + 8 * s, H);
+    }
+    tc::mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == H) {
+    // ------------------------------ producer: 50 bulk copies of 720 B per stage ------------------------------
+    uint32_t it = 0;                                   // stage counter: user-major, head group fastest
+    for (int64_t u = blockIdx.x; u < n_users; u += gridDim.x) {
+      int r0 = hist_rows[u * S + lane];
+      int r1 = lane + 32 < S ? hist_rows[u * S + lane + 32] : 0;
+      r0 = r0 < 0 ? 0 : (r0 >= n_table_rows ? n_table_rows - 1 : r0);
+      r1 = r1 < 0 ? 0 : (r1 >= n_table_rows ? n_table_rows - 1 : r1);
+      const char* s0 = reinterpret_cast<const char*>(table16) + (int64_t)r0 * ROW_BYTES;
+      const char* s1 = reinterpret_cast<const char*>(table16) + (int64_t)r1 * ROW_BYTES;
+      {
+        // L2 prefetch of the rows two users ahead (17 lines of 128 B per 2,160-byte row): the bulk copies then hit L2
+        const int64_t up = u + (int64_t)PREFETCH_AHEAD * gridDim.x;
+        if (PREFETCH_AHEAD > 0 && up < n_users) {
+          int p0 = __ldg(hist_rows + up * S + lane);
+          int p1 = lane + 32 < S ? __ldg(hist_rows + up * S + lane + 32) : 0;
+          p0 = p0 < 0 ? 0 : (p0 >= n_table_rows ? n_table_rows - 1 : p0);
+          p1 = p1 < 0 ? 0 : (p1 >= n_table_rows ? n_table_rows - 1 : p1);
+#pragma unroll 5
+          for (int r = 0; r < S; ++r) {
+            const int pr = __shfl_sync(0xffffffffu, r < 32 ? p0 : p1, r & 31);
+            if (lane < 17) {
+              const char* a = reinterpret_cast<const char*>(table16) + (int64_t)pr * ROW_BYTES + lane * 128;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+            }
+          }
+        }
+        const uint32_t st = it % NSTAGE;
+        tc::mbar_wait(empty_bar + 8 * st, ((it / NSTAGE) & 1) ^ 1);
+        if (lane == 0) mbar_arrive_expect_tx(full_bar + 8 * st, STAGE);
+        __syncwarp();
+        const uint32_t dst = sbase + st * STAGE + lane * PITCH;
+        bulk_copy_g2s(dst, s0, PITCH, full_bar + 8 * st);
+        if (lane + 32 < S) bulk_copy_g2s(dst + 32 * PITCH, s1, PITCH, full_bar + 8 * st);
+        ++it;
+      }
+    }
+  } else {
+    // ------------------------------ compute: warp = head ------------------------------
+    const int hg = warp / HG, hl = warp - hg * HG;
+    const int qoff = hg * GROUP + hl * SLICE, koff = OFF_K + qoff, voff = OFF_V + qoff;
+    const int g = lane >> 2, t = lane & 3;
+    const int mi = lane >> 3, rr = lane & 7;     // ldmatrix: this lane supplies row rr of matrix mi
+    uint32_t itu = 0;
+    for (int64_t u = blockIdx.x; u < n_users; u += gridDim.x, ++itu) {
+      const uint32_t it = itu;
+      const uint32_t st = it % NSTAGE;
+      const uint32_t B = sbase + st * STAGE;
+      tc::mbar_wait(full_bar + 8 * st, (it / NSTAGE) & 1);
+      // ---- K fragments: kb16[nt][0..1] (dims 0-7, 8-15), kb8[nt] (dims 16-23) for key tiles nt = 0..6 ----
+      uint32_t kb16[8][2], kb8[8];
+#pragma unroll
+      for (int p = 0; p < 4; ++p)   // key tiles (2p, 2p+1): matrices [2p,d0-7] [2p,d8-15] [2p+1,d0-7] [2p+1,d8-15]
+        ldsm_x4(row_addr(B, zero, 8 * (2 * p + (mi >> 1)) + rr, koff + (mi & 1) * 16), kb16[2 * p][0], kb16[2 * p][1],
+                kb16[2 * p + 1][0], kb16[2 * p + 1][1]);     // key tile 7 (rows 56..63) is the zero line, unused
+#pragma unroll
+      for (int p = 0; p < 2; ++p)   // dims 16-23 of key tiles 4p..4p+3
+        ldsm_x4(row_addr(B, zero, 8 * (4 * p + mi) + rr, koff + 32), kb8[4 * p], kb8[4 * p + 1], kb8[4 * p + 2],
+                kb8[4 * p + 3]);
+      // ---- V fragments (transposed loads): vb[ks][dt][0..1] keys 16ks..16ks+7 / +8..15, dims 8dt..8dt+7 ----
+      uint32_t vb[4][3][2];
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        // matrices: [keys 16ks+0..7, d0-7] [keys +8..15, d0-7] [keys 0..7, d8-15] [keys +8..15, d8-15]
+        ldsm_x4_t(row_addr(B, zero, 16 * ks + 8 * (mi & 1) + rr, voff + (mi >> 1) * 16), vb[ks][0][0], vb[ks][0][1],
+                  vb[ks][1][0], vb[ks][1][1]);
+        ldsm_x2_t(row_addr(B, zero, 16 * ks + 8 * (mi & 1) + rr, voff + 32), vb[ks][2][0], vb[ks][2][1]);
+      }
+      __half* out = ctx + (u * S) * CP + warp * 20 + 2 * t;
+      // ---- four query tiles of 16 rows ----
+#pragma unroll 1
+      for (int mt = 0; mt < 4; ++mt) {
+        uint32_t qa[4], qb[2];
+        ldsm_x4(row_addr(B, zero, 16 * mt + 8 * (mi & 1) + rr, qoff + (mi >> 1) * 16), qa[0], qa[1], qa[2], qa[3]);
+        ldsm_x2(row_addr(B, zero, 16 * mt + 8 * (mi & 1) + rr, qoff + 32), qb[0], qb[1]);
+        if (mt == 3) {               // last shared-memory read of this stage: hand it back to the producer
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(empty_bar + 8 * st);
+        }
+        float sacc[7][4];
+#pragma unroll
+        for (int nt = 0; nt < 7; ++nt) {
+          sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
+          mma_k16(sacc[nt], qa[0], qa[1], qa[2], qa[3], kb16[nt][0], kb16[nt][1]);
+          mma_k8(sacc[nt], qb[0], qb[1], kb8[nt]);
+        }
+        // P = 2^S (q carries log2(e)/sqrt(20)); keys 50..55 (key tile 6, t > 0) are padding
+        uint32_t pa[7][2];
+        const bool lower = mt < 3;              // rows 16mt+8..+15 exist only in the first three tiles
+#pragma unroll
+        for (int nt = 0; nt < 7; ++nt) {
+          float p0 = ex2_sel<0>(sacc[nt][0]), p1 = ex2_sel<1>(sacc[nt][1]);
+          float p2 = 0.f, p3 = 0.f;
+          if (lower) { p2 = ex2_sel<2>(sacc[nt][2]); p3 = ex2_sel<3>(sacc[nt][3]); }
+          if (nt == 6 && t > 0) { p0 = p1 = p2 = p3 = 0.f; }
+          pa[nt][0] = pack_h2(p0, p1);
+          pa[nt][1] = pack_h2(p2, p3);
+        }
+        float oacc[3][4];
+#pragma unroll
+        for (int dt = 0; dt < 3; ++dt) {
+          oacc[dt][0] = oacc[dt][1] = oacc[dt][2] = oacc[dt][3] = 0.f;
+#pragma unroll
+          for (int ks = 0; ks < 3; ++ks)
+            mma_k16(oacc[dt], pa[2 * ks][0], pa[2 * ks][1], pa[2 * ks + 1][0], pa[2 * ks + 1][1], vb[ks][dt][0],
+                    vb[ks][dt][1]);
+          mma_k8(oacc[dt], pa[6][0], pa[6][1], vb[3][dt][0]);
+        }
+        // Z of rows g / g+8 sits in column 20 = element 0 / 2 of dim tile 2 on the quad's lane t == 2
+        const float z0 = __shfl_sync(0xffffffffu, oacc[2][0], (lane & ~3) | 2);
+        const float z1 = __shfl_sync(0xffffffffu, oacc[2][2], (lane & ~3) | 2);
+        const float i0 = __fdividef(1.f, z0 + 1e-8f), i1 = __fdividef(1.f, z1 + 1e-8f);
+        const int r0 = 16 * mt + g, r1 = r0 + 8;
+        __half* o0 = out + r0 * CP;
+#pragma unroll
+        for (int dt = 0; dt < 3; ++dt) {
+          if (dt < 2 || t < 2) {
+            if (r0 < S) *reinterpret_cast<uint32_t*>(o0 + dt * 8) = pack_h2(oacc[dt][0] * i0, oacc[dt][1] * i0);
+            if (r1 < S) *reinterpret_cast<uint32_t*>(o0 + 8 * CP + dt * 8) = pack_h2(oacc[dt][2] * i1, oacc[dt][3] * i1);
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace k1g
+
+// table16 = half([table | 1] * [W_Q*c | W_K | W_V]^T) in the head-group layout above: one TF32 tensor-core GEMM
+// whose epilogue rounds to fp16 and writes the pads
+int k1g_project_table(const float* table, int64_t n_rows, const float* wqkv, const float* bqkv, void* table16,
+                      cudaStream_t st) {
+  const float qscale = 1.4426950408889634f / sqrtf((float)DH);
+  return tc_gemm_nt_f16out(table, D, wqkv, D, bqkv, table16, k1g::ROW_BYTES / 2, n_rows, D3, D, qscale, D, 1, st);
+}
+
+size_t k1g_table16_bytes(int64_t n_rows) { return (size_t)n_rows * k1g::ROW_BYTES; }
+
+// Cbuf: fp16 context rows [n_users*50][320]; columns 300..319 are never written here (clear them once per buffer)
+int k1g_run(const void* table16, int64_t n_table_rows, const int32_t* hist_rows, int64_t n_users, void* Cbuf,
+            cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k1g::table_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k1g::SMEM);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(table_attn_kernel)");
+    configured = true;
+  }
+  if (n_users <= 0) return NRMS_OK;
+  NRMS_CHECK_ARG(n_table_rows > 0 && n_table_rows < (1ll << 31), NRMS_E_INVALID, "table row count out of range");
+  int grid = num_sms();
+  if (n_users < grid) grid = (int)n_users;
+  k1g::table_attn_kernel<<<grid, k1g::THREADS, k1g::SMEM, st>>>(reinterpret_cast<const __half*>(table16),
+                                                                (int)n_table_rows, hist_rows, n_users,
+                                                                reinterpret_cast<__half*>(Cbuf));
+  NRMS_LAUNCH_CHECK("table_attn_kernel");
+  return NRMS_OK;
+}
+
+}  // namespace nrms

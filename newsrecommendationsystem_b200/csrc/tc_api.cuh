@@ -9,10 +9,14 @@ namespace nrms {
 int tc_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
                int64_t M, int N, int K, cudaStream_t st);
 // Same contraction with an epilogue mode (store / C += / atomic C +=) and an optional split along K (atomic only).
-enum { TC_EPI_STORE = 0, TC_EPI_ACCUM = 1, TC_EPI_ATOMIC = 2 };
+enum { TC_EPI_STORE = 0, TC_EPI_ACCUM = 1, TC_EPI_ATOMIC = 2, TC_EPI_STORE_F16 = 3, TC_EPI_STORE_F16_QKV = 4 };
 int tc_gemm_nt_ex(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
                   int64_t M, int N, int K, int k_splits, int epi, cudaStream_t st);
 int tc_gemm_auto_splits(int64_t M, int N, int K);
+// Same contraction, result rounded to fp16: C16[m*ldc + n] = half((acc + bias[n]) * (n < scale_cols ? scale : 1)), ldc in halfs.
+// qkv_layout = 1 (N = 900): columns are scattered into K1g's padded head-group row layout (k1g_table_attn.cu).
+int tc_gemm_nt_f16out(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, void* C16, int64_t ldc,
+                      int64_t M, int N, int K, float scale, int scale_cols, int qkv_layout, cudaStream_t st);
 // dst[c][r] = src[r][c]: the K-major (NT) tensor-core GEMM sees A^T B and A B contractions through transposed copies
 int transpose_f32(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int64_t R, int C, cudaStream_t st);
 
@@ -28,6 +32,7 @@ int tc_encoder_fused(const float* src, int64_t n_src_rows, const void* idx, int 
                      void* workspace, size_t workspace_bytes, cudaStream_t st, const float* ln_gamma = nullptr,
                      const float* ln_beta = nullptr);
 
+void set_table_attn(bool on);   // indexed user encoder: project the table once + K1g (default on)
 int set_k1_variant(int v);   // 1..6, see tc_fused.cu
 void set_time_k1(bool on);   // CUDA-event timing of the user-encoder K1 launches (bench.py roofline)
 double get_k1_stat(int key); // 0 total ms, 1 launches, 2 sequences

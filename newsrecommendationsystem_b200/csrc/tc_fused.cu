@@ -59,6 +59,26 @@ int k1v5_run(int S, const CUtensorMap& tw, const CUtensorMap& ts, const void* sr
 // K1 v6 (tc_fused7.cu): v5 with two worker groups taking alternate passes
 int k1v6_run(int S, const CUtensorMap& tw, const CUtensorMap& ts, const void* src16, const void* idx, int idx_kind,
              int64_t n, int null_row, void* Cbuf, cudaStream_t st);
+// K1g (k1g_table_attn.cu): indexed user encoder over a pre-projected table (q|k|v rows gathered, no per-user GEMM)
+int k1g_project_table(const float* table, int64_t n_rows, const float* wqkv, const float* bqkv, void* table16,
+                      cudaStream_t st);
+size_t k1g_table16_bytes(int64_t n_rows);
+int k1g_run(const void* table16, int64_t n_table_rows, const int32_t* hist_rows, int64_t n_users, void* Cbuf,
+            cudaStream_t st);
+// "user_table_attn" option: 1 (default) = int32-indexed S=50 calls whose history rows outnumber the table rows 2:1
+// project the table once and run K1g; 0 = always the per-user projection of K1 v1..v6
+static int g_table_attn = -1;
+static bool table_attn_enabled() {
+  if (g_table_attn < 0) {
+    const char* e = getenv("NRMS_USER_TABLE_ATTN");
+    g_table_attn = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_table_attn != 0;
+}
+void set_table_attn(bool on) { g_table_attn = on ? 1 : 0; }
+static bool use_table_attn(int S, int idx_kind, int64_t n_seq, int64_t n_src_rows) {
+  return S == 50 && idx_kind == 2 && n_src_rows > 0 && table_attn_enabled() && n_seq * S >= 2 * n_src_rows;
+}
 constexpr int K1_DEFAULT_VARIANT = 6;
 static int g_k1_variant = -1;
 static int k1_variant() {
@@ -581,8 +601,13 @@ static int64_t fused_chunk_seq() {          // full waves of tiles per launch (d
 }
 
 // workspace: [fp16 W_qkv copy][fp16 W_a copy][fp16 gather source (variant 4)][context rows C of one chunk]
-static size_t fused_src16_bytes(int idx_kind_dense, int64_t n_src_rows, int64_t chunk_rows) {
-  return align_up(k1v4_src16_bytes(idx_kind_dense ? chunk_rows : n_src_rows), 1024);
+static size_t fused_src16_bytes(int S, int idx_kind_dense, int64_t n_src_rows, int64_t chunk_rows) {
+  size_t b = k1v4_src16_bytes(idx_kind_dense ? chunk_rows : n_src_rows);
+  if (!idx_kind_dense && S == 50) {            // room for the projected q|k|v table of K1g (1,800 B per row)
+    const size_t t = k1g_table16_bytes(n_src_rows);
+    if (t > b) b = t;
+  }
+  return align_up(b, 1024);
 }
 
 // In-place LayerNorm(300) over the fp16 context rows [rows][320] that K1 hands to K2 (columns 300..319 stay zero):
@@ -640,10 +665,12 @@ static int run_fused(const float* src, int64_t n_src_rows, const void* idx, int 
   }
   int variant = k1_variant();
   if (ln_gamma && variant < 2) variant = 5;   // the LayerNorm step works on the fp16 context rows of variants 2..5
+  const bool table_attn = use_table_attn(S, idx_kind, n_seq, n_src_rows);
+  if (table_attn && variant < 2) variant = K1_DEFAULT_VARIANT;
   // every variant tiles 5 titles / 2 users, so the chunking (whole waves of tiles) is shared
   const int64_t chunk = fused_chunk_seq<S, SPT>();
   const int64_t first = n_seq < chunk ? n_seq : chunk;
-  const size_t src16_bytes = fused_src16_bytes(idx_kind == 0, n_src_rows, first * S);
+  const size_t src16_bytes = fused_src16_bytes(S, idx_kind == 0, n_src_rows, first * S);
   const size_t need = W16_SLOT_BYTES + WA16_SLOT_BYTES + src16_bytes + (size_t)first * S * D * sizeof(float);
   NRMS_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= need, NRMS_E_WORKSPACE,
                  "workspace too small: need %zu bytes", need);
@@ -657,7 +684,12 @@ static int run_fused(const float* src, int64_t n_src_rows, const void* idx, int 
                           : (variant == 3 ? k1v3_prepare(wqkv, w16, &tw, st) : k1v2_prepare(wqkv, w16, &tw, st));
     if (rc) return rc;
     if (int rc2 = k2v2_prepare(wa, wa16, &twa, st)) return rc2;
-    if (variant >= 4 && idx_kind != 0) {
+    if (table_attn) {
+      if (int rc3 = k1g_project_table(src, n_src_rows, wqkv, bqkv, src16, st)) return rc3;
+      // K1g writes columns 0..299 of the fp16 context rows; K2 multiplies 300..319 by zero weights, so they must be finite
+      cudaError_t e = cudaMemset2DAsync(reinterpret_cast<char*>(Cbuf) + 600, 640, 0, 40, (size_t)first * S, st);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaMemset2DAsync(context tail)");
+    } else if (variant >= 4 && idx_kind != 0) {
       NRMS_CHECK_ARG(n_src_rows > 0, NRMS_E_INVALID, "indexed input needs the row count of its source table");
       if (int rc3 = k1v4_pack_src(src, n_src_rows, src16, &ts, st)) return rc3;
     }
@@ -684,7 +716,9 @@ static int run_fused(const float* src, int64_t n_src_rows, const void* idx, int 
       {
         K1Timer timer(st, n, S == 50);    // only the user-encoder launches (the dominant kernel) are timed
         int rc;
-        if (variant == 6)
+        if (table_attn)
+          rc = k1g_run(src16, n_src_rows, reinterpret_cast<const int32_t*>(idx_c), n, Cbuf, st);
+        else if (variant == 6)
           rc = k1v6_run(S, tw, ts, src16, idx_c, idx_kind, n, (int)(idx_kind == 0 ? n * S : n_src_rows), Cbuf, st);
         else if (variant == 5)
           rc = k1v5_run(S, tw, ts, src16, idx_c, idx_kind, n, (int)(idx_kind == 0 ? n * S : n_src_rows), Cbuf, st);
@@ -725,7 +759,7 @@ size_t tc_fused_workspace_bytes(int64_t n_seq, int S, int64_t n_src_rows) {
   else if (S == 50) chunk = fused_chunk_seq<50, 2>();
   else return (size_t)-1;
   const int64_t first = n_seq < chunk ? n_seq : chunk;
-  return W16_SLOT_BYTES + WA16_SLOT_BYTES + fused_src16_bytes(n_src_rows <= 0, n_src_rows, first * S) +
+  return W16_SLOT_BYTES + WA16_SLOT_BYTES + fused_src16_bytes(S, n_src_rows <= 0, n_src_rows, first * S) +
          (size_t)first * S * D * sizeof(float);
 }
 

@@ -15,6 +15,7 @@
 // The tensor maps are typed TFLOAT32: the TMA unit rounds the fp32 operands to TF32 while copying, so
 // callers pass plain fp32 tensors (no pre-rounding pass) and the tensor core never truncates.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include "tc_common.cuh"
 #include "tc_api.cuh"
@@ -43,7 +44,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int64_t M, int N, int K,
-                  uint32_t stage_tx_bytes, int k_splits, int chunks_per_split, int epi) {
+                  uint32_t stage_tx_bytes, int k_splits, int chunks_per_split, int epi, float f16_scale, int f16_scale_cols) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -162,6 +163,40 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int col = 0; col < n_valid; col += 16) {
         float v[16];
         tmem_ld16(trow + col, v);
+        if (epi >= TC_EPI_STORE_F16) {
+          // C is a __half matrix (ldc in halfs, rows 8-byte aligned): (acc + bias) * (n < f16_scale_cols ? f16_scale : 1)
+          if (m < M) {
+            __half* crow = reinterpret_cast<__half*>(C) + m * ldc;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int n = n0 + col + 4 * j;
+              if (n < N) {
+                float4 r = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                if (add_bias) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+                  r = make_float4(r.x + b4.x, r.y + b4.y, r.z + b4.z, r.w + b4.w);
+                }
+                const float sc = n < f16_scale_cols ? f16_scale : 1.f;
+                const __half2 lo = __floats2half2_rn(r.x * sc, r.y * sc), hi = __floats2half2_rn(r.z * sc, r.w * sc);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+                pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+                if (epi == TC_EPI_STORE_F16_QKV) {
+                  // K1g table row: [head group][q | k | v][5 heads][24 halfs]; column n = which*300 + head*20 + d.
+                  // The 4-half pad of every head slice is written with its last group: 0 (q, k) or (1,0,0,0) (v).
+                  const int which = n / 300, hd = n - which * 300, head = hd / 20, d = hd - head * 20;
+                  const int hgi = head / 5, hl = head - hgi * 5;
+                  __half* dst = crow + hgi * 360 + which * 120 + hl * 24 + d;
+                  *reinterpret_cast<uint2*>(dst) = pk;
+                  if (d == 16) *reinterpret_cast<uint2*>(dst + 4) = make_uint2(which == 2 ? 0x00003C00u : 0u, 0u);
+                } else {
+                  *reinterpret_cast<uint2*>(crow + n) = pk;
+                }
+              }
+            }
+          }
+          continue;
+        }
         if (m < M) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -266,12 +301,29 @@ int make_tmap_store_f16(CUtensorMap* out, const void* base, int64_t rows, int co
   return NRMS_OK;
 }
 
+static int tc_gemm_launch(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
+                         int64_t M, int N, int K, int k_splits, int epi, float f16_scale, int f16_scale_cols, cudaStream_t st);
+
 int tc_gemm_nt_ex(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
                   int64_t M, int N, int K, int k_splits, int epi, cudaStream_t st) {
-  if (M <= 0) return NRMS_OK;
-  NRMS_CHECK_ARG(M < (1ll << 31), NRMS_E_UNSUPPORTED, "M too large for one tensor map");
   NRMS_CHECK_ARG(epi >= TC_EPI_STORE && epi <= TC_EPI_ATOMIC && (k_splits <= 1 || epi == TC_EPI_ATOMIC), NRMS_E_INVALID,
                  "split-K needs the atomic epilogue");
+  return tc_gemm_launch(A, lda, B, ldb, bias, C, ldc, M, N, K, k_splits, epi, 1.f, 0, st);
+}
+
+int tc_gemm_nt_f16out(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, void* C16, int64_t ldc,
+                      int64_t M, int N, int K, float scale, int scale_cols, int qkv_layout, cudaStream_t st) {
+  NRMS_CHECK_ARG((ldc % 4) == 0 && (reinterpret_cast<uintptr_t>(C16) & 7) == 0 && (scale_cols % 4) == 0, NRMS_E_INVALID,
+                 "fp16 output rows must be 8-byte aligned");
+  NRMS_CHECK_ARG(!qkv_layout || (N == 900 && ldc >= 1080), NRMS_E_INVALID, "the q|k|v head-group layout is [*, 1080] from N = 900");
+  return tc_gemm_launch(A, lda, B, ldb, bias, reinterpret_cast<float*>(C16), ldc, M, N, K, 1,
+                        qkv_layout ? TC_EPI_STORE_F16_QKV : TC_EPI_STORE_F16, scale, scale_cols, st);
+}
+
+static int tc_gemm_launch(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
+                         int64_t M, int N, int K, int k_splits, int epi, float f16_scale, int f16_scale_cols, cudaStream_t st) {
+  if (M <= 0) return NRMS_OK;
+  NRMS_CHECK_ARG(M < (1ll << 31), NRMS_E_UNSUPPORTED, "M too large for one tensor map");
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tc_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM);
@@ -294,7 +346,8 @@ int tc_gemm_nt_ex(const float* A, int64_t lda, const float* B, int64_t ldb, cons
   const int64_t items = tiles * k_splits;
   int grid = num_sms();
   if (items < grid) grid = (int)items;
-  tc_gemm_nt_kernel<<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, bias, C, ldc, M, N, K, stage_tx, k_splits, cps, epi);
+  tc_gemm_nt_kernel<<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, bias, C, ldc, M, N, K, stage_tx, k_splits, cps, epi, f16_scale,
+                                                       f16_scale_cols);
   NRMS_LAUNCH_CHECK("tc_gemm_nt");
   return NRMS_OK;
 }

@@ -1,0 +1,25 @@
+import sys, time, numpy as np, torch
+sys.path.insert(0, "/root/repo")
+import bench
+from newsrecommendationsystem_b200 import NRMS, NRMSConfig, synthetic, _lib
+from newsrecommendationsystem_b200.evaluate import EvalHost, EvalInputs, evaluate_tensors
+lib = _lib.load()
+dev = torch.device("cuda", 0)
+sd = synthetic.init_state_dict(num_words=bench.NUM_WORDS, seed=0)
+model = NRMS(NRMSConfig); model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}); model.to(dev).eval().set_precision("tf32")
+news, imp = bench.make_data(1)
+host = EvalHost(news, imp["hist_rows"], imp["cand_offsets"], imp["cand_rows"], imp["labels"])
+inputs = EvalInputs.from_host(host, dev)
+for flag in (0, 1):
+    lib.nrms_set_option(b"user_table_attn", flag)
+    for _ in range(3):
+        ev = {}
+        def mark(n): e = torch.cuda.Event(enable_timing=True); e.record(); ev[n] = e
+        means, det = evaluate_tensors(model, inputs, return_details=True, mark=mark)
+    torch.cuda.synchronize()
+    names = list(ev)
+    print("table_attn", flag, {names[i + 1]: round(ev[names[i]].elapsed_time(ev[names[i + 1]]), 3) for i in range(len(names) - 1)}, means)
+    uv = det["user_vectors"].clone()
+    if flag == 0: uv0 = uv
+d = (uv - uv0).double().norm(dim=1) / uv0.double().norm(dim=1)
+print("max rel diff table vs per-user path", float(d.max()))

@@ -144,7 +144,15 @@ def test_news_encoder_vs_oracle_ragged_sizes(dev, golden_sd, precision, n):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32"])
-def test_user_encoder_indexed_equals_dense(dev, golden_sd, precision):
+def test_user_encoder_indexed_equals_dense(dev, lib, golden_sd, precision):
+    lib.nrms_set_option(b"user_table_attn", 0)      # per-user projection path (K1 v6): the gather is a pure copy
+    try:
+        _indexed_equals_dense(dev, golden_sd, precision)
+    finally:
+        lib.nrms_set_option(b"user_table_attn", 1)
+
+
+def _indexed_equals_dense(dev, golden_sd, precision):
     rng = np.random.default_rng(5)
     table = rng.standard_normal((301, 300)).astype(np.float32) * 0.3
     table[300] = 0
@@ -159,6 +167,35 @@ def test_user_encoder_indexed_equals_dense(dev, golden_sd, precision):
         b = m.get_user_vector(tb[t(rows, dev)])
     assert rel_l2_rows(a.cpu().numpy(), ref) < TOL_VEC[precision]
     assert torch.equal(a, b)      # the in-library gather is a pure copy
+
+
+@pytest.mark.parametrize("n_users,n_rows", [(1, 3), (13, 300), (67, 300), (149, 1000), (2500, 4001)])
+def test_user_encoder_table_attention_path(dev, lib, golden_sd, n_users, n_rows):
+    """K1g (tensor mode, indexed input): the table is projected once (q|k|v rows in fp16) and the attention runs on
+    gathered rows.  Same numbers as the per-user projection within the 1e-3 tolerance: vs the oracle, and vs K1 v6."""
+    rng = np.random.default_rng(n_users)
+    table = (rng.standard_normal((n_rows + 1, 300)) * 0.3).astype(np.float32)
+    table[n_rows] = 0                                     # PADDED_NEWS
+    rows = rng.integers(0, n_rows, size=(n_users, 50))
+    rows[0, :50 - min(49, n_users)] = n_rows              # left-padded history
+    if n_users > 9:
+        rows[9] = n_rows                                  # empty history
+        rows[3] = rows[3, 0]                              # one news repeated 50 times
+    assert n_users * 50 >= 2 * (n_rows + 1)               # the size rule that selects the table path
+    ref, _ = O.user_encoder_forward(golden_sd, table[rows])
+    m = make_model(golden_sd, dev, "tf32")
+    tb, ix = t(table, dev), t(rows.astype(np.int32), dev)
+    with torch.no_grad():
+        a = m.user_encoder.forward_indexed(tb, ix)
+        lib.nrms_set_option(b"user_table_attn", 0)
+        try:
+            b = m.user_encoder.forward_indexed(tb, ix)
+        finally:
+            lib.nrms_set_option(b"user_table_attn", 1)
+    assert rel_l2_rows(a.cpu().numpy(), ref) < TOL_VEC["tf32"]
+    assert rel_l2_rows(b.cpu().numpy(), ref) < TOL_VEC["tf32"]
+    assert not torch.equal(a, b)                          # two different kernels really ran
+    assert rel_l2_rows(a.cpu().numpy(), b.cpu().numpy().astype(np.float64)) < TOL_VEC["tf32"]
 
 
 # ---------------------------------------------------------------------------------------------
