@@ -33,6 +33,9 @@ FLOP_PER_USER = 36_050_000
 BYTES_PER_CANDIDATE = 1212          # fp32 news vector + int64 index + fp32 score (FP32 mode)
 BYTES_PER_CANDIDATE_F16 = 652       # tensor mode: the candidate row is read from the fp16 table copy (640 B)
 BYTES_PER_IMPRESSION = 1208
+# K1g per user: 50 gathered rows x 1,800 B (q|k|v fp16, the useful bytes of the 2,160-byte padded row) + 50 int32
+# history indices + 50 x 300 fp16 context values written for K2
+K1G_BYTES_PER_USER = 50 * 1800 + 50 * 4 + 50 * 600
 
 
 def load_peaks():
@@ -254,8 +257,8 @@ def main():
         ms, means = timed_eval(inputs, record_stages=True)
         times.append(ms)
     launches = int(lib.nrms_launch_count() - l0)
-    k1_ms, k1_n, k1_seq = (lib.nrms_get_stat(b"k1_ms"), lib.nrms_get_stat(b"k1_launches"),
-                           lib.nrms_get_stat(b"k1_sequences"))
+    kstat = {k: tuple(lib.nrms_get_stat(f"{k}_{w}".encode()) for w in ("ms", "launches", "sequences"))
+             for k in ("k1", "k1n", "k1g")}
     lib.nrms_set_option(b"time_k1", 0)
     barrier()
     e2e_times = []
@@ -284,28 +287,46 @@ def main():
     n_imp_rank = n_imp_total / world
     cand_rank = n_cand_total / world
     stage_flops = {"news": n_news_rank * FLOP_PER_TITLE, "users": n_imp_rank * FLOP_PER_USER}
-    # dominant kernel = the fused user-encoder kernel K1 (gather -> QKV tcgen05 -> attention tcgen05); its average
-    # launch duration is measured live (CUDA events on the launching stream, nrms_set_option("time_k1")).
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("encoder_attn_tc6_kernel<50,64,2>")
-    if k1_n > 0 and k1_ms > 0:
-        us_per_launch = 1e3 * k1_ms / k1_n
-        users_per_launch = k1_seq / k1_n
-        # K1 owns everything of the user encoder except the additive projection/pooling (K2): 30.05 of 36.05 MFLOP
-        flop_per_launch = users_per_launch * (FLOP_PER_USER - 6_000_000 - 50_000)
-        ach = flop_per_launch / (us_per_launch * 1e-6) / 1e12
-        roof = dict(bound="tensor", kernel="k1v6::encoder_attn_tc6_kernel<50,64,2> (user encoder: gather+QKV+attention)",
-                    achieved=ach, peak=peaks["bf16_tflops"], unit="TFLOP/s", frac=ach / peaks["bf16_tflops"],
-                    traffic=traffic, us_per_launch=us_per_launch, launches=int(k1_n), users_per_launch=users_per_launch,
-                    algorithmic_flop_per_user=FLOP_PER_USER - 6_050_000,
+    # Dominant kernel = the user-encoder attention kernel.  Its average launch duration is measured live (CUDA events
+    # on the launching stream, nrms_set_option("time_k1")).  Tensor mode runs K1g (k1g_table_attn.cu): the q|k|v rows of
+    # a pre-projected table are gathered per history row, so the kernel is bound by bytes moved, not by the projection
+    # GEMM it no longer contains; FP32-table runs (user_table_attn = 0) keep K1 v6, bound by the tensor pipe.
+    tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))) \
+        if os.path.exists(os.path.join(ROOT, "profiles", "r1_traffic.json")) else {}
+
+    def tensor_roof(kind, name, flop_per_seq, traffic_key):
+        ms, n, seqs = kstat[kind]
+        if not (n > 0 and ms > 0):
+            return None
+        us = 1e3 * ms / n
+        ach = (seqs / n) * flop_per_seq / (us * 1e-6) / 1e12
+        return dict(bound="tensor", kernel=name, achieved=ach, peak=peaks["bf16_tflops"], unit="TFLOP/s",
+                    frac=ach / peaks["bf16_tflops"], traffic=tr.get(traffic_key), us_per_launch=us, launches=int(n),
+                    sequences_per_launch=seqs / n, algorithmic_flop_per_sequence=flop_per_seq,
                     peak_source=f"{peaks['source']} dense bf16/fp16 burst (operands are fp16, fp32 accumulate)")
-    else:
+
+    # K1 owns everything of an encoder except the additive projection/pooling (K2)
+    roof_news = tensor_roof("k1n", "k1v6::encoder_attn_tc6_kernel<20,24,5> (news encoder: gather+QKV+attention)",
+                            FLOP_PER_TITLE - 2_400_000 - 20_000, "encoder_attn_tc6_kernel<20,24,5>")
+    roof = None
+    g_ms, g_n, g_seq = kstat["k1g"]
+    if g_n > 0 and g_ms > 0:
+        us = 1e3 * g_ms / g_n
+        ach = (g_seq / g_n) * K1G_BYTES_PER_USER / (us * 1e-6) / 1e9
+        roof = dict(bound="hbm", kernel="k1g::table_attn_kernel (user encoder: q|k|v row gather + 15-head attention)",
+                    achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s", frac=ach / peaks["hbm_gbs"],
+                    traffic=tr.get("table_attn_kernel"), us_per_launch=us, launches=int(g_n),
+                    users_per_launch=g_seq / g_n, algorithmic_bytes_per_user=K1G_BYTES_PER_USER,
+                    peak_source=f"{peaks['source']} HBM copy bandwidth (burst); the projected table is partly "
+                                f"L2-resident, see traffic")
+    if roof is None:
+        roof = tensor_roof("k1", "k1v6::encoder_attn_tc6_kernel<50,64,2> (user encoder: gather+QKV+attention)",
+                           FLOP_PER_USER - 6_050_000, "encoder_attn_tc6_kernel<50,64,2>")
+    if roof is None:
         dominant = max(st, key=st.get) if st else "news"
         ach = stage_flops.get(dominant, 0.0) / (st[dominant] / 1e3) / 1e12
         roof = dict(bound="tensor", kernel=f"{dominant} encoder stage", achieved=ach, peak=peaks["bf16_tflops"],
-                    unit="TFLOP/s", frac=ach / peaks["bf16_tflops"], traffic=traffic, peak_source=peaks["source"])
+                    unit="TFLOP/s", frac=ach / peaks["bf16_tflops"], traffic=None, peak_source=peaks["source"])
     per_cand = BYTES_PER_CANDIDATE_F16 if args.precision == "tf32" else BYTES_PER_CANDIDATE
     # + the one-off fp16 copy of the table inside the stage (read fp32, write fp16)
     pack_bytes = (NEWS_PER_GPU * world + 1) * (1200 + 640) if args.precision == "tf32" else 0
@@ -320,6 +341,7 @@ def main():
         news_tflops=stage_flops["news"] / (st.get("news", float("nan")) / 1e3) / 1e12,
         users_tflops=stage_flops["users"] / (st.get("users", float("nan")) / 1e3) / 1e12,
         metrics=dict(zip(("auc", "mrr", "ndcg5", "ndcg10"), means)),
+        roofline_news_k1=roof_news,
     )
 
     # ---- training step side measurement (BASELINE configs[2]: B=128, 1+4 candidates) ------------

@@ -574,9 +574,16 @@ int nrms_set_option(const char* key, int value) {
 
 double nrms_get_stat(const char* key) {
   if (!key) return -1.0;
-  if (strcmp(key, "k1_ms") == 0) return get_k1_stat(0);
-  if (strcmp(key, "k1_launches") == 0) return get_k1_stat(1);
-  if (strcmp(key, "k1_sequences") == 0) return get_k1_stat(2);
+  // "<kind>_ms" / "<kind>_launches" / "<kind>_sequences"; kind: k1 = user-encoder K1 (per-user projection),
+  // k1n = news-encoder K1, k1g = user-encoder table attention
+  static const char* kinds[3] = {"k1_", "k1n_", "k1g_"};
+  static const char* whats[3] = {"ms", "launches", "sequences"};
+  for (int k = 0; k < 3; ++k) {
+    const size_t n = strlen(kinds[k]);
+    if (strncmp(key, kinds[k], n) == 0)
+      for (int w = 0; w < 3; ++w)
+        if (strcmp(key + n, whats[w]) == 0) return get_k1_stat(3 * k + w);
+  }
   return -1.0;
 }
 

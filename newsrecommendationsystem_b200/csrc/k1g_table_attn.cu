@@ -226,11 +226,12 @@ table_attn_kernel(const __half* __restrict__ table16, int n_table_rows, const in
         }
         float sacc[7][4];
 #pragma unroll
-        for (int nt = 0; nt < 7; ++nt) {
+        for (int nt = 0; nt < 7; ++nt) {       // the seven k16 steps first, then the dependent k8 steps
           sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
           mma_k16(sacc[nt], qa[0], qa[1], qa[2], qa[3], kb16[nt][0], kb16[nt][1]);
-          mma_k8(sacc[nt], qb[0], qb[1], kb8[nt]);
         }
+#pragma unroll
+        for (int nt = 0; nt < 7; ++nt) mma_k8(sacc[nt], qb[0], qb[1], kb8[nt]);
         // P = 2^S (q carries log2(e)/sqrt(20)); keys 50..55 (key tile 6, t > 0) are padding
         uint32_t pa[7][2];
         const bool lower = mt < 3;              // rows 16mt+8..+15 exist only in the first three tiles
@@ -245,14 +246,15 @@ table_attn_kernel(const __half* __restrict__ table16, int n_table_rows, const in
         }
         float oacc[3][4];
 #pragma unroll
-        for (int dt = 0; dt < 3; ++dt) {
-          oacc[dt][0] = oacc[dt][1] = oacc[dt][2] = oacc[dt][3] = 0.f;
+        for (int dt = 0; dt < 3; ++dt) oacc[dt][0] = oacc[dt][1] = oacc[dt][2] = oacc[dt][3] = 0.f;
 #pragma unroll
-          for (int ks = 0; ks < 3; ++ks)
+        for (int ks = 0; ks < 3; ++ks)           // three independent accumulator chains interleaved
+#pragma unroll
+          for (int dt = 0; dt < 3; ++dt)
             mma_k16(oacc[dt], pa[2 * ks][0], pa[2 * ks][1], pa[2 * ks + 1][0], pa[2 * ks + 1][1], vb[ks][dt][0],
                     vb[ks][dt][1]);
-          mma_k8(oacc[dt], pa[6][0], pa[6][1], vb[3][dt][0]);
-        }
+#pragma unroll
+        for (int dt = 0; dt < 3; ++dt) mma_k8(oacc[dt], pa[6][0], pa[6][1], vb[3][dt][0]);
         // Z of rows g / g+8 sits in column 20 = element 0 / 2 of dim tile 2 on the quad's lane t == 2
         const float z0 = __shfl_sync(0xffffffffu, oacc[2][0], (lane & ~3) | 2);
         const float z1 = __shfl_sync(0xffffffffu, oacc[2][2], (lane & ~3) | 2);

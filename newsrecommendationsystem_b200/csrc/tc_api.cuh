@@ -34,7 +34,7 @@ int tc_encoder_fused(const float* src, int64_t n_src_rows, const void* idx, int 
 
 void set_table_attn(bool on);   // indexed user encoder: project the table once + K1g (default on)
 int set_k1_variant(int v);   // 1..6, see tc_fused.cu
-void set_time_k1(bool on);   // CUDA-event timing of the user-encoder K1 launches (bench.py roofline)
-double get_k1_stat(int key); // 0 total ms, 1 launches, 2 sequences
+void set_time_k1(bool on);   // CUDA-event timing of the K1 launches (bench.py roofline)
+double get_k1_stat(int key); // 3 * kind (0 users K1, 1 news K1, 2 users K1g) + (0 total ms, 1 launches, 2 sequences)
 
 }  // namespace nrms

@@ -88,33 +88,37 @@ static int k1_variant() {
   }
   return g_k1_variant;
 }
-// ---- optional live timing of the dominant kernel (bench.py's roofline): CUDA events around every K1 launch ----
+// ---- optional live timing of the K1 launches (bench.py's roofline): CUDA events around every launch, kept per kind:
+//      0 = user encoder, per-user projection (K1 v1..v6), 1 = news encoder K1, 2 = user encoder, table attention (K1g)
 static bool g_time_k1 = false;
-static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_k1_events;
-static std::vector<int64_t> g_k1_seqs;
+struct K1Record { cudaEvent_t a, b; int64_t seqs; int kind; };
+static std::vector<K1Record> g_k1_records;
 void set_time_k1(bool on) {
   g_time_k1 = on;
-  for (auto& e : g_k1_events) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-  g_k1_events.clear();
-  g_k1_seqs.clear();
+  for (auto& r : g_k1_records) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_k1_records.clear();
 }
-// key: 0 = total ms of the timed K1 launches, 1 = number of launches, 2 = sequences processed by them
+// key = 3 * kind + what; what: 0 = total ms of the timed launches, 1 = number of launches, 2 = sequences processed
 double get_k1_stat(int key) {
-  if (key == 1) return (double)g_k1_events.size();
-  if (key == 2) { double s = 0; for (auto v : g_k1_seqs) s += (double)v; return s; }
+  const int kind = key / 3, what = key % 3;
   double total = 0;
-  for (auto& e : g_k1_events) {
-    float ms = 0.f;
-    if (cudaEventSynchronize(e.second) == cudaSuccess && cudaEventElapsedTime(&ms, e.first, e.second) == cudaSuccess) total += ms;
+  for (auto& r : g_k1_records) {
+    if (r.kind != kind) continue;
+    if (what == 1) total += 1.0;
+    else if (what == 2) total += (double)r.seqs;
+    else {
+      float ms = 0.f;
+      if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) total += ms;
+    }
   }
   return total;
 }
 struct K1Timer {
-  cudaStream_t st; bool on; cudaEvent_t a, b;
-  K1Timer(cudaStream_t s, int64_t n, bool enable) : st(s), on(enable && g_time_k1 && g_k1_events.size() < 4096) {
-    if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); g_k1_seqs.push_back(n); }
+  cudaStream_t st; bool on; K1Record rec;
+  K1Timer(cudaStream_t s, int64_t n, int kind) : st(s), on(g_time_k1 && g_k1_records.size() < 8192) {
+    if (on) { cudaEventCreate(&rec.a); cudaEventCreate(&rec.b); cudaEventRecord(rec.a, st); rec.seqs = n; rec.kind = kind; }
   }
-  ~K1Timer() { if (on) { cudaEventRecord(b, st); g_k1_events.emplace_back(a, b); } }
+  ~K1Timer() { if (on) { cudaEventRecord(rec.b, st); g_k1_records.push_back(rec); } }
 };
 
 int set_k1_variant(int v) {
@@ -714,7 +718,7 @@ static int run_fused(const float* src, int64_t n_src_rows, const void* idx, int 
         if (int rc = k1v4_pack_src(src_c, n * S, src16, &ts, st)) return rc;
       }
       {
-        K1Timer timer(st, n, S == 50);    // only the user-encoder launches (the dominant kernel) are timed
+        K1Timer timer(st, n, S == 50 ? (table_attn ? 2 : 0) : 1);
         int rc;
         if (table_attn)
           rc = k1g_run(src16, n_src_rows, reinterpret_cast<const int32_t*>(idx_c), n, Cbuf, st);
