@@ -46,6 +46,10 @@ constexpr int NSTAGE = 2;
 #define K1G_PREFETCH_AHEAD 0
 #endif
 constexpr int PREFETCH_AHEAD = K1G_PREFETCH_AHEAD;
+#ifndef K1G_V_RELOAD
+#define K1G_V_RELOAD 1
+#endif
+constexpr bool V_RELOAD = K1G_V_RELOAD != 0;   // V fragments reloaded per query tile (registers for the second score tile)
 constexpr int ROW_BYTES = PITCH;
 constexpr int OFF_ZERO = NSTAGE * STAGE;   // 64 B of zeros (rows >= 50 of every ldmatrix)
 constexpr int OFF_BAR = OFF_ZERO + 64;     // full[6], empty[6]
@@ -206,40 +210,51 @@ table_attn_kernel(const __half* __restrict__ table16, int n_table_rows, const in
                 kb8[4 * p + 3]);
       // ---- V fragments (transposed loads): vb[ks][dt][0..1] keys 16ks..16ks+7 / +8..15, dims 8dt..8dt+7 ----
       uint32_t vb[4][3][2];
+      auto load_v = [&]() {
 #pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        // matrices: [keys 16ks+0..7, d0-7] [keys +8..15, d0-7] [keys 0..7, d8-15] [keys +8..15, d8-15]
-        ldsm_x4_t(row_addr(B, zero, 16 * ks + 8 * (mi & 1) + rr, voff + (mi >> 1) * 16), vb[ks][0][0], vb[ks][0][1],
-                  vb[ks][1][0], vb[ks][1][1]);
-        ldsm_x2_t(row_addr(B, zero, 16 * ks + 8 * (mi & 1) + rr, voff + 32), vb[ks][2][0], vb[ks][2][1]);
-      }
+        for (int ks = 0; ks < 4; ++ks) {
+          // matrices: [keys 16ks+0..7, d0-7] [keys +8..15, d0-7] [keys 0..7, d8-15] [keys +8..15, d8-15]
+          ldsm_x4_t(row_addr(B, zero, 16 * ks + 8 * (mi & 1) + rr, voff + (mi >> 1) * 16), vb[ks][0][0], vb[ks][0][1],
+                    vb[ks][1][0], vb[ks][1][1]);
+          ldsm_x2_t(row_addr(B, zero, 16 * ks + 8 * (mi & 1) + rr, voff + 32), vb[ks][2][0], vb[ks][2][1]);
+        }
+      };
+      if (!V_RELOAD) load_v();
       __half* out = ctx + (u * S) * CP + warp * 20 + 2 * t;
-      // ---- four query tiles of 16 rows ----
-#pragma unroll 1
-      for (int mt = 0; mt < 4; ++mt) {
+      // S = Q K^T of query tile mt (16 rows): seven k16 steps, then the dependent k8 steps
+      auto scores = [&](int mt, float (&sacc)[7][4]) {
         uint32_t qa[4], qb[2];
         ldsm_x4(row_addr(B, zero, 16 * mt + 8 * (mi & 1) + rr, qoff + (mi >> 1) * 16), qa[0], qa[1], qa[2], qa[3]);
         ldsm_x2(row_addr(B, zero, 16 * mt + 8 * (mi & 1) + rr, qoff + 32), qb[0], qb[1]);
-        if (mt == 3) {               // last shared-memory read of this stage: hand it back to the producer
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(empty_bar + 8 * st);
-        }
-        float sacc[7][4];
 #pragma unroll
-        for (int nt = 0; nt < 7; ++nt) {       // the seven k16 steps first, then the dependent k8 steps
+        for (int nt = 0; nt < 7; ++nt) {
           sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
           mma_k16(sacc[nt], qa[0], qa[1], qa[2], qa[3], kb16[nt][0], kb16[nt][1]);
         }
 #pragma unroll
         for (int nt = 0; nt < 7; ++nt) mma_k8(sacc[nt], qb[0], qb[1], kb8[nt]);
+      };
+      // ---- four query tiles, software-pipelined: the score MMAs of tile mt+1 are in the tensor pipe while the
+      //      exponentials of tile mt run on the MUFU / FMA pipes ----
+      float sacc[2][7][4];
+      scores(0, sacc[0]);
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        if (mt < 3) scores(mt + 1, sacc[(mt + 1) & 1]);
+        if (V_RELOAD) load_v();
+        if (mt == 3) {               // last shared-memory read of this stage: hand it back to the producer
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(empty_bar + 8 * st);
+        }
+        float (&sc)[7][4] = sacc[mt & 1];
         // P = 2^S (q carries log2(e)/sqrt(20)); keys 50..55 (key tile 6, t > 0) are padding
         uint32_t pa[7][2];
         const bool lower = mt < 3;              // rows 16mt+8..+15 exist only in the first three tiles
 #pragma unroll
         for (int nt = 0; nt < 7; ++nt) {
-          float p0 = ex2_sel<0>(sacc[nt][0]), p1 = ex2_sel<1>(sacc[nt][1]);
+          float p0 = ex2_sel<0>(sc[nt][0]), p1 = ex2_sel<1>(sc[nt][1]);
           float p2 = 0.f, p3 = 0.f;
-          if (lower) { p2 = ex2_sel<2>(sacc[nt][2]); p3 = ex2_sel<3>(sacc[nt][3]); }
+          if (lower) { p2 = ex2_sel<2>(sc[nt][2]); p3 = ex2_sel<3>(sc[nt][3]); }
           if (nt == 6 && t > 0) { p0 = p1 = p2 = p3 = 0.f; }
           pa[nt][0] = pack_h2(p0, p1);
           pa[nt][1] = pack_h2(p2, p3);
@@ -275,15 +290,39 @@ table_attn_kernel(const __half* __restrict__ table16, int n_table_rows, const in
 
 }  // namespace k1g
 
-// table16 = half([table | 1] * [W_Q*c | W_K | W_V]^T) in the head-group layout above: one TF32 tensor-core GEMM
-// whose epilogue rounds to fp16 and writes the pads
-int k1g_project_table(const float* table, int64_t n_rows, const float* wqkv, const float* bqkv, void* table16,
-                      cudaStream_t st) {
-  const float qscale = 1.4426950408889634f / sqrtf((float)DH);
-  return tc_gemm_nt_f16out(table, D, wqkv, D, bqkv, table16, k1g::ROW_BYTES / 2, n_rows, D3, D, qscale, D, 1, st);
+// fp16 copy of the packed projection weights with the bias as column 300: [900][320] halfs
+__global__ void __launch_bounds__(256) pack_wqkv16_bias_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                                                __half* __restrict__ out) {
+  const int n = D3 * 320;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int r = i / 320, k = i - r * 320;
+    out[i] = __float2half_rn(k < D ? w[r * D + k] : (k == D ? bias[r] : 0.f));
+  }
 }
 
-size_t k1g_table16_bytes(int64_t n_rows) { return (size_t)n_rows * k1g::ROW_BYTES; }
+int k1v4_pack_src(const float* src, int64_t n_rows, void* src16, CUtensorMap* ts, cudaStream_t st);
+
+// scratch of the table path: [table16: n_rows x 2,160 B][fp16 copy of the table: (n_rows + 1) x 640 B][fp16 weights]
+static size_t k1g_table16_only(int64_t n_rows) { return align_up((size_t)n_rows * k1g::ROW_BYTES, 1024); }
+static size_t k1g_a16_bytes(int64_t n_rows) { return align_up((size_t)(n_rows + 1) * 640, 1024); }
+size_t k1g_table16_bytes(int64_t n_rows) { return k1g_table16_only(n_rows) + k1g_a16_bytes(n_rows) + (size_t)D3 * 640; }
+
+// table16 = half([table | 1] * [W_Q*c | W_K | W_V | b]^T) in the head-group layout above: fp16 copies of the table (a 1.0
+// in column 300 meets the bias column of the weight copy) and of the weights, then one kind::f16 tensor-core GEMM whose
+// epilogue scales q, rounds to fp16 and writes the pads.  (Same operand precision as K1 v6's in-kernel projection.)
+int k1g_project_table(const float* table, int64_t n_rows, const float* wqkv, const float* bqkv, void* scratch,
+                      cudaStream_t st) {
+  char* base = reinterpret_cast<char*>(scratch);
+  void* table16 = base;
+  void* a16 = base + k1g_table16_only(n_rows);
+  void* b16 = base + k1g_table16_only(n_rows) + k1g_a16_bytes(n_rows);
+  alignas(64) CUtensorMap unused;
+  if (int rc = k1v4_pack_src(table, n_rows, a16, &unused, st)) return rc;
+  pack_wqkv16_bias_kernel<<<148, 256, 0, st>>>(wqkv, bqkv, reinterpret_cast<__half*>(b16));
+  NRMS_LAUNCH_CHECK("pack_wqkv16_bias_kernel");
+  const float qscale = 1.4426950408889634f / sqrtf((float)DH);
+  return tc_gemm_nt_f16(a16, 320, b16, 320, table16, k1g::ROW_BYTES / 2, n_rows, D3, 304, qscale, D, 1, st);
+}
 
 // Cbuf: fp16 context rows [n_users*50][320]; columns 300..319 are never written here (clear them once per buffer)
 int k1g_run(const void* table16, int64_t n_table_rows, const int32_t* hist_rows, int64_t n_users, void* Cbuf,

@@ -32,6 +32,9 @@ int tc_encoder_fused(const float* src, int64_t n_src_rows, const void* idx, int 
                      void* workspace, size_t workspace_bytes, cudaStream_t st, const float* ln_gamma = nullptr,
                      const float* ln_beta = nullptr);
 
+// fp16 operands (A16 [M, lda halfs], B16 [N, ldb halfs], 16-byte aligned rows), kind::f16, same fp16 epilogue (no bias)
+int tc_gemm_nt_f16(const void* A16, int64_t lda, const void* B16, int64_t ldb, void* C16, int64_t ldc, int64_t M, int N,
+                   int K, float scale, int scale_cols, int qkv_layout, cudaStream_t st);
 void set_table_attn(bool on);   // indexed user encoder: project the table once + K1g (default on)
 int set_k1_variant(int v);   // 1..6, see tc_fused.cu
 void set_time_k1(bool on);   // CUDA-event timing of the K1 launches (bench.py roofline)

@@ -598,9 +598,13 @@ constexpr size_t W16_BYTES = (size_t)D3 * W16_LD * 2;   // 576,000 (a multiple o
 // host
 // ---------------------------------------------------------------------------------------------------
 template <int S, int SPT>
-static int64_t fused_chunk_seq() {          // full waves of tiles per launch (default 8 -- 16 and 32 measured the same; NRMS_FUSED_WAVES to experiment)
+static int64_t fused_chunk_seq() {          // full waves of tiles per launch; NRMS_FUSED_WAVES to experiment
+  // Measured on the evaluate bench (K1 v6 / K1g + K2): 4 waves 5.9 ms of encoder time, 8 waves 5.3, 16 waves 4.97,
+  // 32 waves 4.92 (news 1.61 vs 1.66 ms at 16; users equal): every launch pays the K2 prologue (W_a into shared
+  // memory), the pipeline fill and a tail.  Users stay at 16 so the fp16 context chunk (152 MB) is still mostly
+  // L2-resident between K1 and K2.
   static int waves = 0;
-  if (!waves) { const char* e = getenv("NRMS_FUSED_WAVES"); waves = e ? atoi(e) : 8; if (waves < 1) waves = 8; }
+  if (!waves) { const char* e = getenv("NRMS_FUSED_WAVES"); waves = e ? atoi(e) : (S == 20 ? 32 : 16); if (waves < 1) waves = 8; }
   return (int64_t)num_sms() * SPT * waves;
 }
 

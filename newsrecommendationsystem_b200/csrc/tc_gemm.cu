@@ -41,6 +41,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
                : "memory");
 }
 
+// F16 = false: fp32 operands rounded to TF32 by the TMA unit, kind::tf32 (K = 8 per MMA, 32 floats per 128-byte chunk);
+// F16 = true : fp16 operands, kind::f16 (K = 16 per MMA, 64 halfs per chunk): half the operand bytes per flop and half the
+//              MMA count -- the contraction the table projection of K1g uses (bias rides in a 1.0 column of A).
+template <bool F16>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int64_t M, int N, int K,
@@ -62,7 +66,9 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int n_tiles = (N + TG_BN - 1) / TG_BN;
   const int64_t m_tiles = (M + TG_BM - 1) / TG_BM;
   const int64_t total_tiles = m_tiles * n_tiles * k_splits;   // work items: K split fastest
-  const int all_chunks = (K + TG_BK - 1) / TG_BK;
+  constexpr int BK = F16 ? 2 * TG_BK : TG_BK;          // elements per 128-byte K chunk
+  constexpr int KSTEP = F16 ? 16 : 8;                  // elements per MMA
+  const int all_chunks = (K + BK - 1) / BK;
   // chunk range of work item w (the host guarantees every split is non-empty)
   auto chunk_range = [&](int64_t w, int& c0, int& c1) {
     c0 = (int)(w % k_splits) * chunks_per_split;
@@ -103,8 +109,8 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           mbar_wait(empty_bar + 8 * s, ph ^ 1);
           mbar_expect_tx(full_bar + 8 * s, stage_tx_bytes);
           const uint32_t sa = base + s * TG_STAGE_BYTES;
-          tma_load_2d(sa, &tmap_a, kc * TG_BK, m0, full_bar + 8 * s);
-          tma_load_2d(sa + TG_A_BYTES, &tmap_b, kc * TG_BK, n0, full_bar + 8 * s);
+          tma_load_2d(sa, &tmap_a, kc * BK, m0, full_bar + 8 * s);
+          tma_load_2d(sa + TG_A_BYTES, &tmap_b, kc * BK, n0, full_bar + 8 * s);
         }
       }
     }
@@ -119,7 +125,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       int n_valid = N - n0;
       if (n_valid > TG_BN) n_valid = TG_BN;
       const int n_mma = (n_valid + 15) & ~15;
-      const uint32_t idesc = umma_idesc_tf32(TG_BM, n_mma);
+      const uint32_t idesc = F16 ? umma_idesc_f16(TG_BM, n_mma) : umma_idesc_tf32(TG_BM, n_mma);
       const uint32_t as = tile_it & 1;
       int c0, c1;
       chunk_range(w, c0, c1);
@@ -133,13 +139,18 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         tc_fence_after();
         const uint32_t sa = (base + s * TG_STAGE_BYTES) >> 4;
         const uint32_t sb = sa + (TG_A_BYTES >> 4);
-        int ksteps = (K - kc * TG_BK + 7) / 8;
+        int ksteps = (K - kc * BK + KSTEP - 1) / KSTEP;
         if (ksteps > 4) ksteps = 4;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          if (ks < ksteps)
-            umma_tf32_ss_p(d_tmem, desc0 | (uint64_t)((sa + 2 * ks) & 0x3FFF), desc0 | (uint64_t)((sb + 2 * ks) & 0x3FFF),
-                           idesc, (kc > c0 || ks) ? 1u : 0u, el);
+          if (ks < ksteps) {
+            if (F16)
+              umma_f16_ss_p(d_tmem, desc0 | (uint64_t)((sa + 2 * ks) & 0x3FFF), desc0 | (uint64_t)((sb + 2 * ks) & 0x3FFF),
+                            idesc, (kc > c0 || ks) ? 1u : 0u, el);
+            else
+              umma_tf32_ss_p(d_tmem, desc0 | (uint64_t)((sa + 2 * ks) & 0x3FFF), desc0 | (uint64_t)((sb + 2 * ks) & 0x3FFF),
+                             idesc, (kc > c0 || ks) ? 1u : 0u, el);
+          }
         umma_commit_p(empty_bar + 8 * s, el);
         if (kc == c1 - 1) umma_commit_p(tfull_bar + 8 * as, el);
       }
@@ -301,14 +312,15 @@ int make_tmap_store_f16(CUtensorMap* out, const void* base, int64_t rows, int co
   return NRMS_OK;
 }
 
-static int tc_gemm_launch(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
-                         int64_t M, int N, int K, int k_splits, int epi, float f16_scale, int f16_scale_cols, cudaStream_t st);
+static int tc_gemm_launch(const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
+                         int64_t M, int N, int K, int k_splits, int epi, float f16_scale, int f16_scale_cols, bool f16_in,
+                         cudaStream_t st);
 
 int tc_gemm_nt_ex(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
                   int64_t M, int N, int K, int k_splits, int epi, cudaStream_t st) {
   NRMS_CHECK_ARG(epi >= TC_EPI_STORE && epi <= TC_EPI_ATOMIC && (k_splits <= 1 || epi == TC_EPI_ATOMIC), NRMS_E_INVALID,
                  "split-K needs the atomic epilogue");
-  return tc_gemm_launch(A, lda, B, ldb, bias, C, ldc, M, N, K, k_splits, epi, 1.f, 0, st);
+  return tc_gemm_launch(A, lda, B, ldb, bias, C, ldc, M, N, K, k_splits, epi, 1.f, 0, false, st);
 }
 
 int tc_gemm_nt_f16out(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, void* C16, int64_t ldc,
@@ -317,28 +329,48 @@ int tc_gemm_nt_f16out(const float* A, int64_t lda, const float* B, int64_t ldb, 
                  "fp16 output rows must be 8-byte aligned");
   NRMS_CHECK_ARG(!qkv_layout || (N == 900 && ldc >= 1080), NRMS_E_INVALID, "the q|k|v head-group layout is [*, 1080] from N = 900");
   return tc_gemm_launch(A, lda, B, ldb, bias, reinterpret_cast<float*>(C16), ldc, M, N, K, 1,
-                        qkv_layout ? TC_EPI_STORE_F16_QKV : TC_EPI_STORE_F16, scale, scale_cols, st);
+                        qkv_layout ? TC_EPI_STORE_F16_QKV : TC_EPI_STORE_F16, scale, scale_cols, false, st);
 }
 
-static int tc_gemm_launch(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
-                         int64_t M, int N, int K, int k_splits, int epi, float f16_scale, int f16_scale_cols, cudaStream_t st) {
+// fp16 operands (A16 [M, lda halfs], B16 [N, ldb halfs], rows 16-byte aligned), fp16 result; same epilogue as above
+int tc_gemm_nt_f16(const void* A16, int64_t lda, const void* B16, int64_t ldb, void* C16, int64_t ldc, int64_t M, int N,
+                   int K, float scale, int scale_cols, int qkv_layout, cudaStream_t st) {
+  NRMS_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0 && (ldc % 4) == 0 && aligned16(A16) && aligned16(B16) &&
+                     (reinterpret_cast<uintptr_t>(C16) & 7) == 0 && (scale_cols % 4) == 0 && (K % 8) == 0,
+                 NRMS_E_INVALID, "fp16 GEMM operands must be 16-byte aligned rows");
+  NRMS_CHECK_ARG(!qkv_layout || (N == 900 && ldc >= 1080), NRMS_E_INVALID, "the q|k|v head-group layout is [*, 1080] from N = 900");
+  return tc_gemm_launch(A16, lda, B16, ldb, nullptr, reinterpret_cast<float*>(C16), ldc, M, N, K, 1,
+                        qkv_layout ? TC_EPI_STORE_F16_QKV : TC_EPI_STORE_F16, scale, scale_cols, true, st);
+}
+
+static int tc_gemm_launch(const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
+                         int64_t M, int N, int K, int k_splits, int epi, float f16_scale, int f16_scale_cols, bool f16_in,
+                         cudaStream_t st) {
   if (M <= 0) return NRMS_OK;
   NRMS_CHECK_ARG(M < (1ll << 31), NRMS_E_UNSUPPORTED, "M too large for one tensor map");
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_nt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_gemm_nt_kernel)");
+    e = cudaFuncSetAttribute(tc_gemm_nt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_gemm_nt_kernel<f16>)");
     configured = true;
   }
   alignas(64) CUtensorMap ta, tb;
   // boxes never exceed the tensor extent (rows past it would only feed outputs that are not stored)
   const int box_a = M < TG_BM ? (int)M : TG_BM;
   const int box_b = N < TG_BN ? N : TG_BN;
-  if (int rc = make_tmap_k_major(&ta, A, M, K, lda, box_a)) return rc;
-  if (int rc = make_tmap_k_major(&tb, B, N, K, ldb, box_b)) return rc;
-  const uint32_t stage_tx = (uint32_t)(box_a + box_b) * TG_BK * 4;
+  if (f16_in) {
+    if (int rc = make_tmap_k_major_f16(&ta, A, M, K, lda, box_a)) return rc;
+    if (int rc = make_tmap_k_major_f16(&tb, B, N, K, ldb, box_b)) return rc;
+  } else {
+    if (int rc = make_tmap_k_major(&ta, reinterpret_cast<const float*>(A), M, K, lda, box_a)) return rc;
+    if (int rc = make_tmap_k_major(&tb, reinterpret_cast<const float*>(B), N, K, ldb, box_b)) return rc;
+  }
+  const uint32_t stage_tx = (uint32_t)(box_a + box_b) * TG_BK * 4;       // 128 bytes per row and chunk, either type
   const int64_t tiles = ((M + TG_BM - 1) / TG_BM) * ((N + TG_BN - 1) / TG_BN);
-  const int chunks = (K + TG_BK - 1) / TG_BK;
+  const int bk = f16_in ? 2 * TG_BK : TG_BK;
+  const int chunks = (K + bk - 1) / bk;
   if (k_splits < 1) k_splits = 1;
   if (k_splits > chunks) k_splits = chunks;
   const int cps = (chunks + k_splits - 1) / k_splits;
@@ -346,8 +378,12 @@ static int tc_gemm_launch(const float* A, int64_t lda, const float* B, int64_t l
   const int64_t items = tiles * k_splits;
   int grid = num_sms();
   if (items < grid) grid = (int)items;
-  tc_gemm_nt_kernel<<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, bias, C, ldc, M, N, K, stage_tx, k_splits, cps, epi, f16_scale,
-                                                       f16_scale_cols);
+  if (f16_in)
+    tc_gemm_nt_kernel<true><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, bias, C, ldc, M, N, K, stage_tx, k_splits, cps, epi,
+                                                               f16_scale, f16_scale_cols);
+  else
+    tc_gemm_nt_kernel<false><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, bias, C, ldc, M, N, K, stage_tx, k_splits, cps, epi,
+                                                                f16_scale, f16_scale_cols);
   NRMS_LAUNCH_CHECK("tc_gemm_nt");
   return NRMS_OK;
 }
