@@ -178,11 +178,16 @@ table_attn_kernel(const __half* __restrict__ table16, int n_table_rows, const in
         }
         const uint32_t st = it % NSTAGE;
         tc::mbar_wait(empty_bar + 8 * st, ((it / NSTAGE) & 1) ^ 1);
+#ifdef K1G_DBG_NOGATHER      // timing experiment: no copies, the compute warps run on whatever the stage holds
+        if (lane == 0) tc::mbar_arrive(full_bar + 8 * st);
+        (void)s0; (void)s1;
+#else
         if (lane == 0) mbar_arrive_expect_tx(full_bar + 8 * st, STAGE);
         __syncwarp();
         const uint32_t dst = sbase + st * STAGE + lane * PITCH;
         bulk_copy_g2s(dst, s0, PITCH, full_bar + 8 * st);
         if (lane + 32 < S) bulk_copy_g2s(dst + 32 * PITCH, s1, PITCH, full_bar + 8 * st);
+#endif
         ++it;
       }
     }
