@@ -155,9 +155,12 @@ attention_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ ctx, int
 }
 
 // ----------------------------------------------------------------------------------------
-// attention backward.  Phase 1: thread (h,i) -> Zinv_i, delta_i, dQ_i.  Phase 2: thread (h,j)
-// -> dK_j, dV_j (recomputing the probabilities; nothing S x S is stored).
+// attention backward.  Phase 1: thread (h,i) computes row i of the scores once (e_ij = exp(s_ij), da_ij = g_i . v_j),
+// its Zinv_i and delta_i, then dQ_i, leaving attn_ij and ds_ij in shared memory.  Phase 2: thread (h,j) reads
+// column j of both and accumulates dK_j, dV_j -- no score, exponential or dot product is computed twice.
 //   attn = e/(Z+eps)  =>  ds_ij = attn_ij (dattn_ij - sum_k attn_ik dattn_ik) / sqrt(d)
+// P/DS rows have a pitch of S+1 words: phase 1 (threads = consecutive i, same j) and phase 2 (threads = consecutive j)
+// are both bank-conflict free.
 // ----------------------------------------------------------------------------------------
 template <int S, int HC>
 __global__ void __launch_bounds__(((S * HC + 31) / 32) * 32)
@@ -165,13 +168,15 @@ attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
                      int64_t n_seq, float p, float scale, uint64_t seed, uint64_t offset) {
   constexpr int W = HC * DH;
   constexpr int W4 = W / 4;
+  constexpr int SP = S + 1;
+  constexpr float INV_SQRT_DH = 1.f / SQRT_DH;
   extern __shared__ __align__(16) float smem[];
   float* Qs = smem;
   float* Ks = Qs + S * W;
   float* Vs = Ks + S * W;
   float* Gs = Vs + S * W;     // d_ctx (after dropout-2 mask)
-  float* Zi = Gs + S * W;     // [HC*S] 1/(Z+eps)
-  float* De = Zi + HC * S;    // [HC*S] delta
+  float* Ps = Gs + S * W;     // [HC*S][S+1] e, then attn
+  float* Ds = Ps + HC * S * SP;   // [HC*S][S+1] da, then ds
   const int hc = blockIdx.y;
   const int tid = threadIdx.x;
   const int hl = tid / S, i = tid % S;
@@ -203,9 +208,12 @@ attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
     float a[DH], b[DH], r[DH];
     // ---- phase 1 ---------------------------------------------------------------------
     if (active) {
+      float* prow = Ps + (hl * S + i) * SP;
+      float* drow = Ds + (hl * S + i) * SP;
 #pragma unroll
       for (int d = 0; d < DH; ++d) { a[d] = Qs[i * W + hl * DH + d]; b[d] = Gs[i * W + hl * DH + d]; r[d] = 0.f; }
       float Z = 0.f, num = 0.f;
+#pragma unroll 2
       for (int j = 0; j < S; ++j) {
         const float4* kp = reinterpret_cast<const float4*>(Ks + j * W + hl * DH);
         const float4* vp = reinterpret_cast<const float4*>(Vs + j * W + hl * DH);
@@ -216,26 +224,21 @@ attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
           s = fmaf(a[4 * c], k.x, s); s = fmaf(a[4 * c + 1], k.y, s); s = fmaf(a[4 * c + 2], k.z, s); s = fmaf(a[4 * c + 3], k.w, s);
           da = fmaf(b[4 * c], v.x, da); da = fmaf(b[4 * c + 1], v.y, da); da = fmaf(b[4 * c + 2], v.z, da); da = fmaf(b[4 * c + 3], v.w, da);
         }
-        const float e = expf(s / SQRT_DH);
+        const float e = expf(s / SQRT_DH);      // same expression as the forward kernel
         Z += e;
         num = fmaf(e, da, num);
+        prow[j] = e;
+        drow[j] = da;
       }
       const float zinv = 1.f / (Z + ATTN_EPS);
       const float delta = num * zinv;
-      Zi[hl * S + i] = zinv;
-      De[hl * S + i] = delta;
+#pragma unroll 2
       for (int j = 0; j < S; ++j) {
         const float4* kp = reinterpret_cast<const float4*>(Ks + j * W + hl * DH);
-        const float4* vp = reinterpret_cast<const float4*>(Vs + j * W + hl * DH);
-        float s = 0.f, da = 0.f;
-#pragma unroll
-        for (int c = 0; c < DH / 4; ++c) {
-          float4 k = kp[c], v = vp[c];
-          s = fmaf(a[4 * c], k.x, s); s = fmaf(a[4 * c + 1], k.y, s); s = fmaf(a[4 * c + 2], k.z, s); s = fmaf(a[4 * c + 3], k.w, s);
-          da = fmaf(b[4 * c], v.x, da); da = fmaf(b[4 * c + 1], v.y, da); da = fmaf(b[4 * c + 2], v.z, da); da = fmaf(b[4 * c + 3], v.w, da);
-        }
-        const float at = expf(s / SQRT_DH) * zinv;
-        const float ds = at * (da - delta) / SQRT_DH;
+        const float at = prow[j] * zinv;
+        const float ds = at * (drow[j] - delta) * INV_SQRT_DH;
+        prow[j] = at;
+        drow[j] = ds;
 #pragma unroll
         for (int c = 0; c < DH / 4; ++c) {
           float4 k = kp[c];
@@ -251,28 +254,23 @@ attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
     // ---- phase 2 (thread index i now plays the key/value row j) ---------------------------
     if (active) {
       const int j = i;
-      float dk[DH], dv[DH];
+      const float* pcol = Ps + hl * S * SP + j;
+      const float* dcol = Ds + hl * S * SP + j;
 #pragma unroll
-      for (int d = 0; d < DH; ++d) { a[d] = Ks[j * W + hl * DH + d]; b[d] = Vs[j * W + hl * DH + d]; dk[d] = 0.f; dv[d] = 0.f; }
+      for (int d = 0; d < DH; ++d) { a[d] = 0.f; b[d] = 0.f; }     // a = dK_j, b = dV_j
+#pragma unroll 2
       for (int ii = 0; ii < S; ++ii) {
         const float4* qp = reinterpret_cast<const float4*>(Qs + ii * W + hl * DH);
         const float4* gp = reinterpret_cast<const float4*>(Gs + ii * W + hl * DH);
-        float s = 0.f, da = 0.f;
+        const float at = pcol[ii * SP];
+        const float ds = dcol[ii * SP];
 #pragma unroll
         for (int c = 0; c < DH / 4; ++c) {
           float4 qv = qp[c], g = gp[c];
-          s = fmaf(qv.x, a[4 * c], s); s = fmaf(qv.y, a[4 * c + 1], s); s = fmaf(qv.z, a[4 * c + 2], s); s = fmaf(qv.w, a[4 * c + 3], s);
-          da = fmaf(g.x, b[4 * c], da); da = fmaf(g.y, b[4 * c + 1], da); da = fmaf(g.z, b[4 * c + 2], da); da = fmaf(g.w, b[4 * c + 3], da);
-        }
-        const float at = expf(s / SQRT_DH) * Zi[hl * S + ii];
-        const float ds = at * (da - De[hl * S + ii]) / SQRT_DH;
-#pragma unroll
-        for (int c = 0; c < DH / 4; ++c) {
-          float4 qv = qp[c], g = gp[c];
-          dk[4 * c] = fmaf(ds, qv.x, dk[4 * c]); dk[4 * c + 1] = fmaf(ds, qv.y, dk[4 * c + 1]);
-          dk[4 * c + 2] = fmaf(ds, qv.z, dk[4 * c + 2]); dk[4 * c + 3] = fmaf(ds, qv.w, dk[4 * c + 3]);
-          dv[4 * c] = fmaf(at, g.x, dv[4 * c]); dv[4 * c + 1] = fmaf(at, g.y, dv[4 * c + 1]);
-          dv[4 * c + 2] = fmaf(at, g.z, dv[4 * c + 2]); dv[4 * c + 3] = fmaf(at, g.w, dv[4 * c + 3]);
+          a[4 * c] = fmaf(ds, qv.x, a[4 * c]); a[4 * c + 1] = fmaf(ds, qv.y, a[4 * c + 1]);
+          a[4 * c + 2] = fmaf(ds, qv.z, a[4 * c + 2]); a[4 * c + 3] = fmaf(ds, qv.w, a[4 * c + 3]);
+          b[4 * c] = fmaf(at, g.x, b[4 * c]); b[4 * c + 1] = fmaf(at, g.y, b[4 * c + 1]);
+          b[4 * c + 2] = fmaf(at, g.z, b[4 * c + 2]); b[4 * c + 3] = fmaf(at, g.w, b[4 * c + 3]);
         }
       }
       float* orow = d_qkv + (seq * S + j) * D3 + hc * W + hl * DH;
@@ -280,8 +278,8 @@ attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
       float4* ov = reinterpret_cast<float4*>(orow + 2 * D);
 #pragma unroll
       for (int c = 0; c < DH / 4; ++c) {
-        ok[c] = make_float4(dk[4 * c], dk[4 * c + 1], dk[4 * c + 2], dk[4 * c + 3]);
-        ov[c] = make_float4(dv[4 * c], dv[4 * c + 1], dv[4 * c + 2], dv[4 * c + 3]);
+        ok[c] = make_float4(a[4 * c], a[4 * c + 1], a[4 * c + 2], a[4 * c + 3]);
+        ov[c] = make_float4(b[4 * c], b[4 * c + 1], b[4 * c + 2], b[4 * c + 3]);
       }
     }
   }
