@@ -66,11 +66,15 @@ int64_t nrms_launch_count(void);
  * (1 = CUDA-core attention, 2 = tcgen05 attention, 3 = tcgen05 attention with two heads in flight,
  *  4 = 3 + TMA-gathered fp16 source rows, bias/scale folded into the GEMM, q read from tensor memory,
  *  5 = 4 with two projection accumulators and the probabilities kept in place over the scores,
- *  6 [default] = 5 with two worker groups taking alternate passes). */
+ *  6 [default] = 5 with two worker groups taking alternate passes).
+ * "user_table_attn" (default 1): tensor-mode nrms_user_encoder_fwd calls with int32 row indices whose history
+ *  rows outnumber the table rows 2:1 project the TABLE once (q|k|v in fp16) and run the attention on gathered rows
+ *  (K1g, k1g_table_attn.cu) instead of projecting every gathered row; 0 = always the per-user projection. */
 int nrms_set_option(const char* key, int value);
-/* "time_k1" = 1 brackets every user-encoder K1 launch with CUDA events on the launching stream (clears the
- * previous record); nrms_get_stat("k1_ms" | "k1_launches" | "k1_sequences") reads the totals back (syncs on
- * the recorded events).  Used by bench.py for the roofline of the dominant kernel.  Unknown key: -1. */
+/* "time_k1" = 1 brackets every fused K1 launch with CUDA events on the launching stream (clears the previous
+ * record); nrms_get_stat("<kind>_ms" | "<kind>_launches" | "<kind>_sequences") reads the totals back (syncs on the
+ * recorded events) for kind = k1 (user encoder, per-user projection), k1n (news encoder), k1g (user encoder, table
+ * attention).  Used by bench.py for the roofline of the dominant kernel.  Unknown key: -1. */
 double nrms_get_stat(const char* key);
 
 /* ---- sizes ------------------------------------------------------------------------- */
@@ -136,6 +140,11 @@ int nrms_user_encoder_bwd(const float* d_out, int64_t n_users, int S,
  *                      c [n_seq,S,300] -> out [n_seq,300];   workspace >= n_seq*S*(200+1)*4 + 256 bytes */
 int nrms_mhsa_fwd(const float* x, int64_t n_seq, int S, const float* wqkv, const float* bqkv, float* ctx,
                   void* workspace, size_t workspace_bytes, int mode, void* stream);
+/* The `length` branch of MultiHeadSelfAttention.forward (multihead_self.py:60-68 builds attn_mask[b,h,i,j] =
+ * j < length[b]; :18-19 multiplies exp(scores) by it): lengths int32 [n_seq]; keys at positions >= length add nothing
+ * to the sum or the context of ANY query row (rows past the length are still computed, as in the reference). */
+int nrms_mhsa_masked_fwd(const float* x, const int32_t* lengths, int64_t n_seq, int S, const float* wqkv,
+                         const float* bqkv, float* ctx, void* workspace, size_t workspace_bytes, int mode, void* stream);
 int nrms_additive_fwd(const float* c, int64_t n_seq, int S, const float* wa, const float* ba, const float* qa,
                       float* out, void* workspace, size_t workspace_bytes, int mode, void* stream);
 

@@ -79,7 +79,7 @@ static BwdWs carve_bwd(void* base, int64_t rows, bool need_dx, int mode) {
 
 template <int S, int HC>
 static cudaError_t launch_attention_fwd(const float* qkv, float* ctx, int64_t n_seq, float p, uint64_t seed,
-                                        uint64_t offset, cudaStream_t st) {
+                                        uint64_t offset, cudaStream_t st, const int32_t* lengths = nullptr) {
   constexpr int threads = ((S * HC + 31) / 32) * 32;
   const size_t smem = 2 * S * HC * DH * sizeof(float);
   static bool configured = false;
@@ -91,7 +91,7 @@ static cudaError_t launch_attention_fwd(const float* qkv, float* ctx, int64_t n_
   int64_t gx = n_seq < (int64_t)num_sms() * 8 ? n_seq : (int64_t)num_sms() * 8;
   dim3 grid((unsigned)gx, H / HC);
   const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
-  attention_fwd_kernel<S, HC><<<grid, threads, smem, st>>>(qkv, ctx, n_seq, p, scale, seed, offset);
+  attention_fwd_kernel<S, HC><<<grid, threads, smem, st>>>(qkv, ctx, n_seq, p, scale, seed, offset, lengths);
   count_launch();
   return cudaGetLastError();
 }
@@ -512,8 +512,8 @@ int nrms_user_encoder_ln_bwd(const float* d_out, int64_t n_users, int S, const f
 }
 
 // ---- standalone L0 blocks (inference): MultiHeadSelfAttention.forward / AdditiveAttention.forward ----
-int nrms_mhsa_fwd(const float* x, int64_t n_seq, int S, const float* wqkv, const float* bqkv, float* ctx,
-                  void* workspace, size_t workspace_bytes, int mode, void* stream) {
+static int mhsa_fwd_impl(const float* x, const int32_t* lengths, int64_t n_seq, int S, const float* wqkv,
+                         const float* bqkv, float* ctx, void* workspace, size_t workspace_bytes, int mode, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (int rc = check_common(S, mode)) return rc;
   NRMS_CHECK_ARG(n_seq >= 0, NRMS_E_INVALID, "bad sizes");
@@ -527,10 +527,21 @@ int nrms_mhsa_fwd(const float* x, int64_t n_seq, int S, const float* wqkv, const
                  "workspace too small: need %zu bytes", need);
   float* qkv = reinterpret_cast<float*>(workspace);
   if (int rc = gemm_nt_bias(x, D, wqkv, D, bqkv, qkv, D3, rows, D3, D, mode, st)) return rc;
-  cudaError_t e = (S == 20) ? launch_attention_fwd<20, 15>(qkv, ctx, n_seq, 0.f, 0, 0, st)
-                            : launch_attention_fwd<50, 5>(qkv, ctx, n_seq, 0.f, 0, 0, st);
+  cudaError_t e = (S == 20) ? launch_attention_fwd<20, 15>(qkv, ctx, n_seq, 0.f, 0, 0, st, lengths)
+                            : launch_attention_fwd<50, 5>(qkv, ctx, n_seq, 0.f, 0, 0, st, lengths);
   if (e != cudaSuccess) return cuda_fail(e, "attention_fwd");
   return NRMS_OK;
+}
+
+int nrms_mhsa_fwd(const float* x, int64_t n_seq, int S, const float* wqkv, const float* bqkv, float* ctx,
+                  void* workspace, size_t workspace_bytes, int mode, void* stream) {
+  return mhsa_fwd_impl(x, nullptr, n_seq, S, wqkv, bqkv, ctx, workspace, workspace_bytes, mode, stream);
+}
+
+int nrms_mhsa_masked_fwd(const float* x, const int32_t* lengths, int64_t n_seq, int S, const float* wqkv,
+                         const float* bqkv, float* ctx, void* workspace, size_t workspace_bytes, int mode, void* stream) {
+  NRMS_CHECK_ARG(lengths != nullptr || n_seq == 0, NRMS_E_INVALID, "null lengths");
+  return mhsa_fwd_impl(x, lengths, n_seq, S, wqkv, bqkv, ctx, workspace, workspace_bytes, mode, stream);
 }
 
 int nrms_additive_fwd(const float* c, int64_t n_seq, int S, const float* wa, const float* ba, const float* qa,

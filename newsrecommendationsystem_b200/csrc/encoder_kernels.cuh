@@ -83,7 +83,7 @@ scatter_embedding_grad_kernel(const int64_t* __restrict__ tokens, int64_t n_rows
 template <int S, int HC>
 __global__ void __launch_bounds__(((S * HC + 31) / 32) * 32)
 attention_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ ctx, int64_t n_seq,
-                     float p, float scale, uint64_t seed, uint64_t offset) {
+                     float p, float scale, uint64_t seed, uint64_t offset, const int32_t* __restrict__ lengths = nullptr) {
   constexpr int W = HC * DH;  // columns of this head chunk
   extern __shared__ __align__(16) float smem[];
   float* Ks = smem;          // [S][W]
@@ -118,8 +118,12 @@ attention_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ ctx, int
 #pragma unroll
     for (int d = 0; d < DH; ++d) acc[d] = 0.f;
     float Z = 0.f;
+    // `length` mask of multihead_self.py:60-68,18-19: exp(scores) * (j < length) -- keys past the length add nothing
+    // to the sum or the context; length <= 0 leaves 0 / (0 + 1e-8) = 0, like the reference
+    int jmax = S;
+    if (lengths != nullptr) { const int l = lengths[seq]; jmax = l < 0 ? 0 : (l < S ? l : S); }
 #pragma unroll 2
-    for (int j = 0; j < S; ++j) {
+    for (int j = 0; j < jmax; ++j) {
       const float4* kp = reinterpret_cast<const float4*>(Ks + j * W + hl * DH);
       float s = 0.f;
 #pragma unroll

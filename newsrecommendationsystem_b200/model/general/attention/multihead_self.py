@@ -34,15 +34,16 @@ class MultiHeadSelfAttention(nn.Module):
 
     def forward(self, Q, K=None, V=None, length=None):
         """Standalone use (inference).  Inside NewsEncoder / UserEncoder this block is fused into the encoder
-        kernels; NRMS never passes K, V or length (src/model/NRMS/news_encoder.py:41, user_encoder.py:23), so
-        only the self-attention, unmasked form is compiled -- anything else fails loudly."""
-        if (K is not None and K is not Q) or (V is not None and V is not Q) or length is not None:
-            raise NotImplementedError("libnrms_b200 compiles MultiHeadSelfAttention for K = V = Q and length=None "
-                                      "(the only form NRMS uses)")
+        kernels; NRMS never passes K, V or length (src/model/NRMS/news_encoder.py:41, user_encoder.py:23).  The
+        `length` mask branch (reference :60-68: keys at positions >= length[b] are multiplied out of the exp-softmax)
+        is compiled for the self-attention form; cross-attention (K or V different from Q) fails loudly."""
+        if (K is not None and K is not Q) or (V is not None and V is not Q):
+            raise NotImplementedError("libnrms_b200 compiles MultiHeadSelfAttention for K = V = Q (self-attention)")
         if torch.is_grad_enabled() and (Q.requires_grad or self.W_Q.weight.requires_grad):
             raise NotImplementedError("standalone MultiHeadSelfAttention.forward is inference-only; training goes "
                                       "through NewsEncoder / UserEncoder (use torch.no_grad() here)")
         from .... import ops
         from ....config import resolve_mode
         wqkv, bqkv = self.packed()
-        return ops.mhsa_forward(Q.to(self.W_Q.weight.device), wqkv, bqkv, mode=resolve_mode(None, getattr(self, "precision", None)))
+        return ops.mhsa_forward(Q.to(self.W_Q.weight.device), wqkv, bqkv,
+                                mode=resolve_mode(None, getattr(self, "precision", None)), length=length)

@@ -351,8 +351,8 @@ def gemm_nt(a, b, bias=None, mode=_lib.MODE_TF32):
 
 
 @torch.no_grad()
-def mhsa_forward(x, wqkv, bqkv, mode=_lib.MODE_TF32):
-    """Standalone MultiHeadSelfAttention.forward(Q) (K=V=Q, no mask), inference only."""
+def mhsa_forward(x, wqkv, bqkv, mode=_lib.MODE_TF32, length=None):
+    """Standalone MultiHeadSelfAttention.forward(Q, length=length) (K=V=Q), inference only."""
     lib = _lib.load()
     _require_cuda(x, wqkv, bqkv)
     n, S, d = x.shape
@@ -361,6 +361,13 @@ def mhsa_forward(x, wqkv, bqkv, mode=_lib.MODE_TF32):
     x_c, w_c, b_c = map(_f32c, (x, wqkv, bqkv))
     ctx = torch.empty_like(x_c)
     ws = _bytes(n * S * 3 * D * 4, x.device)
+    if length is not None:
+        if length.numel() != n:
+            raise RuntimeError(f"length must hold one entry per sequence ({n}), got {tuple(length.shape)}")
+        len_c = length.to(device=x.device, dtype=torch.int32).contiguous().view(-1)
+        check(lib.nrms_mhsa_masked_fwd(ptr(x_c), ptr(len_c), n, S, ptr(w_c), ptr(b_c), ptr(ctx), ptr(ws), ws.numel(),
+                                       mode, stream_ptr(x.device)), "nrms_mhsa_masked_fwd")
+        return ctx
     check(lib.nrms_mhsa_fwd(ptr(x_c), n, S, ptr(w_c), ptr(b_c), ptr(ctx), ptr(ws), ws.numel(), mode,
                             stream_ptr(x.device)), "nrms_mhsa_fwd")
     return ctx

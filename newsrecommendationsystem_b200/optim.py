@@ -78,6 +78,56 @@ class FusedAdam(torch.optim.Optimizer):
         return loss
 
 
+    # ---- checkpoint interchange with torch.optim.Adam / AdamW (reference src/train.py:266-277 saves
+    #      optimizer.state_dict() next to model.state_dict()) ------------------------------------------------
+    def state_dict(self):
+        """torch.optim.Adam's layout: per-parameter `step` / `exp_avg` / `exp_avg_sq` (clones, not views of the flat
+        buffers) and one param group, so a reference checkpoint written from this optimizer loads into
+        torch.optim.Adam(model.parameters()) and vice versa."""
+        g = self.param_groups[0]
+        state = {}
+        if self.step_count > 0:
+            for i, (p, o) in enumerate(zip(self._params, self._offsets)):
+                state[i] = dict(step=torch.tensor(float(self.step_count)),
+                                exp_avg=self.exp_avg[o:o + p.numel()].view_as(p).clone(),
+                                exp_avg_sq=self.exp_avg_sq[o:o + p.numel()].view_as(p).clone())
+        group = dict(lr=g["lr"], betas=tuple(g["betas"]), eps=g["eps"], weight_decay=g["weight_decay"], amsgrad=False,
+                     maximize=False, foreach=None, capturable=False, differentiable=False, fused=None,
+                     decoupled_weight_decay=bool(g["decoupled"]), params=list(range(len(self._params))))
+        return dict(state=state, param_groups=[group])
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        groups = state_dict["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self._params):
+            raise ValueError("optimizer state has a different parameter list (expected one group of "
+                             f"{len(self._params)} parameters)")
+        src = groups[0]
+        if src.get("amsgrad") or src.get("maximize"):
+            raise ValueError("amsgrad / maximize optimizer states are not supported by the fused Adam kernel")
+        g = self.param_groups[0]
+        g["lr"], g["betas"], g["eps"] = src["lr"], tuple(src["betas"]), src["eps"]
+        g["weight_decay"] = src.get("weight_decay", g["weight_decay"])
+        if "decoupled_weight_decay" in src:
+            g["decoupled"] = bool(src["decoupled_weight_decay"])
+        state = state_dict["state"]
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        steps = set()
+        for i, (p, o) in enumerate(zip(self._params, self._offsets)):
+            st = state.get(src["params"][i])
+            if st is None:
+                continue
+            if tuple(st["exp_avg"].shape) != tuple(p.shape):
+                raise ValueError(f"optimizer state {i}: shape {tuple(st['exp_avg'].shape)} != parameter {tuple(p.shape)}")
+            self.exp_avg[o:o + p.numel()].view_as(p).copy_(st["exp_avg"])
+            self.exp_avg_sq[o:o + p.numel()].view_as(p).copy_(st["exp_avg_sq"])
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"per-parameter step counts differ ({sorted(steps)}): one bias correction per flat buffer")
+        self.step_count = steps.pop() if steps else 0
+
+
 class FusedAdamW(FusedAdam):
     """torch.optim.AdamW semantics (decoupled weight decay, default 0.01)."""
 

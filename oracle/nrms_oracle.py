@@ -70,8 +70,9 @@ def embedding_gather(E: np.ndarray, tokens: np.ndarray) -> np.ndarray:
     return E[tokens]
 
 
-def mhsa_forward(x, p, num_heads):
-    """MultiHeadSelfAttention.forward with K=V=Q and length=None
+def mhsa_forward(x, p, num_heads, length=None):
+    """MultiHeadSelfAttention.forward with K=V=Q; `length` (int [B]) is the optional mask branch (:60-68:
+    attn_mask[b,h,i,j] = j < length[b]; :18-19: exp(scores) * attn_mask).  With length=None:
     (src/model/general/attention/multihead_self.py:46-76) followed by
     ScaledDotProductAttention.forward (:15-23).
 
@@ -90,6 +91,9 @@ def mhsa_forward(x, p, num_heads):
     vh = v.reshape(B, S, num_heads, d).transpose(0, 2, 1, 3)
     s = (qh @ kh.transpose(0, 1, 3, 2)) / dt.type(np.sqrt(d))
     e = np.exp(s)
+    if length is not None:
+        mask = (np.arange(S)[None, :] < np.asarray(length).reshape(-1, 1)).astype(dt)      # [B,S] over key positions
+        e = e * mask[:, None, None, :]
     attn = e / (e.sum(-1, keepdims=True) + dt.type(1e-8))
     ctx = attn @ vh
     out = ctx.transpose(0, 2, 1, 3).reshape(B, S, D)

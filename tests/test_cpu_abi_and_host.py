@@ -113,3 +113,16 @@ def test_synthetic_shapes():
     assert lab[o[0]:o[1]].max() == 1 and lab[o[999]:o[1000]].max() == 0   # every 1000th single-class
     cand, clicked = synthetic.make_train_batch(16, toks, k_neg=4)
     assert cand.shape == (16, 5, 20) and clicked.shape == (16, 50, 20)
+
+
+def test_news2vector_cache_round_trip():
+    """recommend.py:211-243 keeps a dict id -> vector with a PADDED_NEWS zero entry; the table form keeps that row last."""
+    import torch
+    from newsrecommendationsystem_b200 import checkpoint as ck
+    table = torch.arange(12, dtype=torch.float32).view(4, 3)
+    table[3] = 0
+    n2v = ck.news2vector_from_table(["N1", "N2", "N1"], table)        # duplicate id: the first row wins
+    assert set(n2v) == {"N1", "N2", "PADDED_NEWS"} and torch.equal(n2v["N1"], table[0])
+    assert not n2v["PADDED_NEWS"].any()
+    ids, back = ck.table_from_news2vector(n2v)
+    assert ids == ["N1", "N2"] and back.shape == (3, 3) and torch.equal(back[:2], table[:2]) and not back[2].any()

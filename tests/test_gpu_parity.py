@@ -507,7 +507,31 @@ def test_standalone_l0_blocks(dev, golden_sd, precision):
     assert rel_l2_rows(o.cpu().numpy(), ref_o) < tol
     with pytest.raises(NotImplementedError):
         with torch.no_grad():
-            att(t(x, dev), length=torch.tensor([3] * 7))
+            att(t(x, dev), K=t(x[:, :5], dev))          # cross-attention is not compiled
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_mhsa_length_mask(dev, precision):
+    """MultiHeadSelfAttention.forward(Q, length=...) (multihead_self.py:60-68) against vectors produced by the live
+    reference module (tests/golden/mhsa_masked_golden.npz) for both compiled sequence lengths."""
+    import os
+    from newsrecommendationsystem_b200.model.general.attention.multihead_self import MultiHeadSelfAttention
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mhsa_masked_golden.npz"))
+    att = MultiHeadSelfAttention(300, 15)
+    att.load_state_dict({f"W_{n.upper()}.{k}": torch.from_numpy(g[f"{'W' if k == 'weight' else 'b'}{n}"])
+                         for n in "qkv" for k in ("weight", "bias")})
+    att.to(dev).eval()
+    att.precision = precision
+    for S in (20, 50):
+        with torch.no_grad():
+            c = att(t(g[f"S{S}/x"], dev), length=torch.from_numpy(g[f"S{S}/length"]))
+            c0 = att(t(g[f"S{S}/x"], dev))
+        ref = g[f"S{S}/ctx"].reshape(-1, 300)
+        got = c.cpu().numpy().reshape(-1, 300)
+        keep = np.linalg.norm(ref, axis=1) > 0                 # the rows of the length-0 sequence are exactly zero
+        assert not got[~keep].any()
+        assert rel_l2_rows(got[keep], ref[keep]) < (2e-5 if precision == "fp32" else 1e-3)
+        assert torch.equal(c[0], c0[0]) and torch.equal(c[5], c0[5])     # length >= S: the mask is a no-op
 
 
 # ---------------------------------------------------------------------------------------------
@@ -619,3 +643,45 @@ def test_score_csr_f16_table(dev):
     assert np.all(np.abs(s16 - s32) <= bound + 1e-6)
     exact = ops.score_csr(t16[:700, :300].float().contiguous(), t(rows, dev), t(offs, dev), ub).cpu().numpy()
     np.testing.assert_allclose(s16, exact, rtol=0, atol=2e-5)
+
+
+def test_checkpoint_interchange_with_torch_adam(dev, golden, golden_sd, tmp_path):
+    """a checkpoint in the reference's layout (src/train.py:266-277) moves both ways between the fused
+    optimizer and torch.optim.Adam: same parameters, same moments, and the NEXT step from the restored state agrees."""
+    from newsrecommendationsystem_b200 import checkpoint as ck
+    from newsrecommendationsystem_b200.train import TrainStep
+    m, losses, _ = _train_once(golden, golden_sd, dev, "fp32", steps=2)
+    ts = TrainStep(m, lr=1e-4)            # fresh optimizer over the same (already flat) parameters
+    cand, clicked = golden["train/cand"], golden["train/clicked"]
+    titles = torch.from_numpy(np.concatenate([cand, clicked], axis=1))
+    ts.step_tokens(titles, cand.shape[1])
+    path = str(tmp_path / "ckpt-3.pth")
+    ck.save_checkpoint(path, m, ts.optimizer, step=3, early_stop_value=-0.5)
+    raw = torch.load(path, weights_only=False)
+    assert set(raw) == {"model_state_dict", "optimizer_state_dict", "step", "early_stop_value"}
+
+    # -> torch.optim.Adam over plain CPU parameters with the reference's names
+    params = {k: torch.nn.Parameter(v.clone()) for k, v in raw["model_state_dict"].items()}
+    adam = torch.optim.Adam(list(params.values()), lr=1e-4)
+    adam.load_state_dict(raw["optimizer_state_dict"])
+    assert int(adam.state[list(params.values())[0]]["step"]) == 1
+    grads = {k: p.grad.detach().cpu().clone() for k, p in m.named_parameters()}
+    for k, p in params.items():
+        p.grad = grads[k].clone()
+    adam.step()                            # torch's step 2 from the restored moments
+    ts.optimizer.step()                    # the fused kernel's step 2 on the same gradients
+    for k, p in m.named_parameters():
+        np.testing.assert_allclose(p.detach().cpu().numpy(), params[k].detach().numpy(), rtol=2.5e-7, atol=3e-8)  # 1 ulp
+
+    # <- a checkpoint written from torch.optim.Adam restores the fused optimizer
+    torch.save({"model_state_dict": {k: p.detach() for k, p in params.items()}, "optimizer_state_dict": adam.state_dict(),
+                "step": 4, "early_stop_value": -0.6}, path)
+    m2 = make_model(golden_sd, dev, "fp32")
+    ts2 = TrainStep(m2, lr=1e-3)
+    step, es = ck.load_checkpoint(path, m2, ts2.optimizer)
+    assert (step, es) == (4, -0.6) and ts2.optimizer.step_count == 2 and ts2.optimizer.param_groups[0]["lr"] == 1e-4
+    for k, p in m2.named_parameters():
+        assert torch.equal(p.detach().cpu(), params[k].detach())
+    st0 = adam.state[list(params.values())[0]]
+    n0 = list(params.values())[0].numel()
+    assert torch.equal(ts2.optimizer.exp_avg[:n0].cpu().view(-1), st0["exp_avg"].view(-1))

@@ -222,3 +222,19 @@ def test_layernorm_variant_encoder_matches_torch_autograd():
     np.testing.assert_allclose(dx, xt.grad.numpy(), rtol=0, atol=1e-11)
     for k in p:
         np.testing.assert_allclose(g[k], pt[k].grad.numpy(), rtol=0, atol=1e-10, err_msg=k)
+
+
+def test_mhsa_length_mask_matches_reference():
+    """The `length` branch (multihead_self.py:60-68) of the oracle vs vectors generated by the live reference module
+    (tests/golden/make_golden_masked.py): full length, one key, zero keys, length past the end."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mhsa_masked_golden.npz"))
+    p = {f"W{n}": g[f"W{n}"] for n in "qkv"}
+    p.update({f"b{n}": g[f"b{n}"] for n in "qkv"})
+    for S in (20, 50):
+        out, _ = O.mhsa_forward(g[f"S{S}/x"], p, 15, length=g[f"S{S}/length"])
+        np.testing.assert_allclose(out, g[f"S{S}/ctx"], rtol=2e-5, atol=2e-6)
+        out0, _ = O.mhsa_forward(g[f"S{S}/x"], p, 15)
+        assert not out[2].any()                                  # length 0: 0 / (0 + 1e-8)
+        np.testing.assert_array_equal(out[0], out0[0])           # length == S: the mask is a no-op
+        np.testing.assert_array_equal(out[5], out0[5])           # length > S too
