@@ -574,6 +574,10 @@ int nrms_set_option(const char* key, int value) {
     NRMS_CHECK_ARG(set_k1_variant(value) == NRMS_OK, NRMS_E_INVALID, "k1_variant must be 1..6");
     return NRMS_OK;
   }
+  if (strcmp(key, "k1g_variant") == 0) {
+    NRMS_CHECK_ARG(set_k1g_variant(value) == NRMS_OK, NRMS_E_INVALID, "k1g_variant must be 0 or 1");
+    return NRMS_OK;
+  }
   if (strcmp(key, "user_table_attn") == 0) {
     set_table_attn(value != 0);
     return NRMS_OK;

@@ -293,6 +293,139 @@ table_attn_kernel(const __half* __restrict__ table16, int n_table_rows, const in
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Variant "u" (unit-parallel): 24 warps instead of 16.  The work unit is one (head, 16-row query tile) -- 60 per
+// user -- dealt round-robin to 23 compute warps; K, V and Q fragments are loaded per unit and live only for the phase
+// that uses them, so a thread needs <= 80 registers and six warps share a sub-partition's HMMA / MUFU / FMA pipes
+// instead of four.  Costs 4x the ldmatrix traffic of the head-per-warp kernel (~2.9k shared-memory wavefronts per
+// user, below the 3.1k HMMA cycles).  Same stages, producer and output layout.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int U_WARPS = 24;
+constexpr int U_COMPUTE = U_WARPS - 1;
+constexpr int U_THREADS = U_WARPS * 32;
+constexpr int U_UNITS = H * 4;
+
+__global__ void __launch_bounds__(U_THREADS, 1)
+table_attn_units_kernel(const __half* __restrict__ table16, int n_table_rows, const int32_t* __restrict__ hist_rows,
+                        int64_t n_users, __half* __restrict__ ctx) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sbase = tc::smem_u32(smem);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const uint32_t zero = sbase + OFF_ZERO;
+  const uint32_t full_bar = sbase + OFF_BAR, empty_bar = full_bar + 8 * NSTAGE;
+
+  if (tid < 16) reinterpret_cast<uint32_t*>(smem + OFF_ZERO)[tid] = 0u;
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      tc::mbar_init(full_bar + 8 * s, 1);
+      tc::mbar_init(empty_bar + 8 * s, U_COMPUTE);
+    }
+    tc::mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == U_COMPUTE) {
+    uint32_t it = 0;
+    for (int64_t u = blockIdx.x; u < n_users; u += gridDim.x, ++it) {
+      int r0 = hist_rows[u * S + lane];
+      int r1 = lane + 32 < S ? hist_rows[u * S + lane + 32] : 0;
+      r0 = r0 < 0 ? 0 : (r0 >= n_table_rows ? n_table_rows - 1 : r0);
+      r1 = r1 < 0 ? 0 : (r1 >= n_table_rows ? n_table_rows - 1 : r1);
+      const char* s0 = reinterpret_cast<const char*>(table16) + (int64_t)r0 * ROW_BYTES;
+      const char* s1 = reinterpret_cast<const char*>(table16) + (int64_t)r1 * ROW_BYTES;
+      const uint32_t st = it % NSTAGE;
+      tc::mbar_wait(empty_bar + 8 * st, ((it / NSTAGE) & 1) ^ 1);
+      if (lane == 0) mbar_arrive_expect_tx(full_bar + 8 * st, STAGE);
+      __syncwarp();
+      const uint32_t dst = sbase + st * STAGE + lane * PITCH;
+      bulk_copy_g2s(dst, s0, PITCH, full_bar + 8 * st);
+      if (lane + 32 < S) bulk_copy_g2s(dst + 32 * PITCH, s1, PITCH, full_bar + 8 * st);
+    }
+  } else {
+    const int g = lane >> 2, t = lane & 3;
+    const int mi = lane >> 3, rr = lane & 7;
+    uint32_t it = 0;
+    for (int64_t u = blockIdx.x; u < n_users; u += gridDim.x, ++it) {
+      const uint32_t st = it % NSTAGE;
+      const uint32_t B = sbase + st * STAGE;
+      tc::mbar_wait(full_bar + 8 * st, (it / NSTAGE) & 1);
+#pragma unroll 1
+      for (int unit = warp; unit < U_UNITS; unit += U_COMPUTE) {
+        const int head = unit >> 2, mt = unit & 3;
+        const int hg = head / HG, hl = head - hg * HG;
+        const int qoff = hg * GROUP + hl * SLICE, koff = OFF_K + qoff, voff = OFF_V + qoff;
+        float sacc[7][4];
+        {
+          uint32_t qa[4], qb[2], kb16[8][2], kb8[8];
+          ldsm_x4(row_addr(B, zero, 16 * mt + 8 * (mi & 1) + rr, qoff + (mi >> 1) * 16), qa[0], qa[1], qa[2], qa[3]);
+          ldsm_x2(row_addr(B, zero, 16 * mt + 8 * (mi & 1) + rr, qoff + 32), qb[0], qb[1]);
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+            ldsm_x4(row_addr(B, zero, 8 * (2 * p + (mi >> 1)) + rr, koff + (mi & 1) * 16), kb16[2 * p][0], kb16[2 * p][1],
+                    kb16[2 * p + 1][0], kb16[2 * p + 1][1]);
+#pragma unroll
+          for (int p = 0; p < 2; ++p)
+            ldsm_x4(row_addr(B, zero, 8 * (4 * p + mi) + rr, koff + 32), kb8[4 * p], kb8[4 * p + 1], kb8[4 * p + 2],
+                    kb8[4 * p + 3]);
+#pragma unroll
+          for (int nt = 0; nt < 7; ++nt) {
+            sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
+            mma_k16(sacc[nt], qa[0], qa[1], qa[2], qa[3], kb16[nt][0], kb16[nt][1]);
+          }
+#pragma unroll
+          for (int nt = 0; nt < 7; ++nt) mma_k8(sacc[nt], qb[0], qb[1], kb8[nt]);
+        }
+        uint32_t vb[4][3][2];
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          ldsm_x4_t(row_addr(B, zero, 16 * ks + 8 * (mi & 1) + rr, voff + (mi >> 1) * 16), vb[ks][0][0], vb[ks][0][1],
+                    vb[ks][1][0], vb[ks][1][1]);
+          ldsm_x2_t(row_addr(B, zero, 16 * ks + 8 * (mi & 1) + rr, voff + 32), vb[ks][2][0], vb[ks][2][1]);
+        }
+        if (unit + U_COMPUTE >= U_UNITS) {   // this warp's last shared-memory read of the stage
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(empty_bar + 8 * st);
+        }
+        uint32_t pa[7][2];
+        const bool lower = mt < 3;
+#pragma unroll
+        for (int nt = 0; nt < 7; ++nt) {
+          float p0 = ex2_sel<0>(sacc[nt][0]), p1 = ex2_sel<1>(sacc[nt][1]);
+          float p2 = 0.f, p3 = 0.f;
+          if (lower) { p2 = ex2_sel<2>(sacc[nt][2]); p3 = ex2_sel<3>(sacc[nt][3]); }
+          if (nt == 6 && t > 0) { p0 = p1 = p2 = p3 = 0.f; }
+          pa[nt][0] = pack_h2(p0, p1);
+          pa[nt][1] = pack_h2(p2, p3);
+        }
+        float oacc[3][4];
+#pragma unroll
+        for (int dt = 0; dt < 3; ++dt) oacc[dt][0] = oacc[dt][1] = oacc[dt][2] = oacc[dt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 3; ++ks)
+#pragma unroll
+          for (int dt = 0; dt < 3; ++dt)
+            mma_k16(oacc[dt], pa[2 * ks][0], pa[2 * ks][1], pa[2 * ks + 1][0], pa[2 * ks + 1][1], vb[ks][dt][0],
+                    vb[ks][dt][1]);
+#pragma unroll
+        for (int dt = 0; dt < 3; ++dt) mma_k8(oacc[dt], pa[6][0], pa[6][1], vb[3][dt][0]);
+        const float z0 = __shfl_sync(0xffffffffu, oacc[2][0], (lane & ~3) | 2);
+        const float z1 = __shfl_sync(0xffffffffu, oacc[2][2], (lane & ~3) | 2);
+        const float i0 = __fdividef(1.f, z0 + 1e-8f), i1 = __fdividef(1.f, z1 + 1e-8f);
+        const int r0 = 16 * mt + g, r1 = r0 + 8;
+        __half* o0 = ctx + (u * S + r0) * CP + head * 20 + 2 * t;
+#pragma unroll
+        for (int dt = 0; dt < 3; ++dt) {
+          if (dt < 2 || t < 2) {
+            if (r0 < S) *reinterpret_cast<uint32_t*>(o0 + dt * 8) = pack_h2(oacc[dt][0] * i0, oacc[dt][1] * i0);
+            if (r1 < S) *reinterpret_cast<uint32_t*>(o0 + 8 * CP + dt * 8) = pack_h2(oacc[dt][2] * i1, oacc[dt][3] * i1);
+          }
+        }
+      }
+    }
+  }
+}
+
 }  // namespace k1g
 
 // fp16 copy of the packed projection weights with the bias as column 300: [900][320] halfs
@@ -330,21 +463,39 @@ int k1g_project_table(const float* table, int64_t n_rows, const float* wqkv, con
 }
 
 // Cbuf: fp16 context rows [n_users*50][320]; columns 300..319 are never written here (clear them once per buffer)
+// "k1g_variant" option: 0 = head per warp (16 warps), 1 = (head, query tile) units over 23 warps
+#ifndef K1G_DEFAULT_VARIANT
+#define K1G_DEFAULT_VARIANT 0
+#endif
+static int g_k1g_variant = K1G_DEFAULT_VARIANT;
+int set_k1g_variant(int v) {
+  if (v < 0 || v > 1) return NRMS_E_INVALID;
+  g_k1g_variant = v;
+  return NRMS_OK;
+}
+
 int k1g_run(const void* table16, int64_t n_table_rows, const int32_t* hist_rows, int64_t n_users, void* Cbuf,
             cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k1g::table_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k1g::SMEM);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(table_attn_kernel)");
+    e = cudaFuncSetAttribute(k1g::table_attn_units_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k1g::SMEM);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(table_attn_units_kernel)");
     configured = true;
   }
   if (n_users <= 0) return NRMS_OK;
   NRMS_CHECK_ARG(n_table_rows > 0 && n_table_rows < (1ll << 31), NRMS_E_INVALID, "table row count out of range");
   int grid = num_sms();
   if (n_users < grid) grid = (int)n_users;
-  k1g::table_attn_kernel<<<grid, k1g::THREADS, k1g::SMEM, st>>>(reinterpret_cast<const __half*>(table16),
-                                                                (int)n_table_rows, hist_rows, n_users,
-                                                                reinterpret_cast<__half*>(Cbuf));
+  if (g_k1g_variant == 1)
+    k1g::table_attn_units_kernel<<<grid, k1g::U_THREADS, k1g::SMEM, st>>>(reinterpret_cast<const __half*>(table16),
+                                                                          (int)n_table_rows, hist_rows, n_users,
+                                                                          reinterpret_cast<__half*>(Cbuf));
+  else
+    k1g::table_attn_kernel<<<grid, k1g::THREADS, k1g::SMEM, st>>>(reinterpret_cast<const __half*>(table16),
+                                                                  (int)n_table_rows, hist_rows, n_users,
+                                                                  reinterpret_cast<__half*>(Cbuf));
   NRMS_LAUNCH_CHECK("table_attn_kernel");
   return NRMS_OK;
 }

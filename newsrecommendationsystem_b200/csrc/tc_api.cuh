@@ -35,6 +35,7 @@ int tc_encoder_fused(const float* src, int64_t n_src_rows, const void* idx, int 
 // fp16 operands (A16 [M, lda halfs], B16 [N, ldb halfs], 16-byte aligned rows), kind::f16, same fp16 epilogue (no bias)
 int tc_gemm_nt_f16(const void* A16, int64_t lda, const void* B16, int64_t ldb, void* C16, int64_t ldc, int64_t M, int N,
                    int K, float scale, int scale_cols, int qkv_layout, cudaStream_t st);
+int set_k1g_variant(int v);     // 0 = head per warp, 1 = (head, query tile) units over 23 warps
 void set_table_attn(bool on);   // indexed user encoder: project the table once + K1g (default on)
 int set_k1_variant(int v);   // 1..6, see tc_fused.cu
 void set_time_k1(bool on);   // CUDA-event timing of the K1 launches (bench.py roofline)

@@ -10,8 +10,9 @@ model = NRMS(NRMSConfig); model.load_state_dict({k: torch.from_numpy(v) for k, v
 news, imp = bench.make_data(1)
 host = EvalHost(news, imp["hist_rows"], imp["cand_offsets"], imp["cand_rows"], imp["labels"])
 inputs = EvalInputs.from_host(host, dev)
-for flag in (0, 1):
-    lib.nrms_set_option(b"user_table_attn", flag)
+for flag in (0, 1, 2):                      # 0 = K1 v6 (per-user projection), 1 = K1g head per warp, 2 = K1g units
+    lib.nrms_set_option(b"user_table_attn", 1 if flag else 0)
+    lib.nrms_set_option(b"k1g_variant", 1 if flag == 2 else 0)
     for _ in range(3):
         ev = {}
         def mark(n): e = torch.cuda.Event(enable_timing=True); e.record(); ev[n] = e
@@ -21,5 +22,6 @@ for flag in (0, 1):
     print("table_attn", flag, {names[i + 1]: round(ev[names[i]].elapsed_time(ev[names[i + 1]]), 3) for i in range(len(names) - 1)}, means)
     uv = det["user_vectors"].clone()
     if flag == 0: uv0 = uv
-d = (uv - uv0).double().norm(dim=1) / uv0.double().norm(dim=1)
-print("max rel diff table vs per-user path", float(d.max()))
+    else:
+        d = (uv - uv0).double().norm(dim=1) / uv0.double().norm(dim=1)
+        print("  max rel diff vs the per-user path", float(d.max()))

@@ -169,8 +169,9 @@ def _indexed_equals_dense(dev, golden_sd, precision):
     assert torch.equal(a, b)      # the in-library gather is a pure copy
 
 
+@pytest.mark.parametrize("k1g_variant", [0, 1])
 @pytest.mark.parametrize("n_users,n_rows", [(1, 3), (13, 300), (67, 300), (149, 1000), (2500, 4001)])
-def test_user_encoder_table_attention_path(dev, lib, golden_sd, n_users, n_rows):
+def test_user_encoder_table_attention_path(dev, lib, golden_sd, n_users, n_rows, k1g_variant):
     """K1g (tensor mode, indexed input): the table is projected once (q|k|v rows in fp16) and the attention runs on
     gathered rows.  Same numbers as the per-user projection within the 1e-3 tolerance: vs the oracle, and vs K1 v6."""
     rng = np.random.default_rng(n_users)
@@ -185,13 +186,15 @@ def test_user_encoder_table_attention_path(dev, lib, golden_sd, n_users, n_rows)
     ref, _ = O.user_encoder_forward(golden_sd, table[rows])
     m = make_model(golden_sd, dev, "tf32")
     tb, ix = t(table, dev), t(rows.astype(np.int32), dev)
+    assert lib.nrms_set_option(b"k1g_variant", k1g_variant) == 0      # 0 = head per warp, 1 = (head, tile) units
     with torch.no_grad():
-        a = m.user_encoder.forward_indexed(tb, ix)
-        lib.nrms_set_option(b"user_table_attn", 0)
         try:
+            a = m.user_encoder.forward_indexed(tb, ix)
+            lib.nrms_set_option(b"user_table_attn", 0)
             b = m.user_encoder.forward_indexed(tb, ix)
         finally:
             lib.nrms_set_option(b"user_table_attn", 1)
+            lib.nrms_set_option(b"k1g_variant", 0)
     assert rel_l2_rows(a.cpu().numpy(), ref) < TOL_VEC["tf32"]
     assert rel_l2_rows(b.cpu().numpy(), ref) < TOL_VEC["tf32"]
     assert not torch.equal(a, b)                          # two different kernels really ran
