@@ -68,7 +68,7 @@ int64_t nrms_launch_count(void);
  *  5 = 4 with two projection accumulators and the probabilities kept in place over the scores,
  *  6 [default] = 5 with two worker groups taking alternate passes).
  * "user_table_attn" (default 1): tensor-mode nrms_user_encoder_fwd calls with int32 row indices whose history
- *  rows outnumber the table rows 2:1 project the TABLE once (q|k|v in fp16) and run the attention on gathered rows
+ *  rows outnumber the table rows 8:1 project the TABLE once (q|k|v in fp16) and run the attention on gathered rows
  *  (K1g, k1g_table_attn.cu) instead of projecting every gathered row; 0 = always the per-user projection. */
 int nrms_set_option(const char* key, int value);
 /* "time_k1" = 1 brackets every fused K1 launch with CUDA events on the launching stream (clears the previous

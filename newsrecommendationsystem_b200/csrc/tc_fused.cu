@@ -65,7 +65,7 @@ int k1g_project_table(const float* table, int64_t n_rows, const float* wqkv, con
 size_t k1g_table16_bytes(int64_t n_rows);
 int k1g_run(const void* table16, int64_t n_table_rows, const int32_t* hist_rows, int64_t n_users, void* Cbuf,
             cudaStream_t st);
-// "user_table_attn" option: 1 (default) = int32-indexed S=50 calls whose history rows outnumber the table rows 2:1
+// "user_table_attn" option: 1 (default) = int32-indexed S=50 calls whose history rows outnumber the table rows 8:1
 // project the table once and run K1g; 0 = always the per-user projection of K1 v1..v6
 static int g_table_attn = -1;
 static bool table_attn_enabled() {
@@ -77,7 +77,10 @@ static bool table_attn_enabled() {
 }
 void set_table_attn(bool on) { g_table_attn = on ? 1 : 0; }
 static bool use_table_attn(int S, int idx_kind, int64_t n_seq, int64_t n_src_rows) {
-  return S == 50 && idx_kind == 2 && n_src_rows > 0 && table_attn_enabled() && n_seq * S >= 2 * n_src_rows;
+  // The projection costs 2.6 us per 1,000 table rows and every call (rank) pays it for the WHOLE table, and a table16
+  // beyond L2 (126 MB = 58 k rows) turns the 2,160-byte row gather into DRAM traffic: measured 3.2 ms vs 4.4 ms (K1 v6)
+  // at 56 history rows per table row, 4.4 vs ~4.8 ms at 28; the break-even is near 8.
+  return S == 50 && idx_kind == 2 && n_src_rows > 0 && table_attn_enabled() && n_seq * S >= 8 * n_src_rows;
 }
 constexpr int K1_DEFAULT_VARIANT = 6;
 static int g_k1_variant = -1;

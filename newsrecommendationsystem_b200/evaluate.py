@@ -114,15 +114,52 @@ class EvalInputs:
     def _fill(self, host, device):
         self.device = torch.device(device)
         self.n_news, self.n_impressions = host.n_news, host.n_impressions
-        for name in ("news_tokens", "hist_rows", "cand_rows", "cand_offsets", "labels"):
-            setattr(self, name, getattr(host, name).to(self.device, non_blocking=True))
         self.cand_offsets_host = host.cand_offsets_host
+        self._ready = None
+        rest = ("hist_rows", "cand_rows", "cand_offsets", "labels")
+        if self.device.type != "cuda":
+            for name in ("news_tokens",) + rest:
+                setattr(self, name, getattr(host, name).to(self.device))
+            return
+        # The news stage needs only the token table: it goes first on the caller's stream; the impression tables
+        # follow on a copy stream and overlap the news encoders (evaluate_tensors waits on the event before stage B).
+        main = torch.cuda.current_stream(self.device)
+        self.news_tokens = host.news_tokens.to(self.device, non_blocking=True)
+        side = _copy_stream(self.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for name in rest:
+                t = getattr(host, name).to(self.device, non_blocking=True)
+                t.record_stream(main)
+                setattr(self, name, t)
+            self._ready = torch.cuda.Event()
+            self._ready.record(side)
+
+    def wait_ready(self):
+        """Make the caller's stream wait for the impression tables (no host sync)."""
+        if self._ready is not None:
+            torch.cuda.current_stream(self.device).wait_event(self._ready)
+            self._ready = None
+
+
+_copy_streams = {}
+
+
+def _copy_stream(device):
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _copy_streams:
+        _copy_streams[key] = torch.cuda.Stream(device=device)
+    return _copy_streams[key]
+
+
+NEWS_GATHER_BLOCKS = 3      # sub-blocks of a rank's news shard whose all-gathers overlap the encoding of the next one
 
 
 @torch.no_grad()
 def encode_news_table(model, news_tokens: torch.Tensor) -> torch.Tensor:
     """Stage A.  Returns [N_news+1, 300] with a zero last row.  Multi-rank: each rank encodes its
-    contiguous row block straight into its slot of the (padded) table, then one all_gather."""
+    contiguous row block straight into its slot of the (padded) table; the slots are all-gathered in
+    NEWS_GATHER_BLOCKS pieces, each exchange overlapping the encoding of the next piece."""
     dist = _dist()
     n = news_tokens.shape[0]
     dev = news_tokens.device
@@ -138,9 +175,21 @@ def encode_news_table(model, news_tokens: torch.Tensor) -> torch.Tensor:
         per = (n + world - 1) // world
         padded = torch.zeros((world * per + 1, ops.D), dtype=torch.float32, device=dev)
         lo, hi = shard_range(n, rank, world)
-        if hi > lo:
-            padded[lo:hi] = model.get_news_vector({"title": news_tokens[lo:hi]})
-        dist.all_gather_into_tensor(padded[:world * per].view(-1), padded[rank * per:(rank + 1) * per].reshape(-1).clone())
+        # The shard is encoded in NEWS_GATHER_BLOCKS sub-blocks; the all-gather of sub-block j runs (async, on the
+        # process group's stream) while sub-block j+1 is being encoded, so only the last exchange is exposed.
+        sub = (per + NEWS_GATHER_BLOCKS - 1) // NEWS_GATHER_BLOCKS
+        works = []
+        for j in range(NEWS_GATHER_BLOCKS):
+            b0, b1 = j * sub, min((j + 1) * sub, per)          # offsets inside every rank's slot of `per` rows
+            if b1 <= b0:
+                break
+            r0, r1 = min(lo + b0, hi), min(lo + b1, hi)        # rows past the shard stay zero (padding of the last rank)
+            if r1 > r0:
+                padded[r0:r1] = model.get_news_vector({"title": news_tokens[r0:r1]})
+            outs = [padded[r * per + b0:r * per + b1] for r in range(world)]
+            works.append(dist.all_gather(outs, padded[rank * per + b0:rank * per + b1].clone(), async_op=True))
+        for w in works:
+            w.wait()
         table = padded[:n + 1]
         table[n].zero_()
         return table
@@ -166,6 +215,7 @@ def evaluate_tensors(model, inputs: EvalInputs, max_count=None, return_details=F
     mark("start")
     table = encode_news_table(model, inputs.news_tokens)
     mark("news")
+    inputs.wait_ready()
     n_imp = inputs.n_impressions
     if max_count is not None:
         n_imp = max(0, min(n_imp, int(max_count) - 1))
