@@ -89,10 +89,21 @@ class ClockSampler:
                 "power_w_max": float(max(pw)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_data(world):
+MIND_LARGE = (161013, 376471)      # BASELINE configs[3]: news, impressions (strong scaling: fixed total)
+
+
+def workload_sizes(world, workload="small-per-gpu"):
+    """(news, impressions) in total over all ranks."""
+    if workload == "mind-large":
+        return MIND_LARGE
+    return NEWS_PER_GPU * world, IMPRESSIONS_PER_GPU * world
+
+
+def make_data(world, workload="small-per-gpu"):
     from newsrecommendationsystem_b200 import synthetic
-    news = synthetic.make_news(NEWS_PER_GPU * world, num_words=NUM_WORDS, seed=1234)
-    imp = synthetic.make_impressions(IMPRESSIONS_PER_GPU * world, NEWS_PER_GPU * world, seed=1234)
+    n_news, n_imp = workload_sizes(world, workload)
+    news = synthetic.make_news(n_news, num_words=NUM_WORDS, seed=1234)
+    imp = synthetic.make_impressions(n_imp, n_news, seed=1234)
     return news, imp
 
 
@@ -166,9 +177,11 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(world, precision):
-    return dict(workload="NRMS evaluate pipeline, MIND-small-shaped per GPU (BASELINE configs[1])",
-                news_per_gpu=NEWS_PER_GPU, impressions_per_gpu=IMPRESSIONS_PER_GPU, vocab=NUM_WORDS,
+def workload_config(world, precision, workload="small-per-gpu"):
+    n_news, n_imp = workload_sizes(world, workload)
+    name = ("NRMS evaluate pipeline, MIND-large-shaped in total, sharded over the GPUs (BASELINE configs[3])"
+            if workload == "mind-large" else "NRMS evaluate pipeline, MIND-small-shaped per GPU (BASELINE configs[1])")
+    return dict(workload=name, news_per_gpu=n_news / world, impressions_per_gpu=n_imp / world, vocab=NUM_WORDS,
                 title_len=20, history=50, heads=15, dim=300, precision=precision,
                 parallelism=f"dp{world}: news rows + impressions sharded, NCCL all-gather of the news table",
                 l2="flushed between timed steps (256 MiB write); per-step CUDA events summed")
@@ -181,6 +194,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--workload", default="small-per-gpu", choices=["small-per-gpu", "mind-large"],
+                    help="small-per-gpu (default, weak scaling: one MIND-small-shaped shard per GPU, the headline) or "
+                         "mind-large (strong scaling: 161,013 news / 376,471 impressions in total, BASELINE configs[3])")
     ap.add_argument("--no-train", action="store_true", help="skip the train-step side measurement")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
@@ -211,7 +227,8 @@ def main():
     model = NRMS(NRMSConfig)
     model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
     model.to(dev).eval().set_precision(args.precision)
-    news, imp = make_data(world)
+    news, imp = make_data(world, args.workload)
+    news_total, _ = workload_sizes(world, args.workload)
     host = EvalHost(news, imp["hist_rows"], imp["cand_offsets"], imp["cand_rows"], imp["labels"])
     inputs = EvalInputs.from_host(host, dev)
     n_imp_total = host.n_impressions
@@ -283,7 +300,7 @@ def main():
 
     # ---- roofline of the dominant stage --------------------------------------------------------
     peaks = load_peaks()
-    n_news_rank = NEWS_PER_GPU       # per-rank shard
+    n_news_rank = news_total / world       # per-rank shard
     n_imp_rank = n_imp_total / world
     cand_rank = n_cand_total / world
     stage_flops = {"news": n_news_rank * FLOP_PER_TITLE, "users": n_imp_rank * FLOP_PER_USER}
@@ -329,7 +346,7 @@ def main():
                     unit="TFLOP/s", frac=ach / peaks["bf16_tflops"], traffic=None, peak_source=peaks["source"])
     per_cand = BYTES_PER_CANDIDATE_F16 if args.precision == "tf32" else BYTES_PER_CANDIDATE
     # + the one-off fp16 copy of the table inside the stage (read fp32, write fp16)
-    pack_bytes = (NEWS_PER_GPU * world + 1) * (1200 + 640) if args.precision == "tf32" else 0
+    pack_bytes = (news_total + 1) * (1200 + 640) if args.precision == "tf32" else 0
     score_bytes = cand_rank * per_cand + n_imp_rank * BYTES_PER_IMPRESSION + pack_bytes
     extras = dict(
         stage_ms=st,
@@ -374,10 +391,11 @@ def main():
 
     if rank == 0:
         line = dict(metric="evaluate impressions/s", value=value, unit="impressions/s", n_gpus=world, steps=args.steps,
-                    warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True, scaling="weak",
+                    warmup=args.warmup, ms_per_step=ms_per_step, higher_is_better=True,
+                    scaling="strong" if args.workload == "mind-large" else "weak",
                     vs_baseline=None, dtype="f16xf16->f32 (tcgen05 kind::f16; TF32-equivalent 11-bit significand)"
                     if args.precision == "tf32" else "f32", data="synthetic",
-                    config=workload_config(world, args.precision), clocks=clocks,
+                    config=workload_config(world, args.precision, args.workload), clocks=clocks,
                     e2e=dict(value=e2e_value, unit="impressions/s", h2d_bytes_per_step=host.nbytes(),
                              d2h_bytes_per_step=64, ms_per_step=e2e_ms / args.steps),
                     gpu_launches=launches, roofline=roof, cpu_baseline=cpu, train=train, **extras)
