@@ -21,6 +21,8 @@ import time
 
 import numpy as np
 
+# torch reads this when its CUDA allocator starts: VMM-mapped (2 MB page) segments, see _lib._prefer_large_page_segments
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -262,7 +264,9 @@ def main():
                 stage_ms.setdefault(n1, []).append(a.elapsed_time(b))
         return e0.elapsed_time(e1), means
 
-    for _ in range(args.warmup):
+    for w in range(args.warmup):
+        if w == args.warmup - 1:
+            lib.nrms_set_option(b"time_k1", 1)     # the timing events are created (and pooled) outside the timed region
         timed_eval(inputs)
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None

@@ -71,6 +71,7 @@ def load():
             f"{LIB_PATH} not found: the NRMS B200 CUDA library is not built. "
             "Run `python newsrecommendationsystem_b200/csrc/build.py` (nvcc, sm_100a). There is no CPU fallback.")
     import torch  # noqa: F401  (brings libcudart.so.12 into the process before dlopen)
+    _prefer_large_page_segments(torch)
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
@@ -78,6 +79,22 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def _prefer_large_page_segments(torch):
+    """Workspaces (the projected q|k|v table above all: 141 MB gathered in random 2,160-byte rows) must sit on 2 MB
+    pages.  Measured on B200: carved out of a plain cudaMalloc segment the same evaluate pass took 4.3 ms in the user
+    stage instead of 3.2 ms whenever less than ~64 MB had been allocated before it (profiles/k1g_probe.py,
+    PROBE_FLUSHBUF_MB sweep); segments mapped through the CUDA virtual-memory API -- torch's `expandable_segments` --
+    are 3.2 ms in every order.  Only a default: an explicit PYTORCH_CUDA_ALLOC_CONF or NRMS_B200_KEEP_ALLOCATOR=1 wins."""
+    if os.environ.get("PYTORCH_CUDA_ALLOC_CONF") or os.environ.get("NRMS_B200_KEEP_ALLOCATOR"):
+        return
+    try:
+        if torch.cuda.is_available():
+            setter = getattr(torch._C, "_accelerator_setAllocatorSettings", None) or torch.cuda.memory._set_allocator_settings
+            setter("expandable_segments:True")
+    except Exception:      # an allocator backend without the knob: keep its default
+        pass
 
 
 def check(rc: int, what: str = ""):

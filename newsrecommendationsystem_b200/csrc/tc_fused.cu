@@ -96,10 +96,17 @@ static int k1_variant() {
 static bool g_time_k1 = false;
 struct K1Record { cudaEvent_t a, b; int64_t seqs; int kind; };
 static std::vector<K1Record> g_k1_records;
+static std::vector<cudaEvent_t> g_k1_event_pool;     // events are reused: the first cudaEventCreate calls cost ~30 us each
 void set_time_k1(bool on) {
   g_time_k1 = on;
-  for (auto& r : g_k1_records) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto& r : g_k1_records) { g_k1_event_pool.push_back(r.a); g_k1_event_pool.push_back(r.b); }
   g_k1_records.clear();
+}
+static cudaEvent_t k1_timer_event() {
+  cudaEvent_t e;
+  if (!g_k1_event_pool.empty()) { e = g_k1_event_pool.back(); g_k1_event_pool.pop_back(); return e; }
+  cudaEventCreate(&e);
+  return e;
 }
 // key = 3 * kind + what; what: 0 = total ms of the timed launches, 1 = number of launches, 2 = sequences processed
 double get_k1_stat(int key) {
@@ -119,7 +126,7 @@ double get_k1_stat(int key) {
 struct K1Timer {
   cudaStream_t st; bool on; K1Record rec;
   K1Timer(cudaStream_t s, int64_t n, int kind) : st(s), on(g_time_k1 && g_k1_records.size() < 8192) {
-    if (on) { cudaEventCreate(&rec.a); cudaEventCreate(&rec.b); cudaEventRecord(rec.a, st); rec.seqs = n; rec.kind = kind; }
+    if (on) { rec.a = k1_timer_event(); rec.b = k1_timer_event(); cudaEventRecord(rec.a, st); rec.seqs = n; rec.kind = kind; }
   }
   ~K1Timer() { if (on) { cudaEventRecord(rec.b, st); g_k1_records.push_back(rec); } }
 };

@@ -7,6 +7,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import os
+
 import torch
 
 from . import _lib
@@ -250,6 +252,10 @@ def user_encoder_indexed(table, rows, wqkv, bqkv, wa, ba, qa, mode=_lib.MODE_TF3
     out = torch.empty((n, D), dtype=torch.float32, device=dev)
     ws = _bytes(lib.nrms_encoder_fwd_workspace_bytes(n, S, mode, 0, table.shape[0]), dev)
     args = [_f32c(t) for t in (table, wqkv, bqkv, wa, ba, qa)]
+    if os.environ.get("NRMS_B200_DEBUG_WS"):
+        print(f"user_encoder_indexed: ws {ws.data_ptr():#x} ({ws.numel() / 2**20:.1f} MiB), table {args[0].data_ptr():#x}, "
+              f"rows {rows.data_ptr():#x}, out {out.data_ptr():#x}; allocated {torch.cuda.memory_allocated() / 2**20:.0f} MiB, "
+              f"reserved {torch.cuda.memory_reserved() / 2**20:.0f} MiB")
     if ln is not None:
         lw, lb = _f32c(ln[0]), _f32c(ln[1])
         check(lib.nrms_user_encoder_ln_fwd(ptr(args[0]), args[0].shape[0], ptr(rows), n, S, ptr(args[1]), ptr(args[2]),
