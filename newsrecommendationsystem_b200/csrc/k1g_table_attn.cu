@@ -47,7 +47,7 @@ constexpr int NSTAGE = 2;
 #endif
 constexpr int PREFETCH_AHEAD = K1G_PREFETCH_AHEAD;
 #ifndef K1G_V_RELOAD
-#define K1G_V_RELOAD 1
+#define K1G_V_RELOAD 0
 #endif
 constexpr bool V_RELOAD = K1G_V_RELOAD != 0;   // V fragments reloaded per query tile (registers for the second score tile)
 constexpr int ROW_BYTES = PITCH;
@@ -102,7 +102,7 @@ __device__ __forceinline__ float ex2f(float x) {
 // an order below the fp16 rounding of P).  K1G_EX2_FMA = n > 0 sends every n-th exponential of a key tile pair here:
 // the MUFU unit (16 ex2 per clock per SM) is the second-busiest pipe of this kernel after the HMMA pipe.
 #ifndef K1G_EX2_FMA
-#define K1G_EX2_FMA 2
+#define K1G_EX2_FMA 0
 #endif
 __device__ __forceinline__ float ex2_fma(float x) {
   x = fmaxf(x, -100.f);
@@ -124,9 +124,20 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-// smem byte address of row `row` of a stage (the zero line for rows >= 50), plus a byte offset (a multiple of 16)
+// smem byte address of row `row` of a stage plus a byte offset (a multiple of 16).  Rows >= 50 (padding of the 16-row
+// tiles) read row 49 instead: whatever they hold is finite, padded KEYS are masked out of P (so neither their scores nor
+// their v rows count) and padded QUERY rows are never stored.  K1G_ZERO_ROWS=1 keeps the older form that redirected them
+// to a zero line (a compare + select per ldmatrix address; this kernel is bound by instruction issue).
+#ifndef K1G_ZERO_ROWS
+#define K1G_ZERO_ROWS 0
+#endif
 __device__ __forceinline__ uint32_t row_addr(uint32_t stage, uint32_t zero, int row, int off) {
+#if K1G_ZERO_ROWS
   return row < S ? stage + (uint32_t)(row * PITCH + off) : zero + (uint32_t)(off & 31);
+#else
+  (void)zero;
+  return stage + (uint32_t)((row < S ? row : S - 1) * PITCH + off);
+#endif
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -197,6 +208,20 @@ table_attn_kernel(const __half* __restrict__ table16, int n_table_rows, const in
     const int qoff = hg * GROUP + hl * SLICE, koff = OFF_K + qoff, voff = OFF_V + qoff;
     const int g = lane >> 2, t = lane & 3;
     const int mi = lane >> 3, rr = lane & 7;     // ldmatrix: this lane supplies row rr of matrix mi
+    // Byte offsets of this lane's ldmatrix rows inside a stage: constant over the whole kernel (only the stage base
+    // changes per user), so the per-user address work is one add per load -- the kernel is bound by instruction issue.
+    auto rofs = [](int row) { return (uint32_t)((row < S ? row : S - 1) * PITCH); };     // padded rows read row 49
+    uint32_t k16o[4], k8o[2], v4o[4], v2o[4], q4o[4], q2o[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      k16o[p] = rofs(16 * p + 8 * (mi >> 1) + rr) + koff + (mi & 1) * 16;
+      v4o[p] = rofs(16 * p + 8 * (mi & 1) + rr) + voff + (mi >> 1) * 16;
+      v2o[p] = rofs(16 * p + 8 * (mi & 1) + rr) + voff + 32;
+      q4o[p] = rofs(16 * p + 8 * (mi & 1) + rr) + qoff + (mi >> 1) * 16;
+      q2o[p] = rofs(16 * p + 8 * (mi & 1) + rr) + qoff + 32;
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) k8o[p] = rofs(32 * p + 8 * mi + rr) + koff + 32;
     uint32_t itu = 0;
     for (int64_t u = blockIdx.x; u < n_users; u += gridDim.x, ++itu) {
       const uint32_t it = itu;
@@ -207,30 +232,26 @@ table_attn_kernel(const __half* __restrict__ table16, int n_table_rows, const in
       uint32_t kb16[8][2], kb8[8];
 #pragma unroll
       for (int p = 0; p < 4; ++p)   // key tiles (2p, 2p+1): matrices [2p,d0-7] [2p,d8-15] [2p+1,d0-7] [2p+1,d8-15]
-        ldsm_x4(row_addr(B, zero, 8 * (2 * p + (mi >> 1)) + rr, koff + (mi & 1) * 16), kb16[2 * p][0], kb16[2 * p][1],
-                kb16[2 * p + 1][0], kb16[2 * p + 1][1]);     // key tile 7 (rows 56..63) is the zero line, unused
+        ldsm_x4(B + k16o[p], kb16[2 * p][0], kb16[2 * p][1], kb16[2 * p + 1][0], kb16[2 * p + 1][1]);   // key tile 7 unused
 #pragma unroll
       for (int p = 0; p < 2; ++p)   // dims 16-23 of key tiles 4p..4p+3
-        ldsm_x4(row_addr(B, zero, 8 * (4 * p + mi) + rr, koff + 32), kb8[4 * p], kb8[4 * p + 1], kb8[4 * p + 2],
-                kb8[4 * p + 3]);
+        ldsm_x4(B + k8o[p], kb8[4 * p], kb8[4 * p + 1], kb8[4 * p + 2], kb8[4 * p + 3]);
       // ---- V fragments (transposed loads): vb[ks][dt][0..1] keys 16ks..16ks+7 / +8..15, dims 8dt..8dt+7 ----
       uint32_t vb[4][3][2];
       auto load_v = [&]() {
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           // matrices: [keys 16ks+0..7, d0-7] [keys +8..15, d0-7] [keys 0..7, d8-15] [keys +8..15, d8-15]
-          ldsm_x4_t(row_addr(B, zero, 16 * ks + 8 * (mi & 1) + rr, voff + (mi >> 1) * 16), vb[ks][0][0], vb[ks][0][1],
-                    vb[ks][1][0], vb[ks][1][1]);
-          ldsm_x2_t(row_addr(B, zero, 16 * ks + 8 * (mi & 1) + rr, voff + 32), vb[ks][2][0], vb[ks][2][1]);
+          ldsm_x4_t(B + v4o[ks], vb[ks][0][0], vb[ks][0][1], vb[ks][1][0], vb[ks][1][1]);
+          ldsm_x2_t(B + v2o[ks], vb[ks][2][0], vb[ks][2][1]);
         }
       };
       if (!V_RELOAD) load_v();
-      __half* out = ctx + (u * S) * CP + warp * 20 + 2 * t;
       // S = Q K^T of query tile mt (16 rows): seven k16 steps, then the dependent k8 steps
       auto scores = [&](int mt, float (&sacc)[7][4]) {
         uint32_t qa[4], qb[2];
-        ldsm_x4(row_addr(B, zero, 16 * mt + 8 * (mi & 1) + rr, qoff + (mi >> 1) * 16), qa[0], qa[1], qa[2], qa[3]);
-        ldsm_x2(row_addr(B, zero, 16 * mt + 8 * (mi & 1) + rr, qoff + 32), qb[0], qb[1]);
+        ldsm_x4(B + q4o[mt], qa[0], qa[1], qa[2], qa[3]);
+        ldsm_x2(B + q2o[mt], qb[0], qb[1]);
 #ifdef K1G_DBG_NOS          // timing experiment: no score MMAs
 #pragma unroll
         for (int nt = 0; nt < 7; ++nt) {
@@ -255,10 +276,6 @@ table_attn_kernel(const __half* __restrict__ table16, int n_table_rows, const in
       for (int mt = 0; mt < 4; ++mt) {
         if (mt < 3) scores(mt + 1, sacc[(mt + 1) & 1]);
         if (V_RELOAD) load_v();
-        if (mt == 3) {               // last shared-memory read of this stage: hand it back to the producer
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(empty_bar + 8 * st);
-        }
         float (&sc)[7][4] = sacc[mt & 1];
         // P = 2^S (q carries log2(e)/sqrt(20)); keys 50..55 (key tile 6, t > 0) are padding
         uint32_t pa[7][2];
@@ -303,14 +320,37 @@ table_attn_kernel(const __half* __restrict__ table16, int n_table_rows, const in
         const float z0 = __shfl_sync(0xffffffffu, oacc[2][0], (lane & ~3) | 2);
         const float z1 = __shfl_sync(0xffffffffu, oacc[2][2], (lane & ~3) | 2);
         const float i0 = __fdividef(1.f, z0 + 1e-8f), i1 = __fdividef(1.f, z1 + 1e-8f);
+        // O / (Z + 1e-8) goes back IN PLACE over the head's q slice of these 16 rows (dead since their fragments were
+        // loaded), then the warp copies the 16 x 40 bytes out as 8-byte pieces: one memory request per (row, head)
+        // segment.  Storing the accumulator fragments straight to global (4 bytes per lane, 8 rows per instruction, 10
+        // instructions per tile) made 4,800 write requests per user and was THE limiter of this kernel: removing all the
+        // MMAs and exponentials, or the whole gather, did not change its run time (profiles/ab_k1g.sh, K1G_DBG_*).
         const int r0 = 16 * mt + g, r1 = r0 + 8;
-        __half* o0 = out + r0 * CP;
+        uint8_t* q0 = smem + st * STAGE + r0 * PITCH + qoff + 4 * t;
 #pragma unroll
         for (int dt = 0; dt < 3; ++dt) {
           if (dt < 2 || t < 2) {
-            if (r0 < S) *reinterpret_cast<uint32_t*>(o0 + dt * 8) = pack_h2(oacc[dt][0] * i0, oacc[dt][1] * i0);
-            if (r1 < S) *reinterpret_cast<uint32_t*>(o0 + 8 * CP + dt * 8) = pack_h2(oacc[dt][2] * i1, oacc[dt][3] * i1);
+            if (r0 < S) *reinterpret_cast<uint32_t*>(q0 + dt * 16) = pack_h2(oacc[dt][0] * i0, oacc[dt][1] * i0);
+            if (r1 < S) *reinterpret_cast<uint32_t*>(q0 + 8 * PITCH + dt * 16) = pack_h2(oacc[dt][2] * i1, oacc[dt][3] * i1);
           }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int p = lane + 32 * k;                 // 80 pieces: 16 rows x 5 x 8 bytes
+          const int row = 16 * mt + p / 5, c = p % 5;
+          if (p < 80 && row < S) {
+            const uint2 v = *reinterpret_cast<const uint2*>(smem + st * STAGE + row * PITCH + qoff + c * 8);
+#ifdef K1G_DBG_NOSTORE      // timing experiment: no context stores (one predicated-off store keeps the value alive)
+            if (v.x == 0x7fc07fc1u && v.y == 0x12345678u)
+#endif
+            *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(ctx) + ((u * S + row) * CP + warp * 20) * 2 + c * 8) = v;
+          }
+        }
+        if (mt == 3) {               // last shared-memory access of this stage: hand it back to the producer
+          tc::fence_proxy_async_smem();      // the generic-proxy stores above precede the next bulk copy into these rows
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(empty_bar + 8 * st);
         }
       }
     }
