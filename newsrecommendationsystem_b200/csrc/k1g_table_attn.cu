@@ -128,6 +128,9 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
 // tiles) read row 49 instead: whatever they hold is finite, padded KEYS are masked out of P (so neither their scores nor
 // their v rows count) and padded QUERY rows are never stored.  K1G_ZERO_ROWS=1 keeps the older form that redirected them
 // to a zero line (a compare + select per ldmatrix address; this kernel is bound by instruction issue).
+#ifndef K1G_DIRECT_STORE
+#define K1G_DIRECT_STORE 0      // 1 = accumulator fragments straight to global (4-byte stores), 0 = staged through the q slice
+#endif
 #ifndef K1G_ZERO_ROWS
 #define K1G_ZERO_ROWS 0
 #endif
@@ -326,6 +329,23 @@ table_attn_kernel(const __half* __restrict__ table16, int n_table_rows, const in
         // instructions per tile) made 4,800 write requests per user and was THE limiter of this kernel: removing all the
         // MMAs and exponentials, or the whole gather, did not change its run time (profiles/ab_k1g.sh, K1G_DBG_*).
         const int r0 = 16 * mt + g, r1 = r0 + 8;
+#if K1G_DIRECT_STORE
+        {
+          __half* o0 = ctx + (u * S + r0) * CP + warp * 20 + 2 * t;
+#pragma unroll
+          for (int dt = 0; dt < 3; ++dt) {
+            if (dt < 2 || t < 2) {
+              if (r0 < S) *reinterpret_cast<uint32_t*>(o0 + dt * 8) = pack_h2(oacc[dt][0] * i0, oacc[dt][1] * i0);
+              if (r1 < S) *reinterpret_cast<uint32_t*>(o0 + 8 * CP + dt * 8) = pack_h2(oacc[dt][2] * i1, oacc[dt][3] * i1);
+            }
+          }
+          if (mt == 3) {
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(empty_bar + 8 * st);
+          }
+          continue;
+        }
+#endif
         uint8_t* q0 = smem + st * STAGE + r0 * PITCH + qoff + 4 * t;
 #pragma unroll
         for (int dt = 0; dt < 3; ++dt) {
