@@ -279,7 +279,7 @@ def main():
         times.append(ms)
     launches = int(lib.nrms_launch_count() - l0)
     kstat = {k: tuple(lib.nrms_get_stat(f"{k}_{w}".encode()) for w in ("ms", "launches", "sequences"))
-             for k in ("k1", "k1n", "k1g")}
+             for k in ("k1", "k1n", "k1g", "k1gn")}
     lib.nrms_set_option(b"time_k1", 0)
     barrier()
     e2e_times = []
@@ -329,17 +329,23 @@ def main():
     # K1 owns everything of an encoder except the additive projection/pooling (K2)
     roof_news = tensor_roof("k1n", "k1v6::encoder_attn_tc6_kernel<20,24,5> (news encoder: gather+QKV+attention)",
                             FLOP_PER_TITLE - 2_400_000 - 20_000, "encoder_attn_tc6_kernel<20,24,5>")
-    roof = None
-    g_ms, g_n, g_seq = kstat["k1g"]
-    if g_n > 0 and g_ms > 0:
-        us = 1e3 * g_ms / g_n
-        ach = (g_seq / g_n) * K1G_BYTES_PER_USER / (us * 1e-6) / 1e9
-        roof = dict(bound="hbm", kernel="k1g::table_attn_kernel (user encoder: q|k|v row gather + 15-head attention)",
-                    achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s", frac=ach / peaks["hbm_gbs"],
-                    traffic=tr.get("table_attn_kernel"), us_per_launch=us, launches=int(g_n),
-                    users_per_launch=g_seq / g_n, algorithmic_bytes_per_user=K1G_BYTES_PER_USER,
+    def gather_roof(kind, name, bytes_per_seq, traffic_key):
+        ms, n, seqs = kstat[kind]
+        if not (n > 0 and ms > 0):
+            return None
+        us = 1e3 * ms / n
+        ach = (seqs / n) * bytes_per_seq / (us * 1e-6) / 1e9
+        return dict(bound="hbm", kernel=name, achieved=ach, peak=peaks["hbm_gbs"], unit="GB/s", frac=ach / peaks["hbm_gbs"],
+                    traffic=tr.get(traffic_key), us_per_launch=us, launches=int(n), sequences_per_launch=seqs / n,
+                    algorithmic_bytes_per_sequence=bytes_per_seq,
                     peak_source=f"{peaks['source']} HBM copy bandwidth (burst); the projected table is partly "
                                 f"L2-resident, see traffic")
+
+    roof = gather_roof("k1g", "k1g::seq_attn_kernel<50> (user encoder: q|k|v row gather + 15-head attention)",
+                       K1G_BYTES_PER_USER, "table_attn_kernel")
+    if roof_news is None:       # the news encoder took the table path too: 20 token rows of the projected embedding table
+        roof_news = gather_roof("k1gn", "k1g::seq_attn_kernel<20> (news encoder: q|k|v row gather + 15-head attention)",
+                                20 * 1800 + 20 * 8 + 20 * 600, "seq_attn_kernel<20>")
     if roof is None:
         roof = tensor_roof("k1", "k1v6::encoder_attn_tc6_kernel<50,64,2> (user encoder: gather+QKV+attention)",
                            FLOP_PER_USER - 6_050_000, "encoder_attn_tc6_kernel<50,64,2>")
@@ -362,7 +368,7 @@ def main():
         news_tflops=stage_flops["news"] / (st.get("news", float("nan")) / 1e3) / 1e12,
         users_tflops=stage_flops["users"] / (st.get("users", float("nan")) / 1e3) / 1e12,
         metrics=dict(zip(("auc", "mrr", "ndcg5", "ndcg10"), means)),
-        roofline_news_k1=roof_news,
+        roofline_news=roof_news,
     )
 
     # ---- training step side measurement (BASELINE configs[2]: B=128, 1+4 candidates) ------------

@@ -575,7 +575,11 @@ int nrms_set_option(const char* key, int value) {
     return NRMS_OK;
   }
   if (strcmp(key, "k1g_variant") == 0) {
-    NRMS_CHECK_ARG(set_k1g_variant(value) == NRMS_OK, NRMS_E_INVALID, "k1g_variant must be 0 or 1");
+    NRMS_CHECK_ARG(set_k1g_variant(value) == NRMS_OK, NRMS_E_INVALID, "k1g_variant must be 0, 1 or 2");
+    return NRMS_OK;
+  }
+  if (strcmp(key, "news_table_attn") == 0) {
+    set_news_table_attn(value != 0);
     return NRMS_OK;
   }
   if (strcmp(key, "user_table_attn") == 0) {
@@ -594,9 +598,9 @@ double nrms_get_stat(const char* key) {
   if (!key) return -1.0;
   // "<kind>_ms" / "<kind>_launches" / "<kind>_sequences"; kind: k1 = user-encoder K1 (per-user projection),
   // k1n = news-encoder K1, k1g = user-encoder table attention
-  static const char* kinds[3] = {"k1_", "k1n_", "k1g_"};
+  static const char* kinds[4] = {"k1_", "k1n_", "k1g_", "k1gn_"};
   static const char* whats[3] = {"ms", "launches", "sequences"};
-  for (int k = 0; k < 3; ++k) {
+  for (int k = 3; k >= 0; --k) {          // longest prefix first (k1gn_ before k1g_, k1n_ before k1_)
     const size_t n = strlen(kinds[k]);
     if (strncmp(key, kinds[k], n) == 0)
       for (int w = 0; w < 3; ++w)

@@ -378,6 +378,186 @@ table_attn_kernel(const __half* __restrict__ table16, int n_table_rows, const in
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// The same kernel for any sequence length that fits the tiling (SEQ = 50 users' histories, SEQ = 20 title tokens):
+// head per warp, MT = ceil(SEQ/16) query tiles, NT = ceil(SEQ/8) key tiles (NT odd for both lengths: the last key tile
+// is the k8 step of O = P V), one stage = one sequence = SEQ rows of 2,160 B, as many stages as fit (2 / 5).
+// IdxT = int32 (history rows into the news-vector table) or int64 (token ids into the embedding table).
+// ---------------------------------------------------------------------------------------------------------------
+template <int SEQ>
+struct SeqCfg {
+  static constexpr int MT = (SEQ + 15) / 16;
+  static constexpr int NT = (SEQ + 7) / 8;
+  static constexpr int KS16 = NT / 2;                 // full k16 steps of O = P V; key tile NT-1 is the k8 step
+  static constexpr int REM = SEQ - 8 * (NT - 1);      // valid keys of the last key tile (2 / 4)
+  static constexpr int STAGE_BYTES = SEQ * PITCH;
+  static constexpr int NST = (SEQ == 50) ? 2 : 5;
+  static constexpr int BAR = NST * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = BAR + 16 * NST + 64;
+  static_assert((NT & 1) == 1 && REM % 2 == 0 && SEQ <= 64, "tiling of seq_attn_kernel");
+  static_assert(SMEM_BYTES <= 232448, "shared memory");
+};
+
+template <int SEQ, typename IdxT>
+__global__ void __launch_bounds__(THREADS, 1)
+seq_attn_kernel(const __half* __restrict__ table16, int64_t n_table_rows, const IdxT* __restrict__ seq_rows,
+                int64_t n_seq, __half* __restrict__ ctx) {
+  using Cfg = SeqCfg<SEQ>;
+  constexpr int MT = Cfg::MT, NT = Cfg::NT, KS16 = Cfg::KS16, NST = Cfg::NST, STG = Cfg::STAGE_BYTES;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sbase = tc::smem_u32(smem);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const uint32_t full_bar = sbase + Cfg::BAR, empty_bar = full_bar + 8 * NST;
+
+  if (tid == 0) {
+    for (int s = 0; s < NST; ++s) {
+      tc::mbar_init(full_bar + 8 * s, 1);
+      tc::mbar_init(empty_bar + 8 * s, H);
+    }
+    tc::mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == H) {
+    // ------------------------------ producer: one 2,160-byte bulk copy per row ------------------------------
+    uint32_t it = 0;
+    for (int64_t u = blockIdx.x; u < n_seq; u += gridDim.x, ++it) {
+      int64_t r0 = lane < SEQ ? (int64_t)seq_rows[u * SEQ + lane] : 0;
+      int64_t r1 = lane + 32 < SEQ ? (int64_t)seq_rows[u * SEQ + lane + 32] : 0;
+      r0 = r0 < 0 ? 0 : (r0 >= n_table_rows ? n_table_rows - 1 : r0);
+      r1 = r1 < 0 ? 0 : (r1 >= n_table_rows ? n_table_rows - 1 : r1);
+      const uint32_t st = it % NST;
+      tc::mbar_wait(empty_bar + 8 * st, ((it / NST) & 1) ^ 1);
+      if (lane == 0) mbar_arrive_expect_tx(full_bar + 8 * st, STG);
+      __syncwarp();
+      const uint32_t dst = sbase + st * STG + lane * PITCH;
+      if (lane < SEQ)
+        bulk_copy_g2s(dst, reinterpret_cast<const char*>(table16) + r0 * ROW_BYTES, PITCH, full_bar + 8 * st);
+      if (lane + 32 < SEQ)
+        bulk_copy_g2s(dst + 32 * PITCH, reinterpret_cast<const char*>(table16) + r1 * ROW_BYTES, PITCH, full_bar + 8 * st);
+    }
+  } else {
+    // ------------------------------ compute: warp = head ------------------------------
+    const int hg = warp / HG, hl = warp - hg * HG;
+    const int qoff = hg * GROUP + hl * SLICE, koff = OFF_K + qoff, voff = OFF_V + qoff;
+    const int g = lane >> 2, t = lane & 3;
+    const int mi = lane >> 3, rr = lane & 7;     // ldmatrix: this lane supplies row rr of matrix mi
+    // lane-constant byte offsets of the ldmatrix rows inside a stage (padded rows read the last real row: finite values,
+    // padded keys are masked out of P, padded query rows are never stored)
+    auto rofs = [](int row) { return (uint32_t)((row < SEQ ? row : SEQ - 1) * PITCH); };
+    constexpr int KP = (NT + 1) / 2, K8P = (NT + 3) / 4, VS = KS16 + 1;
+    uint32_t k16o[KP], k8o[K8P], v4o[VS], v2o[VS], q4o[MT], q2o[MT];
+#pragma unroll
+    for (int p = 0; p < KP; ++p) k16o[p] = rofs(16 * p + 8 * (mi >> 1) + rr) + koff + (mi & 1) * 16;
+#pragma unroll
+    for (int p = 0; p < K8P; ++p) k8o[p] = rofs(32 * p + 8 * mi + rr) + koff + 32;
+#pragma unroll
+    for (int p = 0; p < VS; ++p) {
+      v4o[p] = rofs(16 * p + 8 * (mi & 1) + rr) + voff + (mi >> 1) * 16;
+      v2o[p] = rofs(16 * p + 8 * (mi & 1) + rr) + voff + 32;
+    }
+#pragma unroll
+    for (int p = 0; p < MT; ++p) {
+      q4o[p] = rofs(16 * p + 8 * (mi & 1) + rr) + qoff + (mi >> 1) * 16;
+      q2o[p] = rofs(16 * p + 8 * (mi & 1) + rr) + qoff + 32;
+    }
+    uint32_t it = 0;
+    for (int64_t u = blockIdx.x; u < n_seq; u += gridDim.x, ++it) {
+      const uint32_t st = it % NST;
+      const uint32_t B = sbase + st * STG;
+      tc::mbar_wait(full_bar + 8 * st, (it / NST) & 1);
+      // K fragments: kb16[nt][0..1] (dims 0-7, 8-15), kb8[nt] (dims 16-23); V fragments (transposed loads):
+      // vb[ks][dt][0..1] = keys 16ks..+7 / +8..15, dims 8dt..8dt+7.  They stay in registers for the MT query tiles.
+      uint32_t kb16[2 * KP][2], kb8[4 * K8P], vb[VS][3][2];
+#pragma unroll
+      for (int p = 0; p < KP; ++p)
+        ldsm_x4(B + k16o[p], kb16[2 * p][0], kb16[2 * p][1], kb16[2 * p + 1][0], kb16[2 * p + 1][1]);
+#pragma unroll
+      for (int p = 0; p < K8P; ++p) ldsm_x4(B + k8o[p], kb8[4 * p], kb8[4 * p + 1], kb8[4 * p + 2], kb8[4 * p + 3]);
+#pragma unroll
+      for (int ks = 0; ks < VS; ++ks) {
+        ldsm_x4_t(B + v4o[ks], vb[ks][0][0], vb[ks][0][1], vb[ks][1][0], vb[ks][1][1]);
+        ldsm_x2_t(B + v2o[ks], vb[ks][2][0], vb[ks][2][1]);
+      }
+      auto scores = [&](int mt, float (&sacc)[NT][4]) {      // S = Q K^T of one 16-row query tile
+        uint32_t qa[4], qb[2];
+        ldsm_x4(B + q4o[mt], qa[0], qa[1], qa[2], qa[3]);
+        ldsm_x2(B + q2o[mt], qb[0], qb[1]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
+          mma_k16(sacc[nt], qa[0], qa[1], qa[2], qa[3], kb16[nt][0], kb16[nt][1]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_k8(sacc[nt], qb[0], qb[1], kb8[nt]);
+      };
+      float sacc[2][NT][4];
+      scores(0, sacc[0]);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        if (mt + 1 < MT) scores(mt + 1, sacc[(mt + 1) & 1]);
+        float (&sc)[NT][4] = sacc[mt & 1];
+        // P = 2^S (q carries log2(e)/sqrt(20)); the keys past SEQ in the last key tile are padding
+        uint32_t pa[NT][2];
+        const bool lower = mt + 1 < MT;              // rows 16mt+8..+15 exist only before the last tile
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          float p0 = ex2f(sc[nt][0]), p1 = ex2f(sc[nt][1]);
+          float p2 = 0.f, p3 = 0.f;
+          if (lower) { p2 = ex2f(sc[nt][2]); p3 = ex2f(sc[nt][3]); }
+          if (nt == NT - 1 && 2 * t >= Cfg::REM) { p0 = p1 = p2 = p3 = 0.f; }
+          pa[nt][0] = pack_h2(p0, p1);
+          pa[nt][1] = pack_h2(p2, p3);
+        }
+        float oacc[3][4];
+#pragma unroll
+        for (int dt = 0; dt < 3; ++dt) oacc[dt][0] = oacc[dt][1] = oacc[dt][2] = oacc[dt][3] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < KS16; ++ks)
+#pragma unroll
+          for (int dt = 0; dt < 3; ++dt)
+            mma_k16(oacc[dt], pa[2 * ks][0], pa[2 * ks][1], pa[2 * ks + 1][0], pa[2 * ks + 1][1], vb[ks][dt][0],
+                    vb[ks][dt][1]);
+#pragma unroll
+        for (int dt = 0; dt < 3; ++dt) mma_k8(oacc[dt], pa[NT - 1][0], pa[NT - 1][1], vb[KS16][dt][0]);
+        // Z of rows g / g+8 sits in column 20 = element 0 / 2 of dim tile 2 on the quad's lane t == 2
+        const float z0 = __shfl_sync(0xffffffffu, oacc[2][0], (lane & ~3) | 2);
+        const float z1 = __shfl_sync(0xffffffffu, oacc[2][2], (lane & ~3) | 2);
+        const float i0 = __fdividef(1.f, z0 + 1e-8f), i1 = __fdividef(1.f, z1 + 1e-8f);
+        // O / (Z + 1e-8) back in place over the head's q slice of these rows, then out as 8-byte pieces
+        const int r0 = 16 * mt + g, r1 = r0 + 8;
+        uint8_t* q0 = smem + st * STG + r0 * PITCH + qoff + 4 * t;
+#pragma unroll
+        for (int dt = 0; dt < 3; ++dt) {
+          if (dt < 2 || t < 2) {
+            if (r0 < SEQ) *reinterpret_cast<uint32_t*>(q0 + dt * 16) = pack_h2(oacc[dt][0] * i0, oacc[dt][1] * i0);
+            if (r1 < SEQ) *reinterpret_cast<uint32_t*>(q0 + 8 * PITCH + dt * 16) = pack_h2(oacc[dt][2] * i1, oacc[dt][3] * i1);
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int p = lane + 32 * k;                 // 80 pieces: 16 rows x 5 x 8 bytes
+          const int row = 16 * mt + p / 5, c = p % 5;
+          if (p < 80 && row < SEQ) {
+            const uint2 v = *reinterpret_cast<const uint2*>(smem + st * STG + row * PITCH + qoff + c * 8);
+            uint8_t* orow = reinterpret_cast<uint8_t*>(ctx) + (u * SEQ + row) * (CP * 2);
+            *reinterpret_cast<uint2*>(orow + warp * 40 + c * 8) = v;
+            // the last head's warp also clears columns 300..319 (K2 multiplies them by zero weights: they must be finite)
+            if (warp == H - 1) *reinterpret_cast<uint2*>(orow + 600 + c * 8) = make_uint2(0u, 0u);
+          }
+        }
+        if (mt == MT - 1) {          // last shared-memory access of this stage: hand it back to the producer
+          tc::fence_proxy_async_smem();      // the generic-proxy stores above precede the next bulk copy into these rows
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(empty_bar + 8 * st);
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Variant "u" (unit-parallel): 24 warps instead of 16.  The work unit is one (head, 16-row query tile) -- 60 per
 // user -- dealt round-robin to 23 compute warps; K, V and Q fragments are loaded per unit and live only for the phase
 // that uses them, so a thread needs <= 80 registers and six warps share a sub-partition's HMMA / MUFU / FMA pipes
@@ -547,16 +727,18 @@ int k1g_project_table(const float* table, int64_t n_rows, const float* wqkv, con
 }
 
 // Cbuf: fp16 context rows [n_users*50][320]; columns 300..319 are never written here (clear them once per buffer)
-// "k1g_variant" option: 0 = head per warp (16 warps), 1 = (head, query tile) units over 23 warps
+// "k1g_variant" option (user encoder): 0 = head per warp (16 warps, the first S = 50 kernel with its timing switches),
+// 1 = (head, query tile) units over 23 warps, 2 = the length-templated head-per-warp kernel (the one the news encoder uses)
 #ifndef K1G_DEFAULT_VARIANT
-#define K1G_DEFAULT_VARIANT 0
+#define K1G_DEFAULT_VARIANT 2
 #endif
 static int g_k1g_variant = K1G_DEFAULT_VARIANT;
 int set_k1g_variant(int v) {
-  if (v < 0 || v > 1) return NRMS_E_INVALID;
+  if (v < 0 || v > 2) return NRMS_E_INVALID;
   g_k1g_variant = v;
   return NRMS_OK;
 }
+int get_k1g_variant() { return g_k1g_variant; }
 
 int k1g_run(const void* table16, int64_t n_table_rows, const int32_t* hist_rows, int64_t n_users, void* Cbuf,
             cudaStream_t st) {
@@ -582,6 +764,37 @@ int k1g_run(const void* table16, int64_t n_table_rows, const int32_t* hist_rows,
                                                                   reinterpret_cast<__half*>(Cbuf));
   NRMS_LAUNCH_CHECK("table_attn_kernel");
   return NRMS_OK;
+}
+
+// The templated kernel: S = 50 (int32 history rows) or S = 20 (int64 token ids); same Cbuf contract as k1g_run
+template <int SEQ, typename IdxT>
+static int launch_seq_attn(const void* table16, int64_t n_table_rows, const void* rows, int64_t n_seq, void* Cbuf,
+                           cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k1g::seq_attn_kernel<SEQ, IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         k1g::SeqCfg<SEQ>::SMEM_BYTES);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(seq_attn_kernel)");
+    configured = true;
+  }
+  if (n_seq <= 0) return NRMS_OK;
+  NRMS_CHECK_ARG(n_table_rows > 0, NRMS_E_INVALID, "table row count out of range");
+  int grid = num_sms();
+  if (n_seq < grid) grid = (int)n_seq;
+  k1g::seq_attn_kernel<SEQ, IdxT><<<grid, k1g::THREADS, k1g::SeqCfg<SEQ>::SMEM_BYTES, st>>>(
+      reinterpret_cast<const __half*>(table16), n_table_rows, reinterpret_cast<const IdxT*>(rows), n_seq,
+      reinterpret_cast<__half*>(Cbuf));
+  NRMS_LAUNCH_CHECK("seq_attn_kernel");
+  return NRMS_OK;
+}
+
+int k1g_run_seq(int S, int idx_kind, const void* table16, int64_t n_table_rows, const void* rows, int64_t n_seq,
+                void* Cbuf, cudaStream_t st) {
+  if (S == 50 && idx_kind == 2) return launch_seq_attn<50, int32_t>(table16, n_table_rows, rows, n_seq, Cbuf, st);
+  if (S == 20 && idx_kind == 1) return launch_seq_attn<20, int64_t>(table16, n_table_rows, rows, n_seq, Cbuf, st);
+  if (S == 20 && idx_kind == 2) return launch_seq_attn<20, int32_t>(table16, n_table_rows, rows, n_seq, Cbuf, st);
+  set_error("seq_attn_kernel: unsupported (S, index kind) = (%d, %d)", S, idx_kind);
+  return NRMS_E_UNSUPPORTED;
 }
 
 }  // namespace nrms

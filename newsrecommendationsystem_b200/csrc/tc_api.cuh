@@ -35,10 +35,11 @@ int tc_encoder_fused(const float* src, int64_t n_src_rows, const void* idx, int 
 // fp16 operands (A16 [M, lda halfs], B16 [N, ldb halfs], 16-byte aligned rows), kind::f16, same fp16 epilogue (no bias)
 int tc_gemm_nt_f16(const void* A16, int64_t lda, const void* B16, int64_t ldb, void* C16, int64_t ldc, int64_t M, int N,
                    int K, float scale, int scale_cols, int qkv_layout, cudaStream_t st);
-int set_k1g_variant(int v);     // 0 = head per warp, 1 = (head, query tile) units over 23 warps
+int set_k1g_variant(int v);     // 0 = head per warp (S = 50 only), 1 = (head, query tile) units, 2 = length-templated kernel
+void set_news_table_attn(bool on);   // news encoder over the projected embedding table (default on)
 void set_table_attn(bool on);   // indexed user encoder: project the table once + K1g (default on)
 int set_k1_variant(int v);   // 1..6, see tc_fused.cu
 void set_time_k1(bool on);   // CUDA-event timing of the K1 launches (bench.py roofline)
-double get_k1_stat(int key); // 3 * kind (0 users K1, 1 news K1, 2 users K1g) + (0 total ms, 1 launches, 2 sequences)
+double get_k1_stat(int key); // 3 * kind (0 users K1, 1 news K1, 2 users K1g, 3 news K1g) + (0 total ms, 1 launches, 2 sequences)
 
 }  // namespace nrms

@@ -63,11 +63,14 @@ int k1v6_run(int S, const CUtensorMap& tw, const CUtensorMap& ts, const void* sr
 int k1g_project_table(const float* table, int64_t n_rows, const float* wqkv, const float* bqkv, void* table16,
                       cudaStream_t st);
 size_t k1g_table16_bytes(int64_t n_rows);
+int k1g_run_seq(int S, int idx_kind, const void* table16, int64_t n_table_rows, const void* rows, int64_t n_seq,
+                void* Cbuf, cudaStream_t st);
+int get_k1g_variant();
 int k1g_run(const void* table16, int64_t n_table_rows, const int32_t* hist_rows, int64_t n_users, void* Cbuf,
             cudaStream_t st);
 // "user_table_attn" option: 1 (default) = int32-indexed S=50 calls whose history rows outnumber the table rows 8:1
 // project the table once and run K1g; 0 = always the per-user projection of K1 v1..v6
-static int g_table_attn = -1;
+static int g_table_attn = -1, g_news_table_attn = -1;
 static bool table_attn_enabled() {
   if (g_table_attn < 0) {
     const char* e = getenv("NRMS_USER_TABLE_ATTN");
@@ -75,12 +78,25 @@ static bool table_attn_enabled() {
   }
   return g_table_attn != 0;
 }
+// "news_table_attn" option: the same trade for the news encoder -- project the EMBEDDING table once (70,976 rows against
+// 1.3 M token rows at MIND-small shapes) and run the attention on gathered q|k|v rows
+static bool news_table_attn_enabled() {
+  if (g_news_table_attn < 0) {
+    const char* e = getenv("NRMS_NEWS_TABLE_ATTN");
+    g_news_table_attn = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_news_table_attn != 0;
+}
 void set_table_attn(bool on) { g_table_attn = on ? 1 : 0; }
+void set_news_table_attn(bool on) { g_news_table_attn = on ? 1 : 0; }
 static bool use_table_attn(int S, int idx_kind, int64_t n_seq, int64_t n_src_rows) {
   // The projection costs 2.6 us per 1,000 table rows and every call (rank) pays it for the WHOLE table, and a table16
   // beyond L2 (126 MB = 58 k rows) turns the 2,160-byte row gather into DRAM traffic: measured 3.2 ms vs 4.4 ms (K1 v6)
   // at 56 history rows per table row, 4.4 vs ~4.8 ms at 28; the break-even is near 8.
-  return S == 50 && idx_kind == 2 && n_src_rows > 0 && table_attn_enabled() && n_seq * S >= 8 * n_src_rows;
+  if (n_src_rows <= 0 || n_seq * S < 8 * n_src_rows) return false;
+  if (S == 50) return idx_kind == 2 && table_attn_enabled();
+  if (S == 20) return (idx_kind == 1 || idx_kind == 2) && news_table_attn_enabled();
+  return false;
 }
 constexpr int K1_DEFAULT_VARIANT = 6;
 static int g_k1_variant = -1;
@@ -92,7 +108,8 @@ static int k1_variant() {
   return g_k1_variant;
 }
 // ---- optional live timing of the K1 launches (bench.py's roofline): CUDA events around every launch, kept per kind:
-//      0 = user encoder, per-user projection (K1 v1..v6), 1 = news encoder K1, 2 = user encoder, table attention (K1g)
+//      0 = user encoder, per-user projection (K1 v1..v6), 1 = news encoder K1, 2 = user encoder, table attention (K1g),
+//      3 = news encoder, table attention (K1g over the projected embedding table)
 static bool g_time_k1 = false;
 struct K1Record { cudaEvent_t a, b; int64_t seqs; int kind; };
 static std::vector<K1Record> g_k1_records;
@@ -621,7 +638,7 @@ static int64_t fused_chunk_seq() {          // full waves of tiles per launch; N
 // workspace: [fp16 W_qkv copy][fp16 W_a copy][fp16 gather source (variant 4)][context rows C of one chunk]
 static size_t fused_src16_bytes(int S, int idx_kind_dense, int64_t n_src_rows, int64_t chunk_rows) {
   size_t b = k1v4_src16_bytes(idx_kind_dense ? chunk_rows : n_src_rows);
-  if (!idx_kind_dense && S == 50) {            // room for the projected q|k|v table of K1g (1,800 B per row)
+  if (!idx_kind_dense) {                       // room for the projected q|k|v table of K1g (1,800 B per row)
     const size_t t = k1g_table16_bytes(n_src_rows);
     if (t > b) b = t;
   }
@@ -704,9 +721,13 @@ static int run_fused(const float* src, int64_t n_src_rows, const void* idx, int 
     if (int rc2 = k2v2_prepare(wa, wa16, &twa, st)) return rc2;
     if (table_attn) {
       if (int rc3 = k1g_project_table(src, n_src_rows, wqkv, bqkv, src16, st)) return rc3;
-      // K1g writes columns 0..299 of the fp16 context rows; K2 multiplies 300..319 by zero weights, so they must be finite
-      cudaError_t e = cudaMemset2DAsync(reinterpret_cast<char*>(Cbuf) + 600, 640, 0, 40, (size_t)first * S, st);
-      if (e != cudaSuccess) return cuda_fail(e, "cudaMemset2DAsync(context tail)");
+      // K1g variants 0 / 1 write only columns 0..299 of the fp16 context rows; K2 multiplies 300..319 by zero weights, so
+      // they must be finite.  (The templated kernel clears them itself: this strided memset -- 40 bytes in every 640,
+      // 470 k rows -- took ~0.4 ms on the copy engine.)
+      if (S == 50 && get_k1g_variant() != 2) {
+        cudaError_t e = cudaMemset2DAsync(reinterpret_cast<char*>(Cbuf) + 600, 640, 0, 40, (size_t)first * S, st);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMemset2DAsync(context tail)");
+      }
     } else if (variant >= 4 && idx_kind != 0) {
       NRMS_CHECK_ARG(n_src_rows > 0, NRMS_E_INVALID, "indexed input needs the row count of its source table");
       if (int rc3 = k1v4_pack_src(src, n_src_rows, src16, &ts, st)) return rc3;
@@ -732,9 +753,11 @@ static int run_fused(const float* src, int64_t n_src_rows, const void* idx, int 
         if (int rc = k1v4_pack_src(src_c, n * S, src16, &ts, st)) return rc;
       }
       {
-        K1Timer timer(st, n, S == 50 ? (table_attn ? 2 : 0) : 1);
+        K1Timer timer(st, n, S == 50 ? (table_attn ? 2 : 0) : (table_attn ? 3 : 1));
         int rc;
-        if (table_attn)
+        if (table_attn && (S != 50 || get_k1g_variant() == 2))
+          rc = k1g_run_seq(S, idx_kind, src16, n_src_rows, idx_c, n, Cbuf, st);
+        else if (table_attn)
           rc = k1g_run(src16, n_src_rows, reinterpret_cast<const int32_t*>(idx_c), n, Cbuf, st);
         else if (variant == 6)
           rc = k1v6_run(S, tw, ts, src16, idx_c, idx_kind, n, (int)(idx_kind == 0 ? n * S : n_src_rows), Cbuf, st);

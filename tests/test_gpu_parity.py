@@ -169,7 +169,7 @@ def _indexed_equals_dense(dev, golden_sd, precision):
     assert torch.equal(a, b)      # the in-library gather is a pure copy
 
 
-@pytest.mark.parametrize("k1g_variant", [0, 1])
+@pytest.mark.parametrize("k1g_variant", [0, 1, 2])
 @pytest.mark.parametrize("n_users,n_rows", [(1, 3), (13, 60), (67, 300), (200, 1000), (2500, 4001)])
 def test_user_encoder_table_attention_path(dev, lib, golden_sd, n_users, n_rows, k1g_variant):
     """K1g (tensor mode, indexed input): the table is projected once (q|k|v rows in fp16) and the attention runs on
@@ -186,7 +186,7 @@ def test_user_encoder_table_attention_path(dev, lib, golden_sd, n_users, n_rows,
     ref, _ = O.user_encoder_forward(golden_sd, table[rows])
     m = make_model(golden_sd, dev, "tf32")
     tb, ix = t(table, dev), t(rows.astype(np.int32), dev)
-    assert lib.nrms_set_option(b"k1g_variant", k1g_variant) == 0      # 0 = head per warp, 1 = (head, tile) units
+    assert lib.nrms_set_option(b"k1g_variant", k1g_variant) == 0      # 0 = head per warp, 1 = (head, tile) units, 2 = templated
     with torch.no_grad():
         try:
             a = m.user_encoder.forward_indexed(tb, ix)
@@ -194,10 +194,43 @@ def test_user_encoder_table_attention_path(dev, lib, golden_sd, n_users, n_rows,
             b = m.user_encoder.forward_indexed(tb, ix)
         finally:
             lib.nrms_set_option(b"user_table_attn", 1)
-            lib.nrms_set_option(b"k1g_variant", 0)
+            lib.nrms_set_option(b"k1g_variant", 2)
     assert rel_l2_rows(a.cpu().numpy(), ref) < TOL_VEC["tf32"]
     assert rel_l2_rows(b.cpu().numpy(), ref) < TOL_VEC["tf32"]
     assert not torch.equal(a, b)                          # two different kernels really ran
+    assert rel_l2_rows(a.cpu().numpy(), b.cpu().numpy().astype(np.float64)) < TOL_VEC["tf32"]
+
+
+@pytest.mark.parametrize("n_titles,num_words", [(2, 3), (37, 80), (777, 401), (6000, 2001)])
+def test_news_encoder_table_attention_path(dev, lib, golden_sd, n_titles, num_words):
+    """The news encoder over the projected EMBEDDING table (tensor mode, token rows >= 8 x vocabulary rows): same
+    vectors as the per-title projection (K1 v6) within the 1e-3 tolerance, vs the oracle and vs each other."""
+    from newsrecommendationsystem_b200 import synthetic
+    sd = dict(golden_sd)
+    rng = np.random.default_rng(num_words)
+    emb = rng.standard_normal((num_words, 300)).astype(np.float32)
+    emb[0] = 0
+    sd["news_encoder.word_embedding.weight"] = emb
+
+    class C2(Cfg):
+        pass
+    C2.num_words = num_words
+    toks = synthetic.make_news(n_titles, num_words=num_words, seed=n_titles)
+    if n_titles > 11:
+        toks[11] = 0                                        # an all-padding title
+    assert n_titles * 20 >= 8 * num_words
+    ref, _ = O.news_encoder_forward(sd, toks)
+    m = make_model(sd, dev, "tf32", cfg=C2)
+    with torch.no_grad():
+        a = m.get_news_vector({"title": torch.from_numpy(toks)})
+        lib.nrms_set_option(b"news_table_attn", 0)
+        try:
+            b = m.get_news_vector({"title": torch.from_numpy(toks)})
+        finally:
+            lib.nrms_set_option(b"news_table_attn", 1)
+    assert rel_l2_rows(a.cpu().numpy(), ref) < TOL_VEC["tf32"]
+    assert rel_l2_rows(b.cpu().numpy(), ref) < TOL_VEC["tf32"]
+    assert not torch.equal(a, b)                            # two different kernels really ran
     assert rel_l2_rows(a.cpu().numpy(), b.cpu().numpy().astype(np.float64)) < TOL_VEC["tf32"]
 
 
@@ -472,6 +505,7 @@ def test_fused_kernel_generations_agree_with_oracle(dev, lib, golden_sd, variant
     news and users."""
     from newsrecommendationsystem_b200 import synthetic
     assert lib.nrms_set_option(b"k1_variant", variant) == 0
+    lib.nrms_set_option(b"news_table_attn", 0)       # 777 titles over a 401-word vocabulary would take the table path
     try:
         m = make_model(golden_sd, dev, "tf32")
         toks = synthetic.make_news(777, num_words=Cfg.num_words, seed=500 + variant)
@@ -488,6 +522,7 @@ def test_fused_kernel_generations_agree_with_oracle(dev, lib, golden_sd, variant
         assert rel_l2_rows(uv.cpu().numpy(), ref_u) < TOL_VEC["tf32"]
     finally:
         lib.nrms_set_option(b"k1_variant", 6)
+        lib.nrms_set_option(b"news_table_attn", 1)
     assert lib.nrms_set_option(b"k1_variant", 9) == 1 and lib.nrms_set_option(b"nope", 1) == 1
 
 
