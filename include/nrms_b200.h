@@ -69,7 +69,10 @@ int64_t nrms_launch_count(void);
  *  6 [default] = 5 with two worker groups taking alternate passes).
  * "user_table_attn" (default 1): tensor-mode nrms_user_encoder_fwd calls with int32 row indices whose history
  *  rows outnumber the table rows 8:1 project the TABLE once (q|k|v in fp16) and run the attention on gathered rows
- *  (K1g, k1g_table_attn.cu) instead of projecting every gathered row; 0 = always the per-user projection. */
+ *  (K1g, k1g_table_attn.cu) instead of projecting every gathered row; 0 = always the per-user projection.
+ * "news_table_attn" (default 1): the same for nrms_news_encoder_fwd -- the EMBEDDING table is projected once per call
+ *  when the token rows outnumber the vocabulary rows 8:1.
+ * "k1g_variant" (default 2): 2 = length-templated kernel (both encoders), 0 / 1 = the first S = 50 kernels (A/B). */
 int nrms_set_option(const char* key, int value);
 /* "time_k1" = 1 brackets every fused K1 launch with CUDA events on the launching stream (clears the previous
  * record); nrms_get_stat("<kind>_ms" | "<kind>_launches" | "<kind>_sequences") reads the totals back (syncs on the

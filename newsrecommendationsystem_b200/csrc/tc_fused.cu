@@ -625,13 +625,15 @@ constexpr size_t W16_BYTES = (size_t)D3 * W16_LD * 2;   // 576,000 (a multiple o
 // host
 // ---------------------------------------------------------------------------------------------------
 template <int S, int SPT>
-static int64_t fused_chunk_seq() {          // full waves of tiles per launch; NRMS_FUSED_WAVES to experiment
-  // Measured on the evaluate bench (K1 v6 / K1g + K2): 4 waves 5.9 ms of encoder time, 8 waves 5.3, 16 waves 4.97,
-  // 32 waves 4.92 (news 1.61 vs 1.66 ms at 16; users equal): every launch pays the K2 prologue (W_a into shared
-  // memory), the pipeline fill and a tail.  Users stay at 16 so the fp16 context chunk (152 MB) is still mostly
-  // L2-resident between K1 and K2.
-  static int waves = 0;
-  if (!waves) { const char* e = getenv("NRMS_FUSED_WAVES"); waves = e ? atoi(e) : (S == 20 ? 32 : 16); if (waves < 1) waves = 8; }
+static int64_t fused_chunk_seq(bool table_attn) {   // full waves of tiles per launch; NRMS_FUSED_WAVES to experiment
+  // Measured on the evaluate bench.  K1 v6 + K2: 4 waves 5.9 ms of encoder time, 8 waves 5.3, 16 waves 4.97, 32 waves
+  // 4.92 (news 1.61 vs 1.66 ms at 16; users equal): every launch pays the K2 prologue (W_a into shared memory), the
+  // pipeline fill and a tail; users stay at 16 so the fp16 context chunk (152 MB) is still mostly L2-resident between
+  // K1 and K2.  Table path (K1g + K2): monotonic -- users 3.28 ms at 8 waves, 2.92 at 16, 2.73 at 32, 2.63 at 64, 2.60 in
+  // one launch; news 1.50 / 1.35 / 1.30 / 1.25 / 1.24 -- so 64 waves (1.1 GB of context rows).
+  static int env_waves = -1;
+  if (env_waves < 0) { const char* e = getenv("NRMS_FUSED_WAVES"); env_waves = e ? atoi(e) : 0; if (env_waves < 0) env_waves = 0; }
+  const int waves = env_waves ? env_waves : (table_attn ? 64 : (S == 20 ? 32 : 16));
   return (int64_t)num_sms() * SPT * waves;
 }
 
@@ -703,7 +705,7 @@ static int run_fused(const float* src, int64_t n_src_rows, const void* idx, int 
   const bool table_attn = use_table_attn(S, idx_kind, n_seq, n_src_rows);
   if (table_attn && variant < 2) variant = K1_DEFAULT_VARIANT;
   // every variant tiles 5 titles / 2 users, so the chunking (whole waves of tiles) is shared
-  const int64_t chunk = fused_chunk_seq<S, SPT>();
+  const int64_t chunk = fused_chunk_seq<S, SPT>(table_attn);
   const int64_t first = n_seq < chunk ? n_seq : chunk;
   const size_t src16_bytes = fused_src16_bytes(S, idx_kind == 0, n_src_rows, first * S);
   const size_t need = W16_SLOT_BYTES + WA16_SLOT_BYTES + src16_bytes + (size_t)first * S * D * sizeof(float);
@@ -795,9 +797,11 @@ static int run_fused(const float* src, int64_t n_src_rows, const void* idx, int 
 // n_src_rows: rows of the gather source (vocabulary / news-vector table); 0 for dense input
 size_t tc_fused_workspace_bytes(int64_t n_seq, int S, int64_t n_src_rows) {
   if (n_seq <= 0) return (size_t)-1;
+  // sized for the larger launches of the table path whenever the call is big enough to take it (whatever the options say)
+  const bool may_table = n_src_rows > 0 && n_seq * S >= 8 * n_src_rows;
   int64_t chunk;
-  if (S == 20) chunk = fused_chunk_seq<20, 5>();
-  else if (S == 50) chunk = fused_chunk_seq<50, 2>();
+  if (S == 20) chunk = fused_chunk_seq<20, 5>(may_table);
+  else if (S == 50) chunk = fused_chunk_seq<50, 2>(may_table);
   else return (size_t)-1;
   const int64_t first = n_seq < chunk ? n_seq : chunk;
   return W16_SLOT_BYTES + WA16_SLOT_BYTES + fused_src16_bytes(S, n_src_rows <= 0, n_src_rows, first * S) +
