@@ -342,7 +342,7 @@ def main():
                                 f"L2-resident, see traffic")
 
     roof = gather_roof("k1g", "k1g::seq_attn_kernel<50> (user encoder: q|k|v row gather + 15-head attention)",
-                       K1G_BYTES_PER_USER, "table_attn_kernel")
+                       K1G_BYTES_PER_USER, "seq_attn_kernel<50>")
     if roof_news is None:       # the news encoder took the table path too: 20 token rows of the projected embedding table
         roof_news = gather_roof("k1gn", "k1g::seq_attn_kernel<20> (news encoder: q|k|v row gather + 15-head attention)",
                                 20 * 1800 + 20 * 8 + 20 * 600, "seq_attn_kernel<20>")
