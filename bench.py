@@ -243,6 +243,7 @@ def main():
         torch.cuda.synchronize()
 
     stage_ms = {}
+    h2d_bytes = [host.nbytes()]
 
     def timed_eval(resident, record_stages=False):
         marks = []
@@ -256,6 +257,7 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         inp = resident if resident is not None else EvalInputs.from_host(host, dev)
+        h2d_bytes[0] = inp.h2d_bytes
         means = evaluate_tensors(model, inp, mark=mark if record_stages else None)   # ends with the D2H of 8 doubles
         e1.record()
         torch.cuda.synchronize()
@@ -406,7 +408,7 @@ def main():
                     vs_baseline=None, dtype="f16xf16->f32 (tcgen05 kind::f16; TF32-equivalent 11-bit significand)"
                     if args.precision == "tf32" else "f32", data="synthetic",
                     config=workload_config(world, args.precision, args.workload), clocks=clocks,
-                    e2e=dict(value=e2e_value, unit="impressions/s", h2d_bytes_per_step=host.nbytes(),
+                    e2e=dict(value=e2e_value, unit="impressions/s", h2d_bytes_per_step=int(h2d_bytes[0]),
                              d2h_bytes_per_step=64, ms_per_step=e2e_ms / args.steps),
                     gpu_launches=launches, roofline=roof, cpu_baseline=cpu, train=train, **extras)
         print(json.dumps(line), flush=True)

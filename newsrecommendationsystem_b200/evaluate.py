@@ -106,20 +106,35 @@ class EvalInputs:
         self._fill(EvalHost(news_tokens, hist_rows, cand_offsets, cand_rows, labels, news_ids), device)
 
     @classmethod
-    def from_host(cls, host: EvalHost, device="cuda"):
+    def from_host(cls, host: EvalHost, device="cuda", shard=True):
+        """`shard` (multi-rank only): copy just this rank's block of impressions (the block evaluate_tensors assigns it
+        when `max_count` is None) instead of all of them -- the host-to-device traffic per rank stays constant as ranks
+        are added."""
         self = cls.__new__(cls)
-        self._fill(host, device)
+        self._fill(host, device, shard)
         return self
 
-    def _fill(self, host, device):
+    def _fill(self, host, device, shard=False):
         self.device = torch.device(device)
         self.n_news, self.n_impressions = host.n_news, host.n_impressions
         self.cand_offsets_host = host.cand_offsets_host
         self._ready = None
-        rest = ("hist_rows", "cand_rows", "cand_offsets", "labels")
+        self.shard = None                # (lo, hi, c0, c1): the tensors below hold only impressions [lo, hi)
+        dist = _dist()
+        views = dict(hist_rows=host.hist_rows, cand_rows=host.cand_rows, cand_offsets=host.cand_offsets, labels=host.labels)
+        if shard and dist is not None:
+            bounds = shard_impressions_by_candidates(host.cand_offsets_host, dist.get_world_size())
+            lo, hi = int(bounds[dist.get_rank()]), int(bounds[dist.get_rank() + 1])
+            c0, c1 = int(host.cand_offsets_host[lo]), int(host.cand_offsets_host[hi])
+            self.shard = (lo, hi, c0, c1)
+            views = dict(hist_rows=host.hist_rows[lo:hi], cand_rows=host.cand_rows[c0:c1],
+                         cand_offsets=host.cand_offsets[lo:hi + 1], labels=host.labels[c0:c1])
+        self.h2d_bytes = host.news_tokens.numel() * host.news_tokens.element_size() + \
+            sum(v.numel() * v.element_size() for v in views.values())
         if self.device.type != "cuda":
-            for name in ("news_tokens",) + rest:
-                setattr(self, name, getattr(host, name).to(self.device))
+            self.news_tokens = host.news_tokens.to(self.device)
+            for name, v in views.items():
+                setattr(self, name, v.to(self.device))
             return
         # The news stage needs only the token table: it goes first on the caller's stream; the impression tables
         # follow on a copy stream and overlap the news encoders (evaluate_tensors waits on the event before stage B).
@@ -128,8 +143,8 @@ class EvalInputs:
         side = _copy_stream(self.device)
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            for name in rest:
-                t = getattr(host, name).to(self.device, non_blocking=True)
+            for name, v in views.items():
+                t = v.to(self.device, non_blocking=True)
                 t.record_stream(main)
                 setattr(self, name, t)
             self._ready = torch.cuda.Event()
@@ -152,14 +167,10 @@ def _copy_stream(device):
     return _copy_streams[key]
 
 
-NEWS_GATHER_BLOCKS = 3      # sub-blocks of a rank's news shard whose all-gathers overlap the encoding of the next one
-
-
 @torch.no_grad()
 def encode_news_table(model, news_tokens: torch.Tensor) -> torch.Tensor:
     """Stage A.  Returns [N_news+1, 300] with a zero last row.  Multi-rank: each rank encodes its
-    contiguous row block straight into its slot of the (padded) table; the slots are all-gathered in
-    NEWS_GATHER_BLOCKS pieces, each exchange overlapping the encoding of the next piece."""
+    contiguous row block straight into its slot of the (padded) table, then one all_gather."""
     dist = _dist()
     n = news_tokens.shape[0]
     dev = news_tokens.device
@@ -175,21 +186,13 @@ def encode_news_table(model, news_tokens: torch.Tensor) -> torch.Tensor:
         per = (n + world - 1) // world
         padded = torch.zeros((world * per + 1, ops.D), dtype=torch.float32, device=dev)
         lo, hi = shard_range(n, rank, world)
-        # The shard is encoded in NEWS_GATHER_BLOCKS sub-blocks; the all-gather of sub-block j runs (async, on the
-        # process group's stream) while sub-block j+1 is being encoded, so only the last exchange is exposed.
-        sub = (per + NEWS_GATHER_BLOCKS - 1) // NEWS_GATHER_BLOCKS
-        works = []
-        for j in range(NEWS_GATHER_BLOCKS):
-            b0, b1 = j * sub, min((j + 1) * sub, per)          # offsets inside every rank's slot of `per` rows
-            if b1 <= b0:
-                break
-            r0, r1 = min(lo + b0, hi), min(lo + b1, hi)        # rows past the shard stay zero (padding of the last rank)
-            if r1 > r0:
-                padded[r0:r1] = model.get_news_vector({"title": news_tokens[r0:r1]})
-            outs = [padded[r * per + b0:r * per + b1] for r in range(world)]
-            works.append(dist.all_gather(outs, padded[rank * per + b0:rank * per + b1].clone(), async_op=True))
-        for w in works:
-            w.wait()
+        # One encoder call per shard (the table path of the news encoder projects the embedding table once per CALL, and
+        # needs >= 8 token rows per vocabulary row to be selected: splitting the shard to overlap the exchange with the
+        # encoding cost more than the exchange itself -- measured at 2 GPUs: news 1.97 ms in three pieces), then one
+        # all-gather of equal padded slots.
+        if hi > lo:
+            padded[lo:hi] = model.get_news_vector({"title": news_tokens[lo:hi]})
+        dist.all_gather_into_tensor(padded[:world * per].view(-1), padded[rank * per:(rank + 1) * per].reshape(-1).clone())
         table = padded[:n + 1]
         table[n].zero_()
         return table
@@ -225,17 +228,27 @@ def evaluate_tensors(model, inputs: EvalInputs, max_count=None, return_details=F
         lo, hi = int(bounds[dist.get_rank()]), int(bounds[dist.get_rank() + 1])
     dev = inputs.device
     if hi > lo:
-        user_vec = model.user_encoder.forward_indexed(table, inputs.hist_rows[lo:hi])
-        mark("users")
         c0, c1 = int(inputs.cand_offsets_host[lo]), int(inputs.cand_offsets_host[hi])
-        offs = (inputs.cand_offsets[lo:hi + 1] - c0).contiguous()
+        shard = getattr(inputs, "shard", None)
+        if shard is not None:            # the inputs hold only this rank's block: index relative to it
+            if (lo, hi) != shard[:2]:
+                raise RuntimeError(f"inputs were sharded for impressions {shard[:2]} but this call needs {(lo, hi)} "
+                                   "(max_count or a different world size): build them with from_host(..., shard=False)")
+            hist = inputs.hist_rows
+            cand_rows, labels, offs = inputs.cand_rows, inputs.labels, (inputs.cand_offsets - c0).contiguous()
+        else:
+            hist = inputs.hist_rows[lo:hi]
+            cand_rows, labels = inputs.cand_rows[c0:c1], inputs.labels[c0:c1]
+            offs = (inputs.cand_offsets[lo:hi + 1] - c0).contiguous()
+        user_vec = model.user_encoder.forward_indexed(table, hist)
+        mark("users")
         if _tensor_mode(model):
             # tensor mode: candidates are read from an fp16 copy of the table (half the bytes, fp32 accumulation)
-            scores = ops.score_csr_f16(ops.pack_rows_f16(table), inputs.cand_rows[c0:c1], offs, user_vec)
+            scores = ops.score_csr_f16(ops.pack_rows_f16(table), cand_rows, offs, user_vec)
         else:
-            scores = ops.score_csr(table, inputs.cand_rows[c0:c1], offs, user_vec)
+            scores = ops.score_csr(table, cand_rows, offs, user_vec)
         mark("score")
-        per, sums = ops.rank_metrics(scores, inputs.labels[c0:c1], offs)
+        per, sums = ops.rank_metrics(scores, labels, offs)
         mark("metrics")
     else:
         user_vec = torch.empty((0, ops.D), device=dev)

@@ -84,6 +84,13 @@ def _eval_worker(rank, world, port, q):
         imp = synthetic.make_impressions(23, 61, seed=3, single_class_every=5, max_cand=25)
         inp = E.EvalInputs(ntok, imp["hist_rows"], imp["cand_offsets"], imp["cand_rows"], imp["labels"], device="cpu")
         means, det = E.evaluate_tensors(_StubModel(sd), inp, return_details=True)
+        # inputs that carry only this rank's block of impressions (what bench.py's e2e leg copies) give the same answer
+        host = E.EvalHost(ntok, imp["hist_rows"], imp["cand_offsets"], imp["cand_rows"], imp["labels"])
+        inp2 = E.EvalInputs.from_host(host, "cpu", shard=True)
+        lo, hi = det["impression_range"]
+        assert inp2.shard[:2] == (lo, hi) and inp2.hist_rows.shape[0] == hi - lo and inp2.h2d_bytes < host.nbytes()
+        means2 = E.evaluate_tensors(_StubModel(sd), inp2)
+        np.testing.assert_allclose(means2, means, rtol=1e-12)
         q.put((rank, means, det["table"].numpy().copy(), det["impression_range"]))
     finally:
         dist.destroy_process_group()
