@@ -129,17 +129,21 @@ class EvalInputs:
             self.shard = (lo, hi, c0, c1)
             views = dict(hist_rows=host.hist_rows[lo:hi], cand_rows=host.cand_rows[c0:c1],
                          cand_offsets=host.cand_offsets[lo:hi + 1], labels=host.labels[c0:c1])
-        self.h2d_bytes = host.news_tokens.numel() * host.news_tokens.element_size() + \
-            sum(v.numel() * v.element_size() for v in views.values())
+        tokens = host.news_tokens
+        self.news_shard = None           # (lo, hi): news_tokens holds only the rows this rank encodes
+        if shard and dist is not None:
+            self.news_shard = shard_range(host.n_news, dist.get_rank(), dist.get_world_size())
+            tokens = tokens[self.news_shard[0]:self.news_shard[1]]
+        self.h2d_bytes = tokens.numel() * tokens.element_size() + sum(v.numel() * v.element_size() for v in views.values())
         if self.device.type != "cuda":
-            self.news_tokens = host.news_tokens.to(self.device)
+            self.news_tokens = tokens.to(self.device)
             for name, v in views.items():
                 setattr(self, name, v.to(self.device))
             return
         # The news stage needs only the token table: it goes first on the caller's stream; the impression tables
         # follow on a copy stream and overlap the news encoders (evaluate_tensors waits on the event before stage B).
         main = torch.cuda.current_stream(self.device)
-        self.news_tokens = host.news_tokens.to(self.device, non_blocking=True)
+        self.news_tokens = tokens.to(self.device, non_blocking=True)
         side = _copy_stream(self.device)
         side.wait_stream(main)
         with torch.cuda.stream(side):
@@ -168,11 +172,11 @@ def _copy_stream(device):
 
 
 @torch.no_grad()
-def encode_news_table(model, news_tokens: torch.Tensor) -> torch.Tensor:
+def encode_news_table(model, news_tokens: torch.Tensor, n_news=None, local_shard=None) -> torch.Tensor:
     """Stage A.  Returns [N_news+1, 300] with a zero last row.  Multi-rank: each rank encodes its
     contiguous row block straight into its slot of the (padded) table, then one all_gather."""
     dist = _dist()
-    n = news_tokens.shape[0]
+    n = news_tokens.shape[0] if n_news is None else int(n_news)      # `local_shard`: news_tokens = rows [lo, hi) only
     dev = news_tokens.device
     was_training = model.training
     model.eval()
@@ -190,8 +194,10 @@ def encode_news_table(model, news_tokens: torch.Tensor) -> torch.Tensor:
         # needs >= 8 token rows per vocabulary row to be selected: splitting the shard to overlap the exchange with the
         # encoding cost more than the exchange itself -- measured at 2 GPUs: news 1.97 ms in three pieces), then one
         # all-gather of equal padded slots.
+        if local_shard is not None and tuple(local_shard) != (lo, hi):
+            raise RuntimeError(f"token rows were sharded for {tuple(local_shard)} but this rank encodes {(lo, hi)}")
         if hi > lo:
-            padded[lo:hi] = model.get_news_vector({"title": news_tokens[lo:hi]})
+            padded[lo:hi] = model.get_news_vector({"title": news_tokens if local_shard is not None else news_tokens[lo:hi]})
         dist.all_gather_into_tensor(padded[:world * per].view(-1), padded[rank * per:(rank + 1) * per].reshape(-1).clone())
         table = padded[:n + 1]
         table[n].zero_()
@@ -216,7 +222,7 @@ def evaluate_tensors(model, inputs: EvalInputs, max_count=None, return_details=F
     dist = _dist()
     mark = mark or (lambda name: None)
     mark("start")
-    table = encode_news_table(model, inputs.news_tokens)
+    table = encode_news_table(model, inputs.news_tokens, inputs.n_news, getattr(inputs, "news_shard", None))
     mark("news")
     inputs.wait_ready()
     n_imp = inputs.n_impressions
