@@ -178,31 +178,50 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           // C is a __half matrix (ldc in halfs, rows 8-byte aligned): (acc + bias) * (n < f16_scale_cols ? f16_scale : 1)
           if (m < M) {
             __half* crow = reinterpret_cast<__half*>(C) + m * ldc;
+            uint2 pk[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int n = n0 + col + 4 * j;
-              if (n < N) {
-                float4 r = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-                if (add_bias) {
-                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
-                  r = make_float4(r.x + b4.x, r.y + b4.y, r.z + b4.z, r.w + b4.w);
-                }
-                const float sc = n < f16_scale_cols ? f16_scale : 1.f;
-                const __half2 lo = __floats2half2_rn(r.x * sc, r.y * sc), hi = __floats2half2_rn(r.z * sc, r.w * sc);
-                uint2 pk;
-                pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-                pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-                if (epi == TC_EPI_STORE_F16_QKV) {
-                  // K1g table row: [head group][q | k | v][5 heads][24 halfs]; column n = which*300 + head*20 + d.
-                  // The 4-half pad of every head slice is written with its last group: 0 (q, k) or (1,0,0,0) (v).
-                  const int which = n / 300, hd = n - which * 300, head = hd / 20, d = hd - head * 20;
-                  const int hgi = head / 5, hl = head - hgi * 5;
-                  __half* dst = crow + hgi * 360 + which * 120 + hl * 24 + d;
-                  *reinterpret_cast<uint2*>(dst) = pk;
-                  if (d == 16) *reinterpret_cast<uint2*>(dst + 4) = make_uint2(which == 2 ? 0x00003C00u : 0u, 0u);
+              float4 r = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+              if (add_bias && n < N) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+                r = make_float4(r.x + b4.x, r.y + b4.y, r.z + b4.z, r.w + b4.w);
+              }
+              const float sc = n < f16_scale_cols ? f16_scale : 1.f;
+              const __half2 lo = __floats2half2_rn(r.x * sc, r.y * sc), hi = __floats2half2_rn(r.z * sc, r.w * sc);
+              pk[j].x = *reinterpret_cast<const uint32_t*>(&lo);
+              pk[j].y = *reinterpret_cast<const uint32_t*>(&hi);
+            }
+            if (epi == TC_EPI_STORE_F16_QKV) {
+              // K1g table row: [head group][q | k | v][5 heads][24 halfs]; column n = which*300 + head*20 + d.
+              // The 4-half pad of every head slice goes with its last group: 0 (q, k) or (1,0,0,0) (v).  Groups that
+              // are neighbours inside a slice (d = 0|4, 8|12, 16|pad) leave as ONE 16-byte store: the epilogue is
+              // bound by the number of store requests (32 rows per warp instruction), not by bytes.
+              bool merged = false;           // group j already left with group j-1
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int n = n0 + col + 4 * j;
+                const bool skip = merged || n >= N;
+                merged = false;
+                if (skip) continue;
+                const int which = n / 300, hd = n - which * 300, head = hd / 20, d = hd - head * 20;
+                const int hgi = head / 5, hl = head - hgi * 5;
+                __half* dst = crow + hgi * 360 + which * 120 + hl * 24 + d;
+                const uint2 nxt = pk[j < 3 ? j + 1 : 3];
+                if (d == 16) {
+                  *reinterpret_cast<uint4*>(dst) = make_uint4(pk[j].x, pk[j].y, which == 2 ? 0x00003C00u : 0u, 0u);
+                } else if ((d == 0 || d == 8) && j < 3 && n + 4 < N) {
+                  *reinterpret_cast<uint4*>(dst) = make_uint4(pk[j].x, pk[j].y, nxt.x, nxt.y);
+                  merged = true;
                 } else {
-                  *reinterpret_cast<uint2*>(crow + n) = pk;
+                  *reinterpret_cast<uint2*>(dst) = pk[j];
                 }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int n = n0 + col + 4 * j;
+                if (n < N) *reinterpret_cast<uint2*>(crow + n) = pk[j];
               }
             }
           }
