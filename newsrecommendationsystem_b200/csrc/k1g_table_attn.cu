@@ -1,29 +1,34 @@
-// K1g -- user-encoder self-attention over PRE-PROJECTED news rows (evaluate path, indexed input).
+// K1g -- encoder self-attention over PRE-PROJECTED table rows (tensor-mode inference, indexed input).
 //
-// The user encoder's Q/K/V projections are row-wise linear maps of the gathered news vectors
-// (reference: src/model/general/attention/multihead_self.py:53-58 applied to the rows stacked at
-// src/evaluate.py:220-224), and every row comes from the same news-vector table.  Projecting the TABLE once
-// (one [n_rows, 900] GEMM, tc_gemm_nt_f16out) and gathering q, k, v per history row gives the same numbers
-// with 1/56 of the projection work at MIND-small shapes (65 k table rows against 3.66 M history rows); what
-// remains per user is 15 heads x (50 x 50 x 20) of attention on gathered rows: an L2 / MUFU-bound kernel,
-// not a tensor-pipe-bound one.
+// The Q/K/V projections of both encoders are row-wise linear maps of GATHERED rows (reference:
+// src/model/general/attention/multihead_self.py:53-58 applied to the news vectors stacked at src/evaluate.py:220-224,
+// and to the embedding rows of src/model/NRMS/news_encoder.py:38), and every row comes from one table.  Projecting the
+// TABLE once per call (one [n_rows, 900] kind::f16 GEMM, k1g_project_table) and gathering q, k, v per row gives the same
+// numbers with 1/56 (users: 65 k table rows against 3.66 M history rows) or 1/18 (news: 71 k vocabulary rows against
+// 1.3 M token rows) of the projection work at MIND-small shapes.  What remains per sequence is 15 heads of S x S x 20
+// attention on gathered rows.
 //
 //   table16 : [n_rows][3 head groups][q | k | v][5 heads][24 halfs] = 2,160 B per row; q pre-scaled by
 //             log2(e)/sqrt(20), bias included, every 20-half head slice padded to 48 B (pad = 0 for q and k,
 //             (1, 0, 0, 0) for v: the context MMA then also returns Z = sum_j P_ij in column 20)
-//   stage   : one (user, head group) = 50 rows x 720 B, copied row by row with cp.async.bulk (one 720-byte bulk
-//             copy per history row, completion on the stage's mbarrier); 6 stages = two users in flight.
-//             The 720-byte pitch keeps every ldmatrix (8 rows x 16 B) bank-conflict free.
-//   warp 15 : producer (history indices -> bulk copies), runs up to six stages ahead
-//   warp w  : head w (w = 0..14; head group w / 5), FA2-style on mma.sync m16n8k16/k8 (fp16 in, fp32
-//             accumulate): K and V fragments of the head stay in registers for its four 16-row query tiles;
-//             S = Q K^T -> P = 2^S (ex2.approx) -> fp16 A fragments in registers -> O = P V -> O / (Z + 1e-8)
-//             (exp without max subtraction and the 1e-8 of multihead_self.py:17-20) -> fp16 context rows
-//             [50][300] (+ 20 zero columns, cleared once by the host), the layout K2 reads.
+//   stage   : one sequence = S rows x 2,160 B, one cp.async.bulk per row (completion on the stage's mbarrier);
+//             2 stages for S = 50, 5 for S = 20.  The 2,160-byte pitch keeps every ldmatrix (8 rows x 16 B)
+//             bank-conflict free.  (Six 36 KB head-group stages fed by 720-byte copies were tried first: bulk copies
+//             cost ~75 cycles each whatever their size.)
+//   warp 15 : producer (row indices -> bulk copies)
+//   warp w  : head w (w = 0..14), FA2-style on mma.sync m16n8k16/k8 (fp16 in, fp32 accumulate): K and V fragments
+//             of the head stay in registers for its 16-row query tiles; S = Q K^T -> P = 2^S (ex2.approx) -> fp16 A
+//             fragments in registers -> O = P V -> O / (Z + 1e-8) (exp without max subtraction and the 1e-8 of
+//             multihead_self.py:17-20) -> staged in place over the head's q slice -> fp16 context rows [S][300]
+//             (+ 20 zero columns), the layout K2 reads.
 //
-// The tensor work here is ~3 MFLOP per user on tiles of 16 x 8: warp-level mma.sync is the right granularity
-// (a 128-row tcgen05 tile would be 61 % padding, see K1 v6), and the kernel is bound by the row gather and
-// the exponentials, not by the MMA rate.
+// The tensor work here is ~3 MFLOP per user on tiles of 16 x 8: warp-level mma.sync is the right granularity (a 128-row
+// tcgen05 tile would be 61 % padding, see K1 v6).  Measured: the kernel is bound by instruction issue first and the
+// HMMA pipe second; legacy HMMA runs at 8 cycles per instruction and sub-partition on B200.
+//
+// Kernels in this file: seq_attn_kernel<SEQ, IdxT> (the product path, both encoders); table_attn_kernel (the first
+// S = 50 form, kept with its timing switches K1G_DBG_* as "k1g_variant" 0) and table_attn_units_kernel (24 warps, one
+// (head, query tile) per unit, "k1g_variant" 1: measured slower) for A/B runs.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include "tc_common.cuh"
