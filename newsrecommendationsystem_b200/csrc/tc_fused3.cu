@@ -149,6 +149,8 @@ additive_pool_f16_kernel(const __grid_constant__ CUtensorMap tmap_c, const __gri
     const int q4 = warp & 3;
     const int row = q4 * 32 + lane;
     const bool row_ok = row < ROWS;
+    float qa_l1 = 0.f;                       // bound of |s|: sum of |attention_query_vector| (qa_s is padded with zeros)
+    for (int j = 0; j < 208; ++j) qa_l1 += fabsf(qa_s[j]);
     uint32_t tile_it = 0;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++tile_it) {
       const uint32_t as = tile_it & 1;
@@ -176,16 +178,34 @@ additive_pool_f16_kernel(const __grid_constant__ CUtensorMap tmap_c, const __gri
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar + 8 * as);
       mbar_wait(wv_free + 8 * as, ((tile_it >> 1) & 1) ^ 1);   // the pool warps are done with this buffer
-      sc[as * 128 + row] = s;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (row_ok) {
-        const int sq = row / S;
-        const float* scs = sc + as * 128 + sq * S;
-        float m = -INFINITY;
-        for (int j = 0; j < S; ++j) m = fmaxf(m, scs[j]);
-        float sum = 0.f;
-        for (int j = 0; j < S; ++j) sum += __expf(scs[j] - m);
-        wv[as * 128 + row] = __fdividef(__expf(s - m), sum);
+      // softmax over the sequence.  |s_i| <= sum_j |q_j| =: L1 because |tanh| <= 1, so exp(s_i - L1) can neither
+      // overflow nor (for L1 <= 40) underflow: every row takes ONE exponential and the 50-element scan is a plain sum,
+      // instead of a max scan plus 50 exponentials per row on the critical path of the score warps.  Softmax is
+      // shift-invariant, so this is the reference's stable softmax (additive.py:37-39) up to fp32 rounding; a query
+      // vector with L1 > 40 keeps the max-subtracting form.
+      if (qa_l1 <= 40.f) {
+        sc[as * 128 + row] = __expf(s - qa_l1);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (row_ok) {
+          const int sq = row / S;
+          const float* scs = sc + as * 128 + sq * S;
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll 5
+          for (int j = 0; j < S; j += 2) { s0 += scs[j]; s1 += scs[j + 1]; }
+          wv[as * 128 + row] = __fdividef(sc[as * 128 + row], s0 + s1);
+        }
+      } else {
+        sc[as * 128 + row] = s;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (row_ok) {
+          const int sq = row / S;
+          const float* scs = sc + as * 128 + sq * S;
+          float m = -INFINITY;
+          for (int j = 0; j < S; ++j) m = fmaxf(m, scs[j]);
+          float sum = 0.f;
+          for (int j = 0; j < S; ++j) sum += __expf(scs[j] - m);
+          wv[as * 128 + row] = __fdividef(__expf(s - m), sum);
+        }
       }
       mbar_arrive(wv_ready + 8 * as);
     }
