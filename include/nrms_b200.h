@@ -93,7 +93,8 @@ size_t nrms_encoder_bwd_workspace_bytes(int64_t n_seq, int S, int mode);
 /* ---- encoders ---------------------------------------------------------------------- */
 /* News encoder forward: tokens int64 [n_titles, L] -> out fp32 [n_titles, 300].
  * emb: [num_words, 300].  stash: NULL for inference, else nrms_encoder_stash_bytes bytes.
- * dropout_p in [0,1): 0 = eval mode.  (seed, offset) key the in-kernel Philox stream. */
+ * dropout_p in [0,1): 0 = eval mode.  (seed, offset) key the in-kernel Philox stream.
+ * L = 20 (title, config.num_words_title); inference (stash == NULL) also accepts L = 50 (a 50-token text). */
 int nrms_news_encoder_fwd(const int64_t* tokens, int64_t n_titles, int L,
                           const float* emb, int64_t num_words,
                           const float* wqkv, const float* bqkv,

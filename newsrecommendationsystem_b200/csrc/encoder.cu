@@ -297,7 +297,10 @@ static int news_encoder_fwd_impl(const int64_t* tokens, int64_t n_titles, int L,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (int rc = check_ln(ln, false)) return rc;
   if (int rc = check_common(L, mode)) return rc;
-  NRMS_CHECK_ARG(L == 20, NRMS_E_UNSUPPORTED, "news encoder compiled for title length 20, got %d", L);
+  // training (a stash is requested) is compiled for the title length; inference also takes 50-token texts (the
+  // abstract encoder of the reference's Exp1 model is this same block, src/model/Exp1/news_encoder.py:10-34)
+  NRMS_CHECK_ARG(L == 20 || (L == 50 && stash == nullptr), NRMS_E_UNSUPPORTED,
+                 "news encoder compiled for title length 20 (inference: 20 or 50), got %d", L);
   NRMS_CHECK_ARG(n_titles >= 0 && num_words > 0, NRMS_E_INVALID, "bad sizes");
   if (n_titles == 0) return NRMS_OK;
   NRMS_CHECK_ARG(tokens && emb && wqkv && bqkv && wa && ba && qa && out, NRMS_E_INVALID, "null pointer");

@@ -796,6 +796,7 @@ static int launch_seq_attn(const void* table16, int64_t n_table_rows, const void
 int k1g_run_seq(int S, int idx_kind, const void* table16, int64_t n_table_rows, const void* rows, int64_t n_seq,
                 void* Cbuf, cudaStream_t st) {
   if (S == 50 && idx_kind == 2) return launch_seq_attn<50, int32_t>(table16, n_table_rows, rows, n_seq, Cbuf, st);
+  if (S == 50 && idx_kind == 1) return launch_seq_attn<50, int64_t>(table16, n_table_rows, rows, n_seq, Cbuf, st);
   if (S == 20 && idx_kind == 1) return launch_seq_attn<20, int64_t>(table16, n_table_rows, rows, n_seq, Cbuf, st);
   if (S == 20 && idx_kind == 2) return launch_seq_attn<20, int32_t>(table16, n_table_rows, rows, n_seq, Cbuf, st);
   set_error("seq_attn_kernel: unsupported (S, index kind) = (%d, %d)", S, idx_kind);

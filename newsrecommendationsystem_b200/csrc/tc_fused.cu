@@ -94,8 +94,10 @@ static bool use_table_attn(int S, int idx_kind, int64_t n_seq, int64_t n_src_row
   // beyond L2 (126 MB = 58 k rows) turns the 2,160-byte row gather into DRAM traffic: measured 3.2 ms vs 4.4 ms (K1 v6)
   // at 56 history rows per table row, 4.4 vs ~4.8 ms at 28; the break-even is near 8.
   if (n_src_rows <= 0 || n_seq * S < 8 * n_src_rows) return false;
-  if (S == 50) return idx_kind == 2 && table_attn_enabled();
-  if (S == 20) return (idx_kind == 1 || idx_kind == 2) && news_table_attn_enabled();
+  // int32 rows = the user encoder over the news-vector table; int64 ids = the news encoder over the embedding table
+  // (title length 20; a 50-token text, e.g. an abstract, takes the same kernel)
+  if (idx_kind == 2) return S == 50 ? table_attn_enabled() : news_table_attn_enabled();
+  if (idx_kind == 1) return news_table_attn_enabled();
   return false;
 }
 constexpr int K1_DEFAULT_VARIANT = 6;
@@ -726,7 +728,7 @@ static int run_fused(const float* src, int64_t n_src_rows, const void* idx, int 
       // K1g variants 0 / 1 write only columns 0..299 of the fp16 context rows; K2 multiplies 300..319 by zero weights, so
       // they must be finite.  (The templated kernel clears them itself: this strided memset -- 40 bytes in every 640,
       // 470 k rows -- took ~0.4 ms on the copy engine.)
-      if (S == 50 && get_k1g_variant() != 2) {
+      if (S == 50 && idx_kind == 2 && get_k1g_variant() != 2) {
         cudaError_t e = cudaMemset2DAsync(reinterpret_cast<char*>(Cbuf) + 600, 640, 0, 40, (size_t)first * S, st);
         if (e != cudaSuccess) return cuda_fail(e, "cudaMemset2DAsync(context tail)");
       }
@@ -755,9 +757,9 @@ static int run_fused(const float* src, int64_t n_src_rows, const void* idx, int 
         if (int rc = k1v4_pack_src(src_c, n * S, src16, &ts, st)) return rc;
       }
       {
-        K1Timer timer(st, n, S == 50 ? (table_attn ? 2 : 0) : (table_attn ? 3 : 1));
+        K1Timer timer(st, n, idx_kind != 1 && S == 50 ? (table_attn ? 2 : 0) : (table_attn ? 3 : 1));
         int rc;
-        if (table_attn && (S != 50 || get_k1g_variant() == 2))
+        if (table_attn && (S != 50 || idx_kind != 2 || get_k1g_variant() == 2))
           rc = k1g_run_seq(S, idx_kind, src16, n_src_rows, idx_c, n, Cbuf, st);
         else if (table_attn)
           rc = k1g_run(src16, n_src_rows, reinterpret_cast<const int32_t*>(idx_c), n, Cbuf, st);

@@ -144,6 +144,27 @@ def test_news_encoder_vs_oracle_ragged_sizes(dev, golden_sd, precision, n):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("table_path", [0, 1])
+def test_news_encoder_50_token_text(dev, lib, golden_sd, precision, table_path):
+    """The text encoder at the other compiled length (50 tokens, e.g. an abstract: reference
+    src/model/Exp1/news_encoder.py:10-34 is this same block): per-text projection and table path."""
+    from newsrecommendationsystem_b200 import synthetic
+    rng = np.random.default_rng(50)
+    toks = rng.integers(1, Cfg.num_words, size=(333, 50)).astype(np.int64)
+    toks[:, 37:] = 0
+    toks[5] = 0
+    ref, _ = O.news_encoder_forward(golden_sd, toks)
+    m = make_model(golden_sd, dev, precision)
+    lib.nrms_set_option(b"news_table_attn", table_path)
+    try:
+        with torch.no_grad():
+            nv = m.get_news_vector({"title": torch.from_numpy(toks)})
+    finally:
+        lib.nrms_set_option(b"news_table_attn", 1)
+    assert rel_l2_rows(nv.cpu().numpy(), ref) < TOL_VEC[precision]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
 def test_user_encoder_indexed_equals_dense(dev, lib, golden_sd, precision):
     lib.nrms_set_option(b"user_table_attn", 0)      # per-user projection path (K1 v6): the gather is a pure copy
     try:
