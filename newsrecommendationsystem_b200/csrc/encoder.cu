@@ -589,6 +589,18 @@ int nrms_set_option(const char* key, int value) {
     set_table_attn(value != 0);
     return NRMS_OK;
   }
+  if (strcmp(key, "fused_pool") == 0) {
+    set_fused_pool(value != 0);
+    return NRMS_OK;
+  }
+  if (strcmp(key, "k1f_debug") == 0) {
+    set_k1f_debug(value);
+    return NRMS_OK;
+  }
+  if (strcmp(key, "attn_safe_softmax") == 0) {
+    set_attn_safe_softmax(value);
+    return NRMS_OK;
+  }
   if (strcmp(key, "time_k1") == 0) {
     set_time_k1(value != 0);
     return NRMS_OK;

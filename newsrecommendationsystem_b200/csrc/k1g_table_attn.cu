@@ -402,11 +402,20 @@ struct SeqCfg {
   static_assert(SMEM_BYTES <= 232448, "shared memory");
 };
 
-template <int SEQ, typename IdxT>
+// SAFE = the row-shifted softmax form (below).  Both instantiations are launched when the choice is left to the score
+// bound (qk_bound != nullptr): each reads the 30 bounds first and the one that does not apply returns at once (~3 us),
+// so the decision needs no host synchronisation and neither form pays for the other's code (a run-time branch inside one
+// kernel cost the plain form 9 %: 468 instead of 428 us per 18,288 users).
+template <int SEQ, typename IdxT, bool SAFE>
 __global__ void __launch_bounds__(THREADS, 1)
 seq_attn_kernel(const __half* __restrict__ table16, int64_t n_table_rows, const IdxT* __restrict__ seq_rows,
-                int64_t n_seq, __half* __restrict__ ctx) {
+                int64_t n_seq, __half* __restrict__ ctx, const float* __restrict__ qk_bound) {
   using Cfg = SeqCfg<SEQ>;
+  if (qk_bound != nullptr) {
+    const int l = threadIdx.x & 31;
+    const bool big = l < H && !(qk_bound[l] * qk_bound[H + l] <= 225.f);      // (15 log2 units)^2: 2^15 < 65504
+    if ((__ballot_sync(0xffffffffu, big) != 0u) != SAFE) return;
+  }
   constexpr int MT = Cfg::MT, NT = Cfg::NT, KS16 = Cfg::KS16, NST = Cfg::NST, STG = Cfg::STAGE_BYTES;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sbase = tc::smem_u32(smem);
@@ -425,6 +434,7 @@ seq_attn_kernel(const __half* __restrict__ table16, int64_t n_table_rows, const 
 
   if (warp == H) {
     // ------------------------------ producer: one 2,160-byte bulk copy per row ------------------------------
+    // (16-byte cp.async pieces from this one warp were tried: 250 instructions per user, 8.4 ms instead of 2.5 for the user stage)
     uint32_t it = 0;
     for (int64_t u = blockIdx.x; u < n_seq; u += gridDim.x, ++it) {
       int64_t r0 = lane < SEQ ? (int64_t)seq_rows[u * SEQ + lane] : 0;
@@ -466,6 +476,11 @@ seq_attn_kernel(const __half* __restrict__ table16, int64_t n_table_rows, const 
       q4o[p] = rofs(16 * p + 8 * (mi & 1) + rr) + qoff + (mi >> 1) * 16;
       q2o[p] = rofs(16 * p + 8 * (mi & 1) + rr) + qoff + 32;
     }
+    // P = 2^s is packed to fp16 for the context MMA and overflows at s > 16 (a logit of 11.09) where the reference's fp32
+    // exp (multihead_self.py:17) is finite to 88.  When the per-call bound max|q_h| max|k_h| over the projected table
+    // (k1f_qk_bound: Cauchy-Schwarz, log2 units) allows scores above 15 the rows are shifted by their maximum (SAFE):
+    // P = 2^(s - m), O / (Z + 1e-8 * 2^-m) -- algebraically exp(s) / (sum exp(s) + 1e-8) for any m.
+    constexpr bool safe = SAFE;
     uint32_t it = 0;
     for (int64_t u = blockIdx.x; u < n_seq; u += gridDim.x, ++it) {
       const uint32_t st = it % NST;
@@ -505,14 +520,41 @@ seq_attn_kernel(const __half* __restrict__ table16, int64_t n_table_rows, const 
         // P = 2^S (q carries log2(e)/sqrt(20)); the keys past SEQ in the last key tile are padding
         uint32_t pa[NT][2];
         const bool lower = mt + 1 < MT;              // rows 16mt+8..+15 exist only before the last tile
+        float e0 = 1e-8f, e1 = 1e-8f;                // the epsilon of multihead_self.py:20, scaled with the row shift
+        if (safe) {
+          float m0 = sc[0][0], m1 = sc[0][2];
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          float p0 = ex2f(sc[nt][0]), p1 = ex2f(sc[nt][1]);
-          float p2 = 0.f, p3 = 0.f;
-          if (lower) { p2 = ex2f(sc[nt][2]); p3 = ex2f(sc[nt][3]); }
-          if (nt == NT - 1 && 2 * t >= Cfg::REM) { p0 = p1 = p2 = p3 = 0.f; }
-          pa[nt][0] = pack_h2(p0, p1);
-          pa[nt][1] = pack_h2(p2, p3);
+          for (int nt = 0; nt < NT; ++nt) {
+            m0 = fmaxf(m0, fmaxf(sc[nt][0], sc[nt][1]));
+            m1 = fmaxf(m1, fmaxf(sc[nt][2], sc[nt][3]));
+          }
+          m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+          m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+          m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+          m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+          m0 = fminf(fmaxf(m0, -120.f), 120.f);
+          m1 = fminf(fmaxf(m1, -120.f), 120.f);
+          e0 = 1e-8f * ex2f(-m0);
+          e1 = 1e-8f * ex2f(-m1);
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            float p0 = ex2f(sc[nt][0] - m0), p1 = ex2f(sc[nt][1] - m0);
+            float p2 = 0.f, p3 = 0.f;
+            if (lower) { p2 = ex2f(sc[nt][2] - m1); p3 = ex2f(sc[nt][3] - m1); }
+            if (nt == NT - 1 && 2 * t >= Cfg::REM) { p0 = p1 = p2 = p3 = 0.f; }
+            pa[nt][0] = pack_h2(p0, p1);
+            pa[nt][1] = pack_h2(p2, p3);
+          }
+        } else {
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            float p0 = ex2f(sc[nt][0]), p1 = ex2f(sc[nt][1]);
+            float p2 = 0.f, p3 = 0.f;
+            if (lower) { p2 = ex2f(sc[nt][2]); p3 = ex2f(sc[nt][3]); }
+            if (nt == NT - 1 && 2 * t >= Cfg::REM) { p0 = p1 = p2 = p3 = 0.f; }
+            pa[nt][0] = pack_h2(p0, p1);
+            pa[nt][1] = pack_h2(p2, p3);
+          }
         }
         float oacc[3][4];
 #pragma unroll
@@ -528,7 +570,7 @@ seq_attn_kernel(const __half* __restrict__ table16, int64_t n_table_rows, const 
         // Z of rows g / g+8 sits in column 20 = element 0 / 2 of dim tile 2 on the quad's lane t == 2
         const float z0 = __shfl_sync(0xffffffffu, oacc[2][0], (lane & ~3) | 2);
         const float z1 = __shfl_sync(0xffffffffu, oacc[2][2], (lane & ~3) | 2);
-        const float i0 = __fdividef(1.f, z0 + 1e-8f), i1 = __fdividef(1.f, z1 + 1e-8f);
+        const float i0 = __fdividef(1.f, z0 + e0), i1 = __fdividef(1.f, z1 + e1);
         // O / (Z + 1e-8) back in place over the head's q slice of these rows, then out as 8-byte pieces
         const int r0 = 16 * mt + g, r1 = r0 + 8;
         uint8_t* q0 = smem + st * STG + r0 * PITCH + qoff + 4 * t;
@@ -774,31 +816,46 @@ int k1g_run(const void* table16, int64_t n_table_rows, const int32_t* hist_rows,
 // The templated kernel: S = 50 (int32 history rows) or S = 20 (int64 token ids); same Cbuf contract as k1g_run
 template <int SEQ, typename IdxT>
 static int launch_seq_attn(const void* table16, int64_t n_table_rows, const void* rows, int64_t n_seq, void* Cbuf,
-                           cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k1g::seq_attn_kernel<SEQ, IdxT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           const float* qk_bound, cudaStream_t st) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static bool configured[64] = {false};
+  if (dev < 0 || dev >= 64 || !configured[dev]) {      // the attribute is per device
+    cudaError_t e = cudaFuncSetAttribute(k1g::seq_attn_kernel<SEQ, IdxT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          k1g::SeqCfg<SEQ>::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(k1g::seq_attn_kernel<SEQ, IdxT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               k1g::SeqCfg<SEQ>::SMEM_BYTES);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(seq_attn_kernel)");
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   if (n_seq <= 0) return NRMS_OK;
   NRMS_CHECK_ARG(n_table_rows > 0, NRMS_E_INVALID, "table row count out of range");
   int grid = num_sms();
   if (n_seq < grid) grid = (int)n_seq;
-  k1g::seq_attn_kernel<SEQ, IdxT><<<grid, k1g::THREADS, k1g::SeqCfg<SEQ>::SMEM_BYTES, st>>>(
-      reinterpret_cast<const __half*>(table16), n_table_rows, reinterpret_cast<const IdxT*>(rows), n_seq,
-      reinterpret_cast<__half*>(Cbuf));
-  NRMS_LAUNCH_CHECK("seq_attn_kernel");
+  const int force = get_attn_safe_softmax();          // -1: both instantiations read the bound, one of them runs
+  const float* bound = force < 0 ? qk_bound : nullptr;
+  if (force <= 0) {
+    k1g::seq_attn_kernel<SEQ, IdxT, false><<<grid, k1g::THREADS, k1g::SeqCfg<SEQ>::SMEM_BYTES, st>>>(
+        reinterpret_cast<const __half*>(table16), n_table_rows, reinterpret_cast<const IdxT*>(rows), n_seq,
+        reinterpret_cast<__half*>(Cbuf), bound);
+    NRMS_LAUNCH_CHECK("seq_attn_kernel");
+  }
+  if (force != 0 && (force > 0 || bound != nullptr)) {
+    k1g::seq_attn_kernel<SEQ, IdxT, true><<<grid, k1g::THREADS, k1g::SeqCfg<SEQ>::SMEM_BYTES, st>>>(
+        reinterpret_cast<const __half*>(table16), n_table_rows, reinterpret_cast<const IdxT*>(rows), n_seq,
+        reinterpret_cast<__half*>(Cbuf), bound);
+    NRMS_LAUNCH_CHECK("seq_attn_kernel(row-shifted)");
+  }
   return NRMS_OK;
 }
 
 int k1g_run_seq(int S, int idx_kind, const void* table16, int64_t n_table_rows, const void* rows, int64_t n_seq,
-                void* Cbuf, cudaStream_t st) {
-  if (S == 50 && idx_kind == 2) return launch_seq_attn<50, int32_t>(table16, n_table_rows, rows, n_seq, Cbuf, st);
-  if (S == 50 && idx_kind == 1) return launch_seq_attn<50, int64_t>(table16, n_table_rows, rows, n_seq, Cbuf, st);
-  if (S == 20 && idx_kind == 1) return launch_seq_attn<20, int64_t>(table16, n_table_rows, rows, n_seq, Cbuf, st);
-  if (S == 20 && idx_kind == 2) return launch_seq_attn<20, int32_t>(table16, n_table_rows, rows, n_seq, Cbuf, st);
+                void* Cbuf, const float* qk_bound, cudaStream_t st) {
+  if (S == 50 && idx_kind == 2) return launch_seq_attn<50, int32_t>(table16, n_table_rows, rows, n_seq, Cbuf, qk_bound, st);
+  if (S == 50 && idx_kind == 1) return launch_seq_attn<50, int64_t>(table16, n_table_rows, rows, n_seq, Cbuf, qk_bound, st);
+  if (S == 20 && idx_kind == 1) return launch_seq_attn<20, int64_t>(table16, n_table_rows, rows, n_seq, Cbuf, qk_bound, st);
+  if (S == 20 && idx_kind == 2) return launch_seq_attn<20, int32_t>(table16, n_table_rows, rows, n_seq, Cbuf, qk_bound, st);
   set_error("seq_attn_kernel: unsupported (S, index kind) = (%d, %d)", S, idx_kind);
   return NRMS_E_UNSUPPORTED;
 }

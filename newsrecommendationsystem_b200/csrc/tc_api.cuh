@@ -35,6 +35,14 @@ int tc_encoder_fused(const float* src, int64_t n_src_rows, const void* idx, int 
 // fp16 operands (A16 [M, lda halfs], B16 [N, ldb halfs], 16-byte aligned rows), kind::f16, same fp16 epilogue (no bias)
 int tc_gemm_nt_f16(const void* A16, int64_t lda, const void* B16, int64_t ldb, void* C16, int64_t ldc, int64_t M, int N,
                    int K, float scale, int scale_cols, int qkv_layout, cudaStream_t st);
+// K1f (k1f_attn_pool.cu): table attention + additive pooling in one kernel (the context rows stay on the SM)
+int k1f_qk_bound(const void* table16, int64_t n_rows, float* bound, cudaStream_t st);
+int k1f_run(int S, int idx_kind, const void* table16, int64_t n_table_rows, const void* rows, int64_t n_seq,
+            const void* wa16, const float* ba, const float* qa, const float* bound, float* out, cudaStream_t st);
+void set_attn_safe_softmax(int v);
+int get_attn_safe_softmax();   // -1 auto (bound over the projected table), 0 plain 2^s, 1 row-shifted form
+void set_k1f_debug(int v);           // component-removal timing switches of K1f (garbage results)
+void set_fused_pool(bool on);        // table path: 1 (default) = K1f, 0 = K1g + K2 (context rows through HBM)
 int set_k1g_variant(int v);     // 0 = head per warp (S = 50 only), 1 = (head, query tile) units, 2 = length-templated kernel
 void set_news_table_attn(bool on);   // news encoder over the projected embedding table (default on)
 void set_table_attn(bool on);   // indexed user encoder: project the table once + K1g (default on)

@@ -64,7 +64,7 @@ int k1g_project_table(const float* table, int64_t n_rows, const float* wqkv, con
                       cudaStream_t st);
 size_t k1g_table16_bytes(int64_t n_rows);
 int k1g_run_seq(int S, int idx_kind, const void* table16, int64_t n_table_rows, const void* rows, int64_t n_seq,
-                void* Cbuf, cudaStream_t st);
+                void* Cbuf, const float* qk_bound, cudaStream_t st);
 int get_k1g_variant();
 int k1g_run(const void* table16, int64_t n_table_rows, const int32_t* hist_rows, int64_t n_users, void* Cbuf,
             cudaStream_t st);
@@ -87,6 +87,15 @@ static bool news_table_attn_enabled() {
   }
   return g_news_table_attn != 0;
 }
+static int g_fused_pool = -1;
+static bool fused_pool_enabled() {
+  if (g_fused_pool < 0) {
+    const char* e = getenv("NRMS_FUSED_POOL");
+    g_fused_pool = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_fused_pool != 0;
+}
+void set_fused_pool(bool on) { g_fused_pool = on ? 1 : 0; }
 void set_table_attn(bool on) { g_table_attn = on ? 1 : 0; }
 void set_news_table_attn(bool on) { g_news_table_attn = on ? 1 : 0; }
 static bool use_table_attn(int S, int idx_kind, int64_t n_seq, int64_t n_src_rows) {
@@ -704,7 +713,9 @@ static int run_fused(const float* src, int64_t n_src_rows, const void* idx, int 
   }
   int variant = k1_variant();
   if (ln_gamma && variant < 2) variant = 5;   // the LayerNorm step works on the fp16 context rows of variants 2..5
-  const bool table_attn = use_table_attn(S, idx_kind, n_seq, n_src_rows);
+  // The LayerNorm variant keeps the per-sequence projection (K1 v6 -> LayerNorm rows -> K2): the normalisation needs the
+  // whole 300-wide context row, which in the table path is spread over 15 head warps.
+  const bool table_attn = !ln_gamma && use_table_attn(S, idx_kind, n_seq, n_src_rows);
   if (table_attn && variant < 2) variant = K1_DEFAULT_VARIANT;
   // every variant tiles 5 titles / 2 users, so the chunking (whole waves of tiles) is shared
   const int64_t chunk = fused_chunk_seq<S, SPT>(table_attn);
@@ -725,6 +736,15 @@ static int run_fused(const float* src, int64_t n_src_rows, const void* idx, int 
     if (int rc2 = k2v2_prepare(wa, wa16, &twa, st)) return rc2;
     if (table_attn) {
       if (int rc3 = k1g_project_table(src, n_src_rows, wqkv, bqkv, src16, st)) return rc3;
+      // bound on the attention scores over the projected table (30 floats in the 3 KB behind the 128,000-byte fp16 W_a
+      // copy): the attention kernels pick the plain or the row-shifted softmax form from it
+      float* bound = reinterpret_cast<float*>(reinterpret_cast<char*>(wa16) + 128000);
+      if (int rc4 = k1f_qk_bound(src16, n_src_rows, bound, st)) return rc4;
+      if (fused_pool_enabled()) {
+        // K1f: attention + additive pooling in ONE launch over the whole call; no context buffer, no chunking.
+        K1Timer timer(st, n_seq, S == 50 && idx_kind == 2 ? 2 : 3);
+        return k1f_run(S, idx_kind, src16, n_src_rows, idx, n_seq, wa16, ba, qa, bound, out, st);
+      }
       // K1g variants 0 / 1 write only columns 0..299 of the fp16 context rows; K2 multiplies 300..319 by zero weights, so
       // they must be finite.  (The templated kernel clears them itself: this strided memset -- 40 bytes in every 640,
       // 470 k rows -- took ~0.4 ms on the copy engine.)
@@ -760,7 +780,8 @@ static int run_fused(const float* src, int64_t n_src_rows, const void* idx, int 
         K1Timer timer(st, n, idx_kind != 1 && S == 50 ? (table_attn ? 2 : 0) : (table_attn ? 3 : 1));
         int rc;
         if (table_attn && (S != 50 || idx_kind != 2 || get_k1g_variant() == 2))
-          rc = k1g_run_seq(S, idx_kind, src16, n_src_rows, idx_c, n, Cbuf, st);
+          rc = k1g_run_seq(S, idx_kind, src16, n_src_rows, idx_c, n, Cbuf,
+                           reinterpret_cast<const float*>(reinterpret_cast<const char*>(wa16) + 128000), st);
         else if (table_attn)
           rc = k1g_run(src16, n_src_rows, reinterpret_cast<const int32_t*>(idx_c), n, Cbuf, st);
         else if (variant == 6)

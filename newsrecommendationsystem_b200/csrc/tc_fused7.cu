@@ -471,7 +471,7 @@ encoder_attn_tc6_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
           WTRACE(23);
         }
         // ================= W2: score block -> P, in place (two halves: register budget) =================
-        float Z = 0.f;
+        float Z = 0.f, eps_row = 1e-8f;
         {
           mbar_wait(s_ready + 8 * set, ph);
           tc_fence_after();
@@ -482,18 +482,38 @@ encoder_attn_tc6_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
             static_assert(NL > 32 && NL <= 64, "two halves");
             const uint32_t tblk = tS + sq_lo * SLOT;
             const uint32_t t_own = tS + sq_lo * 32, t_oth = tS + (1 - sq_lo) * 32;
+            // Row shift (multihead_self.py:17-20 in its overflow-free form): P = 2^(s - m), Z' = sum P and
+            // 1 / (Z' + 1e-8 * 2^-m) equal exp(s) / (sum exp(s) + 1e-8) for any m; with m = the row maximum P fits
+            // fp16 whatever the scores are (2^s alone overflows fp16 at s > 16, i.e. a logit of 11.09).  The maximum
+            // takes one extra pass over the score block in tensor memory (two halves: register budget).
+            constexpr int N2 = NL - 32;
             uint32_t sv[32], pk[16];
-            tmem_ld16_nw(tblk, sv);
-            tmem_ld16_nw(tblk + 16, sv + 16);
-            tmem_ld_wait();
+            float mrow;
+            {
+              uint32_t sv2[32];
+              tmem_ld16_nw(tblk, sv);
+              tmem_ld16_nw(tblk + 16, sv + 16);
+#pragma unroll
+              for (int c = 0; c + 16 <= N2; c += 16) tmem_ld16_nw(tblk + 32 + c, sv2 + c);
+              if constexpr (N2 % 16 >= 8) tmem_ld8_nw(tblk + 32 + N2 / 16 * 16, sv2 + N2 / 16 * 16);
+              if constexpr (N2 % 8 >= 4) tmem_ld4_nw(tblk + 32 + N2 / 8 * 8, sv2 + N2 / 8 * 8);
+              tmem_ld_wait();
+              mrow = __uint_as_float(sv[0]);
+#pragma unroll
+              for (int j = 1; j < 32; ++j) mrow = fmaxf(mrow, __uint_as_float(sv[j]));
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (32 + j < S) mrow = fmaxf(mrow, __uint_as_float(sv2[j]));
+              mrow = fminf(fmaxf(mrow, -120.f), 120.f);
+            }
+            eps_row = 1e-8f * ex2(-mrow);
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
-              const float e0 = ex2(__uint_as_float(sv[j])), e1 = ex2(__uint_as_float(sv[j + 1]));
+              const float e0 = ex2(__uint_as_float(sv[j]) - mrow), e1 = ex2(__uint_as_float(sv[j + 1]) - mrow);
               Z += e0 + e1;
               pk[j >> 1] = pack_h2(e0, e1);
             }
             // second half of the loads BEFORE the first stores: columns [32, NL) are still scores until then
-            constexpr int N2 = NL - 32;
             uint32_t sv2[32];
 #pragma unroll
             for (int c = 0; c + 16 <= N2; c += 16) tmem_ld16_nw(tblk + 32 + c, sv2 + c);
@@ -503,8 +523,8 @@ encoder_attn_tc6_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
             tmem_st16(t_own, pk);
 #pragma unroll
             for (int j = 0; j < 32; j += 2) {
-              const float e0 = (32 + j < S) ? ex2(__uint_as_float(sv2[j])) : 0.f;
-              const float e1 = (32 + j + 1 < S) ? ex2(__uint_as_float(sv2[j + 1])) : 0.f;
+              const float e0 = (32 + j < S) ? ex2(__uint_as_float(sv2[j]) - mrow) : 0.f;
+              const float e1 = (32 + j + 1 < S) ? ex2(__uint_as_float(sv2[j + 1]) - mrow) : 0.f;
               Z += e0 + e1;
               pk[j >> 1] = (32 + j < S) ? pack_h2(e0, e1) : 0u;
             }
@@ -527,10 +547,15 @@ encoder_attn_tc6_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
             }
             tmem_ld_wait();
             uint32_t pk[12];
+            float mrow = __uint_as_float(own ? sv[1][0] : sv[0][0]);      // row shift, see the SLOT == 64 branch
+#pragma unroll
+            for (int j = 1; j < S; ++j) mrow = fmaxf(mrow, __uint_as_float(own ? sv[1][j] : sv[0][j]));
+            mrow = fminf(fmaxf(mrow, -120.f), 120.f);
+            eps_row = 1e-8f * ex2(-mrow);
 #pragma unroll
             for (int j = 0; j < 20; j += 2) {
-              const float s0 = __uint_as_float(own ? sv[1][j] : sv[0][j]);
-              const float s1 = __uint_as_float(own ? sv[1][j + 1] : sv[0][j + 1]);
+              const float s0 = __uint_as_float(own ? sv[1][j] : sv[0][j]) - mrow;
+              const float s1 = __uint_as_float(own ? sv[1][j + 1] : sv[0][j + 1]) - mrow;
               const float e0 = (j < S) ? ex2(s0) : 0.f;
               const float e1 = (j + 1 < S) ? ex2(s1) : 0.f;
               Z += e0 + e1;
@@ -575,7 +600,7 @@ encoder_attn_tc6_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(o_taken + 8 * set);        // the S MMA of the next pass may overwrite the set
-          const float inv = 1.f / (Z + 1e-8f);
+          const float inv = 1.f / (Z + eps_row);
           // 40 context columns of the pass (heads 2p, 2p+1; the dummy 16th head gives the zero K padding 300..319) go
           // to the staging tile [128 rows][80 B]; the store warp sends it off as one 2-D bulk tensor store per sequence
           if (pass_it > 0) mbar_wait(stg_free + 8 * (par ^ 1), ((pass_it - 1) >> 1) & 1);   // store of pass_it - 1 has read the tile

@@ -19,22 +19,30 @@ for v in vals:
             print(f"  {w:80s} {v[hdr.index(w)]} {rows[1][hdr.index(w)]}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-h = rows[1]
-data = [r for r in rows[2:] if len(r) > 10]
-ix = {k: i for i, k in enumerate(h)}
-tot = sum(int(r[ix["# Samples"]]) for r in data)
-st = [k for k in h if k.startswith("stall_") and "Not Issued" not in k]
-agg = {k: sum(int(r[ix[k]]) for r in data) for k in st}
-print("total samples", tot)
-for k, v in sorted(agg.items(), key=lambda x: -x[1])[:8]:
-    print(f"  {k:26s}{v:8d} {100 * v / tot:5.1f}%")
-print("wait loops (mbarrier try_wait): address, operand, executions, samples in the loop")
-for i, r in enumerate(data):
-    if "TRYWAIT" in r[ix["Source"]]:
-        s = sum(int(x[ix["# Samples"]]) for x in data[i:i + 8])
-        print("  ", r[ix["Address"]][-5:], r[ix["Source"]].strip()[40:80], r[ix["Instructions Executed"]], s)
-print("hottest lines")
-for r in sorted(data, key=lambda r: -int(r[ix["# Samples"]]))[:topn]:
-    s = {k: int(r[ix[k]]) for k in st}
-    m = max(s, key=s.get)
-    print(r[ix["# Samples"]].rjust(6), r[ix["Instructions Executed"]].rjust(9), m[6:].ljust(14), r[ix["Source"]].strip()[:90])
+# one section per profiled launch: a title row, a header row, then the SASS lines
+sections, cur = [], None
+for r in rows:
+    if len(r) > 10 and "# Samples" in r:
+        cur = dict(h=r, data=[])
+        sections.append(cur)
+    elif cur is not None and len(r) > 10:
+        cur["data"].append(r)
+for si, sec in enumerate(sections):
+    h, data = sec["h"], sec["data"]
+    ix = {k: i for i, k in enumerate(h)}
+    tot = sum(int(r[ix["# Samples"]]) for r in data)
+    st = [k for k in h if k.startswith("stall_") and "Not Issued" not in k]
+    agg = {k: sum(int(r[ix[k]]) for r in data) for k in st}
+    print(f"==== launch {si}: total samples", tot)
+    for k, v in sorted(agg.items(), key=lambda x: -x[1])[:8]:
+        print(f"  {k:26s}{v:8d} {100 * v / max(tot, 1):5.1f}%")
+    print("wait loops (mbarrier try_wait): address, operand, executions, samples in the loop")
+    for i, r in enumerate(data):
+        if "TRYWAIT" in r[ix["Source"]]:
+            s = sum(int(x[ix["# Samples"]]) for x in data[i:i + 8])
+            print("  ", r[ix["Address"]][-5:], r[ix["Source"]].strip()[40:80], r[ix["Instructions Executed"]], s)
+    print("hottest lines")
+    for r in sorted(data, key=lambda r: -int(r[ix["# Samples"]]))[:topn]:
+        s = {k: int(r[ix[k]]) for k in st}
+        m = max(s, key=s.get)
+        print(r[ix["# Samples"]].rjust(6), r[ix["Instructions Executed"]].rjust(9), m[6:].ljust(14), r[ix["Source"]].strip()[:90])
