@@ -739,13 +739,28 @@ table_attn_units_kernel(const __half* __restrict__ table16, int n_table_rows, co
 
 }  // namespace k1g
 
-// fp16 copy of the packed projection weights with the bias as column 300: [900][320] halfs
-__global__ void __launch_bounds__(256) pack_wqkv16_bias_kernel(const float* __restrict__ w, const float* __restrict__ bias,
-                                                                __half* __restrict__ out) {
-  const int n = D3 * 320;
+// fp16 copy of the packed projection weights IN THE ORDER OF A TABLE ROW: [1080][320] halfs.  Row j of the copy produces
+// half j of a table16 row: j = head group * 360 + (q | k | v) * 120 + head * 24 + d.  d < 20: row (which * 300 + head * 20 + d)
+// of [W_Q; W_K; W_V], its bias in column 300 (met by the 1.0 column of the operand rows), W_Q and b_Q scaled by
+// log2(e)/sqrt(20); d >= 20: the slice pad -- a zero row, except d = 20 of v whose bias column is 1.0, so the GEMM itself
+// writes the (1, 0, 0, 0) that returns Z from the context MMA.  The table then IS the row-major GEMM result.
+constexpr int TABLE_COLS = k1g::PITCH / 2;      // 1,080
+__global__ void __launch_bounds__(256) pack_wqkv16_table_kernel(const float* __restrict__ w, const float* __restrict__ bias,
+                                                                 __half* __restrict__ out, float qscale) {
+  const int n = TABLE_COLS * 320;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int r = i / 320, k = i - r * 320;
-    out[i] = __float2half_rn(k < D ? w[r * D + k] : (k == D ? bias[r] : 0.f));
+    const int j = i / 320, k = i - j * 320;
+    const int hg = j / 360, r1 = j - hg * 360, which = r1 / 120, r2 = r1 - which * 120, hl = r2 / 24, d = r2 - hl * 24;
+    float v = 0.f;
+    if (d < DH) {
+      const int src = which * D + (hg * k1g::HG + hl) * DH + d;
+      const float sc = which == 0 ? qscale : 1.f;
+      if (k < D) v = w[src * D + k] * sc;
+      else if (k == D) v = bias[src] * sc;
+    } else if (which == 2 && d == DH && k == D) {
+      v = 1.f;
+    }
+    out[i] = __float2half_rn(v);
   }
 }
 
@@ -754,11 +769,12 @@ int k1v4_pack_src(const float* src, int64_t n_rows, void* src16, CUtensorMap* ts
 // scratch of the table path: [table16: n_rows x 2,160 B][fp16 copy of the table: (n_rows + 1) x 640 B][fp16 weights]
 static size_t k1g_table16_only(int64_t n_rows) { return align_up((size_t)n_rows * k1g::ROW_BYTES, 1024); }
 static size_t k1g_a16_bytes(int64_t n_rows) { return align_up((size_t)(n_rows + 1) * 640, 1024); }
-size_t k1g_table16_bytes(int64_t n_rows) { return k1g_table16_only(n_rows) + k1g_a16_bytes(n_rows) + (size_t)D3 * 640; }
+size_t k1g_table16_bytes(int64_t n_rows) { return k1g_table16_only(n_rows) + k1g_a16_bytes(n_rows) + (size_t)TABLE_COLS * 640; }
 
-// table16 = half([table | 1] * [W_Q*c | W_K | W_V | b]^T) in the head-group layout above: fp16 copies of the table (a 1.0
-// in column 300 meets the bias column of the weight copy) and of the weights, then one kind::f16 tensor-core GEMM whose
-// epilogue scales q, rounds to fp16 and writes the pads.  (Same operand precision as K1 v6's in-kernel projection.)
+// table16 = half([table | 1] * B^T) with B = the weight copy above (rows in table order, bias column, q scale and pads
+// included): fp16 copies of the table (a 1.0 in column 300 meets the bias column) and of the weights, then one kind::f16
+// tensor-core GEMM with N = 1,080 whose row-major result IS the table; the epilogue leaves through bulk tensor stores.
+// (Same operand precision as K1 v6's in-kernel projection.)
 int k1g_project_table(const float* table, int64_t n_rows, const float* wqkv, const float* bqkv, void* scratch,
                       cudaStream_t st) {
   char* base = reinterpret_cast<char*>(scratch);
@@ -767,10 +783,10 @@ int k1g_project_table(const float* table, int64_t n_rows, const float* wqkv, con
   void* b16 = base + k1g_table16_only(n_rows) + k1g_a16_bytes(n_rows);
   alignas(64) CUtensorMap unused;
   if (int rc = k1v4_pack_src(table, n_rows, a16, &unused, st)) return rc;
-  pack_wqkv16_bias_kernel<<<148, 256, 0, st>>>(wqkv, bqkv, reinterpret_cast<__half*>(b16));
-  NRMS_LAUNCH_CHECK("pack_wqkv16_bias_kernel");
   const float qscale = 1.4426950408889634f / sqrtf((float)DH);
-  return tc_gemm_nt_f16(a16, 320, b16, 320, table16, k1g::ROW_BYTES / 2, n_rows, D3, 304, qscale, D, 1, st);
+  pack_wqkv16_table_kernel<<<148, 256, 0, st>>>(wqkv, bqkv, reinterpret_cast<__half*>(b16), qscale);
+  NRMS_LAUNCH_CHECK("pack_wqkv16_table_kernel");
+  return tc_gemm_nt_f16_tma(a16, 320, b16, 320, table16, TABLE_COLS, n_rows, TABLE_COLS, 304, st);
 }
 
 // Cbuf: fp16 context rows [n_users*50][320]; columns 300..319 are never written here (clear them once per buffer)

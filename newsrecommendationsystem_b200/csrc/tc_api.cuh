@@ -9,7 +9,7 @@ namespace nrms {
 int tc_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
                int64_t M, int N, int K, cudaStream_t st);
 // Same contraction with an epilogue mode (store / C += / atomic C +=) and an optional split along K (atomic only).
-enum { TC_EPI_STORE = 0, TC_EPI_ACCUM = 1, TC_EPI_ATOMIC = 2, TC_EPI_STORE_F16 = 3, TC_EPI_STORE_F16_QKV = 4 };
+enum { TC_EPI_STORE = 0, TC_EPI_ACCUM = 1, TC_EPI_ATOMIC = 2, TC_EPI_STORE_F16 = 3, TC_EPI_STORE_F16_QKV = 4, TC_EPI_STORE_F16_TMA = 5 };
 int tc_gemm_nt_ex(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
                   int64_t M, int N, int K, int k_splits, int epi, cudaStream_t st);
 int tc_gemm_auto_splits(int64_t M, int N, int K);
@@ -43,6 +43,8 @@ void set_attn_safe_softmax(int v);
 int get_attn_safe_softmax();   // -1 auto (bound over the projected table), 0 plain 2^s, 1 row-shifted form
 void set_k1f_debug(int v);           // component-removal timing switches of K1f (garbage results)
 void set_fused_pool(bool on);        // table path: 1 (default) = K1f, 0 = K1g + K2 (context rows through HBM)
+int tc_gemm_nt_f16_tma(const void* A16, int64_t lda, const void* B16, int64_t ldb, void* C16, int64_t ldc, int64_t M, int N,
+                       int K, cudaStream_t st);   // fp16 in / fp16 out, dense row-major result through bulk tensor stores
 int set_k1g_variant(int v);     // 0 = head per warp (S = 50 only), 1 = (head, query tile) units, 2 = length-templated kernel
 void set_news_table_attn(bool on);   // news encoder over the projected embedding table (default on)
 void set_table_attn(bool on);   // indexed user encoder: project the table once + K1g (default on)

@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
+#include <string.h>
 #include "tc_common.cuh"
 #include "tc_api.cuh"
 
@@ -29,6 +30,11 @@ constexpr int TG_B_BYTES = TG_BN * TG_BK * 4;  // 32 KB
 constexpr int TG_STAGE_BYTES = TG_A_BYTES + TG_B_BYTES;
 constexpr int TG_THREADS = 192;
 constexpr int TG_SMEM = TG_STAGES * TG_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+// TMA-store epilogue (fp16 output): 3 pipeline stages + one 16 KB staging buffer per epilogue warp (4 boxes of 32 rows x 128 B)
+constexpr int TG_STAGES_TMA = 3;
+constexpr int TG_STG_WARP = 4 * 32 * 128;
+constexpr int TG_SMEM_TMA = TG_STAGES_TMA * TG_STAGE_BYTES + 4 * TG_STG_WARP + 1024 + 256;
+static_assert(TG_SMEM_TMA <= 232448, "shared memory");
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap* tmap, int c0, int c1, uint32_t bar) {
   asm volatile(
@@ -44,22 +50,30 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 // F16 = false: fp32 operands rounded to TF32 by the TMA unit, kind::tf32 (K = 8 per MMA, 32 floats per 128-byte chunk);
 // F16 = true : fp16 operands, kind::f16 (K = 16 per MMA, 64 halfs per chunk): half the operand bytes per flop and half the
 //              MMA count -- the contraction the table projection of K1g uses (bias rides in a 1.0 column of A).
-template <bool F16>
+// TMA_EPI = true (F16 only): the epilogue rounds the accumulator to fp16 into a 128B-swizzled staging tile and leaves
+//              with bulk tensor stores (one per 32 rows x 64 columns) instead of per-thread stores: with thread == row
+//              every store instruction touched 32 different rows (32 requests of 16 bytes), which bound the table
+//              projection of K1g at 147 us for 35 GFLOP.
+template <bool F16, bool TMA_EPI = false>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                  const __grid_constant__ CUtensorMap tmap_c,
                   const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int64_t M, int N, int K,
                   uint32_t stage_tx_bytes, int k_splits, int chunks_per_split, int epi, float f16_scale, int f16_scale_cols) {
+  static_assert(!TMA_EPI || F16, "the bulk-store epilogue writes fp16");
+  constexpr int TG_STAGES = TMA_EPI ? TG_STAGES_TMA : nrms::TG_STAGES;
+  constexpr int STG_BYTES = TMA_EPI ? 4 * TG_STG_WARP : 0;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base - raw);
-  const uint32_t bars = base + TG_STAGES * TG_STAGE_BYTES;
+  const uint32_t bars = base + TG_STAGES * TG_STAGE_BYTES + STG_BYTES;
   const uint32_t full_bar = bars;                          // [STAGES]
   const uint32_t empty_bar = bars + 8 * TG_STAGES;         // [STAGES]
   const uint32_t tfull_bar = bars + 16 * TG_STAGES;        // [2]
   const uint32_t tempty_bar = tfull_bar + 16;              // [2]
   volatile uint32_t* tmem_ptr_smem =
-      reinterpret_cast<volatile uint32_t*>(base_ptr + TG_STAGES * TG_STAGE_BYTES + 16 * TG_STAGES + 32);
+      reinterpret_cast<volatile uint32_t*>(base_ptr + TG_STAGES * TG_STAGE_BYTES + STG_BYTES + 16 * TG_STAGES + 32);
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler (converged MMA issue)
@@ -171,6 +185,40 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       tc_fence_after();
       const int64_t m = m0 + q * 32 + lane;
       const uint32_t trow = tmem_base + as * TG_BN + ((uint32_t)(q * 32) << 16);
+      if constexpr (TMA_EPI) {
+        // fp16 tile rows of this warp -> staging (4 boxes of 32 rows x 64 halfs, 16-byte chunk c of row r at c ^ (r & 7))
+        // -> bulk tensor stores; rows / columns past the tensor are clipped by the TMA unit
+        uint8_t* const stg = base_ptr + TG_STAGES * TG_STAGE_BYTES + (warp - 2) * TG_STG_WARP;
+        const uint32_t stg_s = base + TG_STAGES * TG_STAGE_BYTES + (warp - 2) * TG_STG_WARP;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // previous tile's stores have read it
+        __syncwarp();
+        for (int col = 0; col < n_valid; col += 16) {
+          float v[16];
+          tmem_ld16(trow + col, v);
+          uint32_t h[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const __half2 p = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+            h[j] = *reinterpret_cast<const uint32_t*>(&p);
+          }
+          uint8_t* const brow = stg + (col >> 6) * 4096 + lane * 128;
+          const int c16 = (col & 63) >> 3;
+          *reinterpret_cast<uint4*>(brow + (((c16) ^ (lane & 7)) << 4)) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(brow + (((c16 + 1) ^ (lane & 7)) << 4)) = make_uint4(h[4], h[5], h[6], h[7]);
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(tempty_bar + 8 * as);
+          for (int b = 0; b * 64 < n_valid; ++b)
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                         ::"l"(reinterpret_cast<uint64_t>(&tmap_c)), "r"(n0 + 64 * b), "r"((int)(m0 + q * 32)), "r"(stg_s + b * 4096)
+                         : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        continue;
+      }
       for (int col = 0; col < n_valid; col += 16) {
         float v[16];
         tmem_ld16(trow + col, v);
@@ -255,6 +303,7 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       if (lane == 0) mbar_arrive(tempty_bar + 8 * as);
     }
   }
+  if (TMA_EPI && warp >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 512);
@@ -331,9 +380,35 @@ int make_tmap_store_f16(CUtensorMap* out, const void* base, int64_t rows, int co
   return NRMS_OK;
 }
 
+// fp16 row-major [rows, cols]: 128B-swizzled boxes of 32 rows x 64 halfs for the bulk-store epilogue
+static int make_tmap_store_f16_sw128(CUtensorMap* out, const void* base, int64_t rows, int cols, int64_t ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  NRMS_CHECK_ARG(fn != nullptr, NRMS_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, rows < 32 ? (cuuint32_t)rows : 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NRMS_CHECK_ARG(r == CUDA_SUCCESS, NRMS_E_CUDA, "cuTensorMapEncodeTiled(store f16 sw128) failed with CUresult %d", (int)r);
+  return NRMS_OK;
+}
+
 static int tc_gemm_launch(const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
                          int64_t M, int N, int K, int k_splits, int epi, float f16_scale, int f16_scale_cols, bool f16_in,
                          cudaStream_t st);
+
+// fp16 operands, fp16 result C16[m][n] = half(sum_k A16[m][k] B16[n][k]) (row-major, ldc halfs, 16-byte aligned rows), leaving
+// through bulk tensor stores.  No bias / scale: the callers fold them into B (a bias column met by a 1.0 column of A).
+int tc_gemm_nt_f16_tma(const void* A16, int64_t lda, const void* B16, int64_t ldb, void* C16, int64_t ldc, int64_t M, int N,
+                       int K, cudaStream_t st) {
+  NRMS_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0 && (ldc % 8) == 0 && aligned16(A16) && aligned16(B16) && aligned16(C16) &&
+                     (K % 8) == 0 && (N % 8) == 0,
+                 NRMS_E_INVALID, "fp16 GEMM operands must be 16-byte aligned rows");
+  return tc_gemm_launch(A16, lda, B16, ldb, nullptr, reinterpret_cast<float*>(C16), ldc, M, N, K, 1, TC_EPI_STORE_F16_TMA,
+                        1.f, 0, true, st);
+}
 
 int tc_gemm_nt_ex(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
                   int64_t M, int N, int K, int k_splits, int epi, cudaStream_t st) {
@@ -373,9 +448,16 @@ static int tc_gemm_launch(const void* A, int64_t lda, const void* B, int64_t ldb
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_gemm_nt_kernel)");
     e = cudaFuncSetAttribute(tc_gemm_nt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_gemm_nt_kernel<f16>)");
+    e = cudaFuncSetAttribute(tc_gemm_nt_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_TMA);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_gemm_nt_kernel<f16, tma>)");
     configured = true;
   }
-  alignas(64) CUtensorMap ta, tb;
+  alignas(64) CUtensorMap ta, tb, tcm;
+  memset(&tcm, 0, sizeof(tcm));
+  if (epi == TC_EPI_STORE_F16_TMA) {
+    NRMS_CHECK_ARG(f16_in, NRMS_E_INVALID, "the bulk-store epilogue needs fp16 operands");
+    if (int rc = make_tmap_store_f16_sw128(&tcm, C, M, N, ldc)) return rc;
+  }
   // boxes never exceed the tensor extent (rows past it would only feed outputs that are not stored)
   const int box_a = M < TG_BM ? (int)M : TG_BM;
   const int box_b = N < TG_BN ? N : TG_BN;
@@ -397,11 +479,14 @@ static int tc_gemm_launch(const void* A, int64_t lda, const void* B, int64_t ldb
   const int64_t items = tiles * k_splits;
   int grid = num_sms();
   if (items < grid) grid = (int)items;
-  if (f16_in)
-    tc_gemm_nt_kernel<true><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, bias, C, ldc, M, N, K, stage_tx, k_splits, cps, epi,
+  if (epi == TC_EPI_STORE_F16_TMA)
+    tc_gemm_nt_kernel<true, true><<<grid, TG_THREADS, TG_SMEM_TMA, st>>>(ta, tb, tcm, bias, C, ldc, M, N, K, stage_tx, k_splits,
+                                                                          cps, epi, f16_scale, f16_scale_cols);
+  else if (f16_in)
+    tc_gemm_nt_kernel<true><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, tcm, bias, C, ldc, M, N, K, stage_tx, k_splits, cps, epi,
                                                                f16_scale, f16_scale_cols);
   else
-    tc_gemm_nt_kernel<false><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, bias, C, ldc, M, N, K, stage_tx, k_splits, cps, epi,
+    tc_gemm_nt_kernel<false><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, tcm, bias, C, ldc, M, N, K, stage_tx, k_splits, cps, epi,
                                                                 f16_scale, f16_scale_cols);
   NRMS_LAUNCH_CHECK("tc_gemm_nt");
   return NRMS_OK;
