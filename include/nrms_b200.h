@@ -62,22 +62,22 @@ int nrms_abi_version(void);
 /* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t nrms_launch_count(void);
 
-/* Tuning / A-B switches.  "k1_variant": fused tensor-mode encoder kernel generation
- * (1 = CUDA-core attention, 2 = tcgen05 attention, 3 = tcgen05 attention with two heads in flight,
- *  4 = 3 + TMA-gathered fp16 source rows, bias/scale folded into the GEMM, q read from tensor memory,
- *  5 = 4 with two projection accumulators and the probabilities kept in place over the scores,
- *  6 [default] = 5 with two worker groups taking alternate passes).
- * "user_table_attn" (default 1): tensor-mode nrms_user_encoder_fwd calls with int32 row indices whose history
- *  rows outnumber the table rows 8:1 project the TABLE once (q|k|v in fp16) and run the attention on gathered rows
- *  (K1g, k1g_table_attn.cu) instead of projecting every gathered row; 0 = always the per-user projection.
- * "news_table_attn" (default 1): the same for nrms_news_encoder_fwd -- the EMBEDDING table is projected once per call
- *  when the token rows outnumber the vocabulary rows 8:1.
- * "k1g_variant" (default 2): 2 = length-templated kernel (both encoders), 0 / 1 = the first S = 50 kernels (A/B). */
+/* Tuning / A-B switches of the tensor-mode inference encoders.
+ * "user_table_attn" / "news_table_attn" (default 1): indexed calls whose gathered rows outnumber the rows of their source
+ *  table "table_ratio":1 (default 4) project the TABLE once (q|k|v rows in fp16, one kind::f16 GEMM) and run the attention
+ *  on gathered rows (K1g, k1g_table_attn.cu) instead of projecting every gathered row (K1 v6, tc_fused7.cu); 0 = always
+ *  the per-sequence projection.
+ * "fused_pool" (default 0): table path with the additive pooling inside the attention kernel (K1f, k1f_attn_pool.cu: the
+ *  context rows never leave the SM; measured slower than K1g + K2).
+ * "attn_safe_softmax" (default -1): -1 = the attention kernels choose between 2^s and the row-shifted form
+ *  2^(s - max) / (Z + 1e-8 * 2^-max) from a bound on the scores, 0 / 1 force one form (tests).
+ * "k1f_debug": component-removal timing masks of K1f (garbage results; profiles/k1f_probe.py). */
 int nrms_set_option(const char* key, int value);
 /* "time_k1" = 1 brackets every fused K1 launch with CUDA events on the launching stream (clears the previous
  * record); nrms_get_stat("<kind>_ms" | "<kind>_launches" | "<kind>_sequences") reads the totals back (syncs on the
- * recorded events) for kind = k1 (user encoder, per-user projection), k1n (news encoder), k1g (user encoder, table
- * attention).  Used by bench.py for the roofline of the dominant kernel.  Unknown key: -1. */
+ * recorded events) for kind = k1 (user encoder, per-user projection), k1n (news encoder, per-title projection), k1g (user
+ * encoder, table attention), k1gn (news encoder, table attention).  Used by bench.py for the roofline of the dominant
+ * kernel.  Unknown key: -1. */
 double nrms_get_stat(const char* key);
 
 /* ---- sizes ------------------------------------------------------------------------- */
@@ -126,6 +126,16 @@ int nrms_user_encoder_fwd(const float* x, int64_t n_rows, const int32_t* rows, i
                           float* out, void* stash,
                           void* workspace, size_t workspace_bytes,
                           int mode, void* stream);
+
+/* Tensor-mode, inference-only form of the indexed user encoder whose table is already held as fp16 rows: table16 =
+ * [n_rows + 1][320] halfs in nrms_pack_rows_f16's layout (300 values, 1.0 in column 300, zero tail; last row all zero).
+ * This is what evaluate keeps between its stages (src/evaluate.py:193-233): the news stage packs its vectors once, the
+ * all-gather moves 640-byte rows, and both the user encoder and nrms_score_csr_f16 read the same copy. */
+size_t nrms_user_encoder_table16_workspace_bytes(int64_t n_users, int S, int64_t n_rows);
+int nrms_user_encoder_table16_fwd(const void* table16, int64_t n_rows, const int32_t* rows, int64_t n_users, int S,
+                                  const float* wqkv, const float* bqkv,
+                                  const float* wa, const float* ba, const float* qa,
+                                  float* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* User encoder backward (dense input only).  d_x [n_users,S,300] is OVERWRITTEN; weight
  * gradients are accumulated (+=). */

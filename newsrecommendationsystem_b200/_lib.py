@@ -34,6 +34,8 @@ SIGNATURES = {
     "nrms_user_encoder_fwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),
     "nrms_user_encoder_bwd": (_i32, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                      _i32, _vp]),
+    "nrms_user_encoder_table16_workspace_bytes": (_sz, [_i64, _i32, _i64]),
+    "nrms_user_encoder_table16_fwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "nrms_encoder_ln_stash_bytes": (_sz, [_i64, _i32]),
     "nrms_news_encoder_ln_fwd": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                         _sz, _f32, _u64, _u64, _i32, _vp]),

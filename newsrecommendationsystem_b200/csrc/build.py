@@ -8,7 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 OUT = os.path.join(PKG, "libnrms_b200.so")
 OBJ = os.path.join(HERE, "_obj")
-SOURCES = ["encoder.cu", "misc.cu", "tc_gemm.cu", "tc_fused.cu", "tc_fused2.cu", "tc_fused3.cu", "tc_fused4.cu", "tc_fused5.cu", "tc_fused6.cu", "tc_fused7.cu", "k1g_table_attn.cu", "k1f_attn_pool.cu"]
+SOURCES = ["encoder.cu", "misc.cu", "pack.cu", "tc_gemm.cu", "fused_host.cu", "tc_fused3.cu", "tc_fused7.cu", "k1g_table_attn.cu",
+           "k1f_attn_pool.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -321,7 +321,7 @@ static int news_encoder_fwd_impl(const int64_t* tokens, int64_t n_titles, int L,
   }
   // inference
   if (mode == NRMS_MODE_TF32 && dropout_p == 0.f && tc_fused_workspace_bytes(n_titles, L, num_words) != (size_t)-1) {
-    return tc_encoder_fused(emb, num_words, tokens, 1, n_titles, L, wqkv, bqkv, wa, ba, qa, out, workspace,
+    return tc_encoder_fused(emb, nullptr, num_words, tokens, 1, n_titles, L, wqkv, bqkv, wa, ba, qa, out, workspace,
                             workspace_bytes, st, ln ? ln->gamma : nullptr, ln ? ln->beta : nullptr);
   }
   const int64_t chunk_seq = INFER_CHUNK_ROWS / L;
@@ -435,7 +435,7 @@ static int user_encoder_fwd_impl(const float* x, int64_t n_rows, const int32_t* 
   }
   NRMS_CHECK_ARG(rows_idx == nullptr || n_rows > 0, NRMS_E_INVALID, "indexed input needs n_rows (rows of the table)");
   if (mode == NRMS_MODE_TF32 && tc_fused_workspace_bytes(n_users, S, rows_idx ? n_rows : 0) != (size_t)-1) {
-    return tc_encoder_fused(x, rows_idx ? n_rows : 0, rows_idx, rows_idx ? 2 : 0, n_users, S, wqkv, bqkv, wa, ba, qa, out,
+    return tc_encoder_fused(x, nullptr, rows_idx ? n_rows : 0, rows_idx, rows_idx ? 2 : 0, n_users, S, wqkv, bqkv, wa, ba, qa, out,
                             workspace, workspace_bytes, st, ln ? ln->gamma : nullptr, ln ? ln->beta : nullptr);
   }
   const int64_t chunk_seq = INFER_CHUNK_ROWS / S;
@@ -474,6 +474,28 @@ int nrms_user_encoder_ln_fwd(const float* x, int64_t n_rows, const int32_t* rows
   const LnArgs ln{ln_gamma, ln_beta, nullptr, nullptr};
   return user_encoder_fwd_impl(x, n_rows, rows_idx, n_users, S, wqkv, bqkv, wa, ba, qa, out, stash, workspace,
                                workspace_bytes, mode, stream, &ln);
+}
+
+size_t nrms_user_encoder_table16_workspace_bytes(int64_t n_users, int S, int64_t n_rows) {
+  if (n_users <= 0 || S <= 0 || n_rows <= 0) return 0;
+  size_t fused = tc_fused_workspace_bytes(n_users, S, n_rows, true);
+  return fused == (size_t)-1 ? 0 : fused + 256;
+}
+
+int nrms_user_encoder_table16_fwd(const void* table16, int64_t n_rows, const int32_t* rows_idx, int64_t n_users, int S,
+                                  const float* wqkv, const float* bqkv, const float* wa, const float* ba, const float* qa,
+                                  float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (int rc = check_common(S, NRMS_MODE_TF32)) return rc;
+  NRMS_CHECK_ARG(n_users >= 0 && n_rows > 0, NRMS_E_INVALID, "bad sizes");
+  if (n_users == 0) return NRMS_OK;
+  NRMS_CHECK_ARG(table16 && rows_idx && wqkv && bqkv && wa && ba && qa && out, NRMS_E_INVALID, "null pointer");
+  NRMS_CHECK_ARG(aligned16(table16) && aligned16(wqkv) && aligned16(bqkv) && aligned16(wa) && aligned16(ba) && aligned16(out),
+                 NRMS_E_INVALID, "pointers must be 16-byte aligned");
+  NRMS_CHECK_ARG(tc_fused_workspace_bytes(n_users, S, n_rows, true) != (size_t)-1, NRMS_E_UNSUPPORTED,
+                 "sequence length not compiled");
+  return tc_encoder_fused(nullptr, table16, n_rows, rows_idx, 2, n_users, S, wqkv, bqkv, wa, ba, qa, out, workspace,
+                          workspace_bytes, st);
 }
 
 static int user_encoder_bwd_impl(const float* d_out, int64_t n_users, int S, const float* wqkv, const float* wa,
@@ -573,12 +595,8 @@ int nrms_additive_fwd(const float* c, int64_t n_seq, int S, const float* wa, con
 
 int nrms_set_option(const char* key, int value) {
   NRMS_CHECK_ARG(key != nullptr, NRMS_E_INVALID, "null option key");
-  if (strcmp(key, "k1_variant") == 0) {
-    NRMS_CHECK_ARG(set_k1_variant(value) == NRMS_OK, NRMS_E_INVALID, "k1_variant must be 1..6");
-    return NRMS_OK;
-  }
-  if (strcmp(key, "k1g_variant") == 0) {
-    NRMS_CHECK_ARG(set_k1g_variant(value) == NRMS_OK, NRMS_E_INVALID, "k1g_variant must be 0, 1 or 2");
+  if (strcmp(key, "table_ratio") == 0) {
+    NRMS_CHECK_ARG(set_table_ratio(value) == NRMS_OK, NRMS_E_INVALID, "table_ratio must be 1..1024");
     return NRMS_OK;
   }
   if (strcmp(key, "news_table_attn") == 0) {

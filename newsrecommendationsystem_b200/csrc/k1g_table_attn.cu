@@ -26,9 +26,9 @@
 // tcgen05 tile would be 61 % padding, see K1 v6).  Measured: the kernel is bound by instruction issue first and the
 // HMMA pipe second; legacy HMMA runs at 8 cycles per instruction and sub-partition on B200.
 //
-// Kernels in this file: seq_attn_kernel<SEQ, IdxT> (the product path, both encoders); table_attn_kernel (the first
-// S = 50 form, kept with its timing switches K1G_DBG_* as "k1g_variant" 0) and table_attn_units_kernel (24 warps, one
-// (head, query tile) per unit, "k1g_variant" 1: measured slower) for A/B runs.
+// Kernels in this file: seq_attn_kernel<SEQ, IdxT, SAFE> (both encoders) and the table projection's operand packing.
+// (The first S = 50 forms -- table_attn_kernel with its component-removal switches and the 24-warp unit-parallel
+// table_attn_units_kernel, measured slower -- were removed in round 2; their measurements are in DESIGN.md.)
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include "tc_common.cuh"
@@ -47,18 +47,7 @@ constexpr int OFF_V = 2 * HG * SLICE;   // 480
 constexpr int PITCH = 3 * GROUP;        // 2,160 B: one table16 row
 constexpr int STAGE = S * PITCH;        // 108,000 B: one user
 constexpr int NSTAGE = 2;
-#ifndef K1G_PREFETCH_AHEAD
-#define K1G_PREFETCH_AHEAD 0
-#endif
-constexpr int PREFETCH_AHEAD = K1G_PREFETCH_AHEAD;
-#ifndef K1G_V_RELOAD
-#define K1G_V_RELOAD 0
-#endif
-constexpr bool V_RELOAD = K1G_V_RELOAD != 0;   // V fragments reloaded per query tile (registers for the second score tile)
 constexpr int ROW_BYTES = PITCH;
-constexpr int OFF_ZERO = NSTAGE * STAGE;   // 64 B of zeros (rows >= 50 of every ldmatrix)
-constexpr int OFF_BAR = OFF_ZERO + 64;     // full[6], empty[6]
-constexpr int SMEM = OFF_BAR + 128;        // 216,192 B
 constexpr int THREADS = 512;
 constexpr int CP = 320;            // pitch (halfs) of the context rows K2 reads
 
@@ -103,283 +92,9 @@ __device__ __forceinline__ float ex2f(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 2^x on the FMA / integer pipes (Cody-Waite split by the 1.5*2^23 trick + degree-4 polynomial, relative error < 5e-5,
-// an order below the fp16 rounding of P).  K1G_EX2_FMA = n > 0 sends every n-th exponential of a key tile pair here:
-// the MUFU unit (16 ex2 per clock per SM) is the second-busiest pipe of this kernel after the HMMA pipe.
-#ifndef K1G_EX2_FMA
-#define K1G_EX2_FMA 0
-#endif
-__device__ __forceinline__ float ex2_fma(float x) {
-  x = fmaxf(x, -100.f);
-  const float t = x + 12582912.f;
-  const float f = x - (t - 12582912.f);
-  float p = fmaf(f, 0.009618129f, 0.05550411f);
-  p = fmaf(f, p, 0.2402265f);
-  p = fmaf(f, p, 0.6931472f);
-  p = fmaf(f, p, 1.f);
-  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(t) << 23));
-}
-template <int J>
-__device__ __forceinline__ float ex2_sel(float x) {
-  if (K1G_EX2_FMA > 0 && (J % K1G_EX2_FMA) == K1G_EX2_FMA - 1) return ex2_fma(x);
-  return ex2f(x);
-}
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
   const __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&h);
-}
-
-// smem byte address of row `row` of a stage plus a byte offset (a multiple of 16).  Rows >= 50 (padding of the 16-row
-// tiles) read row 49 instead: whatever they hold is finite, padded KEYS are masked out of P (so neither their scores nor
-// their v rows count) and padded QUERY rows are never stored.  K1G_ZERO_ROWS=1 keeps the older form that redirected them
-// to a zero line (a compare + select per ldmatrix address; this kernel is bound by instruction issue).
-#ifndef K1G_DIRECT_STORE
-#define K1G_DIRECT_STORE 0      // 1 = accumulator fragments straight to global (4-byte stores), 0 = staged through the q slice
-#endif
-#ifndef K1G_ZERO_ROWS
-#define K1G_ZERO_ROWS 0
-#endif
-__device__ __forceinline__ uint32_t row_addr(uint32_t stage, uint32_t zero, int row, int off) {
-#if K1G_ZERO_ROWS
-  return row < S ? stage + (uint32_t)(row * PITCH + off) : zero + (uint32_t)(off & 31);
-#else
-  (void)zero;
-  return stage + (uint32_t)((row < S ? row : S - 1) * PITCH + off);
-#endif
-}
-
-__global__ void __launch_bounds__(THREADS, 1)
-table_attn_kernel(const __half* __restrict__ table16, int n_table_rows, const int32_t* __restrict__ hist_rows,
-                  int64_t n_users, __half* __restrict__ ctx) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const uint32_t sbase = tc::smem_u32(smem);
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const uint32_t zero = sbase + OFF_ZERO;
-  const uint32_t full_bar = sbase + OFF_BAR, empty_bar = full_bar + 8 * NSTAGE;
-
-  if (tid < 16) reinterpret_cast<uint32_t*>(smem + OFF_ZERO)[tid] = 0u;
-  if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) {
-      tc::mbar_init(full_bar + 8 * s, 1);
-      tc::mbar_init(empty_bar + 8 * s, H);
-    }
-    tc::mbar_fence_init();
-  }
-  __syncthreads();
-
-  if (warp == H) {
-    // ------------------------------ producer: 50 bulk copies of 720 B per stage ------------------------------
-    uint32_t it = 0;                                   // stage counter: user-major, head group fastest
-    for (int64_t u = blockIdx.x; u < n_users; u += gridDim.x) {
-      int r0 = hist_rows[u * S + lane];
-      int r1 = lane + 32 < S ? hist_rows[u * S + lane + 32] : 0;
-      r0 = r0 < 0 ? 0 : (r0 >= n_table_rows ? n_table_rows - 1 : r0);
-      r1 = r1 < 0 ? 0 : (r1 >= n_table_rows ? n_table_rows - 1 : r1);
-      const char* s0 = reinterpret_cast<const char*>(table16) + (int64_t)r0 * ROW_BYTES;
-      const char* s1 = reinterpret_cast<const char*>(table16) + (int64_t)r1 * ROW_BYTES;
-      {
-        // L2 prefetch of the rows two users ahead (17 lines of 128 B per 2,160-byte row): the bulk copies then hit L2
-        const int64_t up = u + (int64_t)PREFETCH_AHEAD * gridDim.x;
-        if (PREFETCH_AHEAD > 0 && up < n_users) {
-          int p0 = __ldg(hist_rows + up * S + lane);
-          int p1 = lane + 32 < S ? __ldg(hist_rows + up * S + lane + 32) : 0;
-          p0 = p0 < 0 ? 0 : (p0 >= n_table_rows ? n_table_rows - 1 : p0);
-          p1 = p1 < 0 ? 0 : (p1 >= n_table_rows ? n_table_rows - 1 : p1);
-#pragma unroll 5
-          for (int r = 0; r < S; ++r) {
-            const int pr = __shfl_sync(0xffffffffu, r < 32 ? p0 : p1, r & 31);
-            if (lane < 17) {
-              const char* a = reinterpret_cast<const char*>(table16) + (int64_t)pr * ROW_BYTES + lane * 128;
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-            }
-          }
-        }
-        const uint32_t st = it % NSTAGE;
-        tc::mbar_wait(empty_bar + 8 * st, ((it / NSTAGE) & 1) ^ 1);
-#ifdef K1G_DBG_NOGATHER      // timing experiment: no copies, the compute warps run on whatever the stage holds
-        if (lane == 0) tc::mbar_arrive(full_bar + 8 * st);
-        (void)s0; (void)s1;
-#else
-        if (lane == 0) mbar_arrive_expect_tx(full_bar + 8 * st, STAGE);
-        __syncwarp();
-        const uint32_t dst = sbase + st * STAGE + lane * PITCH;
-        bulk_copy_g2s(dst, s0, PITCH, full_bar + 8 * st);
-        if (lane + 32 < S) bulk_copy_g2s(dst + 32 * PITCH, s1, PITCH, full_bar + 8 * st);
-#endif
-        ++it;
-      }
-    }
-  } else {
-    // ------------------------------ compute: warp = head ------------------------------
-    const int hg = warp / HG, hl = warp - hg * HG;
-    const int qoff = hg * GROUP + hl * SLICE, koff = OFF_K + qoff, voff = OFF_V + qoff;
-    const int g = lane >> 2, t = lane & 3;
-    const int mi = lane >> 3, rr = lane & 7;     // ldmatrix: this lane supplies row rr of matrix mi
-    // Byte offsets of this lane's ldmatrix rows inside a stage: constant over the whole kernel (only the stage base
-    // changes per user), so the per-user address work is one add per load -- the kernel is bound by instruction issue.
-    auto rofs = [](int row) { return (uint32_t)((row < S ? row : S - 1) * PITCH); };     // padded rows read row 49
-    uint32_t k16o[4], k8o[2], v4o[4], v2o[4], q4o[4], q2o[4];
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      k16o[p] = rofs(16 * p + 8 * (mi >> 1) + rr) + koff + (mi & 1) * 16;
-      v4o[p] = rofs(16 * p + 8 * (mi & 1) + rr) + voff + (mi >> 1) * 16;
-      v2o[p] = rofs(16 * p + 8 * (mi & 1) + rr) + voff + 32;
-      q4o[p] = rofs(16 * p + 8 * (mi & 1) + rr) + qoff + (mi >> 1) * 16;
-      q2o[p] = rofs(16 * p + 8 * (mi & 1) + rr) + qoff + 32;
-    }
-#pragma unroll
-    for (int p = 0; p < 2; ++p) k8o[p] = rofs(32 * p + 8 * mi + rr) + koff + 32;
-    uint32_t itu = 0;
-    for (int64_t u = blockIdx.x; u < n_users; u += gridDim.x, ++itu) {
-      const uint32_t it = itu;
-      const uint32_t st = it % NSTAGE;
-      const uint32_t B = sbase + st * STAGE;
-      tc::mbar_wait(full_bar + 8 * st, (it / NSTAGE) & 1);
-      // ---- K fragments: kb16[nt][0..1] (dims 0-7, 8-15), kb8[nt] (dims 16-23) for key tiles nt = 0..6 ----
-      uint32_t kb16[8][2], kb8[8];
-#pragma unroll
-      for (int p = 0; p < 4; ++p)   // key tiles (2p, 2p+1): matrices [2p,d0-7] [2p,d8-15] [2p+1,d0-7] [2p+1,d8-15]
-        ldsm_x4(B + k16o[p], kb16[2 * p][0], kb16[2 * p][1], kb16[2 * p + 1][0], kb16[2 * p + 1][1]);   // key tile 7 unused
-#pragma unroll
-      for (int p = 0; p < 2; ++p)   // dims 16-23 of key tiles 4p..4p+3
-        ldsm_x4(B + k8o[p], kb8[4 * p], kb8[4 * p + 1], kb8[4 * p + 2], kb8[4 * p + 3]);
-      // ---- V fragments (transposed loads): vb[ks][dt][0..1] keys 16ks..16ks+7 / +8..15, dims 8dt..8dt+7 ----
-      uint32_t vb[4][3][2];
-      auto load_v = [&]() {
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          // matrices: [keys 16ks+0..7, d0-7] [keys +8..15, d0-7] [keys 0..7, d8-15] [keys +8..15, d8-15]
-          ldsm_x4_t(B + v4o[ks], vb[ks][0][0], vb[ks][0][1], vb[ks][1][0], vb[ks][1][1]);
-          ldsm_x2_t(B + v2o[ks], vb[ks][2][0], vb[ks][2][1]);
-        }
-      };
-      if (!V_RELOAD) load_v();
-      // S = Q K^T of query tile mt (16 rows): seven k16 steps, then the dependent k8 steps
-      auto scores = [&](int mt, float (&sacc)[7][4]) {
-        uint32_t qa[4], qb[2];
-        ldsm_x4(B + q4o[mt], qa[0], qa[1], qa[2], qa[3]);
-        ldsm_x2(B + q2o[mt], qb[0], qb[1]);
-#ifdef K1G_DBG_NOS          // timing experiment: no score MMAs
-#pragma unroll
-        for (int nt = 0; nt < 7; ++nt) {
-          sacc[nt][0] = __uint_as_float(qa[0] & 0x3f800000u); sacc[nt][1] = __uint_as_float(qb[0] & 0x3f800000u);
-          sacc[nt][2] = __uint_as_float(kb16[nt][0] & 0x3f800000u); sacc[nt][3] = __uint_as_float(kb8[nt] & 0x3f800000u);
-        }
-#else
-#pragma unroll
-        for (int nt = 0; nt < 7; ++nt) {
-          sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
-          mma_k16(sacc[nt], qa[0], qa[1], qa[2], qa[3], kb16[nt][0], kb16[nt][1]);
-        }
-#pragma unroll
-        for (int nt = 0; nt < 7; ++nt) mma_k8(sacc[nt], qb[0], qb[1], kb8[nt]);
-#endif
-      };
-      // ---- four query tiles, software-pipelined: the score MMAs of tile mt+1 are in the tensor pipe while the
-      //      exponentials of tile mt run on the MUFU / FMA pipes ----
-      float sacc[2][7][4];
-      scores(0, sacc[0]);
-#pragma unroll
-      for (int mt = 0; mt < 4; ++mt) {
-        if (mt < 3) scores(mt + 1, sacc[(mt + 1) & 1]);
-        if (V_RELOAD) load_v();
-        float (&sc)[7][4] = sacc[mt & 1];
-        // P = 2^S (q carries log2(e)/sqrt(20)); keys 50..55 (key tile 6, t > 0) are padding
-        uint32_t pa[7][2];
-        const bool lower = mt < 3;              // rows 16mt+8..+15 exist only in the first three tiles
-#pragma unroll
-        for (int nt = 0; nt < 7; ++nt) {
-#ifdef K1G_DBG_NOEXP        // timing experiment: no exponentials
-          float p0 = sc[nt][0] + 1.f, p1 = sc[nt][1] + 1.f;
-          float p2 = 0.f, p3 = 0.f;
-          if (lower) { p2 = sc[nt][2] + 1.f; p3 = sc[nt][3] + 1.f; }
-#else
-          float p0 = ex2_sel<0>(sc[nt][0]), p1 = ex2_sel<1>(sc[nt][1]);
-          float p2 = 0.f, p3 = 0.f;
-          if (lower) { p2 = ex2_sel<2>(sc[nt][2]); p3 = ex2_sel<3>(sc[nt][3]); }
-#endif
-          if (nt == 6 && t > 0) { p0 = p1 = p2 = p3 = 0.f; }
-          pa[nt][0] = pack_h2(p0, p1);
-          pa[nt][1] = pack_h2(p2, p3);
-        }
-        float oacc[3][4];
-#pragma unroll
-        for (int dt = 0; dt < 3; ++dt) oacc[dt][0] = oacc[dt][1] = oacc[dt][2] = oacc[dt][3] = 0.f;
-#ifdef K1G_DBG_NOPV         // timing experiment: no context MMAs
-#pragma unroll
-        for (int dt = 0; dt < 3; ++dt) {
-          oacc[dt][0] = __uint_as_float((pa[dt][0] ^ vb[0][dt][0]) & 0x3f800000u) + 1.f;
-          oacc[dt][1] = __uint_as_float((pa[dt + 3][1] ^ vb[1][dt][1]) & 0x3f800000u);
-          oacc[dt][2] = __uint_as_float((pa[6][0] ^ vb[2][dt][0]) & 0x3f800000u) + 1.f;
-          oacc[dt][3] = __uint_as_float((pa[dt][1] ^ vb[3][dt][0]) & 0x3f800000u);
-        }
-#else
-#pragma unroll
-        for (int ks = 0; ks < 3; ++ks)           // three independent accumulator chains interleaved
-#pragma unroll
-          for (int dt = 0; dt < 3; ++dt)
-            mma_k16(oacc[dt], pa[2 * ks][0], pa[2 * ks][1], pa[2 * ks + 1][0], pa[2 * ks + 1][1], vb[ks][dt][0],
-                    vb[ks][dt][1]);
-#pragma unroll
-        for (int dt = 0; dt < 3; ++dt) mma_k8(oacc[dt], pa[6][0], pa[6][1], vb[3][dt][0]);
-#endif
-        // Z of rows g / g+8 sits in column 20 = element 0 / 2 of dim tile 2 on the quad's lane t == 2
-        const float z0 = __shfl_sync(0xffffffffu, oacc[2][0], (lane & ~3) | 2);
-        const float z1 = __shfl_sync(0xffffffffu, oacc[2][2], (lane & ~3) | 2);
-        const float i0 = __fdividef(1.f, z0 + 1e-8f), i1 = __fdividef(1.f, z1 + 1e-8f);
-        // O / (Z + 1e-8) goes back IN PLACE over the head's q slice of these 16 rows (dead since their fragments were
-        // loaded), then the warp copies the 16 x 40 bytes out as 8-byte pieces: one memory request per (row, head)
-        // segment.  Storing the accumulator fragments straight to global (4 bytes per lane, 8 rows per instruction, 10
-        // instructions per tile) made 4,800 write requests per user and was THE limiter of this kernel: removing all the
-        // MMAs and exponentials, or the whole gather, did not change its run time (profiles/ab_k1g.sh, K1G_DBG_*).
-        const int r0 = 16 * mt + g, r1 = r0 + 8;
-#if K1G_DIRECT_STORE
-        {
-          __half* o0 = ctx + (u * S + r0) * CP + warp * 20 + 2 * t;
-#pragma unroll
-          for (int dt = 0; dt < 3; ++dt) {
-            if (dt < 2 || t < 2) {
-              if (r0 < S) *reinterpret_cast<uint32_t*>(o0 + dt * 8) = pack_h2(oacc[dt][0] * i0, oacc[dt][1] * i0);
-              if (r1 < S) *reinterpret_cast<uint32_t*>(o0 + 8 * CP + dt * 8) = pack_h2(oacc[dt][2] * i1, oacc[dt][3] * i1);
-            }
-          }
-          if (mt == 3) {
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(empty_bar + 8 * st);
-          }
-          continue;
-        }
-#endif
-        uint8_t* q0 = smem + st * STAGE + r0 * PITCH + qoff + 4 * t;
-#pragma unroll
-        for (int dt = 0; dt < 3; ++dt) {
-          if (dt < 2 || t < 2) {
-            if (r0 < S) *reinterpret_cast<uint32_t*>(q0 + dt * 16) = pack_h2(oacc[dt][0] * i0, oacc[dt][1] * i0);
-            if (r1 < S) *reinterpret_cast<uint32_t*>(q0 + 8 * PITCH + dt * 16) = pack_h2(oacc[dt][2] * i1, oacc[dt][3] * i1);
-          }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int p = lane + 32 * k;                 // 80 pieces: 16 rows x 5 x 8 bytes
-          const int row = 16 * mt + p / 5, c = p % 5;
-          if (p < 80 && row < S) {
-            const uint2 v = *reinterpret_cast<const uint2*>(smem + st * STAGE + row * PITCH + qoff + c * 8);
-#ifdef K1G_DBG_NOSTORE      // timing experiment: no context stores (one predicated-off store keeps the value alive)
-            if (v.x == 0x7fc07fc1u && v.y == 0x12345678u)
-#endif
-            *reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(ctx) + ((u * S + row) * CP + warp * 20) * 2 + c * 8) = v;
-          }
-        }
-        if (mt == 3) {               // last shared-memory access of this stage: hand it back to the producer
-          tc::fence_proxy_async_smem();      // the generic-proxy stores above precede the next bulk copy into these rows
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(empty_bar + 8 * st);
-        }
-      }
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -604,139 +319,6 @@ seq_attn_kernel(const __half* __restrict__ table16, int64_t n_table_rows, const 
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Variant "u" (unit-parallel): 24 warps instead of 16.  The work unit is one (head, 16-row query tile) -- 60 per
-// user -- dealt round-robin to 23 compute warps; K, V and Q fragments are loaded per unit and live only for the phase
-// that uses them, so a thread needs <= 80 registers and six warps share a sub-partition's HMMA / MUFU / FMA pipes
-// instead of four.  Costs 4x the ldmatrix traffic of the head-per-warp kernel (~2.9k shared-memory wavefronts per
-// user, below the 3.1k HMMA cycles).  Same stages, producer and output layout.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int U_WARPS = 24;
-constexpr int U_COMPUTE = U_WARPS - 1;
-constexpr int U_THREADS = U_WARPS * 32;
-constexpr int U_UNITS = H * 4;
-
-__global__ void __launch_bounds__(U_THREADS, 1)
-table_attn_units_kernel(const __half* __restrict__ table16, int n_table_rows, const int32_t* __restrict__ hist_rows,
-                        int64_t n_users, __half* __restrict__ ctx) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  const uint32_t sbase = tc::smem_u32(smem);
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const uint32_t zero = sbase + OFF_ZERO;
-  const uint32_t full_bar = sbase + OFF_BAR, empty_bar = full_bar + 8 * NSTAGE;
-
-  if (tid < 16) reinterpret_cast<uint32_t*>(smem + OFF_ZERO)[tid] = 0u;
-  if (tid == 0) {
-    for (int s = 0; s < NSTAGE; ++s) {
-      tc::mbar_init(full_bar + 8 * s, 1);
-      tc::mbar_init(empty_bar + 8 * s, U_COMPUTE);
-    }
-    tc::mbar_fence_init();
-  }
-  __syncthreads();
-
-  if (warp == U_COMPUTE) {
-    uint32_t it = 0;
-    for (int64_t u = blockIdx.x; u < n_users; u += gridDim.x, ++it) {
-      int r0 = hist_rows[u * S + lane];
-      int r1 = lane + 32 < S ? hist_rows[u * S + lane + 32] : 0;
-      r0 = r0 < 0 ? 0 : (r0 >= n_table_rows ? n_table_rows - 1 : r0);
-      r1 = r1 < 0 ? 0 : (r1 >= n_table_rows ? n_table_rows - 1 : r1);
-      const char* s0 = reinterpret_cast<const char*>(table16) + (int64_t)r0 * ROW_BYTES;
-      const char* s1 = reinterpret_cast<const char*>(table16) + (int64_t)r1 * ROW_BYTES;
-      const uint32_t st = it % NSTAGE;
-      tc::mbar_wait(empty_bar + 8 * st, ((it / NSTAGE) & 1) ^ 1);
-      if (lane == 0) mbar_arrive_expect_tx(full_bar + 8 * st, STAGE);
-      __syncwarp();
-      const uint32_t dst = sbase + st * STAGE + lane * PITCH;
-      bulk_copy_g2s(dst, s0, PITCH, full_bar + 8 * st);
-      if (lane + 32 < S) bulk_copy_g2s(dst + 32 * PITCH, s1, PITCH, full_bar + 8 * st);
-    }
-  } else {
-    const int g = lane >> 2, t = lane & 3;
-    const int mi = lane >> 3, rr = lane & 7;
-    uint32_t it = 0;
-    for (int64_t u = blockIdx.x; u < n_users; u += gridDim.x, ++it) {
-      const uint32_t st = it % NSTAGE;
-      const uint32_t B = sbase + st * STAGE;
-      tc::mbar_wait(full_bar + 8 * st, (it / NSTAGE) & 1);
-#pragma unroll 1
-      for (int unit = warp; unit < U_UNITS; unit += U_COMPUTE) {
-        const int head = unit >> 2, mt = unit & 3;
-        const int hg = head / HG, hl = head - hg * HG;
-        const int qoff = hg * GROUP + hl * SLICE, koff = OFF_K + qoff, voff = OFF_V + qoff;
-        float sacc[7][4];
-        {
-          uint32_t qa[4], qb[2], kb16[8][2], kb8[8];
-          ldsm_x4(row_addr(B, zero, 16 * mt + 8 * (mi & 1) + rr, qoff + (mi >> 1) * 16), qa[0], qa[1], qa[2], qa[3]);
-          ldsm_x2(row_addr(B, zero, 16 * mt + 8 * (mi & 1) + rr, qoff + 32), qb[0], qb[1]);
-#pragma unroll
-          for (int p = 0; p < 4; ++p)
-            ldsm_x4(row_addr(B, zero, 8 * (2 * p + (mi >> 1)) + rr, koff + (mi & 1) * 16), kb16[2 * p][0], kb16[2 * p][1],
-                    kb16[2 * p + 1][0], kb16[2 * p + 1][1]);
-#pragma unroll
-          for (int p = 0; p < 2; ++p)
-            ldsm_x4(row_addr(B, zero, 8 * (4 * p + mi) + rr, koff + 32), kb8[4 * p], kb8[4 * p + 1], kb8[4 * p + 2],
-                    kb8[4 * p + 3]);
-#pragma unroll
-          for (int nt = 0; nt < 7; ++nt) {
-            sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
-            mma_k16(sacc[nt], qa[0], qa[1], qa[2], qa[3], kb16[nt][0], kb16[nt][1]);
-          }
-#pragma unroll
-          for (int nt = 0; nt < 7; ++nt) mma_k8(sacc[nt], qb[0], qb[1], kb8[nt]);
-        }
-        uint32_t vb[4][3][2];
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          ldsm_x4_t(row_addr(B, zero, 16 * ks + 8 * (mi & 1) + rr, voff + (mi >> 1) * 16), vb[ks][0][0], vb[ks][0][1],
-                    vb[ks][1][0], vb[ks][1][1]);
-          ldsm_x2_t(row_addr(B, zero, 16 * ks + 8 * (mi & 1) + rr, voff + 32), vb[ks][2][0], vb[ks][2][1]);
-        }
-        if (unit + U_COMPUTE >= U_UNITS) {   // this warp's last shared-memory read of the stage
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(empty_bar + 8 * st);
-        }
-        uint32_t pa[7][2];
-        const bool lower = mt < 3;
-#pragma unroll
-        for (int nt = 0; nt < 7; ++nt) {
-          float p0 = ex2_sel<0>(sacc[nt][0]), p1 = ex2_sel<1>(sacc[nt][1]);
-          float p2 = 0.f, p3 = 0.f;
-          if (lower) { p2 = ex2_sel<2>(sacc[nt][2]); p3 = ex2_sel<3>(sacc[nt][3]); }
-          if (nt == 6 && t > 0) { p0 = p1 = p2 = p3 = 0.f; }
-          pa[nt][0] = pack_h2(p0, p1);
-          pa[nt][1] = pack_h2(p2, p3);
-        }
-        float oacc[3][4];
-#pragma unroll
-        for (int dt = 0; dt < 3; ++dt) oacc[dt][0] = oacc[dt][1] = oacc[dt][2] = oacc[dt][3] = 0.f;
-#pragma unroll
-        for (int ks = 0; ks < 3; ++ks)
-#pragma unroll
-          for (int dt = 0; dt < 3; ++dt)
-            mma_k16(oacc[dt], pa[2 * ks][0], pa[2 * ks][1], pa[2 * ks + 1][0], pa[2 * ks + 1][1], vb[ks][dt][0],
-                    vb[ks][dt][1]);
-#pragma unroll
-        for (int dt = 0; dt < 3; ++dt) mma_k8(oacc[dt], pa[6][0], pa[6][1], vb[3][dt][0]);
-        const float z0 = __shfl_sync(0xffffffffu, oacc[2][0], (lane & ~3) | 2);
-        const float z1 = __shfl_sync(0xffffffffu, oacc[2][2], (lane & ~3) | 2);
-        const float i0 = __fdividef(1.f, z0 + 1e-8f), i1 = __fdividef(1.f, z1 + 1e-8f);
-        const int r0 = 16 * mt + g, r1 = r0 + 8;
-        __half* o0 = ctx + (u * S + r0) * CP + head * 20 + 2 * t;
-#pragma unroll
-        for (int dt = 0; dt < 3; ++dt) {
-          if (dt < 2 || t < 2) {
-            if (r0 < S) *reinterpret_cast<uint32_t*>(o0 + dt * 8) = pack_h2(oacc[dt][0] * i0, oacc[dt][1] * i0);
-            if (r1 < S) *reinterpret_cast<uint32_t*>(o0 + 8 * CP + dt * 8) = pack_h2(oacc[dt][2] * i1, oacc[dt][3] * i1);
-          }
-        }
-      }
-    }
-  }
-}
-
 }  // namespace k1g
 
 // fp16 copy of the packed projection weights IN THE ORDER OF A TABLE ROW: [1080][320] halfs.  Row j of the copy produces
@@ -764,72 +346,41 @@ __global__ void __launch_bounds__(256) pack_wqkv16_table_kernel(const float* __r
   }
 }
 
-int k1v4_pack_src(const float* src, int64_t n_rows, void* src16, CUtensorMap* ts, cudaStream_t st);
+int pack_rows16(const float* src, int64_t n_rows, void* src16, cudaStream_t st);      // pack.cu
 
-// scratch of the table path: [table16: n_rows x 2,160 B][fp16 copy of the table: (n_rows + 1) x 640 B][fp16 weights]
+// scratch of the table path: [table16: n_rows x 2,160 B][fp16 copy of the source rows: (n_rows + 1) x 640 B, unless the
+// caller already has one][fp16 weights in table order]
 static size_t k1g_table16_only(int64_t n_rows) { return align_up((size_t)n_rows * k1g::ROW_BYTES, 1024); }
 static size_t k1g_a16_bytes(int64_t n_rows) { return align_up((size_t)(n_rows + 1) * 640, 1024); }
-size_t k1g_table16_bytes(int64_t n_rows) { return k1g_table16_only(n_rows) + k1g_a16_bytes(n_rows) + (size_t)TABLE_COLS * 640; }
+size_t k1g_table16_bytes(int64_t n_rows, bool rows16_given) {
+  return k1g_table16_only(n_rows) + k1g_a16_bytes(n_rows) * (rows16_given ? 0 : 1) + (size_t)TABLE_COLS * 640;
+}
+const void* k1g_table16_ptr(void* scratch) { return scratch; }
 
 // table16 = half([table | 1] * B^T) with B = the weight copy above (rows in table order, bias column, q scale and pads
 // included): fp16 copies of the table (a 1.0 in column 300 meets the bias column) and of the weights, then one kind::f16
 // tensor-core GEMM with N = 1,080 whose row-major result IS the table; the epilogue leaves through bulk tensor stores.
-// (Same operand precision as K1 v6's in-kernel projection.)
-int k1g_project_table(const float* table, int64_t n_rows, const float* wqkv, const float* bqkv, void* scratch,
-                      cudaStream_t st) {
+// (Same operand precision as K1 v6's in-kernel projection.)  rows16: the fp16 copy of the source rows when the caller
+// already holds one (pack_rows16 layout), else nullptr and `table` (fp32) is packed here.
+int k1g_project_table(const float* table, const void* rows16, int64_t n_rows, const float* wqkv, const float* bqkv,
+                      void* scratch, cudaStream_t st) {
   char* base = reinterpret_cast<char*>(scratch);
   void* table16 = base;
-  void* a16 = base + k1g_table16_only(n_rows);
-  void* b16 = base + k1g_table16_only(n_rows) + k1g_a16_bytes(n_rows);
-  alignas(64) CUtensorMap unused;
-  if (int rc = k1v4_pack_src(table, n_rows, a16, &unused, st)) return rc;
+  const void* a16 = rows16;
+  char* next = base + k1g_table16_only(n_rows);
+  if (a16 == nullptr) {
+    if (int rc = pack_rows16(table, n_rows, next, st)) return rc;
+    a16 = next;
+    next += k1g_a16_bytes(n_rows);
+  }
+  void* b16 = next;
   const float qscale = 1.4426950408889634f / sqrtf((float)DH);
   pack_wqkv16_table_kernel<<<148, 256, 0, st>>>(wqkv, bqkv, reinterpret_cast<__half*>(b16), qscale);
   NRMS_LAUNCH_CHECK("pack_wqkv16_table_kernel");
   return tc_gemm_nt_f16_tma(a16, 320, b16, 320, table16, TABLE_COLS, n_rows, TABLE_COLS, 304, st);
 }
 
-// Cbuf: fp16 context rows [n_users*50][320]; columns 300..319 are never written here (clear them once per buffer)
-// "k1g_variant" option (user encoder): 0 = head per warp (16 warps, the first S = 50 kernel with its timing switches),
-// 1 = (head, query tile) units over 23 warps, 2 = the length-templated head-per-warp kernel (the one the news encoder uses)
-#ifndef K1G_DEFAULT_VARIANT
-#define K1G_DEFAULT_VARIANT 2
-#endif
-static int g_k1g_variant = K1G_DEFAULT_VARIANT;
-int set_k1g_variant(int v) {
-  if (v < 0 || v > 2) return NRMS_E_INVALID;
-  g_k1g_variant = v;
-  return NRMS_OK;
-}
-int get_k1g_variant() { return g_k1g_variant; }
-
-int k1g_run(const void* table16, int64_t n_table_rows, const int32_t* hist_rows, int64_t n_users, void* Cbuf,
-            cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k1g::table_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k1g::SMEM);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(table_attn_kernel)");
-    e = cudaFuncSetAttribute(k1g::table_attn_units_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k1g::SMEM);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(table_attn_units_kernel)");
-    configured = true;
-  }
-  if (n_users <= 0) return NRMS_OK;
-  NRMS_CHECK_ARG(n_table_rows > 0 && n_table_rows < (1ll << 31), NRMS_E_INVALID, "table row count out of range");
-  int grid = num_sms();
-  if (n_users < grid) grid = (int)n_users;
-  if (g_k1g_variant == 1)
-    k1g::table_attn_units_kernel<<<grid, k1g::U_THREADS, k1g::SMEM, st>>>(reinterpret_cast<const __half*>(table16),
-                                                                          (int)n_table_rows, hist_rows, n_users,
-                                                                          reinterpret_cast<__half*>(Cbuf));
-  else
-    k1g::table_attn_kernel<<<grid, k1g::THREADS, k1g::SMEM, st>>>(reinterpret_cast<const __half*>(table16),
-                                                                  (int)n_table_rows, hist_rows, n_users,
-                                                                  reinterpret_cast<__half*>(Cbuf));
-  NRMS_LAUNCH_CHECK("table_attn_kernel");
-  return NRMS_OK;
-}
-
-// The templated kernel: S = 50 (int32 history rows) or S = 20 (int64 token ids); same Cbuf contract as k1g_run
+// S = 50 (int32 history rows / int64 ids) or S = 20; Cbuf: fp16 context rows [n_seq * S][320] (columns 300..319 cleared here)
 template <int SEQ, typename IdxT>
 static int launch_seq_attn(const void* table16, int64_t n_table_rows, const void* rows, int64_t n_seq, void* Cbuf,
                            const float* qk_bound, cudaStream_t st) {

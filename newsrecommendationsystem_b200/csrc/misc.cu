@@ -7,7 +7,7 @@
 #include <atomic>
 
 namespace nrms {
-int k1v4_pack_rows(const float* src, int64_t n_rows, void* src16, cudaStream_t st);   // tc_fused5.cu
+int pack_rows16(const float* src, int64_t n_rows, void* src16, cudaStream_t st);   // pack.cu
 
 static thread_local char g_err[512] = "";
 
@@ -396,7 +396,7 @@ int nrms_pack_rows_f16(const float* src, int64_t n_rows, void* dst16, void* stre
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   NRMS_CHECK_ARG(n_rows >= 0, NRMS_E_INVALID, "bad sizes");
   NRMS_CHECK_ARG(src && dst16 && aligned16(src) && aligned16(dst16), NRMS_E_INVALID, "null/misaligned pointer");
-  return k1v4_pack_rows(src, n_rows, dst16, st);
+  return pack_rows16(src, n_rows, dst16, st);
 }
 
 int nrms_score_csr_f16(const void* table16, const int32_t* cand_rows, const int64_t* offsets, const float* user_vec,

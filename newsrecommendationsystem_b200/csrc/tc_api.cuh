@@ -20,17 +20,19 @@ int tc_gemm_nt_f16out(const float* A, int64_t lda, const float* B, int64_t ldb, 
 // dst[c][r] = src[r][c]: the K-major (NT) tensor-core GEMM sees A^T B and A B contractions through transposed copies
 int transpose_f32(const float* src, int64_t ld_src, float* dst, int64_t ld_dst, int64_t R, int C, cudaStream_t st);
 
-// Fused tensor-core encoder forward (inference): gather -> QKV (tcgen05) -> attention (K1), then
-// additive GEMM (tcgen05) -> tanh/softmax/pool (K2).  Input rows come from `src` [*,300]:
+// Tensor-mode encoder forward (inference), fused_host.cu: table path (K1g / K1f) or per-sequence projection (K1 v6),
+// then additive pooling (K2).  Input rows come from `src` [*,300] fp32 -- or from `src16`, the caller's fp16 copy of the
+// gather source in pack_rows16's layout ([n_src_rows + 1][320] halfs, 1.0 in column 300, zero last row), when src is null:
 //   idx_kind 0: dense rows (sequence s, position i -> row s*S+i), 1: int64 ids, 2: int32 ids.
 // tc_fused_workspace_bytes returns (size_t)-1 when the fused path does not apply (S not 20/50).
-// n_src_rows = rows of `src` when it is a gather source (idx_kind 1/2), 0 for dense input.
-size_t tc_fused_workspace_bytes(int64_t n_seq, int S, int64_t n_src_rows);
+// n_src_rows = rows of the gather source (idx_kind 1/2), 0 for dense input.
+size_t tc_fused_workspace_bytes(int64_t n_seq, int S, int64_t n_src_rows, bool rows16_given = false);
 // ln_gamma / ln_beta (nullable): LayerNorm(300) on the context rows between K1 and K2 (config-5 variant).
-int tc_encoder_fused(const float* src, int64_t n_src_rows, const void* idx, int idx_kind, int64_t n_seq, int S,
-                     const float* wqkv, const float* bqkv, const float* wa, const float* ba, const float* qa, float* out,
-                     void* workspace, size_t workspace_bytes, cudaStream_t st, const float* ln_gamma = nullptr,
+int tc_encoder_fused(const float* src, const void* src16, int64_t n_src_rows, const void* idx, int idx_kind, int64_t n_seq,
+                     int S, const float* wqkv, const float* bqkv, const float* wa, const float* ba, const float* qa,
+                     float* out, void* workspace, size_t workspace_bytes, cudaStream_t st, const float* ln_gamma = nullptr,
                      const float* ln_beta = nullptr);
+int pack_rows16(const float* src, int64_t n_rows, void* src16, cudaStream_t st);    // pack.cu
 
 // fp16 operands (A16 [M, lda halfs], B16 [N, ldb halfs], 16-byte aligned rows), kind::f16, same fp16 epilogue (no bias)
 int tc_gemm_nt_f16(const void* A16, int64_t lda, const void* B16, int64_t ldb, void* C16, int64_t ldc, int64_t M, int N,
@@ -45,11 +47,10 @@ void set_k1f_debug(int v);           // component-removal timing switches of K1f
 void set_fused_pool(bool on);        // table path: 1 (default) = K1f, 0 = K1g + K2 (context rows through HBM)
 int tc_gemm_nt_f16_tma(const void* A16, int64_t lda, const void* B16, int64_t ldb, void* C16, int64_t ldc, int64_t M, int N,
                        int K, cudaStream_t st);   // fp16 in / fp16 out, dense row-major result through bulk tensor stores
-int set_k1g_variant(int v);     // 0 = head per warp (S = 50 only), 1 = (head, query tile) units, 2 = length-templated kernel
 void set_news_table_attn(bool on);   // news encoder over the projected embedding table (default on)
 void set_table_attn(bool on);   // indexed user encoder: project the table once + K1g (default on)
-int set_k1_variant(int v);   // 1..6, see tc_fused.cu
+int set_table_ratio(int v);  // gathered rows per source row from which the table path is taken (default 4)
 void set_time_k1(bool on);   // CUDA-event timing of the K1 launches (bench.py roofline)
-double get_k1_stat(int key); // 3 * kind (0 users K1, 1 news K1, 2 users K1g, 3 news K1g) + (0 total ms, 1 launches, 2 sequences)
+double get_k1_stat(int key); // 3 * kind (0 users K1 v6, 1 news K1 v6, 2 users table attention, 3 news table attention) + (0 total ms, 1 launches, 2 sequences)
 
 }  // namespace nrms

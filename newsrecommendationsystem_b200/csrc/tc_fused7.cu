@@ -50,7 +50,7 @@ constexpr int NST = 5;                          // weight ring stages (= one who
 static_assert(NST == KCH, "the projection issuer relies on stage == K chunk");
 constexpr int B_STAGE = PN * 128;               // 16,384
 constexpr int CP = 320;                         // pitch (halfs) of the fp16 context rows handed to K2
-constexpr int SRC_LD = 320;                     // pitch (halfs) of the fp16 gather source (k1v4_pack_src)
+constexpr int SRC_LD = 320;                     // pitch (halfs) of the fp16 gather source (pack_rows16)
 constexpr int THREADS = 704;                    // 22 warps
 constexpr int NGW = 2;                          // A-tile gather warps (20, 21)
 constexpr int OFF_A = 0;                        // 5 x [128 rows x 128 B]
@@ -132,7 +132,7 @@ __device__ __forceinline__ uint32_t rna_tf32(uint32_t x) { return (x + 0x1000u) 
 // S = sequence length, SLOT = padded slot (rows of the tile per sequence), SPT = sequences per tile
 template <int S, int SLOT, int SPT>
 __global__ void __launch_bounds__(THREADS, 1)
-encoder_attn_tc6_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_src,
+encoder_attn_tc6_kernel(const __grid_constant__ CUtensorMap tmap_w,
                         const __grid_constant__ CUtensorMap tmap_c, const __half* __restrict__ src16,
                         const void* __restrict__ idx, int idx_kind, int64_t n_seq, int null_row) {
   static_assert(SLOT % 8 == 0 && SLOT >= S && SPT * SLOT <= 128, "slot layout");
@@ -220,7 +220,7 @@ encoder_attn_tc6_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid
     // K-major layout; sequences missing from a partial tile are zero-filled (src-size 0).  The tile is
     // single-buffered, so the time from "chunk free" (last projection pass done with it) to "chunk full" is exposed
     // once per tile: TMA gather4 (v4) needed ~8,000 cycles, cp.async ~5,500 (profiles/r1_k1v5_trace_*.txt).
-    (void)tmap_src; (void)null_row;
+    (void)null_row;
     constexpr int NREAL = S * SPT;                   // real rows of a tile (100)
     constexpr int NIT = (NREAL + 3) / 4;             // 4-row copy instructions per chunk (25)
     constexpr int NMINE = (NIT + NGW - 1) / NGW;     // ... per gather warp (7)
@@ -655,7 +655,7 @@ extern "C" int nrms_debug_read_trace6(long long* host, int* counts) {
 }
 
 template <int S, int SLOT, int SPT>
-static int launch_k1v6(const CUtensorMap& tw, const CUtensorMap& ts, const void* src16, const void* idx, int idx_kind,
+static int launch_k1v6(const CUtensorMap& tw, const void* src16, const void* idx, int idx_kind,
                        int64_t n, int null_row, void* Cbuf, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
@@ -670,16 +670,16 @@ static int launch_k1v6(const CUtensorMap& tw, const CUtensorMap& ts, const void*
   alignas(64) CUtensorMap tc_;     // context rows [n*S][320] halfs, store box = S rows x 40 halfs (one sequence, one pass)
   if (int rc = make_tmap_store_f16(&tc_, Cbuf, n * S, k1v6::CP, k1v6::CP, 40, S)) return rc;
   k1v6::encoder_attn_tc6_kernel<S, SLOT, SPT><<<grid, k1v6::THREADS, k1v6::SMEM, st>>>(
-      tw, ts, tc_, reinterpret_cast<const __half*>(src16), idx, idx_kind, n, null_row);
+      tw, tc_, reinterpret_cast<const __half*>(src16), idx, idx_kind, n, null_row);
   NRMS_LAUNCH_CHECK("encoder_attn_tc6_kernel");
   return NRMS_OK;
 }
 
-// Same operands as k1v4_run (the fp16 weight copy and gather source of k1v4_prepare / k1v4_pack_src).
-int k1v6_run(int S, const CUtensorMap& tw, const CUtensorMap& ts, const void* src16, const void* idx, int idx_kind,
-             int64_t n, int null_row, void* Cbuf, cudaStream_t st) {
-  if (S == 20) return launch_k1v6<20, 24, 5>(tw, ts, src16, idx, idx_kind, n, null_row, Cbuf, st);
-  if (S == 50) return launch_k1v6<50, 64, 2>(tw, ts, src16, idx, idx_kind, n, null_row, Cbuf, st);
+// Operands: the fp16 weight copy (pack_weights_k1) and the fp16 gather source (pack_rows16), pack.cu.
+int k1v6_run(int S, const CUtensorMap& tw, const void* src16, const void* idx, int idx_kind, int64_t n, int null_row,
+             void* Cbuf, cudaStream_t st) {
+  if (S == 20) return launch_k1v6<20, 24, 5>(tw, src16, idx, idx_kind, n, null_row, Cbuf, st);
+  if (S == 50) return launch_k1v6<50, 64, 2>(tw, src16, idx, idx_kind, n, null_row, Cbuf, st);
   set_error("encoder_attn_tc6_kernel compiled for S = 20 or 50, got %d", S);
   return NRMS_E_UNSUPPORTED;
 }

@@ -207,6 +207,54 @@ def encode_news_table(model, news_tokens: torch.Tensor, n_news=None, local_shard
 
 
 @torch.no_grad()
+def encode_news_table16(model, news_tokens: torch.Tensor, n_news=None, local_shard=None, want_fp32=False):
+    """Stage A of the tensor-mode pipeline.  Returns (table16, table32): table16 = fp16 [N_news + 2, 320] in
+    `ops.pack_rows_f16`'s layout -- row N_news is the PADDED_NEWS zero vector (evaluate.py:203-204; zeros with the 1.0 of the bias
+    column), the row after it the all-zero closing row the kernels expect -- and table32 = the fp32 [N_news + 1, 300] table when `want_fp32`, else None.
+
+    Nothing downstream of the news encoder reads fp32 rows in tensor mode: the user encoder projects the fp16 copy and the
+    scoring kernel reads it, so the copy is made ONCE, by the rank that encoded the rows, straight into its slot of the
+    gather buffer, and the NCCL all-gather moves 640-byte rows in place (no staging copy, half the bytes of fp32)."""
+    dist = _dist()
+    n = news_tokens.shape[0] if n_news is None else int(n_news)
+    dev = news_tokens.device
+    was_training = model.training
+    model.eval()
+    try:
+        world, rank = (dist.get_world_size(), dist.get_rank()) if dist is not None else (1, 0)
+        per = (n + world - 1) // world
+        buf = torch.empty((world * per + 2, 320), dtype=torch.float16, device=dev)
+        lo, hi = shard_range(n, rank, world)
+        if local_shard is not None and tuple(local_shard) != (lo, hi):
+            raise RuntimeError(f"token rows were sharded for {tuple(local_shard)} but this rank encodes {(lo, hi)}")
+        vec = None
+        if hi > lo:
+            vec = model.get_news_vector({"title": news_tokens if (local_shard is not None or dist is None) else news_tokens[lo:hi]})
+            ops.pack_rows_f16(vec, out=buf[lo:hi + 1])          # rows [lo, hi) + a zero row at hi
+        if dist is not None:
+            if buf.is_cuda:       # NCCL gathers in place: every rank's slot already sits at rank * per
+                dist.all_gather_into_tensor(buf[:world * per].view(-1), buf[rank * per:(rank + 1) * per].view(-1))
+            else:                 # gloo (CPU tests of the plumbing)
+                dist.all_gather_into_tensor(buf[:world * per].view(-1), buf[rank * per:(rank + 1) * per].reshape(-1).clone())
+        buf[n:].zero_()           # PADDED_NEWS, the closing row and the slot padding
+        buf[n, 300] = 1.0         # ... PADDED_NEWS is a zero VECTOR that still meets the biases (q = 0 W + b): its 1.0 column stays
+        table32 = None
+        if want_fp32:
+            if dist is None:
+                table32 = torch.zeros((n + 1, ops.D), dtype=torch.float32, device=dev)
+                table32[:n] = vec
+            else:
+                padded = torch.zeros((world * per + 1, ops.D), dtype=torch.float32, device=dev)
+                if hi > lo:
+                    padded[lo:hi] = vec
+                dist.all_gather_into_tensor(padded[:world * per].view(-1), padded[rank * per:(rank + 1) * per].reshape(-1).clone())
+                table32 = padded[:n + 1]
+                table32[n].zero_()
+        return buf[:n + 2], table32
+    finally:
+        model.train(was_training)
+
+
 def _tensor_mode(model):
     from . import _lib
     from .config import resolve_mode
@@ -222,7 +270,14 @@ def evaluate_tensors(model, inputs: EvalInputs, max_count=None, return_details=F
     dist = _dist()
     mark = mark or (lambda name: None)
     mark("start")
-    table = encode_news_table(model, inputs.news_tokens, inputs.n_news, getattr(inputs, "news_shard", None))
+    # tensor mode (plain NRMS): one fp16 copy of the news vectors feeds the all-gather, the user encoder and the scoring
+    f16_flow = _tensor_mode(model) and model.user_encoder.layer_norm is None
+    table16 = None
+    if f16_flow:
+        table16, table = encode_news_table16(model, inputs.news_tokens, inputs.n_news, getattr(inputs, "news_shard", None),
+                                             want_fp32=return_details)
+    else:
+        table = encode_news_table(model, inputs.news_tokens, inputs.n_news, getattr(inputs, "news_shard", None))
     mark("news")
     inputs.wait_ready()
     n_imp = inputs.n_impressions
@@ -246,10 +301,12 @@ def evaluate_tensors(model, inputs: EvalInputs, max_count=None, return_details=F
             hist = inputs.hist_rows[lo:hi]
             cand_rows, labels = inputs.cand_rows[c0:c1], inputs.labels[c0:c1]
             offs = (inputs.cand_offsets[lo:hi + 1] - c0).contiguous()
-        user_vec = model.user_encoder.forward_indexed(table, hist)
+        user_vec = model.user_encoder.forward_indexed(table16 if f16_flow else table, hist)
         mark("users")
-        if _tensor_mode(model):
-            # tensor mode: candidates are read from an fp16 copy of the table (half the bytes, fp32 accumulation)
+        if f16_flow:
+            scores = ops.score_csr_f16(table16, cand_rows, offs, user_vec)
+        elif _tensor_mode(model):
+            # tensor mode (LayerNorm variant): candidates are read from an fp16 copy of the table
             scores = ops.score_csr_f16(ops.pack_rows_f16(table), cand_rows, offs, user_vec)
         else:
             scores = ops.score_csr(table, cand_rows, offs, user_vec)

@@ -1,4 +1,5 @@
 """UserEncoder (reference src/model/NRMS/user_encoder.py:6-26) on libnrms_b200."""
+import torch
 import torch.nn as nn
 
 from ... import ops
@@ -33,6 +34,12 @@ class UserEncoder(nn.Module):
                                 mode=resolve_mode(self.config, self.precision), ln=self._ln())
 
     def forward_indexed(self, table, rows):
-        """Inference: history rows gathered from the news-vector table (int32 [B, 50])."""
+        """Inference: history rows gathered from the news-vector table (int32 [B, 50]).  `table` is the fp32 [n, 300]
+        table, or (tensor mode, no LayerNorm) its fp16 copy [n + 1, 320] from `ops.pack_rows_f16`."""
+        if table.dtype == torch.float16:
+            from ... import _lib
+            if self.layer_norm is not None or resolve_mode(self.config, self.precision) != _lib.MODE_TF32:
+                raise RuntimeError("the fp16 table form of forward_indexed is the tensor-mode path of the plain NRMS encoder")
+            return ops.user_encoder_table16(table, rows, *self._weights())
         return ops.user_encoder_indexed(table, rows, *self._weights(),
                                         mode=resolve_mode(self.config, self.precision), ln=self._ln())

@@ -269,6 +269,28 @@ def user_encoder_indexed(table, rows, wqkv, bqkv, wa, ba, qa, mode=_lib.MODE_TF3
     return out
 
 
+@torch.no_grad()
+def user_encoder_table16(table16, rows, wqkv, bqkv, wa, ba, qa):
+    """Tensor-mode indexed user encoder over the caller's fp16 copy of the table (`pack_rows_f16` layout:
+    [n_rows + 1, 320] halfs, last row zero) -- the form evaluate keeps between its stages."""
+    lib = _lib.load()
+    _require_cuda(table16, rows)
+    if table16.dtype != torch.float16 or table16.dim() != 2 or table16.shape[1] != 320 or not table16.is_contiguous():
+        raise RuntimeError("table16 must be a contiguous fp16 [n_rows + 1, 320] tensor (ops.pack_rows_f16)")
+    if rows.dtype != torch.int32:
+        rows = rows.int()
+    rows = rows.contiguous()
+    n, S = rows.shape
+    n_rows = table16.shape[0] - 1
+    out = torch.empty((n, D), dtype=torch.float32, device=table16.device)
+    ws = _bytes(lib.nrms_user_encoder_table16_workspace_bytes(n, S, n_rows), table16.device)
+    args = [_f32c(t) for t in (wqkv, bqkv, wa, ba, qa)]
+    check(lib.nrms_user_encoder_table16_fwd(ptr(table16), n_rows, ptr(rows), n, S, ptr(args[0]), ptr(args[1]), ptr(args[2]),
+                                            ptr(args[3]), ptr(args[4]), ptr(out), ptr(ws), ws.numel(),
+                                            stream_ptr(table16.device)), "nrms_user_encoder_table16_fwd")
+    return out
+
+
 def click_score(cand, user):
     return _ScoreFn.apply(cand, user)
 
@@ -289,12 +311,17 @@ def score_csr(table, cand_rows, offsets, user_vec):
 
 
 @torch.no_grad()
-def pack_rows_f16(table):
-    """fp16 copy of an fp32 [n,300] table in the layout the tensor-mode kernels read: [n+1, 320] halfs."""
+def pack_rows_f16(table, out=None):
+    """fp16 copy of an fp32 [n,300] table in the layout the tensor-mode kernels read: [n+1, 320] halfs (300 values, 1.0 in
+    column 300, zero tail; the extra last row all zero).  `out`: a contiguous fp16 [>= n+1, 320] view to write into (e.g.
+    a rank's slot of the all-gather buffer of evaluate)."""
     lib = _lib.load()
     _require_cuda(table)
     t = _f32c(table)
-    out = torch.empty((t.shape[0] + 1, 320), dtype=torch.float16, device=t.device)
+    if out is None:
+        out = torch.empty((t.shape[0] + 1, 320), dtype=torch.float16, device=t.device)
+    elif out.dtype != torch.float16 or out.shape[0] < t.shape[0] + 1 or out.shape[1] != 320 or not out.is_contiguous():
+        raise RuntimeError("pack_rows_f16: `out` must be a contiguous fp16 [>= n+1, 320] tensor")
     check(lib.nrms_pack_rows_f16(ptr(t), t.shape[0], ptr(out), stream_ptr(t.device)), "nrms_pack_rows_f16")
     return out
 

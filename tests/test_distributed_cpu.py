@@ -96,6 +96,80 @@ def _eval_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+class _StubUserEncoder16(_StubUserEncoder):
+    precision = "tf32"          # evaluate_tensors then keeps ONE fp16 copy of the news vectors (encode_news_table16)
+    layer_norm = None
+
+    def forward_indexed(self, table16, rows):
+        from oracle import torch_port as TP
+        assert table16.dtype == torch.float16 and table16.shape[1] == 320
+        return TP.user_vectors(self.sd, table16[:, :300].float()[rows.long()])
+
+
+def _cpu_pack_rows_f16(table, out=None):
+    n = table.shape[0]
+    if out is None:
+        out = torch.empty((n + 1, 320), dtype=torch.float16)
+    out[:n + 1].zero_()
+    out[:n, :300] = table.to(torch.float16)
+    out[:n, 300] = 1.0
+    return out
+
+
+def _eval_worker_f16(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(2)
+        from newsrecommendationsystem_b200 import evaluate as E, ops, synthetic
+        ops.pack_rows_f16 = _cpu_pack_rows_f16
+        ops.score_csr_f16 = lambda t16, cand, offs, uv: _cpu_score_csr(t16[:, :300].float(), cand, offs, uv)
+        ops.rank_metrics = _cpu_rank_metrics
+        sd = synthetic.init_state_dict(num_words=301, seed=1)
+        ntok = synthetic.make_news(61, num_words=301, seed=2)
+        imp = synthetic.make_impressions(23, 61, seed=3, single_class_every=5, max_cand=25)
+        model = _StubModel(sd)
+        model.user_encoder = _StubUserEncoder16(sd)
+        host = E.EvalHost(ntok, imp["hist_rows"], imp["cand_offsets"], imp["cand_rows"], imp["labels"])
+        inp = E.EvalInputs.from_host(host, "cpu", shard=True)          # token rows and impressions of this rank only
+        t16, t32 = E.encode_news_table16(model, inp.news_tokens, inp.n_news, inp.news_shard, want_fp32=True)
+        means = E.evaluate_tensors(model, inp)
+        q.put((rank, means, t16.float().numpy().copy(), t32.numpy().copy()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_evaluate_fp16_table_flow_world2():
+    """Tensor-mode evaluate across two ranks: every rank packs ITS news vectors to fp16 straight into its slot of the
+    gather buffer, one all-gather of 640-byte rows, the same copy feeds the user encoder and the scoring."""
+    from newsrecommendationsystem_b200 import synthetic
+    from oracle import nrms_oracle as O
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_eval_worker_f16, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in procs], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sd = synthetic.init_state_dict(num_words=301, seed=1)
+    ntok = synthetic.make_news(61, num_words=301, seed=2)
+    imp = synthetic.make_impressions(23, 61, seed=3, single_class_every=5, max_cand=25)
+    ref_means, _, _, ref_table, _ = O.evaluate_pipeline(sd, ntok, imp["hist_rows"], imp["cand_offsets"],
+                                                         imp["cand_rows"], imp["labels"])
+    (r0, m0, a0, f0), (r1, m1, a1, f1) = res
+    assert a0.shape == (63, 320)                                          # 61 news + PADDED_NEWS + the closing row
+    assert np.array_equal(a0, a1) and np.array_equal(f0, f1)              # every rank holds the same tables
+    np.testing.assert_allclose(a0[:61, :300], ref_table[:61], rtol=2e-3, atol=2e-4)     # fp16 rounding of the rows
+    assert np.all(a0[:62, 300] == 1.0) and not a0[:61, 301:].any() and not a0[61, :300].any() and not a0[62].any()
+    np.testing.assert_allclose(f0[:61], ref_table[:61], rtol=2e-4, atol=2e-6)
+    assert not f0[61].any()
+    np.testing.assert_allclose(m0, m1, rtol=1e-12)
+    np.testing.assert_allclose(m0, ref_means, atol=5e-3)
+
+
 def test_evaluate_sharding_allgather_allreduce_world2():
     from newsrecommendationsystem_b200 import synthetic
     from oracle import nrms_oracle as O

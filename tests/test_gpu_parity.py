@@ -190,9 +190,8 @@ def _indexed_equals_dense(dev, golden_sd, precision):
     assert torch.equal(a, b)      # the in-library gather is a pure copy
 
 
-@pytest.mark.parametrize("k1g_variant", [0, 1, 2])
 @pytest.mark.parametrize("n_users,n_rows", [(1, 3), (13, 60), (67, 300), (200, 1000), (2500, 4001)])
-def test_user_encoder_table_attention_path(dev, lib, golden_sd, n_users, n_rows, k1g_variant):
+def test_user_encoder_table_attention_path(dev, lib, golden_sd, n_users, n_rows):
     """K1g (tensor mode, indexed input): the table is projected once (q|k|v rows in fp16) and the attention runs on
     gathered rows.  Same numbers as the per-user projection within the 1e-3 tolerance: vs the oracle, and vs K1 v6."""
     rng = np.random.default_rng(n_users)
@@ -203,11 +202,10 @@ def test_user_encoder_table_attention_path(dev, lib, golden_sd, n_users, n_rows,
     if n_users > 9:
         rows[9] = n_rows                                  # empty history
         rows[3] = rows[3, 0]                              # one news repeated 50 times
-    assert n_users * 50 >= 8 * (n_rows + 1)               # the size rule that selects the table path
+    assert n_users * 50 >= 8 * (n_rows + 1)               # well inside the size rule that selects the table path
     ref, _ = O.user_encoder_forward(golden_sd, table[rows])
     m = make_model(golden_sd, dev, "tf32")
     tb, ix = t(table, dev), t(rows.astype(np.int32), dev)
-    assert lib.nrms_set_option(b"k1g_variant", k1g_variant) == 0      # 0 = head per warp, 1 = (head, tile) units, 2 = templated
     with torch.no_grad():
         try:
             a = m.user_encoder.forward_indexed(tb, ix)
@@ -215,7 +213,6 @@ def test_user_encoder_table_attention_path(dev, lib, golden_sd, n_users, n_rows,
             b = m.user_encoder.forward_indexed(tb, ix)
         finally:
             lib.nrms_set_option(b"user_table_attn", 1)
-            lib.nrms_set_option(b"k1g_variant", 2)
     assert rel_l2_rows(a.cpu().numpy(), ref) < TOL_VEC["tf32"]
     assert rel_l2_rows(b.cpu().numpy(), ref) < TOL_VEC["tf32"]
     assert not torch.equal(a, b)                          # two different kernels really ran
@@ -518,21 +515,18 @@ def test_unsupported_shape_and_cpu_inputs_fail_loudly(dev, golden_sd):
         ops.click_score(torch.zeros(2, 3, 300), torch.zeros(2, 300))           # CPU tensors: no fallback
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3, 4, 5, 6])
-def test_fused_kernel_generations_agree_with_oracle(dev, lib, golden_sd, variant):
-    """All generations of the fused tensor-mode encoder kernel (1 CUDA-core attention; 2 tcgen05 attention; 3 two
-    heads in flight with P in tensor memory; 4 TMA-gathered fp16 rows with the bias folded into the GEMM; 5 two
-    projection accumulators, P in place; 6 two worker groups on alternate passes) stay inside the 1e-3 tolerance,
-    news and users."""
+@pytest.mark.parametrize("seed", [1, 2])
+def test_per_sequence_projection_kernel_agrees_with_oracle(dev, lib, golden_sd, seed):
+    """K1 v6 (per-sequence projection on tcgen05: the path of dense input, small calls and the LayerNorm variant) stays
+    inside the 1e-3 tolerance, news and users; unknown options / out-of-range values are refused."""
     from newsrecommendationsystem_b200 import synthetic
-    assert lib.nrms_set_option(b"k1_variant", variant) == 0
     lib.nrms_set_option(b"news_table_attn", 0)       # 777 titles over a 401-word vocabulary would take the table path
     try:
         m = make_model(golden_sd, dev, "tf32")
-        toks = synthetic.make_news(777, num_words=Cfg.num_words, seed=500 + variant)
+        toks = synthetic.make_news(777, num_words=Cfg.num_words, seed=500 + seed)
         toks[11] = 0
         ref_n, _ = O.news_encoder_forward(golden_sd, toks)
-        rng = np.random.default_rng(variant)
+        rng = np.random.default_rng(seed)
         ux = (rng.standard_normal((93, 50, 300)) * 0.4).astype(np.float32)
         ux[5, :40] = 0
         ref_u, _ = O.user_encoder_forward(golden_sd, ux)
@@ -542,9 +536,56 @@ def test_fused_kernel_generations_agree_with_oracle(dev, lib, golden_sd, variant
         assert rel_l2_rows(nv.cpu().numpy(), ref_n) < TOL_VEC["tf32"]
         assert rel_l2_rows(uv.cpu().numpy(), ref_u) < TOL_VEC["tf32"]
     finally:
-        lib.nrms_set_option(b"k1_variant", 6)
         lib.nrms_set_option(b"news_table_attn", 1)
-    assert lib.nrms_set_option(b"k1_variant", 9) == 1 and lib.nrms_set_option(b"nope", 1) == 1
+    assert lib.nrms_set_option(b"table_ratio", 0) == 1 and lib.nrms_set_option(b"nope", 1) == 1
+    assert lib.nrms_set_option(b"table_ratio", 4) == 0
+
+
+def test_table_ratio_option_selects_the_path(dev, lib, golden_sd):
+    """The size rule of the table path (gathered rows >= table_ratio x table rows): the same call run on both sides of
+    the rule gives two different kernels' results, both inside the tolerance."""
+    rng = np.random.default_rng(12)
+    table = (rng.standard_normal((301, 300)) * 0.3).astype(np.float32)
+    table[300] = 0
+    rows = rng.integers(0, 300, size=(40, 50))            # 2,000 gathered rows over 301 table rows: ratio 6.6
+    ref, _ = O.user_encoder_forward(golden_sd, table[rows])
+    m = make_model(golden_sd, dev, "tf32")
+    tb, ix = t(table, dev), t(rows.astype(np.int32), dev)
+    with torch.no_grad():
+        try:
+            a = m.user_encoder.forward_indexed(tb, ix)                 # default ratio 4 -> table path
+            assert lib.nrms_set_option(b"table_ratio", 8) == 0
+            b = m.user_encoder.forward_indexed(tb, ix)                 # ratio 8 -> per-sequence projection
+        finally:
+            lib.nrms_set_option(b"table_ratio", 4)
+    assert rel_l2_rows(a.cpu().numpy(), ref) < TOL_VEC["tf32"] and rel_l2_rows(b.cpu().numpy(), ref) < TOL_VEC["tf32"]
+    assert not torch.equal(a, b)
+
+
+def test_user_encoder_fp16_table_form(dev, lib, golden_sd):
+    """nrms_user_encoder_table16_fwd: the indexed user encoder fed with the caller's fp16 copy of the table (the form
+    evaluate keeps between its stages) gives bit-identical vectors to the fp32-table call, on both kernel paths."""
+    from newsrecommendationsystem_b200 import ops
+    rng = np.random.default_rng(21)
+    table = (rng.standard_normal((401, 300)) * 0.3).astype(np.float32)
+    table[400] = 0
+    rows = rng.integers(0, 401, size=(77, 50))
+    rows[3, :20] = 400
+    m = make_model(golden_sd, dev, "tf32")
+    tb, ix = t(table, dev), t(rows.astype(np.int32), dev)
+    ref, _ = O.user_encoder_forward(golden_sd, table[rows])
+    with torch.no_grad():
+        t16 = ops.pack_rows_f16(tb)
+        assert t16.shape == (402, 320) and not t16[401].any() and float(t16[0, 300]) == 1.0
+        for ratio in (4, 64):                                            # table path, then per-sequence projection
+            try:
+                lib.nrms_set_option(b"table_ratio", ratio)
+                a = m.user_encoder.forward_indexed(tb, ix)
+                b = m.user_encoder.forward_indexed(t16, ix)
+            finally:
+                lib.nrms_set_option(b"table_ratio", 4)
+            assert torch.equal(a, b)
+            assert rel_l2_rows(b.cpu().numpy(), ref) < TOL_VEC["tf32"]
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32"])
