@@ -21,8 +21,13 @@ def save_checkpoint(path, model, optimizer, step, early_stop_value):
         for k, v in st.items():
             if torch.is_tensor(v):
                 st[k] = v.detach().cpu()
-    torch.save({"model_state_dict": sd, "optimizer_state_dict": osd, "step": step,
-                "early_stop_value": early_stop_value}, path)
+    ckpt = {"model_state_dict": sd, "optimizer_state_dict": osd, "step": step, "early_stop_value": early_stop_value}
+    ne = getattr(model, "news_encoder", None)
+    if ne is not None and hasattr(ne, "_dropout_calls"):
+        # position of the in-kernel Philox dropout stream: a resumed run continues it instead of replaying it from 0
+        # (an extra key the reference's loader ignores: it reads the four keys above only, train.py:144-153)
+        ckpt["b200_dropout_state"] = {"seed": int(ne.dropout_seed), "offset": int(ne._dropout_calls)}
+    torch.save(ckpt, path)
 
 
 def load_checkpoint(path, model, optimizer=None, map_location="cpu"):
@@ -32,6 +37,10 @@ def load_checkpoint(path, model, optimizer=None, map_location="cpu"):
     model.load_state_dict(ckpt["model_state_dict"])
     if optimizer is not None and ckpt.get("optimizer_state_dict") is not None:
         optimizer.load_state_dict(ckpt["optimizer_state_dict"])
+    ds = ckpt.get("b200_dropout_state")
+    ne = getattr(model, "news_encoder", None)
+    if ds is not None and ne is not None and hasattr(ne, "_dropout_calls"):
+        ne.dropout_seed, ne._dropout_calls = int(ds["seed"]), int(ds["offset"])
     return ckpt.get("step"), ckpt.get("early_stop_value")
 
 

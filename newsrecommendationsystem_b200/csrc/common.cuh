@@ -43,15 +43,29 @@ void count_launch();  // bumps the per-process kernel-launch counter (nrms_launc
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+// SM count of the CURRENT device (cached per device: a process may drive several GPUs)
 inline int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (n[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
   }
-  return n;
+  return n[dev];
+}
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: `done` is the call site's static flag array,
+// one entry per device ordinal.
+template <typename F>
+inline cudaError_t set_max_dynamic_smem(F func, int bytes, bool (&done)[64]) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && done[dev]) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) done[dev] = true;
+  return e;
 }
 
 // ---- Philox4x32-10 (counter-based RNG for in-kernel dropout) -------------------------------

@@ -82,12 +82,8 @@ static cudaError_t launch_attention_fwd(const float* qkv, float* ctx, int64_t n_
                                         uint64_t offset, cudaStream_t st, const int32_t* lengths = nullptr) {
   constexpr int threads = ((S * HC + 31) / 32) * 32;
   const size_t smem = 2 * S * HC * DH * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_fwd_kernel<S, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static bool configured[64] = {false};
+  if (cudaError_t e = set_max_dynamic_smem(attention_fwd_kernel<S, HC>, (int)smem, configured)) return e;
   int64_t gx = n_seq < (int64_t)num_sms() * 8 ? n_seq : (int64_t)num_sms() * 8;
   dim3 grid((unsigned)gx, H / HC);
   const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
@@ -101,12 +97,8 @@ static cudaError_t launch_attention_bwd(const float* qkv, const float* d_ctx, fl
                                         uint64_t seed, uint64_t offset, cudaStream_t st) {
   constexpr int threads = ((S * HC + 31) / 32) * 32;
   const size_t smem = (4 * S * HC * DH + 2 * HC * S * (S + 1)) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel<S, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  static bool configured[64] = {false};
+  if (cudaError_t e = set_max_dynamic_smem(attention_bwd_kernel<S, HC>, (int)smem, configured)) return e;
   int64_t gx = n_seq < (int64_t)num_sms() * 4 ? n_seq : (int64_t)num_sms() * 4;
   dim3 grid((unsigned)gx, H / HC);
   const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;

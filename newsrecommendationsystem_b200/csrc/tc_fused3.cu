@@ -272,13 +272,9 @@ int k2v2_prepare(const float* wa, void* wa16, CUtensorMap* twa, cudaStream_t st)
 template <int S, int SPT>
 static int launch_k2v2(const CUtensorMap& twa, const void* Cbuf, int64_t n, const float* ba, const float* qa,
                        float* out, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k2v2::additive_pool_f16_kernel<S, SPT>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, k2v2::SMEM);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(additive_pool_f16_kernel)");
-    configured = true;
-  }
+  static bool configured[64] = {false};
+  cudaError_t e = set_max_dynamic_smem(k2v2::additive_pool_f16_kernel<S, SPT>, k2v2::SMEM, configured);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(additive_pool_f16_kernel)");
   constexpr int ROWS = S * SPT;
   alignas(64) CUtensorMap tc_;
   const int box_c = (int)((n * S < ROWS) ? n * S : ROWS);

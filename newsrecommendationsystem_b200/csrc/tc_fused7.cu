@@ -657,13 +657,9 @@ extern "C" int nrms_debug_read_trace6(long long* host, int* counts) {
 template <int S, int SLOT, int SPT>
 static int launch_k1v6(const CUtensorMap& tw, const void* src16, const void* idx, int idx_kind,
                        int64_t n, int null_row, void* Cbuf, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k1v6::encoder_attn_tc6_kernel<S, SLOT, SPT>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, k1v6::SMEM);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(encoder_attn_tc6_kernel)");
-    configured = true;
-  }
+  static bool configured[64] = {false};
+  cudaError_t e = set_max_dynamic_smem(k1v6::encoder_attn_tc6_kernel<S, SLOT, SPT>, k1v6::SMEM, configured);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(encoder_attn_tc6_kernel)");
   const int64_t tiles = (n + SPT - 1) / SPT;
   int grid = num_sms();
   if (tiles < grid) grid = (int)tiles;

@@ -442,16 +442,11 @@ static int tc_gemm_launch(const void* A, int64_t lda, const void* B, int64_t ldb
                          cudaStream_t st) {
   if (M <= 0) return NRMS_OK;
   NRMS_CHECK_ARG(M < (1ll << 31), NRMS_E_UNSUPPORTED, "M too large for one tensor map");
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_nt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_gemm_nt_kernel)");
-    e = cudaFuncSetAttribute(tc_gemm_nt_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_gemm_nt_kernel<f16>)");
-    e = cudaFuncSetAttribute(tc_gemm_nt_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_TMA);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_gemm_nt_kernel<f16, tma>)");
-    configured = true;
-  }
+  static bool cfg_a[64] = {false}, cfg_b[64] = {false}, cfg_c[64] = {false};
+  cudaError_t e = set_max_dynamic_smem(tc_gemm_nt_kernel<false>, TG_SMEM, cfg_a);
+  if (e == cudaSuccess) e = set_max_dynamic_smem(tc_gemm_nt_kernel<true>, TG_SMEM, cfg_b);
+  if (e == cudaSuccess) e = set_max_dynamic_smem(tc_gemm_nt_kernel<true, true>, TG_SMEM_TMA, cfg_c);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_gemm_nt_kernel)");
   alignas(64) CUtensorMap ta, tb, tcm;
   memset(&tcm, 0, sizeof(tcm));
   if (epi == TC_EPI_STORE_F16_TMA) {

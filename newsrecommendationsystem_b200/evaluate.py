@@ -40,9 +40,10 @@ def build_history(clicked_rows_list, num_clicked=50, pad_row=-1) -> np.ndarray:
     return out
 
 
-def _dist():
+def _dist(distributed=True):
+    """torch.distributed when it is initialised with more than one rank (and the caller wants it), else None."""
     import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    if distributed and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         return dist
     return None
 
@@ -70,7 +71,7 @@ class EvalHost:
     cand_rows    int32 [sumC]             cand_offsets int64 [I+1]   labels int8 [sumC]
     """
 
-    def __init__(self, news_tokens, hist_rows, cand_offsets, cand_rows, labels, news_ids=None):
+    def __init__(self, news_tokens, hist_rows, cand_offsets, cand_rows, labels, news_ids=None, num_words=None):
         n_news = int(news_tokens.shape[0])
         hist = np.asarray(hist_rows, dtype=np.int64).copy()
         cand = np.asarray(cand_rows, dtype=np.int64)
@@ -79,6 +80,15 @@ class EvalHost:
             valid = hist >= 0
             hist[valid] = owner[hist[valid]]
             cand = owner[cand]
+        # the reference raises on an unknown id (KeyError in news2vector[...], evaluate.py:221,252; IndexError inside
+        # nn.Embedding); the device kernels would clamp silently, so the ranges are checked here, once, on the host
+        if hist.size and int(hist.max()) >= n_news:
+            raise IndexError(f"history row {int(hist.max())} out of range for {n_news} news")
+        if cand.size and (int(cand.min()) < 0 or int(cand.max()) >= n_news):
+            raise IndexError(f"candidate rows must lie in [0, {n_news}), got [{int(cand.min())}, {int(cand.max())}]")
+        tok = np.asarray(news_tokens)
+        if num_words is not None and tok.size and (int(tok.min()) < 0 or int(tok.max()) >= int(num_words)):
+            raise IndexError(f"token ids must lie in [0, {int(num_words)}), got [{int(tok.min())}, {int(tok.max())}]")
         hist[hist < 0] = n_news           # PADDED_NEWS -> the all-zero last row of the table
         self.n_news = n_news
         self.n_impressions = int(hist.shape[0])
@@ -106,21 +116,21 @@ class EvalInputs:
         self._fill(EvalHost(news_tokens, hist_rows, cand_offsets, cand_rows, labels, news_ids), device)
 
     @classmethod
-    def from_host(cls, host: EvalHost, device="cuda", shard=True):
+    def from_host(cls, host: EvalHost, device="cuda", shard=True, distributed=True):
         """`shard` (multi-rank only): copy just this rank's block of impressions (the block evaluate_tensors assigns it
         when `max_count` is None) instead of all of them -- the host-to-device traffic per rank stays constant as ranks
         are added."""
         self = cls.__new__(cls)
-        self._fill(host, device, shard)
+        self._fill(host, device, shard, distributed)
         return self
 
-    def _fill(self, host, device, shard=False):
+    def _fill(self, host, device, shard=False, distributed=True):
         self.device = torch.device(device)
         self.n_news, self.n_impressions = host.n_news, host.n_impressions
         self.cand_offsets_host = host.cand_offsets_host
         self._ready = None
         self.shard = None                # (lo, hi, c0, c1): the tensors below hold only impressions [lo, hi)
-        dist = _dist()
+        dist = _dist(distributed)
         views = dict(hist_rows=host.hist_rows, cand_rows=host.cand_rows, cand_offsets=host.cand_offsets, labels=host.labels)
         if shard and dist is not None:
             bounds = shard_impressions_by_candidates(host.cand_offsets_host, dist.get_world_size())
@@ -172,10 +182,10 @@ def _copy_stream(device):
 
 
 @torch.no_grad()
-def encode_news_table(model, news_tokens: torch.Tensor, n_news=None, local_shard=None) -> torch.Tensor:
+def encode_news_table(model, news_tokens: torch.Tensor, n_news=None, local_shard=None, distributed=True) -> torch.Tensor:
     """Stage A.  Returns [N_news+1, 300] with a zero last row.  Multi-rank: each rank encodes its
     contiguous row block straight into its slot of the (padded) table, then one all_gather."""
-    dist = _dist()
+    dist = _dist(distributed)
     n = news_tokens.shape[0] if n_news is None else int(n_news)      # `local_shard`: news_tokens = rows [lo, hi) only
     dev = news_tokens.device
     was_training = model.training
@@ -207,7 +217,7 @@ def encode_news_table(model, news_tokens: torch.Tensor, n_news=None, local_shard
 
 
 @torch.no_grad()
-def encode_news_table16(model, news_tokens: torch.Tensor, n_news=None, local_shard=None, want_fp32=False):
+def encode_news_table16(model, news_tokens: torch.Tensor, n_news=None, local_shard=None, want_fp32=False, distributed=True):
     """Stage A of the tensor-mode pipeline.  Returns (table16, table32): table16 = fp16 [N_news + 2, 320] in
     `ops.pack_rows_f16`'s layout -- row N_news is the PADDED_NEWS zero vector (evaluate.py:203-204; zeros with the 1.0 of the bias
     column), the row after it the all-zero closing row the kernels expect -- and table32 = the fp32 [N_news + 1, 300] table when `want_fp32`, else None.
@@ -215,7 +225,7 @@ def encode_news_table16(model, news_tokens: torch.Tensor, n_news=None, local_sha
     Nothing downstream of the news encoder reads fp32 rows in tensor mode: the user encoder projects the fp16 copy and the
     scoring kernel reads it, so the copy is made ONCE, by the rank that encoded the rows, straight into its slot of the
     gather buffer, and the NCCL all-gather moves 640-byte rows in place (no staging copy, half the bytes of fp32)."""
-    dist = _dist()
+    dist = _dist(distributed)
     n = news_tokens.shape[0] if n_news is None else int(n_news)
     dev = news_tokens.device
     was_training = model.training
@@ -262,12 +272,14 @@ def _tensor_mode(model):
     return resolve_mode(ue.config, ue.precision) == _lib.MODE_TF32
 
 
-def evaluate_tensors(model, inputs: EvalInputs, max_count=None, return_details=False, mark=None):
+def evaluate_tensors(model, inputs: EvalInputs, max_count=None, return_details=False, mark=None, distributed=True):
     """evaluate() on resident tensors -> (AUC, MRR, nDCG@5, nDCG@10) as Python floats.
 
     One D2H read (the 8 sums/counts) at the very end; no per-impression host work.
-    `mark(name)` (optional) is called at stage boundaries (bench.py records CUDA events there)."""
-    dist = _dist()
+    `mark(name)` (optional) is called at stage boundaries (bench.py records CUDA events there).
+    `distributed=False` evaluates everything on this rank even when torch.distributed is initialised (bench.py uses it
+    to check that N ranks and one rank give the same metric means)."""
+    dist = _dist(distributed)
     mark = mark or (lambda name: None)
     mark("start")
     # tensor mode (plain NRMS): one fp16 copy of the news vectors feeds the all-gather, the user encoder and the scoring
@@ -275,9 +287,10 @@ def evaluate_tensors(model, inputs: EvalInputs, max_count=None, return_details=F
     table16 = None
     if f16_flow:
         table16, table = encode_news_table16(model, inputs.news_tokens, inputs.n_news, getattr(inputs, "news_shard", None),
-                                             want_fp32=return_details)
+                                             want_fp32=return_details, distributed=distributed)
     else:
-        table = encode_news_table(model, inputs.news_tokens, inputs.n_news, getattr(inputs, "news_shard", None))
+        table = encode_news_table(model, inputs.news_tokens, inputs.n_news, getattr(inputs, "news_shard", None),
+                                  distributed=distributed)
     mark("news")
     inputs.wait_ready()
     n_imp = inputs.n_impressions

@@ -24,7 +24,7 @@ class NewsEncoder(nn.Module):
         self.layer_norm = nn.LayerNorm(config.word_embedding_dim) if getattr(config, "use_layernorm", False) else None
         self.precision = None          # None -> config.precision / $NRMS_B200_PRECISION / "tf32"
         self._dropout_calls = 0
-        self.dropout_seed = 0x5EED
+        self.dropout_seed = 0x5EED     # base seed; data-parallel ranks draw from different streams (see _seed)
 
     def _check_dims(self):
         c = self.config
@@ -32,10 +32,23 @@ class NewsEncoder(nn.Module):
             raise RuntimeError("libnrms_b200 is compiled for word_embedding_dim=300, num_attention_heads=15, "
                                "query_vector_dim=200 (reference src/config.py:33-45)")
 
+    def _seed(self):
+        """Philox key of this process: the base seed with the data-parallel rank folded in, so that G ranks apply G
+        independent dropout masks (the reference's single process draws one mask for its whole batch)."""
+        import torch.distributed as dist
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        return (int(self.dropout_seed) + 0x9E3779B97F4A7C15 * rank) & 0xFFFFFFFFFFFFFFFF
+
     def encode_tokens(self, title):
         """title: integer tensor [n, num_words_title] (any device) -> fp32 [n, 300]."""
         self._check_dims()
         dev = self.word_embedding.weight.device
+        if not title.is_cuda and title.numel():
+            # host input (the reference's DataLoader path): nn.Embedding would raise on an id outside the vocabulary; the
+            # gather kernels do not check, so the check happens here while the ids are still on the host
+            lo, hi = int(title.min()), int(title.max())
+            if lo < 0 or hi >= self.word_embedding.num_embeddings:
+                raise IndexError(f"token ids must lie in [0, {self.word_embedding.num_embeddings}), got [{lo}, {hi}]")
         title = title.to(dev, non_blocking=True)
         wqkv, bqkv = self.multihead_self_attention.packed()
         p = float(self.config.dropout_probability) if self.training else 0.0
@@ -47,7 +60,7 @@ class NewsEncoder(nn.Module):
         return ops.news_encoder(title, self.word_embedding.weight, wqkv, bqkv,
                                 self.additive_attention.linear.weight, self.additive_attention.linear.bias,
                                 self.additive_attention.attention_query_vector,
-                                dropout_p=p, seed=self.dropout_seed, offset=offset,
+                                dropout_p=p, seed=self._seed(), offset=offset,
                                 mode=resolve_mode(self.config, self.precision),
                                 ln=None if self.layer_norm is None else (self.layer_norm.weight, self.layer_norm.bias))
 

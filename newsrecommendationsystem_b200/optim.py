@@ -44,6 +44,11 @@ class FusedAdam(torch.optim.Optimizer):
                 p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
         self._params, self._offsets = ps, offs
         self.step_count = 0
+        # data parallel: every replica starts from rank 0's parameters (the gradient all-reduce keeps them identical from
+        # then on; replicas built from different seeds would otherwise diverge silently)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.broadcast(self.flat_param, src=0)
 
     def zero_grad(self, set_to_none=False):
         # keep the .grad views alive (autograd accumulates into them in place)

@@ -58,3 +58,28 @@ def user_vectors(params, clicked):
 def prediction(news_vector, user_vector):
     """NRMS.get_prediction (NRMS/__init__.py:73-84) incl. the reference's .tolist() (evaluate.py:260)."""
     return torch.bmm(news_vector.unsqueeze(0), user_vector.unsqueeze(0).unsqueeze(-1)).squeeze(-1).squeeze(0).tolist()
+
+
+def train_step(params, cand_tokens, clicked_tokens, lr=1e-4, adam_state=None):
+    """One iteration of the reference's training loop on the CPU (src/train.py:202-206,227-233): NRMS.forward
+    (NRMS/__init__.py:19-48: every title through the news encoder, the 50 clicked vectors through the user encoder,
+    dot-product scores), CrossEntropyLoss against label 0, loss.backward(), torch.optim.Adam(lr=1e-4).step().
+    Eval-mode forward (dropout = identity; the reference's two F.dropout calls are elementwise and do not change the
+    cost measurably).  cand_tokens int [B, 1+K, L], clicked_tokens int [B, N, L].  Returns (loss, parameters, optimizer)."""
+    P = {k: torch.as_tensor(v).clone().requires_grad_(True) for k, v in params.items()}
+    opt = torch.optim.Adam(list(P.values()), lr=lr) if adam_state is None else adam_state
+    B, C1, L = cand_tokens.shape
+    N = clicked_tokens.shape[1]
+    with torch.enable_grad():
+        toks = torch.as_tensor(np.concatenate([cand_tokens, clicked_tokens], axis=1)).reshape(B * (C1 + N), L)
+        x = F.embedding(toks, P[O.EMB_KEY], padding_idx=0)
+        pn = {k: P[v] for k, v in O.enc_keys(O.NEWS).items()}
+        pu = {k: P[v] for k, v in O.enc_keys(O.USER).items()}
+        vec = additive(mhsa(x, pn), pn).view(B, C1 + N, -1)
+        user = additive(mhsa(vec[:, C1:], pu), pu)
+        logits = torch.bmm(vec[:, :C1], user.unsqueeze(-1)).squeeze(-1)
+        loss = F.cross_entropy(logits, torch.zeros(B, dtype=torch.long))
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+    return float(loss.item()), P, opt

@@ -126,3 +126,53 @@ def test_news2vector_cache_round_trip():
     assert not n2v["PADDED_NEWS"].any()
     ids, back = ck.table_from_news2vector(n2v)
     assert ids == ["N1", "N2"] and back.shape == (3, 3) and torch.equal(back[:2], table[:2]) and not back[2].any()
+
+
+def test_out_of_range_indices_raise_like_the_reference():
+    """The reference raises on unknown ids (KeyError in news2vector[...], evaluate.py:221,252; IndexError inside
+    nn.Embedding, news_encoder.py:38).  The device kernels do not check, so the host formats do."""
+    from newsrecommendationsystem_b200 import synthetic
+    from newsrecommendationsystem_b200.evaluate import EvalHost
+    ntok = synthetic.make_news(30, num_words=101, seed=2)
+    imp = synthetic.make_impressions(9, 30, seed=3, max_cand=12)
+    EvalHost(ntok, imp["hist_rows"], imp["cand_offsets"], imp["cand_rows"], imp["labels"], num_words=101)      # in range
+    bad = imp["hist_rows"].copy(); bad[2, 49] = 30
+    with pytest.raises(IndexError):
+        EvalHost(ntok, bad, imp["cand_offsets"], imp["cand_rows"], imp["labels"])
+    bad = imp["cand_rows"].copy(); bad[5] = -1
+    with pytest.raises(IndexError):
+        EvalHost(ntok, imp["hist_rows"], imp["cand_offsets"], bad, imp["labels"])
+    bad = ntok.copy(); bad[3, 0] = 101
+    with pytest.raises(IndexError):
+        EvalHost(bad, imp["hist_rows"], imp["cand_offsets"], imp["cand_rows"], imp["labels"], num_words=101)
+
+
+def test_checkpoint_keeps_the_dropout_stream_position(tmp_path):
+    """save_checkpoint / load_checkpoint carry the Philox dropout counter next to the reference's four keys."""
+    import torch
+    from newsrecommendationsystem_b200 import checkpoint
+
+    class _Enc:
+        dropout_seed, _dropout_calls = 0x5EED, 12345
+
+    class _Model:
+        news_encoder = _Enc()
+
+        def state_dict(self):
+            return {"w": torch.ones(2)}
+
+        def load_state_dict(self, sd):
+            assert set(sd) == {"w"}
+
+    class _Opt:
+        def state_dict(self):
+            return {"state": {}, "param_groups": []}
+
+    path = str(tmp_path / "ckpt-7.pth")
+    checkpoint.save_checkpoint(path, _Model(), _Opt(), 7, 0.5)
+    raw = torch.load(path, weights_only=False)
+    assert {"model_state_dict", "optimizer_state_dict", "step", "early_stop_value"} <= set(raw)
+    m2 = _Model()
+    m2.news_encoder = type("E", (), {"dropout_seed": 1, "_dropout_calls": 0})()
+    assert checkpoint.load_checkpoint(path, m2) == (7, 0.5)
+    assert (m2.news_encoder.dropout_seed, m2.news_encoder._dropout_calls) == (0x5EED, 12345)

@@ -181,6 +181,16 @@ def test_torch_port_matches_golden(golden, golden_sd):
     np.testing.assert_allclose(s, golden["fwd/scores_single"], rtol=1e-5, atol=1e-6)
 
 
+def test_torch_port_train_step_matches_golden(golden, golden_sd):
+    """bench.py's CPU training baseline (torch-CPU port: forward, CE(label 0), autograd backward, torch.optim.Adam) is
+    pinned against the live reference's loss and first Adam step."""
+    from oracle import torch_port as TP
+    loss, P, _ = TP.train_step(golden_sd, golden["train/cand"], golden["train/clicked"])
+    assert abs(loss - float(golden["train/loss"])) < 2e-6
+    for k in golden_sd:
+        close_adam(clip(P[k].detach().numpy()), golden["train/adam1/" + k], k, gscale=gs(golden, k))
+
+
 def _torch_ln_encoder(x, p, heads=15):
     """The config-5 encoder composed from stock torch pieces in float64: the reference's MHSA arithmetic
     (multihead_self.py:15-23,46-76), torch.nn.functional.layer_norm, the reference's additive attention
