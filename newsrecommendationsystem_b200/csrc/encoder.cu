@@ -166,13 +166,13 @@ static int encoder_core_bwd(const Stash& s, const BwdWs& w, const float* d_out, 
   if (S == 20) additive_bwd_kernel<20><<<nb, 256, 0, st>>>(d_out, cin, s.t, s.w, qa, w.d_c, w.d_u, w.partial, n_seq);
   else additive_bwd_kernel<50><<<nb, 256, 0, st>>>(d_out, cin, s.t, s.w, qa, w.d_c, w.d_u, w.partial, n_seq);
   NRMS_LAUNCH_CHECK("additive_bwd");
-  partial_reduce_accum_kernel<<<1, 256, 0, st>>>(w.partial, nb, QD, d_qa);
+  launch_partial_reduce_accum(w.partial, nb, QD, QD, d_qa, st);
   NRMS_LAUNCH_CHECK("dqa_reduce");
   // d_ba = colsum(dU)
   int cb = (int)(rows < REDUCE_BLOCKS ? rows : REDUCE_BLOCKS);
   colsum_partial_kernel<<<cb, 256, 0, st>>>(w.d_u, rows, QD, w.partial);
   NRMS_LAUNCH_CHECK("colsum_du");
-  partial_reduce_accum_kernel<<<1, 256, 0, st>>>(w.partial, cb, QD, d_ba);
+  launch_partial_reduce_accum(w.partial, cb, QD, QD, d_ba, st);
   NRMS_LAUNCH_CHECK("dba_reduce");
   int splits = (int)((rows + 4095) / 4096);
   if (splits > 64) splits = 64;
@@ -198,9 +198,9 @@ static int encoder_core_bwd(const Stash& s, const BwdWs& w, const float* d_out, 
     int lb = (int)((rows + 7) / 8 < REDUCE_BLOCKS ? (rows + 7) / 8 : REDUCE_BLOCKS);
     layernorm_bwd_kernel<<<lb, 256, 0, st>>>(w.d_c, s.c, s.stats, ln->gamma, w.partial, rows);
     NRMS_LAUNCH_CHECK("layernorm_bwd");
-    partial_reduce_accum_strided_kernel<<<(D + 255) / 256, 256, 0, st>>>(w.partial, lb, 2 * D, D, ln->d_gamma);
+    launch_partial_reduce_accum(w.partial, lb, 2 * D, D, ln->d_gamma, st);
     NRMS_LAUNCH_CHECK("dgamma_reduce");
-    partial_reduce_accum_strided_kernel<<<(D + 255) / 256, 256, 0, st>>>(w.partial + D, lb, 2 * D, D, ln->d_beta);
+    launch_partial_reduce_accum(w.partial + D, lb, 2 * D, D, ln->d_beta, st);
     NRMS_LAUNCH_CHECK("dbeta_reduce");
   }
   // attention backward (applies the dropout-2 mask to d_c on load)
@@ -213,7 +213,7 @@ static int encoder_core_bwd(const Stash& s, const BwdWs& w, const float* d_out, 
   // d_bqkv = colsum(dQKV)
   colsum_partial_kernel<<<cb, 256, 0, st>>>(w.d_qkv, rows, D3, w.partial);
   NRMS_LAUNCH_CHECK("colsum_dqkv");
-  partial_reduce_accum_kernel<<<(D3 + 255) / 256, 256, 0, st>>>(w.partial, cb, D3, d_bqkv);
+  launch_partial_reduce_accum(w.partial, cb, D3, D3, d_bqkv, st);
   NRMS_LAUNCH_CHECK("dbqkv_reduce");
   if (tc) {
     // d_wqkv[900,300] += dQKV^T X
@@ -601,6 +601,10 @@ int nrms_set_option(const char* key, int value) {
   }
   if (strcmp(key, "fused_pool") == 0) {
     set_fused_pool(value != 0);
+    return NRMS_OK;
+  }
+  if (strcmp(key, "gemm_tma_epilogue") == 0) {
+    set_gemm_tma_epilogue(value != 0);
     return NRMS_OK;
   }
   if (strcmp(key, "k1f_debug") == 0) {

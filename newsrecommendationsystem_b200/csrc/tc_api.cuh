@@ -43,6 +43,7 @@ int k1f_run(int S, int idx_kind, const void* table16, int64_t n_table_rows, cons
             const void* wa16, const float* ba, const float* qa, const float* bound, float* out, cudaStream_t st);
 void set_attn_safe_softmax(int v);
 int get_attn_safe_softmax();   // -1 auto (bound over the projected table), 0 plain 2^s, 1 row-shifted form
+void set_gemm_tma_epilogue(bool on); // fp32 GEMM results through bulk tensor stores / reductions (default 1)
 void set_k1f_debug(int v);           // component-removal timing switches of K1f (garbage results)
 void set_fused_pool(bool on);        // table path: 1 (default) = K1f, 0 = K1g + K2 (context rows through HBM)
 int tc_gemm_nt_f16_tma(const void* A16, int64_t lda, const void* B16, int64_t ldb, void* C16, int64_t ldc, int64_t M, int N,

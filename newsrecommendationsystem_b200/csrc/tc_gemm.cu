@@ -54,13 +54,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 //              with bulk tensor stores (one per 32 rows x 64 columns) instead of per-thread stores: with thread == row
 //              every store instruction touched 32 different rows (32 requests of 16 bytes), which bound the table
 //              projection of K1g at 147 us for 35 GFLOP.
+// (MN-major operand descriptors for kind::tf32 -- which would let the weight gradients dW = dY^T X read the activations
+// in place -- were tried in round 2: with either major bit of the instruction descriptor set the MMA returns zeros on
+// sm_100a, as on Hopper where only 16-bit operands may be MN-major.  The transposed copies of the backward stay.)
 template <bool F16, bool TMA_EPI = false>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_c,
                   const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int64_t M, int N, int K,
                   uint32_t stage_tx_bytes, int k_splits, int chunks_per_split, int epi, float f16_scale, int f16_scale_cols) {
-  static_assert(!TMA_EPI || F16, "the bulk-store epilogue writes fp16");
   constexpr int TG_STAGES = TMA_EPI ? TG_STAGES_TMA : nrms::TG_STAGES;
   constexpr int STG_BYTES = TMA_EPI ? 4 * TG_STG_WARP : 0;
   extern __shared__ uint8_t smem_raw[];
@@ -185,7 +187,58 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       tc_fence_after();
       const int64_t m = m0 + q * 32 + lane;
       const uint32_t trow = tmem_base + as * TG_BN + ((uint32_t)(q * 32) << 16);
-      if constexpr (TMA_EPI) {
+      if constexpr (TMA_EPI && !F16) {
+        // fp32 result: the warp's 32 rows leave through a 128B-swizzled staging tile (4 boxes of 32 rows x 32 floats =
+        // 128 columns at a time) and bulk tensor stores -- or bulk tensor REDUCTIONS (add.f32, performed in L2) for the
+        // accumulate / split-K epilogues.  With thread == row a plain store instruction touched 32 different rows (32
+        // requests of 16 bytes); the forward QKV projection of a training step ran at 1.3 TB/s of its 676 MB because of it.
+        uint8_t* const stg = base_ptr + TG_STAGES * TG_STAGE_BYTES + (warp - 2) * TG_STG_WARP;
+        const uint32_t stg_s = base + TG_STAGES * TG_STAGE_BYTES + (warp - 2) * TG_STG_WARP;
+        for (int h0 = 0; h0 < n_valid; h0 += 128) {
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // earlier stores have read the tile
+          __syncwarp();
+          const int h1 = (h0 + 128 < n_valid) ? h0 + 128 : n_valid;
+          for (int col = h0; col < h1; col += 16) {
+            float v[16];
+            tmem_ld16(trow + col, v);
+            if (add_bias) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int n = n0 + col + 4 * j;
+                if (n < N) {
+                  const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n));
+                  v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+                }
+              }
+            }
+            uint8_t* const brow = stg + ((col - h0) >> 5) * 4096 + lane * 128;
+            const int c4 = (col & 31) >> 2;                 // first 16-byte chunk of these 16 floats inside the 32-float row
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<float4*>(brow + (((c4 + j) ^ (lane & 7)) << 4)) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (h1 == n_valid) tc_fence_before();             // the accumulator stage is fully read
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (h1 == n_valid) mbar_arrive(tempty_bar + 8 * as);
+            for (int b = 0; h0 + 32 * b < h1; ++b) {
+              if (epi == TC_EPI_STORE)
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                             ::"l"(reinterpret_cast<uint64_t>(&tmap_c)), "r"(n0 + h0 + 32 * b), "r"((int)(m0 + q * 32)),
+                               "r"(stg_s + b * 4096) : "memory");
+              else
+                asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];"
+                             ::"l"(reinterpret_cast<uint64_t>(&tmap_c)), "r"(n0 + h0 + 32 * b), "r"((int)(m0 + q * 32)),
+                               "r"(stg_s + b * 4096) : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        continue;
+      }
+      if constexpr (TMA_EPI && F16) {
         // fp16 tile rows of this warp -> staging (4 boxes of 32 rows x 64 halfs, 16-byte chunk c of row r at c ^ (r & 7))
         // -> bulk tensor stores; rows / columns past the tensor are clipped by the TMA unit
         uint8_t* const stg = base_ptr + TG_STAGES * TG_STAGE_BYTES + (warp - 2) * TG_STG_WARP;
@@ -395,6 +448,24 @@ static int make_tmap_store_f16_sw128(CUtensorMap* out, const void* base, int64_t
   return NRMS_OK;
 }
 
+static bool g_f32_tma_epilogue = true;      // "gemm_tma_epilogue" option (A/B): 0 = per-thread stores / atomics
+void set_gemm_tma_epilogue(bool on) { g_f32_tma_epilogue = on; }
+
+// fp32 row-major [rows, cols]: 128B-swizzled boxes of 32 rows x 32 floats for the bulk-store / bulk-reduce epilogue
+static int make_tmap_store_f32_sw128(CUtensorMap* out, const void* base, int64_t rows, int cols, int64_t ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  NRMS_CHECK_ARG(fn != nullptr, NRMS_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32u, rows < 32 ? (cuuint32_t)rows : 32u};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  NRMS_CHECK_ARG(r == CUDA_SUCCESS, NRMS_E_CUDA, "cuTensorMapEncodeTiled(store f32 sw128) failed with CUresult %d", (int)r);
+  return NRMS_OK;
+}
+
 static int tc_gemm_launch(const void* A, int64_t lda, const void* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
                          int64_t M, int N, int K, int k_splits, int epi, float f16_scale, int f16_scale_cols, bool f16_in,
                          cudaStream_t st);
@@ -442,8 +513,9 @@ static int tc_gemm_launch(const void* A, int64_t lda, const void* B, int64_t ldb
                          cudaStream_t st) {
   if (M <= 0) return NRMS_OK;
   NRMS_CHECK_ARG(M < (1ll << 31), NRMS_E_UNSUPPORTED, "M too large for one tensor map");
-  static bool cfg_a[64] = {false}, cfg_b[64] = {false}, cfg_c[64] = {false};
+  static bool cfg_a[64] = {false}, cfg_b[64] = {false}, cfg_c[64] = {false}, cfg_d[64] = {false};
   cudaError_t e = set_max_dynamic_smem(tc_gemm_nt_kernel<false>, TG_SMEM, cfg_a);
+  if (e == cudaSuccess) e = set_max_dynamic_smem(tc_gemm_nt_kernel<false, true>, TG_SMEM_TMA, cfg_d);
   if (e == cudaSuccess) e = set_max_dynamic_smem(tc_gemm_nt_kernel<true>, TG_SMEM, cfg_b);
   if (e == cudaSuccess) e = set_max_dynamic_smem(tc_gemm_nt_kernel<true, true>, TG_SMEM_TMA, cfg_c);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(tc_gemm_nt_kernel)");
@@ -452,6 +524,11 @@ static int tc_gemm_launch(const void* A, int64_t lda, const void* B, int64_t ldb
   if (epi == TC_EPI_STORE_F16_TMA) {
     NRMS_CHECK_ARG(f16_in, NRMS_E_INVALID, "the bulk-store epilogue needs fp16 operands");
     if (int rc = make_tmap_store_f16_sw128(&tcm, C, M, N, ldc)) return rc;
+  }
+  // fp32 results (store / accumulate / split-K) leave through bulk tensor stores / reductions
+  const bool f32_tma = !f16_in && epi <= TC_EPI_ATOMIC && g_f32_tma_epilogue;
+  if (f32_tma) {
+    if (int rc = make_tmap_store_f32_sw128(&tcm, C, M, N, ldc)) return rc;
   }
   // boxes never exceed the tensor extent (rows past it would only feed outputs that are not stored)
   const int box_a = M < TG_BM ? (int)M : TG_BM;
@@ -477,6 +554,9 @@ static int tc_gemm_launch(const void* A, int64_t lda, const void* B, int64_t ldb
   if (epi == TC_EPI_STORE_F16_TMA)
     tc_gemm_nt_kernel<true, true><<<grid, TG_THREADS, TG_SMEM_TMA, st>>>(ta, tb, tcm, bias, C, ldc, M, N, K, stage_tx, k_splits,
                                                                           cps, epi, f16_scale, f16_scale_cols);
+  else if (f32_tma)
+    tc_gemm_nt_kernel<false, true><<<grid, TG_THREADS, TG_SMEM_TMA, st>>>(ta, tb, tcm, bias, C, ldc, M, N, K, stage_tx, k_splits,
+                                                                           cps, epi, f16_scale, f16_scale_cols);
   else if (f16_in)
     tc_gemm_nt_kernel<true><<<grid, TG_THREADS, TG_SMEM, st>>>(ta, tb, tcm, bias, C, ldc, M, N, K, stage_tx, k_splits, cps, epi,
                                                                f16_scale, f16_scale_cols);

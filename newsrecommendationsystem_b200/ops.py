@@ -15,6 +15,9 @@ from . import _lib
 from ._lib import check, ptr, stream_ptr
 
 D, H, QD = 300, 15, 200
+# True (set by optim.FusedAdam): the news encoder's backward accumulates the embedding gradient directly into the
+# parameter's existing .grad buffer instead of returning a fresh 85 MB tensor for autograd to add.
+EMB_GRAD_IN_PLACE = False
 
 
 def _require_cuda(*tensors):
@@ -76,6 +79,7 @@ class _NewsEncoderFn(torch.autograd.Function):
         if needs_grad:
             ctx.save_for_backward(tokens, wqkv_c, wa_c, qa_c, stash, *([lnw_c] if ln else []))
             ctx.meta = (n, L, emb_c.shape[0], float(dropout_p), int(seed), int(offset), mode, ln)
+            ctx.emb_param = emb if (EMB_GRAD_IN_PLACE and emb.is_leaf) else None
         return out
 
     @staticmethod
@@ -85,7 +89,14 @@ class _NewsEncoderFn(torch.autograd.Function):
         tokens, wqkv, wa, qa, stash = ctx.saved_tensors[:5]
         dev = d_out.device
         d_out = d_out.contiguous().float()
-        d_emb = torch.zeros((V, D), dtype=torch.float32, device=dev)
+        # The embedding gradient is 85 MB: when the optimizer owns a gradient buffer for the table (FusedAdam's flat
+        # gradient, zeroed by zero_grad) the scatter kernel accumulates straight into it -- no 85 MB zero fill here and no
+        # 85 MB add by autograd afterwards; autograd is told "no gradient" for that input.
+        sink = getattr(ctx, "emb_param", None)
+        g = sink.grad if sink is not None else None
+        in_place = (g is not None and g.dtype == torch.float32 and g.is_contiguous() and tuple(g.shape) == (V, D)
+                    and g.device == dev)
+        d_emb = g if in_place else torch.zeros((V, D), dtype=torch.float32, device=dev)
         d_wqkv = torch.zeros((3 * D, D), dtype=torch.float32, device=dev)
         d_bqkv = torch.zeros((3 * D,), dtype=torch.float32, device=dev)
         d_wa = torch.zeros((QD, D), dtype=torch.float32, device=dev)
@@ -106,7 +117,7 @@ class _NewsEncoderFn(torch.autograd.Function):
                                             ptr(d_emb), ptr(d_wqkv), ptr(d_bqkv), ptr(d_wa), ptr(d_ba), ptr(d_qa),
                                             ptr(ws), ws.numel(), p, seed, offset, mode, stream_ptr(dev)),
                   "nrms_news_encoder_bwd")
-        return None, d_emb, d_wqkv, d_bqkv, d_wa, d_ba, d_qa, None, None, None, None, None, d_lnw, d_lnb
+        return None, (None if in_place else d_emb), d_wqkv, d_bqkv, d_wa, d_ba, d_qa, None, None, None, None, None, d_lnw, d_lnb
 
 
 class _UserEncoderFn(torch.autograd.Function):

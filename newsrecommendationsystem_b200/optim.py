@@ -44,6 +44,7 @@ class FusedAdam(torch.optim.Optimizer):
                 p.grad = self.flat_grad[o:o + p.numel()].view_as(p)
         self._params, self._offsets = ps, offs
         self.step_count = 0
+        ops.EMB_GRAD_IN_PLACE = True       # .grad of every parameter is a live view of flat_grad from here on
         # data parallel: every replica starts from rank 0's parameters (the gradient all-reduce keeps them identical from
         # then on; replicas built from different seeds would otherwise diverge silently)
         import torch.distributed as dist

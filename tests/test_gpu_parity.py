@@ -758,7 +758,8 @@ def test_checkpoint_interchange_with_torch_adam(dev, golden, golden_sd, tmp_path
     path = str(tmp_path / "ckpt-3.pth")
     ck.save_checkpoint(path, m, ts.optimizer, step=3, early_stop_value=-0.5)
     raw = torch.load(path, weights_only=False)
-    assert set(raw) == {"model_state_dict", "optimizer_state_dict", "step", "early_stop_value"}
+    # the reference's four keys (train.py:266-277) + the position of the in-kernel dropout stream
+    assert set(raw) == {"model_state_dict", "optimizer_state_dict", "step", "early_stop_value", "b200_dropout_state"}
 
     # -> torch.optim.Adam over plain CPU parameters with the reference's names
     params = {k: torch.nn.Parameter(v.clone()) for k, v in raw["model_state_dict"].items()}
