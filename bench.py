@@ -522,7 +522,9 @@ def main():
                              d2h_bytes_per_step=64, ms_per_step=head["e2e_ms_per_step"]),
                     gpu_launches=head["launches"], roofline=roof, roofline_news=roof_news, roofline_score=roof_score,
                     cpu_baseline=cpu, train=train, train_ln=train_ln, stage_ms=st, metrics=head["metrics"],
-                    news_per_s=head["n_news"] / (st.get("news", float("nan")) / 1e3),
+                    stage_note="news_encode = this rank's titles (incl. the embedding-table projection) + the fp16 pack; news = "
+                               "what follows it in the news stage: the NCCL all-gather of the fp16 table and the pad rows",
+                    news_per_s=head["n_news"] / ((st.get("news", float("nan")) + st.get("news_encode", 0.0)) / 1e3),
                     users_per_s=head["n_impressions"] / (st.get("users", float("nan")) / 1e3),
                     score_candidates_per_s=head["n_candidates"] / (st.get("score", float("nan")) / 1e3),
                     mind_large=eval_extra(large) if large else None)

@@ -678,7 +678,8 @@ static int launch_attn_pool(const void* table16, int64_t n_table_rows, const voi
   if (n_seq < grid) grid = (int)n_seq;
   k1f::attn_pool_kernel<SEQ, IdxT><<<grid, k1f::THREADS, k1f::Cfg<SEQ>::SMEM_BYTES, st>>>(
       reinterpret_cast<const __half*>(table16), n_table_rows, reinterpret_cast<const IdxT*>(rows), n_seq,
-      reinterpret_cast<const __half*>(wa16), ba, qa, bound, g_force_safe, g_k1f_debug, out);
+      reinterpret_cast<const __half*>(wa16), ba, qa, bound, (g_force_safe < 0 && bound == nullptr) ? 1 : g_force_safe,
+      g_k1f_debug, out);
   NRMS_LAUNCH_CHECK("attn_pool_kernel");
   return NRMS_OK;
 }

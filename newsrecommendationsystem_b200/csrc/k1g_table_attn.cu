@@ -400,7 +400,8 @@ static int launch_seq_attn(const void* table16, int64_t n_table_rows, const void
   NRMS_CHECK_ARG(n_table_rows > 0, NRMS_E_INVALID, "table row count out of range");
   int grid = num_sms();
   if (n_seq < grid) grid = (int)n_seq;
-  const int force = get_attn_safe_softmax();          // -1: both instantiations read the bound, one of them runs
+  int force = get_attn_safe_softmax();                // -1: both instantiations read the bound, one of them runs
+  if (force < 0 && qk_bound == nullptr) force = 1;    // no bound given: the row-shifted form (always valid)
   const float* bound = force < 0 ? qk_bound : nullptr;
   if (force <= 0) {
     k1g::seq_attn_kernel<SEQ, IdxT, false><<<grid, k1g::THREADS, k1g::SeqCfg<SEQ>::SMEM_BYTES, st>>>(

@@ -217,7 +217,8 @@ def encode_news_table(model, news_tokens: torch.Tensor, n_news=None, local_shard
 
 
 @torch.no_grad()
-def encode_news_table16(model, news_tokens: torch.Tensor, n_news=None, local_shard=None, want_fp32=False, distributed=True):
+def encode_news_table16(model, news_tokens: torch.Tensor, n_news=None, local_shard=None, want_fp32=False, distributed=True,
+                        mark=None):
     """Stage A of the tensor-mode pipeline.  Returns (table16, table32): table16 = fp16 [N_news + 2, 320] in
     `ops.pack_rows_f16`'s layout -- row N_news is the PADDED_NEWS zero vector (evaluate.py:203-204; zeros with the 1.0 of the bias
     column), the row after it the all-zero closing row the kernels expect -- and table32 = the fp32 [N_news + 1, 300] table when `want_fp32`, else None.
@@ -241,6 +242,8 @@ def encode_news_table16(model, news_tokens: torch.Tensor, n_news=None, local_sha
         if hi > lo:
             vec = model.get_news_vector({"title": news_tokens if (local_shard is not None or dist is None) else news_tokens[lo:hi]})
             ops.pack_rows_f16(vec, out=buf[lo:hi + 1])          # rows [lo, hi) + a zero row at hi
+        if mark is not None:
+            mark("news_encode")
         if dist is not None:
             if buf.is_cuda:       # NCCL gathers in place: every rank's slot already sits at rank * per
                 dist.all_gather_into_tensor(buf[:world * per].view(-1), buf[rank * per:(rank + 1) * per].view(-1))
@@ -272,6 +275,7 @@ def _tensor_mode(model):
     return resolve_mode(ue.config, ue.precision) == _lib.MODE_TF32
 
 
+@torch.no_grad()
 def evaluate_tensors(model, inputs: EvalInputs, max_count=None, return_details=False, mark=None, distributed=True):
     """evaluate() on resident tensors -> (AUC, MRR, nDCG@5, nDCG@10) as Python floats.
 
@@ -287,7 +291,7 @@ def evaluate_tensors(model, inputs: EvalInputs, max_count=None, return_details=F
     table16 = None
     if f16_flow:
         table16, table = encode_news_table16(model, inputs.news_tokens, inputs.n_news, getattr(inputs, "news_shard", None),
-                                             want_fp32=return_details, distributed=distributed)
+                                             want_fp32=return_details, distributed=distributed, mark=mark)
     else:
         table = encode_news_table(model, inputs.news_tokens, inputs.n_news, getattr(inputs, "news_shard", None),
                                   distributed=distributed)

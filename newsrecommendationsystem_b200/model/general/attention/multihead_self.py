@@ -28,9 +28,20 @@ class MultiHeadSelfAttention(nn.Module):
                 nn.init.xavier_uniform_(m.weight, gain=1)
 
     def packed(self):
-        """([W_Q;W_K;W_V] [3D,D], [b_Q;b_K;b_V] [3D]) -- autograd splits the gradients back."""
-        return (torch.cat([self.W_Q.weight, self.W_K.weight, self.W_V.weight], dim=0),
-                torch.cat([self.W_Q.bias, self.W_K.bias, self.W_V.bias], dim=0))
+        """([W_Q;W_K;W_V] [3D,D], [b_Q;b_K;b_V] [3D]) -- autograd splits the gradients back.
+
+        Without grad mode (inference: evaluate encodes thousands of batches with fixed parameters) the concatenation is
+        cached and reused until a parameter is written (tensor version counters) or moved."""
+        ps = (self.W_Q.weight, self.W_K.weight, self.W_V.weight, self.W_Q.bias, self.W_K.bias, self.W_V.bias)
+        if torch.is_grad_enabled():
+            return torch.cat(ps[:3], dim=0), torch.cat(ps[3:], dim=0)
+        key = tuple((p.data_ptr(), p._version) for p in ps)
+        cache = getattr(self, "_packed_cache", None)
+        if cache is None or cache[0] != key:
+            with torch.no_grad():
+                cache = (key, torch.cat(ps[:3], dim=0), torch.cat(ps[3:], dim=0))
+            self._packed_cache = cache
+        return cache[1], cache[2]
 
     def forward(self, Q, K=None, V=None, length=None):
         """Standalone use (inference).  Inside NewsEncoder / UserEncoder this block is fused into the encoder
