@@ -379,9 +379,9 @@ def main():
                                 f"in, vector out); design bytes = what this kernel moves (fp16 q|k|v rows gathered from a "
                                 f"partly L2-resident projected table + fp16 context rows out)")
 
-    roof = attn_roof("k1g", "k1g::seq_attn_kernel<50,int,false> (user encoder: q|k|v row gather + 15-head attention)",
+    roof = attn_roof("k1g", "k1g::seq_attn_kernel<50,int,false> (user encoder: q|k|v row gather + 15-head attention; <..,true> when the score bound asks for the row-shifted softmax)",
                      BYTES_PER_USER, K1G_BYTES_PER_USER, FLOP_PER_USER, "seq_attn_kernel<50>")
-    roof_news = attn_roof("k1gn", "k1g::seq_attn_kernel<20,long,false> (news encoder: q|k|v row gather + 15-head attention)",
+    roof_news = attn_roof("k1gn", "k1g::seq_attn_kernel<20,int,true> (news encoder: q|k|v row gather + 15-head attention, row-shifted softmax)",
                           BYTES_PER_TITLE, K1G_BYTES_PER_TITLE, FLOP_PER_TITLE, "seq_attn_kernel<20>")
 
     def tensor_roof(kind, name, flop_per_seq):

@@ -104,6 +104,15 @@ int nrms_news_encoder_fwd(const int64_t* tokens, int64_t n_titles, int L,
                           float dropout_p, uint64_t seed, uint64_t offset,
                           int mode, void* stream);
 
+/* Inference-only, tensor-mode form of the news encoder over int32 token ids (the pre-tokenised evaluate table: half the
+ * host-to-device bytes of the int64 LongTensor the reference's DataLoader ships, src/evaluate.py:51-78).  Workspace:
+ * nrms_encoder_fwd_workspace_bytes(n_titles, L, NRMS_MODE_TF32, 0, num_words). */
+int nrms_news_encoder_i32_fwd(const int32_t* tokens, int64_t n_titles, int L,
+                              const float* emb, int64_t num_words,
+                              const float* wqkv, const float* bqkv,
+                              const float* wa, const float* ba, const float* qa,
+                              float* out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* News encoder backward.  d_out [n_titles,300].  Gradients are ACCUMULATED (+=) into
  * d_emb [num_words,300] (row 0 = padding_idx is never touched), d_wqkv [900,300],
  * d_bqkv [900], d_wa [200,300], d_ba [200], d_qa [200]. */

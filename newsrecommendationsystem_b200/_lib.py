@@ -29,6 +29,7 @@ SIGNATURES = {
     "nrms_encoder_bwd_workspace_bytes": (_sz, [_i64, _i32, _i32]),
     "nrms_news_encoder_fwd": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                      _f32, _u64, _u64, _i32, _vp]),
+    "nrms_news_encoder_i32_fwd": (_i32, [_vp, _i64, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "nrms_news_encoder_bwd": (_i32, [_vp, _vp, _i64, _i32, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                      _vp, _sz, _f32, _u64, _u64, _i32, _vp]),
     "nrms_user_encoder_fwd": (_i32, [_vp, _i64, _vp, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i32, _vp]),

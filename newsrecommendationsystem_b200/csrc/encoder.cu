@@ -345,6 +345,21 @@ int nrms_news_encoder_fwd(const int64_t* tokens, int64_t n_titles, int L, const 
                                workspace_bytes, dropout_p, seed, offset, mode, stream, nullptr);
 }
 
+int nrms_news_encoder_i32_fwd(const int32_t* tokens, int64_t n_titles, int L, const float* emb, int64_t num_words,
+                              const float* wqkv, const float* bqkv, const float* wa, const float* ba, const float* qa,
+                              float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (int rc = check_common(L, NRMS_MODE_TF32)) return rc;
+  NRMS_CHECK_ARG(n_titles >= 0 && num_words > 0, NRMS_E_INVALID, "bad sizes");
+  if (n_titles == 0) return NRMS_OK;
+  NRMS_CHECK_ARG(tokens && emb && wqkv && bqkv && wa && ba && qa && out, NRMS_E_INVALID, "null pointer");
+  NRMS_CHECK_ARG(aligned16(emb) && aligned16(wqkv) && aligned16(bqkv) && aligned16(wa) && aligned16(ba) && aligned16(out),
+                 NRMS_E_INVALID, "pointers must be 16-byte aligned");
+  NRMS_CHECK_ARG(tc_fused_workspace_bytes(n_titles, L, num_words) != (size_t)-1, NRMS_E_UNSUPPORTED, "title length not compiled");
+  return tc_encoder_fused(emb, nullptr, num_words, tokens, 2, n_titles, L, wqkv, bqkv, wa, ba, qa, out, workspace,
+                          workspace_bytes, st);
+}
+
 int nrms_news_encoder_ln_fwd(const int64_t* tokens, int64_t n_titles, int L, const float* emb, int64_t num_words,
                              const float* wqkv, const float* bqkv, const float* ln_gamma, const float* ln_beta,
                              const float* wa, const float* ba, const float* qa, float* out, void* stash, void* workspace,

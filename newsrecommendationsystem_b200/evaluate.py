@@ -97,7 +97,9 @@ class EvalHost:
         def t(a, dt):
             x = torch.as_tensor(np.ascontiguousarray(a), dtype=dt)
             return x.pin_memory() if pin else x
-        self.news_tokens = t(news_tokens, torch.int64)
+        # token ids travel as int32 when the vocabulary allows it (always, in practice): half the bytes of the reference's
+        # LongTensor over PCIe; the tensor-mode news encoder reads them directly, every other path widens them on the device
+        self.news_tokens = t(news_tokens, torch.int32 if (tok.size == 0 or int(tok.max()) < 2 ** 31) else torch.int64)
         self.hist_rows = t(hist, torch.int32)
         self.cand_rows = t(cand, torch.int32)
         self.cand_offsets = t(cand_offsets, torch.int64)

@@ -4,6 +4,7 @@ import torch.nn as nn
 
 from ... import ops
 from ...config import resolve_mode
+from ..._lib import MODE_TF32 as _TF32
 from ..general.attention.multihead_self import MultiHeadSelfAttention
 from ..general.attention.additive import AdditiveAttention
 
@@ -51,6 +52,11 @@ class NewsEncoder(nn.Module):
                 raise IndexError(f"token ids must lie in [0, {self.word_embedding.num_embeddings}), got [{lo}, {hi}]")
         title = title.to(dev, non_blocking=True)
         wqkv, bqkv = self.multihead_self_attention.packed()
+        if (title.dtype == torch.int32 and not self.training and not torch.is_grad_enabled() and self.layer_norm is None
+                and resolve_mode(self.config, self.precision) == _TF32):
+            # evaluate's pre-tokenised table ships int32 ids (half the H2D bytes of the reference's LongTensor)
+            return ops.news_encoder_i32(title, self.word_embedding.weight, wqkv, bqkv, self.additive_attention.linear.weight,
+                                        self.additive_attention.linear.bias, self.additive_attention.attention_query_vector)
         p = float(self.config.dropout_probability) if self.training else 0.0
         offset = 0
         if p > 0.0:

@@ -281,6 +281,25 @@ def user_encoder_indexed(table, rows, wqkv, bqkv, wa, ba, qa, mode=_lib.MODE_TF3
 
 
 @torch.no_grad()
+def news_encoder_i32(tokens, emb, wqkv, bqkv, wa, ba, qa):
+    """Tensor-mode, inference-only news encoder over int32 token ids [n, L] (evaluate's pre-tokenised table)."""
+    lib = _lib.load()
+    _require_cuda(tokens, emb)
+    if tokens.dtype != torch.int32:
+        raise RuntimeError("news_encoder_i32 takes int32 token ids")
+    tokens = tokens.contiguous()
+    n, L = tokens.shape
+    dev = emb.device
+    out = torch.empty((n, D), dtype=torch.float32, device=dev)
+    args = [_f32c(t) for t in (emb, wqkv, bqkv, wa, ba, qa)]
+    ws = _bytes(lib.nrms_encoder_fwd_workspace_bytes(n, L, _lib.MODE_TF32, 0, args[0].shape[0]), dev)
+    check(lib.nrms_news_encoder_i32_fwd(ptr(tokens), n, L, ptr(args[0]), args[0].shape[0], ptr(args[1]), ptr(args[2]),
+                                        ptr(args[3]), ptr(args[4]), ptr(args[5]), ptr(out), ptr(ws), ws.numel(),
+                                        stream_ptr(dev)), "nrms_news_encoder_i32_fwd")
+    return out
+
+
+@torch.no_grad()
 def user_encoder_table16(table16, rows, wqkv, bqkv, wa, ba, qa):
     """Tensor-mode indexed user encoder over the caller's fp16 copy of the table (`pack_rows_f16` layout:
     [n_rows + 1, 320] halfs, last row zero) -- the form evaluate keeps between its stages."""

@@ -562,6 +562,20 @@ def test_table_ratio_option_selects_the_path(dev, lib, golden_sd):
     assert not torch.equal(a, b)
 
 
+def test_news_encoder_int32_tokens(dev, lib, golden_sd):
+    """nrms_news_encoder_i32_fwd (evaluate's int32 token table): bit-identical to the int64 call, on both kernel paths."""
+    from newsrecommendationsystem_b200 import synthetic
+    m = make_model(golden_sd, dev, "tf32")
+    for n in (5, 777):                                   # per-title projection (small call), table path
+        toks = synthetic.make_news(n, num_words=Cfg.num_words, seed=n)
+        with torch.no_grad():
+            a = m.get_news_vector({"title": torch.from_numpy(toks)})
+            b = m.get_news_vector({"title": torch.from_numpy(toks.astype(np.int32))})
+        assert torch.equal(a, b)
+    with pytest.raises(IndexError):
+        m.get_news_vector({"title": torch.full((2, 20), Cfg.num_words, dtype=torch.int32)})
+
+
 def test_user_encoder_fp16_table_form(dev, lib, golden_sd):
     """nrms_user_encoder_table16_fwd: the indexed user encoder fed with the caller's fp16 copy of the table (the form
     evaluate keeps between its stages) gives bit-identical vectors to the fp32-table call, on both kernel paths."""
