@@ -15,6 +15,11 @@
  *   nrms_ce_loss_fwd_bwd        CrossEntropyLoss(y_pred, zeros)    src/train.py:126,205-206
  *   nrms_adam_step              torch.optim.Adam(lr=1e-4).step()   src/train.py:127-128,233 (AdamW: decoupled=1)
  *   nrms_rank_metrics           calculate_single_user_metric + nanmean  src/evaluate.py:24-42,160-168,270-272
+ *   nrms_news_encoder_rows_fwd/bwd  NewsEncoder over an index-only minibatch    src/dataset.py:17-85, src/train.py:118-124
+ *   nrms_recommend_user         the single-user path of the demo            src/recommend.py:245-341
+ *   nrms_element_encoder_fwd/bwd, nrms_add_position_fwd/bwd, nrms_additive_fwd/bwd at 2..4 candidates
+ *                               model/Exp1                                  src/model/Exp1/news_encoder.py:37-111,
+ *                                                                           src/model/Exp1/user_encoder.py:15-31
  *
  * Conventions
  *   - All pointers are DEVICE pointers unless the name ends in _host.  Buffers are
@@ -42,6 +47,7 @@ extern "C" {
 #define NRMS_H 15
 #define NRMS_DH 20
 #define NRMS_QD 200
+#define NRMS_CE 100 /* category_embedding_dim (model/Exp1 element encoders, src/config.py:34) */
 
 enum {
   NRMS_OK = 0,
@@ -170,6 +176,68 @@ int nrms_mhsa_masked_fwd(const float* x, const int32_t* lengths, int64_t n_seq, 
                          const float* bqkv, float* ctx, void* workspace, size_t workspace_bytes, int mode, void* stream);
 int nrms_additive_fwd(const float* c, int64_t n_seq, int S, const float* wa, const float* ba, const float* qa,
                       float* out, void* workspace, size_t workspace_bytes, int mode, void* stream);
+
+/* AdditiveAttention backward for the standalone block.  nrms_additive_fwd accepts S = 20, 50 and 2..4 (the final attention
+ * over the 2..4 element vectors of model/Exp1, src/model/Exp1/news_encoder.py:104-110; that form always runs on the CUDA
+ * cores).  fwd_workspace = the workspace the forward call filled (tanh activations | softmax weights).  d_c [n_seq,S,300]
+ * is OVERWRITTEN; d_wa [200,300], d_ba [200], d_qa [200] are accumulated into. */
+size_t nrms_additive_bwd_workspace_bytes(int64_t n_seq, int S, int mode);
+int nrms_additive_bwd(const float* d_out, const float* c, int64_t n_seq, int S, const float* wa, const float* qa,
+                      const void* fwd_workspace, float* d_c, float* d_wa, float* d_ba, float* d_qa, void* workspace,
+                      size_t workspace_bytes, int mode, void* stream);
+
+/* ---- index-only training minibatch ----------------------------------------
+ * The reference DataLoader ships 1+K+50 token tensors per step (src/dataset.py:17-85, src/train.py:118-124); here the
+ * pre-tokenised news table int64 [n_news, L] lives on the device and a minibatch is news-row indices: title t of the call
+ * is row news_rows[t] (int64, in [0, n_news)) of token_table, gathered inside the embedding gather / gradient scatter
+ * kernels.  Training form only (stash required); ln_* NULL = plain NRMS, else the config-5 variant.  Stash / workspace
+ * sizes and the gradient contract are those of nrms_news_encoder_fwd / _bwd. */
+int nrms_news_encoder_rows_fwd(const int64_t* token_table, int64_t n_news, const int64_t* news_rows, int64_t n_titles,
+                               int L, const float* emb, int64_t num_words, const float* wqkv, const float* bqkv,
+                               const float* ln_gamma, const float* ln_beta, const float* wa, const float* ba,
+                               const float* qa, float* out, void* stash, float dropout_p, uint64_t seed, uint64_t offset,
+                               int mode, void* stream);
+int nrms_news_encoder_rows_bwd(const float* d_out, const int64_t* token_table, int64_t n_news, const int64_t* news_rows,
+                               int64_t n_titles, int L, int64_t num_words, const float* wqkv, const float* ln_gamma,
+                               const float* wa, const float* qa, const void* stash, float* d_emb, float* d_wqkv,
+                               float* d_bqkv, float* d_ln_gamma, float* d_ln_beta, float* d_wa, float* d_ba, float* d_qa,
+                               void* workspace, size_t workspace_bytes, float dropout_p, uint64_t seed, uint64_t offset,
+                               int mode, void* stream);
+
+/* ---- model/Exp1 blocks ------------------------------------------------------
+ * ElementEncoder.forward = relu(linear(embedding(element)))  (src/model/Exp1/news_encoder.py:37-44):
+ * idx int64 [n] in [0, num_categories), emb [num_categories, 100], w [300, 100], b [300] -> out [n, 300].
+ * `table` ([num_categories, 300], nrms_element_encoder_table_bytes) receives relu(W emb^T + b) for every category -- the
+ * linear layer runs over the vocabulary once, the per-element work is a row gather -- and is what the backward reads.
+ * Backward accumulates into d_emb (row 0 = padding_idx untouched), d_w, d_b; workspace = table bytes. */
+size_t nrms_element_encoder_table_bytes(int64_t num_categories);
+int nrms_element_encoder_fwd(const int64_t* idx, int64_t n, const float* emb, int64_t num_categories, const float* w,
+                             const float* b, float* out, void* table, void* stream);
+int nrms_element_encoder_bwd(const float* d_out, const int64_t* idx, int64_t n, const float* emb, int64_t num_categories,
+                             const float* w, const void* table, float* d_emb, float* d_w, float* d_b, void* workspace,
+                             size_t workspace_bytes, void* stream);
+/* out[u,i,:] = x[u,i,:] + pos[i,:]  (user_vector + position_embedding, src/model/Exp1/user_encoder.py:25-26);
+ * backward: d_pos [S,300] += sum_u d_out[u,:,:]  (d_x = d_out). */
+int nrms_add_position_fwd(const float* x, const float* pos, int64_t n_users, int S, float* out, void* stream);
+size_t nrms_add_position_bwd_workspace_bytes(int S);
+int nrms_add_position_bwd(const float* d_out, int64_t n_users, int S, float* d_pos, void* workspace,
+                          size_t workspace_bytes, void* stream);
+/* dst[r*dst_stride .. +width) = src[r*src_stride .. +width): torch.stack(all_vectors, dim=1) and its backward
+ * (src/model/Exp1/news_encoder.py:109); strides and width in floats, multiples of 4. */
+int nrms_copy_rows_strided(const float* src, int64_t src_stride, float* dst, int64_t dst_stride, int64_t n, int width,
+                           void* stream);
+
+/* ---- single-user latency path (src/recommend.py:245-341) ---------------------
+ * One user, two cluster launches: user_vec [300] = UserEncoder(table[hist_rows[0..50)]), scores[c] = table[cand_rows[c]] .
+ * user_vec, order = candidate positions by descending score (equal scores in ascending position: np.argsort(-y) of
+ * recommend.py:339 on a stable sort).  table fp32 [n_rows, 300] (the news2vector cache, PADDED_NEWS = a zero row);
+ * hist_rows int32 [50] and cand_rows int32 [C] are DEVICE arrays with values in [0, n_rows) (an out-of-range value
+ * reads row n_rows - 1).  order may be NULL (scores only); with order, C <= 4096.  FP32 arithmetic. */
+size_t nrms_recommend_workspace_bytes(void);
+int nrms_recommend_user(const float* table, int64_t n_rows, const int32_t* hist_rows, const int32_t* cand_rows, int C,
+                        const float* wqkv, const float* bqkv, const float* wa, const float* ba, const float* qa,
+                        float* user_vec, float* scores, int32_t* order, void* workspace, size_t workspace_bytes,
+                        void* stream);
 
 /* ---- click predictor --------------------------------------------------------------- */
 /* scores[b,c] = cand[b,c,:] . user[b,:]     cand [B,C,X], user [B,X] */

@@ -5,15 +5,18 @@ hand-written sm_100a library `libnrms_b200.so` through the C-ABI in `include/nrm
 Importing the package does not load CUDA; the first op call does, and raises if the library
 is missing (there is no CPU fallback).
 """
-from .config import NRMSConfig, NRMSLNConfig, BaseConfig  # noqa: F401
+from .config import NRMSConfig, NRMSLNConfig, Exp1Config, BaseConfig  # noqa: F401
 
-__all__ = ["NRMSConfig", "NRMSLNConfig", "BaseConfig", "NRMS", "NewsEncoder", "UserEncoder", "DotProductClickPredictor"]
+__all__ = ["NRMSConfig", "NRMSLNConfig", "Exp1Config", "BaseConfig", "NRMS", "Exp1", "NewsEncoder", "UserEncoder", "DotProductClickPredictor"]
 
 
 def __getattr__(name):
     if name == "NRMS":
         from .model.NRMS import NRMS
         return NRMS
+    if name == "Exp1":
+        from .model.Exp1 import Exp1
+        return Exp1
     if name == "NewsEncoder":
         from .model.NRMS.news_encoder import NewsEncoder
         return NewsEncoder

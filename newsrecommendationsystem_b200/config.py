@@ -47,6 +47,13 @@ class NRMSLNConfig(NRMSConfig):
     use_layernorm = True
 
 
+class Exp1Config(BaseConfig):
+    """reference src/config.py:99-107"""
+    dataset_attributes = {"news": ['category', 'subcategory', 'title'], "record": []}
+    num_attention_heads = 15
+    ensemble_factor = 1
+
+
 def resolve_mode(config=None, override=None):
     from . import _lib
     name = override or getattr(config, "precision", None) or os.environ.get("NRMS_B200_PRECISION", "tf32")

@@ -115,6 +115,36 @@ static int gemm_nt_bias(const float* A, int64_t lda, const float* B, int64_t ldb
   return NRMS_OK;
 }
 
+// additive pooling kernels at every compiled sequence length: 20 (titles), 50 (history / abstracts) and 2..4 (the
+// final attention over the element vectors of model/Exp1, reference src/model/Exp1/news_encoder.py:106-110)
+static bool additive_len_ok(int S) { return S == 20 || S == 50 || (S >= 2 && S <= 4); }
+static cudaError_t launch_additive_fwd(const float* cin, float* t, const float* qa, float* wv, float* out, int64_t n_seq,
+                                       int S, cudaStream_t st) {
+  const unsigned gx = (unsigned)(n_seq < (int64_t)num_sms() * 8 ? n_seq : (int64_t)num_sms() * 8);
+  switch (S) {
+    case 20: additive_fwd_kernel<20><<<gx, 256, 0, st>>>(cin, t, qa, wv, out, n_seq); break;
+    case 50: additive_fwd_kernel<50><<<gx, 256, 0, st>>>(cin, t, qa, wv, out, n_seq); break;
+    case 2: additive_fwd_kernel<2><<<gx, 256, 0, st>>>(cin, t, qa, wv, out, n_seq); break;
+    case 3: additive_fwd_kernel<3><<<gx, 256, 0, st>>>(cin, t, qa, wv, out, n_seq); break;
+    default: additive_fwd_kernel<4><<<gx, 256, 0, st>>>(cin, t, qa, wv, out, n_seq); break;
+  }
+  count_launch();
+  return cudaGetLastError();
+}
+static cudaError_t launch_additive_bwd(const float* d_out, const float* cin, const float* t, const float* wv,
+                                       const float* qa, float* d_c, float* d_u, float* partial, int64_t n_seq, int S,
+                                       int nb, cudaStream_t st) {
+  switch (S) {
+    case 20: additive_bwd_kernel<20><<<nb, 256, 0, st>>>(d_out, cin, t, wv, qa, d_c, d_u, partial, n_seq); break;
+    case 50: additive_bwd_kernel<50><<<nb, 256, 0, st>>>(d_out, cin, t, wv, qa, d_c, d_u, partial, n_seq); break;
+    case 2: additive_bwd_kernel<2><<<nb, 256, 0, st>>>(d_out, cin, t, wv, qa, d_c, d_u, partial, n_seq); break;
+    case 3: additive_bwd_kernel<3><<<nb, 256, 0, st>>>(d_out, cin, t, wv, qa, d_c, d_u, partial, n_seq); break;
+    default: additive_bwd_kernel<4><<<nb, 256, 0, st>>>(d_out, cin, t, wv, qa, d_c, d_u, partial, n_seq); break;
+  }
+  count_launch();
+  return cudaGetLastError();
+}
+
 // Forward over `n_seq` sequences whose input rows X are already materialised in st.x.
 static int encoder_core_fwd(const Stash& s, int64_t n_seq, int S, const float* wqkv, const float* bqkv,
                             const float* wa, const float* ba, const float* qa, float* out, float p2,
@@ -139,10 +169,51 @@ static int encoder_core_fwd(const Stash& s, int64_t n_seq, int S, const float* w
   }
   rc = gemm_nt_bias(cin, D, wa, D, ba, s.t, QD, rows, QD, D, mode, st);
   if (rc) return rc;
-  int64_t gx = n_seq < (int64_t)num_sms() * 8 ? n_seq : (int64_t)num_sms() * 8;
-  if (S == 20) additive_fwd_kernel<20><<<(unsigned)gx, 256, 0, st>>>(cin, s.t, qa, s.w, out, n_seq);
-  else additive_fwd_kernel<50><<<(unsigned)gx, 256, 0, st>>>(cin, s.t, qa, s.w, out, n_seq);
-  NRMS_LAUNCH_CHECK("additive_fwd");
+  if (cudaError_t e2 = launch_additive_fwd(cin, s.t, qa, s.w, out, n_seq, S, st)) return cuda_fail(e2, "additive_fwd");
+  return NRMS_OK;
+}
+
+// Backward of the additive block (additive.py:27-53) over n_seq sequences of S rows: cin = its input rows, t / wv = the
+// tanh activations and softmax weights its forward saved.  d_c [rows,300] is OVERWRITTEN with dL/d(cin); d_wa, d_ba,
+// d_qa are accumulated into.  Tensor mode (S = 20 / 50 only) needs the transposed operand copies t1 / t2 / wt.
+struct AddBwdWs {
+  float *d_u, *partial, *t1, *t2, *wt;
+  int64_t ldr;
+};
+static int additive_block_bwd(const float* d_out, const float* cin, const float* t, const float* wv, const float* wa,
+                              const float* qa, float* d_c, const AddBwdWs& w, int64_t n_seq, int S, float* d_wa,
+                              float* d_ba, float* d_qa, bool tc, cudaStream_t st) {
+  const int64_t rows = n_seq * S;
+  int nb = (int)(n_seq < REDUCE_BLOCKS ? n_seq : REDUCE_BLOCKS);
+  if (cudaError_t e2 = launch_additive_bwd(d_out, cin, t, wv, qa, d_c, w.d_u, w.partial, n_seq, S, nb, st))
+    return cuda_fail(e2, "additive_bwd");
+  launch_partial_reduce_accum(w.partial, nb, QD, QD, d_qa, st);
+  NRMS_LAUNCH_CHECK("dqa_reduce");
+  // d_ba = colsum(dU)
+  int cb = (int)(rows < REDUCE_BLOCKS ? rows : REDUCE_BLOCKS);
+  colsum_partial_kernel<<<cb, 256, 0, st>>>(w.d_u, rows, QD, w.partial);
+  NRMS_LAUNCH_CHECK("colsum_du");
+  launch_partial_reduce_accum(w.partial, cb, QD, QD, d_ba, st);
+  NRMS_LAUNCH_CHECK("dba_reduce");
+  int splits = (int)((rows + 4095) / 4096);
+  if (splits > 64) splits = 64;
+  if (tc) {
+    // d_wa[200,300] += dU^T C
+    if (int rc = transpose_f32(w.d_u, QD, w.t1, w.ldr, rows, QD, st)) return rc;
+    if (int rc = transpose_f32(cin, D, w.t2, w.ldr, rows, D, st)) return rc;
+    if (int rc = tc_gemm_nt_ex(w.t1, w.ldr, w.t2, w.ldr, nullptr, d_wa, D, QD, D, (int)rows,
+                               tc_gemm_auto_splits(QD, D, (int)rows), TC_EPI_ATOMIC, st)) return rc;
+    // d_c += dU * Wa
+    if (int rc = transpose_f32(wa, D, w.wt, QD, QD, D, st)) return rc;
+    if (int rc = tc_gemm_nt_ex(w.d_u, QD, w.wt, QD, nullptr, d_c, D, rows, D, QD, 1, TC_EPI_ACCUM, st)) return rc;
+  } else {
+    // d_wa[200,300] += dU^T C   (reduction over rows, split-K + fp32 atomics)
+    cudaError_t e = sgemm_launch<1, 1, EPI_ATOMIC>(w.d_u, QD, cin, D, nullptr, d_wa, D, QD, D, rows, splits, st);
+    if (e != cudaSuccess) return cuda_fail(e, "sgemm dWa");
+    // d_c += dU * Wa   ([rows,200] x [200,300])
+    e = sgemm_launch<0, 1, EPI_ACCUM>(w.d_u, QD, wa, D, nullptr, d_c, D, rows, D, QD, 1, st);
+    if (e != cudaSuccess) return cuda_fail(e, "sgemm dC");
+  }
   return NRMS_OK;
 }
 
@@ -162,38 +233,14 @@ static int encoder_core_bwd(const Stash& s, const BwdWs& w, const float* d_out, 
   const bool tc = (mode == NRMS_MODE_TF32);
   const int64_t rows = n_seq * S;
   const float* cin = ln ? s.cn : s.c;        // input of the additive block
-  int nb = (int)(n_seq < REDUCE_BLOCKS ? n_seq : REDUCE_BLOCKS);
-  if (S == 20) additive_bwd_kernel<20><<<nb, 256, 0, st>>>(d_out, cin, s.t, s.w, qa, w.d_c, w.d_u, w.partial, n_seq);
-  else additive_bwd_kernel<50><<<nb, 256, 0, st>>>(d_out, cin, s.t, s.w, qa, w.d_c, w.d_u, w.partial, n_seq);
-  NRMS_LAUNCH_CHECK("additive_bwd");
-  launch_partial_reduce_accum(w.partial, nb, QD, QD, d_qa, st);
-  NRMS_LAUNCH_CHECK("dqa_reduce");
-  // d_ba = colsum(dU)
+  {
+    const AddBwdWs aw{w.d_u, w.partial, w.t1, w.t2, w.wt, w.ldr};
+    if (int rc = additive_block_bwd(d_out, cin, s.t, s.w, wa, qa, w.d_c, aw, n_seq, S, d_wa, d_ba, d_qa, tc, st)) return rc;
+  }
   int cb = (int)(rows < REDUCE_BLOCKS ? rows : REDUCE_BLOCKS);
-  colsum_partial_kernel<<<cb, 256, 0, st>>>(w.d_u, rows, QD, w.partial);
-  NRMS_LAUNCH_CHECK("colsum_du");
-  launch_partial_reduce_accum(w.partial, cb, QD, QD, d_ba, st);
-  NRMS_LAUNCH_CHECK("dba_reduce");
   int splits = (int)((rows + 4095) / 4096);
   if (splits > 64) splits = 64;
   cudaError_t e;
-  if (tc) {
-    // d_wa[200,300] += dU^T C
-    if (int rc = transpose_f32(w.d_u, QD, w.t1, w.ldr, rows, QD, st)) return rc;
-    if (int rc = transpose_f32(cin, D, w.t2, w.ldr, rows, D, st)) return rc;
-    if (int rc = tc_gemm_nt_ex(w.t1, w.ldr, w.t2, w.ldr, nullptr, d_wa, D, QD, D, (int)rows,
-                               tc_gemm_auto_splits(QD, D, (int)rows), TC_EPI_ATOMIC, st)) return rc;
-    // d_c += dU * Wa
-    if (int rc = transpose_f32(wa, D, w.wt, QD, QD, D, st)) return rc;
-    if (int rc = tc_gemm_nt_ex(w.d_u, QD, w.wt, QD, nullptr, w.d_c, D, rows, D, QD, 1, TC_EPI_ACCUM, st)) return rc;
-  } else {
-    // d_wa[200,300] += dU^T C   (reduction over rows, split-K + fp32 atomics)
-    e = sgemm_launch<1, 1, EPI_ATOMIC>(w.d_u, QD, cin, D, nullptr, d_wa, D, QD, D, rows, splits, st);
-    if (e != cudaSuccess) return cuda_fail(e, "sgemm dWa");
-    // d_c += dU * Wa   ([rows,200] x [200,300])
-    e = sgemm_launch<0, 1, EPI_ACCUM>(w.d_u, QD, wa, D, nullptr, w.d_c, D, rows, D, QD, 1, st);
-    if (e != cudaSuccess) return cuda_fail(e, "sgemm dC");
-  }
   if (ln) {   // d_c holds dL/dCN: through the LayerNorm, in place; d_gamma / d_beta via per-block partial sums
     int lb = (int)((rows + 7) / 8 < REDUCE_BLOCKS ? (rows + 7) / 8 : REDUCE_BLOCKS);
     layernorm_bwd_kernel<<<lb, 256, 0, st>>>(w.d_c, s.c, s.stats, ln->gamma, w.partial, rows);
@@ -285,10 +332,13 @@ static int check_ln(const LnArgs* ln, bool bwd) {
 static int news_encoder_fwd_impl(const int64_t* tokens, int64_t n_titles, int L, const float* emb, int64_t num_words,
                                  const float* wqkv, const float* bqkv, const float* wa, const float* ba, const float* qa,
                                  float* out, void* stash, void* workspace, size_t workspace_bytes, float dropout_p,
-                                 uint64_t seed, uint64_t offset, int mode, void* stream, const LnArgs* ln) {
+                                 uint64_t seed, uint64_t offset, int mode, void* stream, const LnArgs* ln,
+                                 const int64_t* news_rows = nullptr) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (int rc = check_ln(ln, false)) return rc;
   if (int rc = check_common(L, mode)) return rc;
+  NRMS_CHECK_ARG(news_rows == nullptr || stash != nullptr, NRMS_E_UNSUPPORTED,
+                 "the index-only form (token table + news rows) is the training form: pass a stash");
   // training (a stash is requested) is compiled for the title length; inference also takes 50-token texts (the
   // abstract encoder of the reference's Exp1 model is this same block, src/model/Exp1/news_encoder.py:10-34)
   NRMS_CHECK_ARG(L == 20 || (L == 50 && stash == nullptr), NRMS_E_UNSUPPORTED,
@@ -307,7 +357,8 @@ static int news_encoder_fwd_impl(const int64_t* tokens, int64_t n_titles, int L,
     const int64_t rows = n_titles * L;
     int64_t gb = (rows + 7) / 8;
     if (gb > (int64_t)num_sms() * 16) gb = (int64_t)num_sms() * 16;
-    gather_embedding_kernel<<<(unsigned)gb, 256, 0, st>>>(tokens, rows, emb, s.x, dropout_p, scale, seed, offset);
+    gather_embedding_kernel<<<(unsigned)gb, 256, 0, st>>>(tokens, rows, emb, s.x, dropout_p, scale, seed, offset,
+                                                          news_rows, L);
     NRMS_LAUNCH_CHECK("gather_embedding");
     return encoder_core_fwd(s, n_titles, L, wqkv, bqkv, wa, ba, qa, out, dropout_p, seed, offset, 0, mode, st, ln);
   }
@@ -374,7 +425,7 @@ static int news_encoder_bwd_impl(const float* d_out, const int64_t* tokens, int6
                                  const float* wqkv, const float* wa, const float* qa, const void* stash, float* d_emb,
                                  float* d_wqkv, float* d_bqkv, float* d_wa, float* d_ba, float* d_qa, void* workspace,
                                  size_t workspace_bytes, float dropout_p, uint64_t seed, uint64_t offset, int mode,
-                                 void* stream, const LnArgs* ln) {
+                                 void* stream, const LnArgs* ln, const int64_t* news_rows = nullptr) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (int rc = check_ln(ln, true)) return rc;
   if (int rc = check_common(L, mode)) return rc;
@@ -396,7 +447,8 @@ static int news_encoder_bwd_impl(const float* d_out, const int64_t* tokens, int6
   const float scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
   int64_t gb = (rows + 7) / 8;
   if (gb > (int64_t)num_sms() * 16) gb = (int64_t)num_sms() * 16;
-  scatter_embedding_grad_kernel<<<(unsigned)gb, 256, 0, st>>>(tokens, rows, w.d_x, d_emb, dropout_p, scale, seed, offset);
+  scatter_embedding_grad_kernel<<<(unsigned)gb, 256, 0, st>>>(tokens, rows, w.d_x, d_emb, dropout_p, scale, seed, offset,
+                                                              news_rows, L);
   NRMS_LAUNCH_CHECK("scatter_embedding_grad");
   return NRMS_OK;
 }
@@ -419,6 +471,31 @@ int nrms_news_encoder_ln_bwd(const float* d_out, const int64_t* tokens, int64_t 
   const LnArgs ln{ln_gamma, nullptr, d_ln_gamma, d_ln_beta};
   return news_encoder_bwd_impl(d_out, tokens, n_titles, L, num_words, wqkv, wa, qa, stash, d_emb, d_wqkv, d_bqkv, d_wa,
                                d_ba, d_qa, workspace, workspace_bytes, dropout_p, seed, offset, mode, stream, &ln);
+}
+
+int nrms_news_encoder_rows_fwd(const int64_t* token_table, int64_t n_news, const int64_t* news_rows, int64_t n_titles,
+                               int L, const float* emb, int64_t num_words, const float* wqkv, const float* bqkv,
+                               const float* ln_gamma, const float* ln_beta, const float* wa, const float* ba,
+                               const float* qa, float* out, void* stash, float dropout_p, uint64_t seed, uint64_t offset,
+                               int mode, void* stream) {
+  NRMS_CHECK_ARG(n_news > 0 && (n_titles == 0 || news_rows), NRMS_E_INVALID, "bad token table / news rows");
+  NRMS_CHECK_ARG((ln_gamma == nullptr) == (ln_beta == nullptr), NRMS_E_INVALID, "LayerNorm needs both weight and bias");
+  const LnArgs ln{ln_gamma, ln_beta, nullptr, nullptr};
+  return news_encoder_fwd_impl(token_table, n_titles, L, emb, num_words, wqkv, bqkv, wa, ba, qa, out, stash, nullptr, 0,
+                               dropout_p, seed, offset, mode, stream, ln_gamma ? &ln : nullptr, news_rows);
+}
+
+int nrms_news_encoder_rows_bwd(const float* d_out, const int64_t* token_table, int64_t n_news, const int64_t* news_rows,
+                               int64_t n_titles, int L, int64_t num_words, const float* wqkv, const float* ln_gamma,
+                               const float* wa, const float* qa, const void* stash, float* d_emb, float* d_wqkv,
+                               float* d_bqkv, float* d_ln_gamma, float* d_ln_beta, float* d_wa, float* d_ba, float* d_qa,
+                               void* workspace, size_t workspace_bytes, float dropout_p, uint64_t seed, uint64_t offset,
+                               int mode, void* stream) {
+  NRMS_CHECK_ARG(n_news > 0 && (n_titles == 0 || news_rows), NRMS_E_INVALID, "bad token table / news rows");
+  const LnArgs ln{ln_gamma, nullptr, d_ln_gamma, d_ln_beta};
+  return news_encoder_bwd_impl(d_out, token_table, n_titles, L, num_words, wqkv, wa, qa, stash, d_emb, d_wqkv, d_bqkv,
+                               d_wa, d_ba, d_qa, workspace, workspace_bytes, dropout_p, seed, offset, mode, stream,
+                               ln_gamma ? &ln : nullptr, news_rows);
 }
 
 static int user_encoder_fwd_impl(const float* x, int64_t n_rows, const int32_t* rows_idx, int64_t n_users, int S,
@@ -579,7 +656,8 @@ int nrms_mhsa_masked_fwd(const float* x, const int32_t* lengths, int64_t n_seq, 
 int nrms_additive_fwd(const float* c, int64_t n_seq, int S, const float* wa, const float* ba, const float* qa,
                       float* out, void* workspace, size_t workspace_bytes, int mode, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (int rc = check_common(S, mode)) return rc;
+  NRMS_CHECK_ARG(additive_len_ok(S), NRMS_E_UNSUPPORTED, "candidate size %d unsupported (compiled: 2, 3, 4, 20, 50)", S);
+  NRMS_CHECK_ARG(mode == NRMS_MODE_FP32 || mode == NRMS_MODE_TF32, NRMS_E_INVALID, "bad mode %d", mode);
   NRMS_CHECK_ARG(n_seq >= 0, NRMS_E_INVALID, "bad sizes");
   if (n_seq == 0) return NRMS_OK;
   NRMS_CHECK_ARG(c && wa && ba && qa && out, NRMS_E_INVALID, "null pointer");
@@ -592,12 +670,58 @@ int nrms_additive_fwd(const float* c, int64_t n_seq, int S, const float* wa, con
                  "workspace too small: need %zu bytes", need);
   float* t = reinterpret_cast<float*>(workspace);
   float* w = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + t_bytes);
-  if (int rc = gemm_nt_bias(c, D, wa, D, ba, t, QD, rows, QD, D, mode, st)) return rc;
-  int64_t gx = n_seq < (int64_t)num_sms() * 8 ? n_seq : (int64_t)num_sms() * 8;
-  if (S == 20) additive_fwd_kernel<20><<<(unsigned)gx, 256, 0, st>>>(c, t, qa, w, out, n_seq);
-  else additive_fwd_kernel<50><<<(unsigned)gx, 256, 0, st>>>(c, t, qa, w, out, n_seq);
-  NRMS_LAUNCH_CHECK("additive_fwd");
+  // the 2..4-row form (Exp1's final attention) is 3 % of a text encoder's work: always on the CUDA cores
+  if (int rc = gemm_nt_bias(c, D, wa, D, ba, t, QD, rows, QD, D, S < 20 ? NRMS_MODE_FP32 : mode, st)) return rc;
+  if (cudaError_t e = launch_additive_fwd(c, t, qa, w, out, n_seq, S, st)) return cuda_fail(e, "additive_fwd");
   return NRMS_OK;
+}
+
+size_t nrms_additive_bwd_workspace_bytes(int64_t n_seq, int S, int mode) {
+  const int64_t rows = n_seq * S;
+  const int64_t ldr = (rows + 3) / 4 * 4;
+  size_t b = align_up((size_t)rows * QD * sizeof(float), 256) + align_up((size_t)REDUCE_BLOCKS * D3 * sizeof(float), 256);
+  if (mode == NRMS_MODE_TF32 && S >= 20)
+    b += align_up((size_t)ldr * QD * sizeof(float), 256) + align_up((size_t)ldr * D * sizeof(float), 256) +
+         align_up((size_t)D * QD * sizeof(float), 256);
+  return b;
+}
+
+int nrms_additive_bwd(const float* d_out, const float* c, int64_t n_seq, int S, const float* wa, const float* qa,
+                      const void* fwd_workspace, float* d_c, float* d_wa, float* d_ba, float* d_qa, void* workspace,
+                      size_t workspace_bytes, int mode, void* stream) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  NRMS_CHECK_ARG(additive_len_ok(S), NRMS_E_UNSUPPORTED, "candidate size %d unsupported (compiled: 2, 3, 4, 20, 50)", S);
+  NRMS_CHECK_ARG(mode == NRMS_MODE_FP32 || mode == NRMS_MODE_TF32, NRMS_E_INVALID, "bad mode %d", mode);
+  NRMS_CHECK_ARG(n_seq >= 0, NRMS_E_INVALID, "bad sizes");
+  if (n_seq == 0) return NRMS_OK;
+  NRMS_CHECK_ARG(d_out && c && wa && qa && fwd_workspace && d_c && d_wa && d_ba && d_qa, NRMS_E_INVALID, "null pointer");
+  NRMS_CHECK_ARG(aligned16(d_out) && aligned16(c) && aligned16(wa) && aligned16(d_c) && aligned16(d_wa) &&
+                     aligned16(fwd_workspace), NRMS_E_INVALID, "pointers must be 16-byte aligned");
+  const size_t need = nrms_additive_bwd_workspace_bytes(n_seq, S, mode);
+  NRMS_CHECK_ARG(workspace && aligned16(workspace) && workspace_bytes >= need, NRMS_E_WORKSPACE,
+                 "workspace too small: need %zu bytes", need);
+  const int64_t rows = n_seq * S;
+  const bool tc = (mode == NRMS_MODE_TF32 && S >= 20);
+  const float* t = reinterpret_cast<const float*>(fwd_workspace);
+  const float* wv = reinterpret_cast<const float*>(reinterpret_cast<const char*>(fwd_workspace) +
+                                                   align_up((size_t)rows * QD * sizeof(float), 256));
+  AddBwdWs aw{};
+  char* p = reinterpret_cast<char*>(workspace);
+  size_t off = 0;
+  auto take = [&](size_t nfloat) {
+    float* r = reinterpret_cast<float*>(p + off);
+    off += align_up(nfloat * sizeof(float), 256);
+    return r;
+  };
+  aw.d_u = take((size_t)rows * QD);
+  aw.partial = take((size_t)REDUCE_BLOCKS * D3);
+  aw.ldr = (rows + 3) / 4 * 4;
+  if (tc) {
+    aw.t1 = take((size_t)aw.ldr * QD);
+    aw.t2 = take((size_t)aw.ldr * D);
+    aw.wt = take((size_t)D * QD);
+  }
+  return additive_block_bwd(d_out, c, t, wv, wa, qa, d_c, aw, n_seq, S, d_wa, d_ba, d_qa, tc, st);
 }
 
 int nrms_set_option(const char* key, int value) {

@@ -15,14 +15,23 @@ constexpr uint32_t DROPOUT_STREAM_EMB = 1, DROPOUT_STREAM_CTX = 2;
 // ----------------------------------------------------------------------------------------
 // a1: embedding gather (+ dropout #1).  One warp per token row: 75 coalesced float4.
 // ----------------------------------------------------------------------------------------
+// news_rows (nullable, with L = tokens per title): the index-only minibatch form -- row r of the batch is
+// token r % L of title news_rows[r / L] of the device-resident pre-tokenised table (reference dataset.py:17-85 ships the
+// token tensors themselves); null = tokens already holds the batch's own rows.
+__device__ __forceinline__ int64_t token_of_row(const int64_t* __restrict__ tokens, const int64_t* __restrict__ news_rows,
+                                                int L, int64_t r) {
+  return news_rows ? tokens[news_rows[r / L] * L + r % L] : tokens[r];
+}
+
 static __global__ void __launch_bounds__(256)
 gather_embedding_kernel(const int64_t* __restrict__ tokens, int64_t n_rows, const float* __restrict__ emb,
-                        float* __restrict__ x, float p, float scale, uint64_t seed, uint64_t offset) {
+                        float* __restrict__ x, float p, float scale, uint64_t seed, uint64_t offset,
+                        const int64_t* __restrict__ news_rows = nullptr, int L = 1) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t r = warp; r < n_rows; r += nwarps) {
-    const int64_t tok = tokens[r];
+    const int64_t tok = token_of_row(tokens, news_rows, L, r);
     const float4* src = reinterpret_cast<const float4*>(emb + tok * D);
     float4* dst = reinterpret_cast<float4*>(x + r * D);
 #pragma unroll
@@ -55,12 +64,13 @@ gather_rows_kernel(const float* __restrict__ src, const IdxT* __restrict__ rows,
 // embedding backward: dE[tok] += dX[row] * mask1 ; token 0 (padding_idx) skipped.
 static __global__ void __launch_bounds__(256)
 scatter_embedding_grad_kernel(const int64_t* __restrict__ tokens, int64_t n_rows, const float* __restrict__ dx,
-                              float* __restrict__ d_emb, float p, float scale, uint64_t seed, uint64_t offset) {
+                              float* __restrict__ d_emb, float p, float scale, uint64_t seed, uint64_t offset,
+                              const int64_t* __restrict__ news_rows = nullptr, int L = 1) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
   for (int64_t r = warp; r < n_rows; r += nwarps) {
-    const int64_t tok = tokens[r];
+    const int64_t tok = token_of_row(tokens, news_rows, L, r);
     if (tok == 0) continue;
     const float4* src = reinterpret_cast<const float4*>(dx + r * D);
     float4* dst = reinterpret_cast<float4*>(d_emb + tok * D);

@@ -42,6 +42,16 @@ class NRMS(torch.nn.Module):
         user_vector = self.user_encoder(clicked_news_vector)
         return self.click_predictor(candidate_news_vector, user_vector)
 
+    def forward_rows(self, token_table, cand_rows, hist_rows):
+        """Index-only minibatch: token_table int64 [N_news, L] on the device, cand_rows [B, 1+K] and
+        hist_rows [B, N] news-row indices -> logits [B, 1+K]."""
+        B, n_cand = cand_rows.shape
+        dev = token_table.device
+        rows = torch.cat([cand_rows.to(dev, non_blocking=True), hist_rows.to(dev, non_blocking=True)], dim=1)
+        vec = self.news_encoder.encode_tokens(token_table, news_rows=rows.reshape(-1)).view(B, rows.shape[1], -1)
+        user_vector = self.user_encoder(vec[:, n_cand:])
+        return self.click_predictor(vec[:, :n_cand], user_vector)
+
     def get_news_vector(self, news):
         """news: {"title": B x L} -> B x word_embedding_dim"""
         return self.news_encoder(news)

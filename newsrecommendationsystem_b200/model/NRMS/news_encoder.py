@@ -40,8 +40,9 @@ class NewsEncoder(nn.Module):
         rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
         return (int(self.dropout_seed) + 0x9E3779B97F4A7C15 * rank) & 0xFFFFFFFFFFFFFFFF
 
-    def encode_tokens(self, title):
-        """title: integer tensor [n, num_words_title] (any device) -> fp32 [n, 300]."""
+    def encode_tokens(self, title, news_rows=None):
+        """title: integer tensor [n, num_words_title] (any device) -> fp32 [n, 300].  With news_rows (int64 [m] on the
+        device) `title` is the device-resident token table and the call encodes its rows news_rows."""
         self._check_dims()
         dev = self.word_embedding.weight.device
         if not title.is_cuda and title.numel():
@@ -52,7 +53,7 @@ class NewsEncoder(nn.Module):
                 raise IndexError(f"token ids must lie in [0, {self.word_embedding.num_embeddings}), got [{lo}, {hi}]")
         title = title.to(dev, non_blocking=True)
         wqkv, bqkv = self.multihead_self_attention.packed()
-        if (title.dtype == torch.int32 and not self.training and not torch.is_grad_enabled() and self.layer_norm is None
+        if (news_rows is None and title.dtype == torch.int32 and not self.training and not torch.is_grad_enabled() and self.layer_norm is None
                 and resolve_mode(self.config, self.precision) == _TF32):
             # evaluate's pre-tokenised table ships int32 ids (half the H2D bytes of the reference's LongTensor)
             return ops.news_encoder_i32(title, self.word_embedding.weight, wqkv, bqkv, self.additive_attention.linear.weight,
@@ -62,13 +63,15 @@ class NewsEncoder(nn.Module):
         if p > 0.0:
             # a fresh Philox offset per call (n*20*300/4 counters per dropout site)
             offset = self._dropout_calls
-            self._dropout_calls += (title.numel() * ops.D) // 4 + 1
+            n_tok = title.numel() if news_rows is None else news_rows.numel() * title.shape[1]
+            self._dropout_calls += (n_tok * ops.D) // 4 + 1
         return ops.news_encoder(title, self.word_embedding.weight, wqkv, bqkv,
                                 self.additive_attention.linear.weight, self.additive_attention.linear.bias,
                                 self.additive_attention.attention_query_vector,
                                 dropout_p=p, seed=self._seed(), offset=offset,
                                 mode=resolve_mode(self.config, self.precision),
-                                ln=None if self.layer_norm is None else (self.layer_norm.weight, self.layer_norm.bias))
+                                ln=None if self.layer_norm is None else (self.layer_norm.weight, self.layer_norm.bias),
+                                news_rows=news_rows)
 
     def forward(self, news):
         """news: {"title": batch_size * num_words_title} -> batch_size, word_embedding_dim"""

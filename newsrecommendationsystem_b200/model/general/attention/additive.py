@@ -20,12 +20,11 @@ class AdditiveAttention(nn.Module):
 
     def forward(self, candidate_vector):
         """candidate_vector: batch_size, candidate_size, candidate_vector_dim -> batch_size, candidate_vector_dim.
-        Standalone use (inference); inside the encoders this block is fused into the encoder kernels."""
-        if torch.is_grad_enabled() and (candidate_vector.requires_grad or self.linear.weight.requires_grad):
-            raise NotImplementedError("standalone AdditiveAttention.forward is inference-only; training goes "
-                                      "through NewsEncoder / UserEncoder (use torch.no_grad() here)")
+        Standalone use (candidate_size 20, 50, or 2..4 as in model/Exp1's final attention), forward and backward in
+        libnrms_b200; inside the NRMS encoders this block is fused into the encoder kernels."""
         from .... import ops
         from ....config import resolve_mode
         dev = self.linear.weight.device
-        return ops.additive_forward(candidate_vector.to(dev), self.linear.weight, self.linear.bias,
-                                    self.attention_query_vector, mode=resolve_mode(None, getattr(self, "precision", None)))
+        return ops.additive_attention(candidate_vector.to(dev), self.linear.weight, self.linear.bias,
+                                      self.attention_query_vector,
+                                      mode=resolve_mode(None, getattr(self, "precision", None)))

@@ -46,21 +46,37 @@ class _NewsEncoderFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, tokens, emb, wqkv, bqkv, wa, ba, qa, dropout_p, seed, offset, mode, track_grad,
-                ln_w=None, ln_b=None):
+                ln_w=None, ln_b=None, news_rows=None):
         lib = _lib.load()
-        _require_cuda(tokens, emb, wqkv, bqkv, wa, ba, qa)
+        _require_cuda(tokens, emb, wqkv, bqkv, wa, ba, qa, news_rows)
         ln = ln_w is not None          # config-5 variant: LayerNorm between self-attention and additive attention
         tokens = tokens.contiguous()
         if tokens.dtype != torch.int64:
             tokens = tokens.long()
-        n, L = tokens.shape
+        # index-only minibatch: `tokens` is the resident [n_news, L] table, `news_rows` picks the titles
+        rows = None if news_rows is None else news_rows.contiguous().long().view(-1)
+        n_news, L = tokens.shape
+        n = n_news if rows is None else rows.numel()
         dev = emb.device
         emb_c, wqkv_c, bqkv_c, wa_c, ba_c, qa_c = map(_f32c, (emb, wqkv, bqkv, wa, ba, qa))
         out = torch.empty((n, D), dtype=torch.float32, device=dev)
         needs_grad = track_grad and any(ctx.needs_input_grad)   # grad mode is always off inside forward()
         stash = None
-        if needs_grad:
+        if needs_grad or rows is not None:
             stash = _bytes((lib.nrms_encoder_ln_stash_bytes if ln else lib.nrms_encoder_stash_bytes)(n, L), dev)
+        if rows is not None:
+            lnw_c, lnb_c = (_f32c(ln_w), _f32c(ln_b)) if ln else (None, None)
+            check(lib.nrms_news_encoder_rows_fwd(ptr(tokens), n_news, ptr(rows), n, L, ptr(emb_c), emb_c.shape[0],
+                                                 ptr(wqkv_c), ptr(bqkv_c), ptr(lnw_c), ptr(lnb_c), ptr(wa_c), ptr(ba_c),
+                                                 ptr(qa_c), ptr(out), ptr(stash), float(dropout_p), int(seed), int(offset),
+                                                 mode, stream_ptr(dev)), "nrms_news_encoder_rows_fwd")
+            if needs_grad:
+                ctx.save_for_backward(tokens, wqkv_c, wa_c, qa_c, stash, *([lnw_c] if ln else []))
+                ctx.meta = (n, L, emb_c.shape[0], float(dropout_p), int(seed), int(offset), mode, ln)
+                ctx.emb_param = emb if (EMB_GRAD_IN_PLACE and emb.is_leaf) else None
+                ctx.rows = rows
+            return out
+        ctx.rows = None
         ws_bytes = lib.nrms_encoder_fwd_workspace_bytes(n, L, mode, 1 if needs_grad else 0, emb_c.shape[0])
         ws = _bytes(ws_bytes, dev)
         if ln:
@@ -108,6 +124,14 @@ class _NewsEncoderFn(torch.autograd.Function):
             lnw = ctx.saved_tensors[5]
             d_lnw = torch.zeros((D,), dtype=torch.float32, device=dev)
             d_lnb = torch.zeros((D,), dtype=torch.float32, device=dev)
+        rows = getattr(ctx, "rows", None)
+        if rows is not None:
+            check(lib.nrms_news_encoder_rows_bwd(ptr(d_out), ptr(tokens), tokens.shape[0], ptr(rows), n, L, V, ptr(wqkv),
+                                                 ptr(lnw) if ln else None, ptr(wa), ptr(qa), ptr(stash), ptr(d_emb),
+                                                 ptr(d_wqkv), ptr(d_bqkv), ptr(d_lnw), ptr(d_lnb), ptr(d_wa), ptr(d_ba),
+                                                 ptr(d_qa), ptr(ws), ws.numel(), p, seed, offset, mode, stream_ptr(dev)),
+                  "nrms_news_encoder_rows_bwd")
+        elif ln:
             check(lib.nrms_news_encoder_ln_bwd(ptr(d_out), ptr(tokens), n, L, V, ptr(wqkv), ptr(lnw), ptr(wa), ptr(qa),
                                                ptr(stash), ptr(d_emb), ptr(d_wqkv), ptr(d_bqkv), ptr(d_lnw), ptr(d_lnb),
                                                ptr(d_wa), ptr(d_ba), ptr(d_qa), ptr(ws), ws.numel(), p, seed, offset,
@@ -117,7 +141,8 @@ class _NewsEncoderFn(torch.autograd.Function):
                                             ptr(d_emb), ptr(d_wqkv), ptr(d_bqkv), ptr(d_wa), ptr(d_ba), ptr(d_qa),
                                             ptr(ws), ws.numel(), p, seed, offset, mode, stream_ptr(dev)),
                   "nrms_news_encoder_bwd")
-        return None, (None if in_place else d_emb), d_wqkv, d_bqkv, d_wa, d_ba, d_qa, None, None, None, None, None, d_lnw, d_lnb
+        return (None, (None if in_place else d_emb), d_wqkv, d_bqkv, d_wa, d_ba, d_qa, None, None, None, None, None, d_lnw,
+                d_lnb, None)
 
 
 class _UserEncoderFn(torch.autograd.Function):
@@ -237,11 +262,13 @@ class _CrossEntropyLabel0Fn(torch.autograd.Function):
 
 # ---- functional API ---------------------------------------------------------------------------
 def news_encoder(tokens, emb, wqkv, bqkv, wa, ba, qa, dropout_p=0.0, seed=0, offset=0, mode=_lib.MODE_TF32,
-                 ln=None):
-    """ln = (weight, bias) of the optional LayerNorm(300) (config-5 variant), None for the reference NRMS."""
+                 ln=None, news_rows=None):
+    """ln = (weight, bias) of the optional LayerNorm(300) (config-5 variant), None for the reference NRMS.
+    news_rows (int64 [n], device): index-only minibatch -- `tokens` is then the device-resident pre-tokenised news table
+    [n_news, L] and title t of the call is its row news_rows[t], gathered inside the embedding kernels."""
     lw, lb = ln if ln is not None else (None, None)
     return _NewsEncoderFn.apply(tokens, emb, wqkv, bqkv, wa, ba, qa, dropout_p, seed, offset, mode,
-                                torch.is_grad_enabled(), lw, lb)
+                                torch.is_grad_enabled(), lw, lb, news_rows)
 
 
 def user_encoder(x, wqkv, bqkv, wa, ba, qa, mode=_lib.MODE_TF32, ln=None):
@@ -434,6 +461,184 @@ def mhsa_forward(x, wqkv, bqkv, mode=_lib.MODE_TF32, length=None):
     check(lib.nrms_mhsa_fwd(ptr(x_c), n, S, ptr(w_c), ptr(b_c), ptr(ctx), ptr(ws), ws.numel(), mode,
                             stream_ptr(x.device)), "nrms_mhsa_fwd")
     return ctx
+
+
+class _AdditiveFn(torch.autograd.Function):
+    """AdditiveAttention.forward (reference src/model/general/attention/additive.py:27-53) with its backward, for
+    candidate sizes 20 / 50 and 2..4 (the final attention of model/Exp1)."""
+
+    @staticmethod
+    def forward(ctx, c, wa, ba, qa, mode, track_grad):
+        lib = _lib.load()
+        _require_cuda(c, wa, ba, qa)
+        n, S, d = c.shape
+        if d != D or wa.shape[0] != QD:
+            raise RuntimeError(f"compiled for candidate dim {D} / query dim {QD}")
+        c_c, wa_c, ba_c, qa_c = map(_f32c, (c, wa, ba, qa))
+        out = torch.empty((n, D), dtype=torch.float32, device=c.device)
+        ws = _bytes(n * S * (QD + 1) * 4 + 512, c.device)
+        check(lib.nrms_additive_fwd(ptr(c_c), n, S, ptr(wa_c), ptr(ba_c), ptr(qa_c), ptr(out), ptr(ws), ws.numel(), mode,
+                                    stream_ptr(c.device)), "nrms_additive_fwd")
+        if track_grad and any(ctx.needs_input_grad):
+            ctx.save_for_backward(c_c, wa_c, qa_c, ws)
+            ctx.meta = (n, S, mode)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        c, wa, qa, fws = ctx.saved_tensors
+        n, S, mode = ctx.meta
+        dev = d_out.device
+        d_out = d_out.contiguous().float()
+        d_c = torch.empty_like(c)
+        d_wa = torch.zeros((QD, D), dtype=torch.float32, device=dev)
+        d_ba = torch.zeros((QD,), dtype=torch.float32, device=dev)
+        d_qa = torch.zeros((QD,), dtype=torch.float32, device=dev)
+        ws = _bytes(lib.nrms_additive_bwd_workspace_bytes(n, S, mode), dev)
+        check(lib.nrms_additive_bwd(ptr(d_out), ptr(c), n, S, ptr(wa), ptr(qa), ptr(fws), ptr(d_c), ptr(d_wa), ptr(d_ba),
+                                    ptr(d_qa), ptr(ws), ws.numel(), mode, stream_ptr(dev)), "nrms_additive_bwd")
+        return d_c, d_wa, d_ba, d_qa, None, None
+
+
+def additive_attention(c, wa, ba, qa, mode=_lib.MODE_TF32):
+    """AdditiveAttention.forward, autograd-connected (forward and backward in libnrms_b200)."""
+    return _AdditiveFn.apply(c, wa, ba, qa, mode, torch.is_grad_enabled())
+
+
+class _ElementEncoderFn(torch.autograd.Function):
+    """ElementEncoder.forward = relu(linear(embedding(element)))  (reference src/model/Exp1/news_encoder.py:37-44)."""
+
+    @staticmethod
+    def forward(ctx, idx, emb, w, b, track_grad):
+        lib = _lib.load()
+        _require_cuda(idx, emb, w, b)
+        if emb.shape[1] != 100 or tuple(w.shape) != (D, 100):
+            raise RuntimeError("libnrms_b200 is compiled for category_embedding_dim 100 -> word_embedding_dim 300")
+        shape = idx.shape
+        idx_c = idx.contiguous().long().view(-1)
+        emb_c, w_c, b_c = map(_f32c, (emb, w, b))
+        n, ncat = idx_c.numel(), emb_c.shape[0]
+        out = torch.empty((n, D), dtype=torch.float32, device=emb.device)
+        table = _bytes(lib.nrms_element_encoder_table_bytes(ncat), emb.device)
+        check(lib.nrms_element_encoder_fwd(ptr(idx_c), n, ptr(emb_c), ncat, ptr(w_c), ptr(b_c), ptr(out), ptr(table),
+                                           stream_ptr(emb.device)), "nrms_element_encoder_fwd")
+        if track_grad and any(ctx.needs_input_grad):
+            ctx.save_for_backward(idx_c, emb_c, w_c, table)
+        return out.view(*shape, D)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        idx, emb, w, table = ctx.saved_tensors
+        dev = d_out.device
+        n, ncat = idx.numel(), emb.shape[0]
+        d_out = d_out.contiguous().float().view(n, D)
+        d_emb = torch.zeros_like(emb)
+        d_w = torch.zeros_like(w)
+        d_b = torch.zeros((D,), dtype=torch.float32, device=dev)
+        ws = _bytes(lib.nrms_element_encoder_table_bytes(ncat), dev)
+        check(lib.nrms_element_encoder_bwd(ptr(d_out), ptr(idx), n, ptr(emb), ncat, ptr(w), ptr(table), ptr(d_emb),
+                                           ptr(d_w), ptr(d_b), ptr(ws), ws.numel(), stream_ptr(dev)),
+              "nrms_element_encoder_bwd")
+        return None, d_emb, d_w, d_b, None
+
+
+def element_encoder(idx, emb, w, b):
+    return _ElementEncoderFn.apply(idx, emb, w, b, torch.is_grad_enabled())
+
+
+class _AddPositionFn(torch.autograd.Function):
+    """user_vector + position_embedding.expand_as(user_vector)  (reference src/model/Exp1/user_encoder.py:25-26)."""
+
+    @staticmethod
+    def forward(ctx, x, pos):
+        lib = _lib.load()
+        _require_cuda(x, pos)
+        n, S, d = x.shape
+        if d != D or tuple(pos.shape) != (S, D):
+            raise RuntimeError(f"expected x [n, S, {D}] and position_embedding [S, {D}]")
+        x_c, pos_c = _f32c(x), _f32c(pos)
+        out = torch.empty_like(x_c)
+        check(lib.nrms_add_position_fwd(ptr(x_c), ptr(pos_c), n, S, ptr(out), stream_ptr(x.device)), "nrms_add_position_fwd")
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        d_out = d_out.contiguous().float()
+        n, S, _ = d_out.shape
+        d_pos = None
+        if ctx.needs_input_grad[1]:
+            d_pos = torch.zeros((S, D), dtype=torch.float32, device=d_out.device)
+            ws = _bytes(lib.nrms_add_position_bwd_workspace_bytes(S), d_out.device)
+            check(lib.nrms_add_position_bwd(ptr(d_out), n, S, ptr(d_pos), ptr(ws), ws.numel(), stream_ptr(d_out.device)),
+                  "nrms_add_position_bwd")
+        return (d_out if ctx.needs_input_grad[0] else None), d_pos
+
+
+def add_position(x, pos):
+    return _AddPositionFn.apply(x, pos)
+
+
+class _StackFn(torch.autograd.Function):
+    """torch.stack(vectors, dim=1) of 300-wide rows (reference src/model/Exp1/news_encoder.py:109) through
+    nrms_copy_rows_strided; the backward hands every vector its slice."""
+
+    @staticmethod
+    def forward(ctx, *vectors):
+        lib = _lib.load()
+        _require_cuda(*vectors)
+        k, n = len(vectors), vectors[0].shape[0]
+        dev = vectors[0].device
+        out = torch.empty((n, k, D), dtype=torch.float32, device=dev)
+        for j, v in enumerate(vectors):
+            v_c = _f32c(v)
+            check(lib.nrms_copy_rows_strided(ptr(v_c), D, C.c_void_p(out.data_ptr() + 4 * D * j), k * D, n, D,
+                                             stream_ptr(dev)), "nrms_copy_rows_strided")
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = _lib.load()
+        d_out = d_out.contiguous().float()
+        n, k, _ = d_out.shape
+        grads = []
+        for j in range(k):
+            g = torch.empty((n, D), dtype=torch.float32, device=d_out.device)
+            check(lib.nrms_copy_rows_strided(C.c_void_p(d_out.data_ptr() + 4 * D * j), k * D, ptr(g), D, n, D,
+                                             stream_ptr(d_out.device)), "nrms_copy_rows_strided")
+            grads.append(g)
+        return tuple(grads)
+
+
+def stack_vectors(vectors):
+    return _StackFn.apply(*vectors)
+
+
+@torch.no_grad()
+def recommend_user(table, hist_rows, cand_rows, wqkv, bqkv, wa, ba, qa, rank=True):
+    """Single-user latency path (reference src/recommend.py:245-341): user vector from the 50 history rows of the
+    news-vector table, scores of the candidate rows, and (rank=True) the candidate positions by descending score.
+    Two kernel launches; returns (user_vec [300], scores [C], order int32 [C] or None) on the device."""
+    lib = _lib.load()
+    _require_cuda(table, hist_rows, cand_rows)
+    if hist_rows.numel() != 50:
+        raise RuntimeError("the latency path is compiled for num_clicked_news_a_user = 50")
+    dev = table.device
+    table_c = _f32c(table)
+    hist = hist_rows.to(torch.int32).contiguous().view(-1)
+    cand = cand_rows.to(torch.int32).contiguous().view(-1)
+    Cn = cand.numel()
+    args = [_f32c(t) for t in (wqkv, bqkv, wa, ba, qa)]
+    user = torch.empty((D,), dtype=torch.float32, device=dev)
+    scores = torch.empty((Cn,), dtype=torch.float32, device=dev)
+    order = torch.empty((Cn,), dtype=torch.int32, device=dev) if rank else None
+    ws = _bytes(lib.nrms_recommend_workspace_bytes(), dev)
+    check(lib.nrms_recommend_user(ptr(table_c), table_c.shape[0], ptr(hist), ptr(cand), Cn, ptr(args[0]), ptr(args[1]),
+                                  ptr(args[2]), ptr(args[3]), ptr(args[4]), ptr(user), ptr(scores), ptr(order), ptr(ws),
+                                  ws.numel(), stream_ptr(dev)), "nrms_recommend_user")
+    return user, scores, order
 
 
 @torch.no_grad()

@@ -44,9 +44,23 @@ class TrainStep:
         """Index-only minibatch: `token_table` is the pre-tokenised news table int64 [N_news, L]
         resident on the GPU, `cand_rows` [B, 1+K] and `hist_rows` [B, N] are news-row indices -- 55 x B x 8 bytes of
         H2D per step instead of the 55 token tensors the reference DataLoader ships (dataset.py:17-85,
-        train.py:118-124).  The token rows are gathered on the device."""
-        rows = torch.cat([cand_rows, hist_rows], dim=1).to(token_table.device, non_blocking=True)
-        return self.step_tokens(token_table[rows], cand_rows.shape[1])
+        train.py:118-124).  The token rows are read through the indices inside the embedding gather / gradient scatter
+        kernels (nrms_news_encoder_rows_fwd/bwd): no gathered token tensor is materialised."""
+        if self.cosine_total_steps:
+            self.optimizer.param_groups[0]["lr"] = cosine_lr(self.base_lr, self.steps, self.cosine_total_steps)
+        if not cand_rows.is_cuda and cand_rows.numel():
+            lo = min(int(cand_rows.min()), int(hist_rows.min()))
+            hi = max(int(cand_rows.max()), int(hist_rows.max()))
+            if lo < 0 or hi >= token_table.shape[0]:
+                raise IndexError(f"news rows must lie in [0, {token_table.shape[0]}), got [{lo}, {hi}]")
+        logits = self.model.forward_rows(token_table, cand_rows, hist_rows)
+        loss = ops.cross_entropy_label0(logits)
+        self.optimizer.zero_grad()
+        loss.backward()
+        scale = self.optimizer.allreduce_grads()
+        self.optimizer.step(grad_scale=scale)
+        self.steps += 1
+        return loss.detach()
 
     def step(self, candidate_news, clicked_news):
         """Reference minibatch format: lists of {"title": LongTensor[B, L]} (src/train.py:202-203)."""

@@ -444,3 +444,79 @@ def evaluate_pipeline(params, news_tokens, hist_rows, cand_offsets, cand_rows, l
     with np.errstate(all="ignore"):
         means = np.nanmean(per, axis=0)
     return means, per, scores, table, uvec
+
+
+# --------------------------------------------------------------------------------------
+# model/Exp1 and the single-user path of recommend.py
+# (pinned by tests/golden/make_golden_exp1.py against the live reference modules)
+# --------------------------------------------------------------------------------------
+def _block_params(params, m_prefix, a_prefix):
+    return dict(
+        Wq=params[f"{m_prefix}.W_Q.weight"], bq=params[f"{m_prefix}.W_Q.bias"],
+        Wk=params[f"{m_prefix}.W_K.weight"], bk=params[f"{m_prefix}.W_K.bias"],
+        Wv=params[f"{m_prefix}.W_V.weight"], bv=params[f"{m_prefix}.W_V.bias"],
+        Wa=params[f"{a_prefix}.linear.weight"], ba=params[f"{a_prefix}.linear.bias"],
+        qa=params[f"{a_prefix}.attention_query_vector"])
+
+
+def element_encoder_forward(E, W, b, element):
+    """ElementEncoder.forward (src/model/Exp1/news_encoder.py:43-44): F.relu(self.linear(self.embedding(element)))."""
+    return np.maximum(E[element] @ W.T + b, 0).astype(E.dtype)
+
+
+def exp1_text_encoder_forward(params, name, text, num_heads=15):
+    """TextEncoder.forward in eval mode (src/model/Exp1/news_encoder.py:20-34): the NRMS news-encoder block over the
+    shared word embedding with the text encoder's own attention weights."""
+    pre = f"news_encoder.text_encoders.{name}"
+    x = embedding_gather(params[f"{pre}.word_embedding.weight"], text)
+    out, _ = encoder_forward(x, _block_params(params, f"{pre}.multihead_self_attention", f"{pre}.additive_attention"),
+                             num_heads)
+    return out
+
+
+def exp1_news_encoder_forward(params, news, attributes, num_heads=15):
+    """Exp1 NewsEncoder.forward (src/model/Exp1/news_encoder.py:83-111): text vectors + element vectors, stacked on
+    dim 1 and pooled by the final additive attention (a single vector is returned as is, :106-107)."""
+    texts = [a for a in ("title", "abstract") if a in attributes]
+    elems = [a for a in ("category", "subcategory") if a in attributes]
+    vecs = [exp1_text_encoder_forward(params, a, news[a], num_heads) for a in texts]
+    for a in elems:
+        pre = f"news_encoder.element_encoders.{a}"
+        vecs.append(element_encoder_forward(params[f"{pre}.embedding.weight"], params[f"{pre}.linear.weight"],
+                                            params[f"{pre}.linear.bias"], news[a]))
+    if len(vecs) == 1:
+        return vecs[0]
+    pf = "news_encoder.final_attention"
+    out, _ = additive_forward(np.stack(vecs, axis=1),
+                              dict(Wa=params[f"{pf}.linear.weight"], ba=params[f"{pf}.linear.bias"],
+                                   qa=params[f"{pf}.attention_query_vector"]))
+    return out
+
+
+def exp1_user_encoder_forward(params, clicked_news_vector, num_heads=15):
+    """Exp1 UserEncoder.forward (src/model/Exp1/user_encoder.py:15-31): the NRMS user-encoder block over
+    user_vector + position_embedding."""
+    x = clicked_news_vector + params["user_encoder.position_embedding"][None]
+    out, _ = encoder_forward(x, _block_params(params, "user_encoder.multihead_self_attention",
+                                              "user_encoder.additive_attention"), num_heads)
+    return out
+
+
+def exp1_forward(params, news, n_cand, attributes, num_heads=15):
+    """Exp1.forward (src/model/Exp1/__init__.py:15-46).  news: {attribute: [B, 1+K+N, ...]} (candidates first)."""
+    B, T = news["title"].shape[:2]
+    flat = {a: news[a].reshape(B * T, *news[a].shape[2:]) for a in attributes}
+    vec = exp1_news_encoder_forward(params, flat, attributes, num_heads).reshape(B, T, -1)
+    uv = exp1_user_encoder_forward(params, vec[:, n_cand:], num_heads)
+    return click_score(vec[:, :n_cand], uv)
+
+
+def recommend_user(params, table, hist_rows, cand_rows, num_heads=15):
+    """The single target user of recommend.py: user vector from the stacked cache rows (src/recommend.py:264-279),
+    get_prediction over the impression's candidates (:301-315), y = (score + 1) / 2 in python floats (:338) and
+    np.argsort(-y) (:339).  numpy's default sort leaves the order of EXACTLY equal scores unspecified; the order is
+    defined here as stable (ascending candidate position), like the metric order in `_order_desc`."""
+    uv, _ = user_encoder_forward(params, table[np.asarray(hist_rows)][None].astype(np.float32), num_heads)
+    scores = table[np.asarray(cand_rows, dtype=np.int64)] @ uv[0] if len(cand_rows) else np.zeros(0, np.float32)
+    y = (scores.astype(np.float64) + 1.0) / 2.0
+    return uv[0], y, np.argsort(-y, kind="stable")
