@@ -184,16 +184,16 @@ static int additive_block_bwd(const float* d_out, const float* cin, const float*
                               const float* qa, float* d_c, const AddBwdWs& w, int64_t n_seq, int S, float* d_wa,
                               float* d_ba, float* d_qa, bool tc, cudaStream_t st) {
   const int64_t rows = n_seq * S;
-  int nb = (int)(n_seq < REDUCE_BLOCKS ? n_seq : REDUCE_BLOCKS);
+  // 4 CTAs per SM; the partial buffer (REDUCE_BLOCKS x 900 floats) holds two 200-wide blocks per CTA
+  constexpr int ADD_BWD_BLOCKS = 592;
+  static_assert(2 * ADD_BWD_BLOCKS * QD <= REDUCE_BLOCKS * D3, "partial buffer too small");
+  int nb = (int)(n_seq < ADD_BWD_BLOCKS ? n_seq : ADD_BWD_BLOCKS);
   if (cudaError_t e2 = launch_additive_bwd(d_out, cin, t, wv, qa, d_c, w.d_u, w.partial, n_seq, S, nb, st))
     return cuda_fail(e2, "additive_bwd");
   launch_partial_reduce_accum(w.partial, nb, QD, QD, d_qa, st);
   NRMS_LAUNCH_CHECK("dqa_reduce");
-  // d_ba = colsum(dU)
-  int cb = (int)(rows < REDUCE_BLOCKS ? rows : REDUCE_BLOCKS);
-  colsum_partial_kernel<<<cb, 256, 0, st>>>(w.d_u, rows, QD, w.partial);
-  NRMS_LAUNCH_CHECK("colsum_du");
-  launch_partial_reduce_accum(w.partial, cb, QD, QD, d_ba, st);
+  // d_ba = colsum(dU): per-thread sums inside additive_bwd_kernel, second block of the partial buffer
+  launch_partial_reduce_accum(w.partial + (size_t)nb * QD, nb, QD, QD, d_ba, st);
   NRMS_LAUNCH_CHECK("dba_reduce");
   int splits = (int)((rows + 4095) / 4096);
   if (splits > 64) splits = 64;

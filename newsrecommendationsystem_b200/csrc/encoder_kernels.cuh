@@ -132,16 +132,18 @@ attention_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ ctx, int
     // to the sum or the context; length <= 0 leaves 0 / (0 + 1e-8) = 0, like the reference
     int jmax = S;
     if (lengths != nullptr) { const int l = lengths[seq]; jmax = l < 0 ? 0 : (l < S ? l : S); }
-#pragma unroll 2
+    // one key per step, but the 20-term dot product runs as five independent 4-term chains (the serial 20-FMA chain
+    // left the FMA pipe at ~1/4 of its rate: 4 cycles per dependent FMA and few warps per scheduler)
+#pragma unroll 4
     for (int j = 0; j < jmax; ++j) {
       const float4* kp = reinterpret_cast<const float4*>(Ks + j * W + hl * DH);
-      float s = 0.f;
+      float sp[DH / 4];
 #pragma unroll
       for (int c = 0; c < DH / 4; ++c) {
         float4 k = kp[c];
-        s = fmaf(q[4 * c], k.x, s); s = fmaf(q[4 * c + 1], k.y, s);
-        s = fmaf(q[4 * c + 2], k.z, s); s = fmaf(q[4 * c + 3], k.w, s);
+        sp[c] = fmaf(q[4 * c + 3], k.w, fmaf(q[4 * c + 2], k.z, fmaf(q[4 * c + 1], k.y, q[4 * c] * k.x)));
       }
+      const float s = ((sp[0] + sp[1]) + (sp[2] + sp[3])) + sp[4];
       const float e = expf(s / SQRT_DH);
       Z += e;
       const float4* vp = reinterpret_cast<const float4*>(Vs + j * W + hl * DH);
@@ -227,17 +229,19 @@ attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
 #pragma unroll
       for (int d = 0; d < DH; ++d) { a[d] = Qs[i * W + hl * DH + d]; b[d] = Gs[i * W + hl * DH + d]; r[d] = 0.f; }
       float Z = 0.f, num = 0.f;
-#pragma unroll 2
+#pragma unroll 4
       for (int j = 0; j < S; ++j) {
         const float4* kp = reinterpret_cast<const float4*>(Ks + j * W + hl * DH);
         const float4* vp = reinterpret_cast<const float4*>(Vs + j * W + hl * DH);
-        float s = 0.f, da = 0.f;
+        float sp[DH / 4], dp[DH / 4];      // five independent 4-term chains per dot product, in the forward's order
 #pragma unroll
         for (int c = 0; c < DH / 4; ++c) {
           float4 k = kp[c], v = vp[c];
-          s = fmaf(a[4 * c], k.x, s); s = fmaf(a[4 * c + 1], k.y, s); s = fmaf(a[4 * c + 2], k.z, s); s = fmaf(a[4 * c + 3], k.w, s);
-          da = fmaf(b[4 * c], v.x, da); da = fmaf(b[4 * c + 1], v.y, da); da = fmaf(b[4 * c + 2], v.z, da); da = fmaf(b[4 * c + 3], v.w, da);
+          sp[c] = fmaf(a[4 * c + 3], k.w, fmaf(a[4 * c + 2], k.z, fmaf(a[4 * c + 1], k.y, a[4 * c] * k.x)));
+          dp[c] = fmaf(b[4 * c + 3], v.w, fmaf(b[4 * c + 2], v.z, fmaf(b[4 * c + 1], v.y, b[4 * c] * v.x)));
         }
+        const float s = ((sp[0] + sp[1]) + (sp[2] + sp[3])) + sp[4];
+        const float da = ((dp[0] + dp[1]) + (dp[2] + dp[3])) + dp[4];
         const float e = expf(s / SQRT_DH);      // same expression as the forward kernel
         Z += e;
         num = fmaf(e, da, num);
@@ -246,7 +250,7 @@ attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
       }
       const float zinv = 1.f / (Z + ATTN_EPS);
       const float delta = num * zinv;
-#pragma unroll 2
+#pragma unroll 4
       for (int j = 0; j < S; ++j) {
         const float4* kp = reinterpret_cast<const float4*>(Ks + j * W + hl * DH);
         const float at = prow[j] * zinv;
@@ -272,7 +276,7 @@ attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_
       const float* dcol = Ds + hl * S * SP + j;
 #pragma unroll
       for (int d = 0; d < DH; ++d) { a[d] = 0.f; b[d] = 0.f; }     // a = dK_j, b = dV_j
-#pragma unroll 2
+#pragma unroll 4
       for (int ii = 0; ii < S; ++ii) {
         const float4* qp = reinterpret_cast<const float4*>(Qs + ii * W + hl * DH);
         const float4* gp = reinterpret_cast<const float4*>(Gs + ii * W + hl * DH);
@@ -347,6 +351,7 @@ additive_fwd_kernel(const float* __restrict__ c, float* __restrict__ t, const fl
 //   d_c[i,:]  = w_i * d_out           (first term; the GEMM adds dU * Wa afterwards)
 //   d_u[i,q]  = ds_i * qa[q] * (1 - t^2)
 //   partial_dqa[block, q] = sum over this block's sequences of ds_i * t[i,q]
+//   partial_dqa[gridDim.x + block, q] = sum over this block's rows of d_u[i,q]   (the bias gradient: no colsum pass)
 template <int S>
 __global__ void __launch_bounds__(256)
 additive_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ c, const float* __restrict__ t,
@@ -358,7 +363,7 @@ additive_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ c
   __shared__ float wv[S];
   __shared__ __align__(16) float go[D];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float dqa_acc = 0.f;
+  float dqa_acc = 0.f, dba_acc = 0.f;
   const float qv = (tid < QD) ? qa[tid] : 0.f;
   for (int64_t seq = blockIdx.x; seq < n_seq; seq += gridDim.x) {
     for (int d = tid; d < D; d += 256) go[d] = d_out[seq * D + d];
@@ -384,7 +389,9 @@ additive_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ c
         const int64_t row = seq * S + i;
         const float tv = t[row * QD + tid];
         const float ds = dsv[i];
-        d_u[row * QD + tid] = ds * qv * (1.f - tv * tv);
+        const float du = ds * qv * (1.f - tv * tv);
+        d_u[row * QD + tid] = du;
+        dba_acc += du;
         dqa_acc = fmaf(ds, tv, dqa_acc);
       }
     }
@@ -396,7 +403,10 @@ additive_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ c
     }
     __syncthreads();
   }
-  if (tid < QD) partial_dqa[(int64_t)blockIdx.x * QD + tid] = dqa_acc;
+  if (tid < QD) {
+    partial_dqa[(int64_t)blockIdx.x * QD + tid] = dqa_acc;
+    partial_dqa[(int64_t)(gridDim.x + blockIdx.x) * QD + tid] = dba_acc;
+  }
 }
 
 // ----------------------------------------------------------------------------------------
