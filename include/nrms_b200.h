@@ -77,6 +77,8 @@ int64_t nrms_launch_count(void);
  *  context rows never leave the SM; measured slower than K1g + K2).
  * "attn_safe_softmax" (default -1): -1 = the attention kernels choose between 2^s and the row-shifted form
  *  2^(s - max) / (Z + 1e-8 * 2^-max) from a bound on the scores, 0 / 1 force one form (tests).
+ * "train_attn_mma" (default 1): tensor-mode training attention over titles on mma.sync TF32 tiles (attn_mma.cu); 0 = the
+ *  CUDA-core kernels of the FP32 mode.
  * "k1f_debug": component-removal timing masks of K1f (garbage results; profiles/k1f_probe.py). */
 int nrms_set_option(const char* key, int value);
 /* "time_k1" = 1 brackets every fused K1 launch with CUDA events on the launching stream (clears the previous

@@ -42,6 +42,7 @@ static Stash carve_stash(void* base, int64_t rows, bool ln = false) {
   return s;
 }
 
+static bool g_train_attn_mma = true;   // nrms_set_option("train_attn_mma"): tensor-mode title attention on mma.sync tiles
 constexpr int64_t INFER_CHUNK_ROWS = 2048 * 20;  // rows processed per pass in inference (reference batch 2048 titles)
 constexpr int REDUCE_BLOCKS = 296;
 
@@ -156,7 +157,11 @@ static int encoder_core_fwd(const Stash& s, int64_t n_seq, int S, const float* w
   // dropout #2 mask indices are global row indices: offset the Philox counter by row_base*D/4
   const uint64_t off2 = offset + (uint64_t)row_base * D / 4;
   cudaError_t e;
-  if (S == 20) e = launch_attention_fwd<20, 15>(s.qkv, s.c, n_seq, p2, seed, off2, st);
+  if (S == 20 && mode == NRMS_MODE_TF32 && g_train_attn_mma) {
+    // tensor mode, titles: exp-softmax attention on mma.sync TF32 tiles (attn_mma.cu)
+    if (int rc2 = attn_mma_fwd(s.qkv, s.c, n_seq, p2, seed, off2, st)) return rc2;
+    e = cudaSuccess;
+  } else if (S == 20) e = launch_attention_fwd<20, 15>(s.qkv, s.c, n_seq, p2, seed, off2, st);
   else e = launch_attention_fwd<50, 5>(s.qkv, s.c, n_seq, p2, seed, off2, st);
   if (e != cudaSuccess) return cuda_fail(e, "attention_fwd");
   const float* cin = s.c;
@@ -254,7 +259,10 @@ static int encoder_core_bwd(const Stash& s, const BwdWs& w, const float* d_out, 
 #ifndef NRMS_ATTN_BWD_HC20
 #define NRMS_ATTN_BWD_HC20 5        // heads per CTA of the title-length attention backward (measured: 5 -> 807 us, 15 -> 1,086 us per 7,040 titles)
 #endif
-  if (S == 20) e = launch_attention_bwd<20, NRMS_ATTN_BWD_HC20>(s.qkv, w.d_c, w.d_qkv, n_seq, p2, seed, offset, st);
+  if (S == 20 && tc && g_train_attn_mma) {
+    if (int rc2 = attn_mma_bwd(s.qkv, w.d_c, w.d_qkv, n_seq, p2, seed, offset, st)) return rc2;
+    e = cudaSuccess;
+  } else if (S == 20) e = launch_attention_bwd<20, NRMS_ATTN_BWD_HC20>(s.qkv, w.d_c, w.d_qkv, n_seq, p2, seed, offset, st);
   else e = launch_attention_bwd<50, 5>(s.qkv, w.d_c, w.d_qkv, n_seq, p2, seed, offset, st);
   if (e != cudaSuccess) return cuda_fail(e, "attention_bwd");
   // d_bqkv = colsum(dQKV)
@@ -752,6 +760,10 @@ int nrms_set_option(const char* key, int value) {
   }
   if (strcmp(key, "attn_safe_softmax") == 0) {
     set_attn_safe_softmax(value);
+    return NRMS_OK;
+  }
+  if (strcmp(key, "train_attn_mma") == 0) {
+    g_train_attn_mma = value != 0;
     return NRMS_OK;
   }
   if (strcmp(key, "time_k1") == 0) {

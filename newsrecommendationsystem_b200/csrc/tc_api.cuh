@@ -37,6 +37,11 @@ int pack_rows16(const float* src, int64_t n_rows, void* src16, cudaStream_t st);
 // fp16 operands (A16 [M, lda halfs], B16 [N, ldb halfs], 16-byte aligned rows), kind::f16, same fp16 epilogue (no bias)
 int tc_gemm_nt_f16(const void* A16, int64_t lda, const void* B16, int64_t ldb, void* C16, int64_t ldc, int64_t M, int N,
                    int K, float scale, int scale_cols, int qkv_layout, cudaStream_t st);
+// attn_mma.cu: tensor-mode TRAINING attention over 20-token titles on mma.sync TF32 tiles (forward, and the backward that
+// recomputes the probabilities from the stashed q|k|v rows); qkv [n_seq*20, 900], ctx / d_ctx [n_seq*20, 300]
+int attn_mma_fwd(const float* qkv, float* ctx, int64_t n_seq, float p, uint64_t seed, uint64_t offset, cudaStream_t st);
+int attn_mma_bwd(const float* qkv, const float* d_ctx, float* d_qkv, int64_t n_seq, float p, uint64_t seed, uint64_t offset,
+                 cudaStream_t st);
 // K1f (k1f_attn_pool.cu): table attention + additive pooling in one kernel (the context rows stay on the SM)
 int k1f_qk_bound(const void* table16, int64_t n_rows, float* bound, cudaStream_t st);
 int k1f_run(int S, int idx_kind, const void* table16, int64_t n_table_rows, const void* rows, int64_t n_seq,

@@ -702,7 +702,9 @@ def test_layernorm_variant_train_step_gradients(dev, golden, golden_sd, precisio
     ts = TrainStep(m, lr=1e-4, adamw=True, weight_decay=0.01)
     titles = torch.from_numpy(np.concatenate([cand, clicked], axis=1))
     loss = float(ts.step_tokens(titles, cand.shape[1]).item())
-    assert abs(loss - float(loss_ref)) < (1e-5 if precision == "fp32" else 2e-3)
+    # LayerNorm makes the logits large (loss ~ 18.8 at this init): the tensor-mode bound is relative, 2e-4 of the loss
+    # (TF32 operands in the projections and in the title attention); FP32 mode stays absolute
+    assert abs(loss - float(loss_ref)) < (1e-5 if precision == "fp32" else 2e-4 * max(1.0, abs(float(loss_ref))))
     grads = {k: p.grad.detach().cpu().numpy() for k, p in m.named_parameters()}
     assert set(grads) == set(grads_ref)
     # b_K's gradient is zero in exact arithmetic (a common shift of the scores of a row cancels in the softmax), so
@@ -800,3 +802,33 @@ def test_checkpoint_interchange_with_torch_adam(dev, golden, golden_sd, tmp_path
     st0 = adam.state[list(params.values())[0]]
     n0 = list(params.values())[0].numel()
     assert torch.equal(ts2.optimizer.exp_avg[:n0].cpu().view(-1), st0["exp_avg"].view(-1))
+
+
+def test_training_attention_mma_vs_cuda_core(golden_sd, dev, lib):
+    """Tensor-mode title attention on mma.sync TF32 tiles (attn_mma.cu) against the CUDA-core kernels it replaces: same
+    stashed q|k|v rows, dropout 0.2 (same Philox stream), loss and every gradient within the tensor-mode tolerance; the
+    two runs must differ somewhere (two kernels ran)."""
+    from newsrecommendationsystem_b200 import ops
+    rng = np.random.default_rng(21)
+    titles = rng.integers(0, Cfg.num_words, size=(24, 55, 20)).astype(np.int64)
+    titles[:, 40:, 10:] = 0
+    res = []
+    for use_mma in (0, 1):
+        assert lib.nrms_set_option(b"train_attn_mma", use_mma) == 0
+        m = make_model(golden_sd, dev, "tf32")
+        m.train()
+        loss = ops.cross_entropy_label0(m.forward_tokens(t(titles, dev), 5))
+        loss.backward()
+        res.append((float(loss.detach()), {k: p.grad.detach().cpu().numpy() for k, p in m.named_parameters()}))
+    assert lib.nrms_set_option(b"train_attn_mma", 1) == 0
+    (l0, g0), (l1, g1) = res
+    assert abs(l0 - l1) < 2e-3
+    differs = False
+    # b_K's gradient is zero in exact arithmetic (both kernels hold rounding noise there): floor as in the LayerNorm test
+    floor = 1e-6 * max(float(np.abs(v).max()) for v in g0.values())
+    for k in g0:
+        scale = max(float(np.abs(g0[k]).max()), 1e-12)
+        err = float(np.abs(g0[k] - g1[k]).max())
+        assert err <= 3e-3 * scale + floor, (k, err, scale)
+        differs = differs or err > 0
+    assert differs

@@ -149,7 +149,7 @@ def test_dropout_masks_keep_rate_scale_and_train_forward(dev, lib, golden_sd, pr
     kept2 = Cm != 0
     ratio = Cm[big & kept2] / ctx[big & kept2]
     assert np.all(np.abs(ratio - scale) < 2e-2), (ratio.min(), ratio.max())      # |ctx| > 1e-4: fp32 rounding of the scores
-    assert abs(float(np.median(ratio)) - float(scale)) < 1e-6
+    assert abs(float(np.median(ratio)) - float(scale)) < (1e-6 if precision == "fp32" else 1e-4)
     n2 = int(big.sum())
     rate2 = float((big & kept2).sum()) / n2
     assert abs(rate2 - 0.8) < 4 * np.sqrt(0.8 * 0.2 / n2), rate2
