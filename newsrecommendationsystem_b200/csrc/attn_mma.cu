@@ -21,9 +21,7 @@
 //   backward: dP = G V^T (NT), dS = attn (dP - sum_j attn dP) / sqrt 20, dQ = dS K (fragments in place, like O),
 //             dK = dS^T Q and dV = attn^T G read dS / attn back TRANSPOSED from shared memory: they are parked in the V
 //             and K tiles, which are dead by then (their padding stays zero: only the 20x20 block is written).
-// Global loads: 16-byte async copies into double-buffered tiles, the next title's in flight while the current one is
-// computed (the first version staged with a load -> store loop and ran at 1.3 TB/s: ten dependent L2 round trips per
-// title; holding the next title in registers instead cost 207 registers and all but one CTA per SM).
+// Global loads: warp-private 16-byte async copies, no block-wide barrier in the title loop (see warp_fetch).
 #include "common.cuh"
 #include "tc_api.cuh"
 
@@ -39,10 +37,7 @@ constexpr int THREADS = HC * 32;
 constexpr float SQRT_DH = 4.47213595499957939f;
 constexpr float ATTN_EPS = 1e-8f;
 constexpr uint32_t DROPOUT_STREAM_CTX = 2;     // encoder_kernels.cuh
-#ifndef NRMS_AMMA_NBUF
-#define NRMS_AMMA_NBUF 1        // tile buffers per CTA: 1 = more CTAs per SM hide the copies, 2 = next title's copies under the compute
-#endif
-constexpr int NBUF = NRMS_AMMA_NBUF;
+constexpr int NBUF = 1;          // one set of tiles per warp (a second set, filled under the compute, halved the resident warps: slower)
 
 __device__ __forceinline__ float tf32_round(float x) {
   uint32_t r;
@@ -63,6 +58,12 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+#ifdef NRMS_AMMA_TRACE
+#define AT(k) do { if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) tr[k] = clock64(); } while (0)
+#else
+#define AT(k)
+#endif
 
 typedef float Frag[2][3][4];     // [m tile][n tile][accumulator register]
 
@@ -203,39 +204,83 @@ __device__ __forceinline__ void store_rows(float* dst, int64_t ld_, const Frag& 
       }
 }
 
-// Cooperative staging of NTILES tiles per head for one title with 16-byte async copies (no registers held): tile k of
-// head hl <- columns [k*300 + hc*100 + hl*20, +20) of the title's 20 qkv rows (k < 3) or d_ctx rows (k == 3).  The tiles
-// are double-buffered: the next title's copies are in flight while the current one is computed.
-template <int NTILES>
-__device__ __forceinline__ void issue(float* buf, const float* __restrict__ qkv_seq, const float* __restrict__ g_seq, int hc,
-                                      int tid) {
-  constexpr int W4 = HC * DH / 4;      // 25 float4 per row of the head chunk
-  for (int f = tid; f < NTILES * S * W4; f += THREADS) {
-    const int which = f / (S * W4), rem = f % (S * W4), j = rem / W4, c4 = rem % W4;
-    const float* src = (which < 3) ? qkv_seq + (int64_t)j * D3 + which * D + hc * (HC * DH) + c4 * 4
-                                   : g_seq + (int64_t)j * D + hc * (HC * DH) + c4 * 4;
-    const int hl = c4 / (DH / 4), d4 = c4 % (DH / 4);
-    cp_async16(buf + (hl * NTILES + which) * TILE + j * ST + d4 * 4, src);
+// the same 20 x 20 block written TRANSPOSED: dstT[col * ldt + row].  The weight-gradient contraction dW = dQKV^T X reads
+// dQKV^T as a K-major operand (tc_gemm.cu); writing it here replaces a 507 MB read + 507 MB write transposition pass per
+// step.  The fragment is turned through a dead tile (scratch[col][row], 20 x 20 block only: the padding stays zero) and
+// leaves as 16-byte stores: a column of the block is 20 consecutive floats = 80 contiguous, 16-byte aligned bytes of a
+// row of dstT.  (Storing the fragments transposed directly -- 72 scalar stores per lane and matrix -- took the kernel
+// from 383 to 804 us and 215 registers.)
+__device__ __forceinline__ void store_rows_t(float* dstT, int64_t ldt, float* scratch, const Frag& c, int lane, int g, int t) {
+  __syncwarp();
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int row = mt * 16 + g + 8 * half, col = nt * 8 + 2 * t;
+        if (row < S && col < S) {
+          scratch[col * ST + row] = c[mt][nt][half * 2];
+          scratch[(col + 1) * ST + row] = c[mt][nt][half * 2 + 1];
+        }
+      }
+  __syncwarp();
+  for (int f = lane; f < S * (S / 4); f += 32) {
+    const int col = f / (S / 4), r4 = f % (S / 4);
+    *reinterpret_cast<float4*>(dstT + (int64_t)col * ldt + 4 * r4) = *reinterpret_cast<const float4*>(scratch + col * ST + 4 * r4);
   }
+  __syncwarp();
 }
 
-// the owning warp rounds the 20 x 20 blocks of its NTILES tiles to TF32 in place; tile 3 (d_ctx) also takes the dropout-2
-// mask of its 4-column groups here (the forward's Philox stream): 100 groups over 32 lanes = 4 evaluations per lane
+// Warp-private staging: each warp copies the 20 x 20 blocks of its own head's NTILES tiles (tile k <- columns
+// [k*300 + head*20, +20) of the title's 20 qkv rows for k < 3, of its d_ctx rows for k == 3) with 16-byte async copies,
+// waits for them, and rounds them to TF32 in place (cvt.rna; a bare fp32 pattern would be truncated by the tensor core;
+// the d_ctx tile also takes the dropout-2 mask of the forward's Philox stream here).  Every lane converts exactly the 16-byte
+// pieces it copied itself, so there is no barrier between the copy and the conversion, and no block-wide barrier at all:
+// the warps of a CTA drift apart and hide each other's copy latency.  (The first version staged cooperatively with two
+// __syncthreads per title: clock64 stamps showed 4.2k cycles at the barrier, 3k waiting for the copies and 4.5k in a
+// rolled conversion loop, against 5.7k of contractions.)
 template <int NTILES>
-__device__ __forceinline__ void round_tiles(float* tiles, int lane, int64_t seq, int colbase, float p, float scale,
-                                            uint64_t seed, uint64_t offset) {
+__device__ __forceinline__ void warp_fetch(float* tiles, const float* __restrict__ qkv_head, const float* __restrict__ g_head,
+                                           int lane, int64_t row0, int col0, float p, float scale, uint64_t seed,
+                                           uint64_t offset) {
+  constexpr int PT = 4;                       // 100 sixteen-byte pieces per tile over 32 lanes
+  int j[PT], d4[PT];
 #pragma unroll
-  for (int k = 0; k < NTILES; ++k)
-    for (int f = lane; f < S * (DH / 4); f += 32) {
-      const int j = f / (DH / 4), d4 = f % (DH / 4);
-      float4* q = reinterpret_cast<float4*>(tiles + k * TILE + j * ST + d4 * 4);
-      float4 x = *q;
-      if (k == 3 && p > 0.f) {
-        const float4 m = dropout_mask4((uint64_t)(seq * S + j) * D + colbase + d4 * 4, DROPOUT_STREAM_CTX, p, scale, seed, offset);
-        x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+  for (int k = 0; k < PT; ++k) {
+    const int f = lane + 32 * k;
+    j[k] = f / (DH / 4);
+    d4[k] = f % (DH / 4);
+  }
+#pragma unroll
+  for (int w = 0; w < NTILES; ++w)
+#pragma unroll
+    for (int k = 0; k < PT; ++k)
+      if (lane + 32 * k < S * (DH / 4)) {
+        const float* src = (w < 3) ? qkv_head + (int64_t)j[k] * D3 + w * D + d4[k] * 4 : g_head + (int64_t)j[k] * D + d4[k] * 4;
+        cp_async16(tiles + w * TILE + j[k] * ST + d4[k] * 4, src);
       }
-      *q = make_float4(tf32_round(x.x), tf32_round(x.y), tf32_round(x.z), tf32_round(x.w));
+  cp_async_wait_all();
+#pragma unroll
+  for (int w = 0; w < NTILES; ++w) {
+    float4 x[PT];
+#pragma unroll
+    for (int k = 0; k < PT; ++k)
+      if (lane + 32 * k < S * (DH / 4)) x[k] = *reinterpret_cast<const float4*>(tiles + w * TILE + j[k] * ST + d4[k] * 4);
+    if (w == 3 && p > 0.f) {
+#pragma unroll
+      for (int k = 0; k < PT; ++k)
+        if (lane + 32 * k < S * (DH / 4)) {
+          const float4 m = dropout_mask4((uint64_t)(row0 + j[k]) * D + col0 + d4[k] * 4, DROPOUT_STREAM_CTX, p, scale, seed, offset);
+          x[k].x *= m.x; x[k].y *= m.y; x[k].z *= m.z; x[k].w *= m.w;
+        }
     }
+#pragma unroll
+    for (int k = 0; k < PT; ++k)
+      if (lane + 32 * k < S * (DH / 4))
+        *reinterpret_cast<float4*>(tiles + w * TILE + j[k] * ST + d4[k] * 4) =
+            make_float4(tf32_round(x[k].x), tf32_round(x[k].y), tf32_round(x[k].z), tf32_round(x[k].w));
+  }
   __syncwarp();
 }
 
@@ -243,26 +288,17 @@ __global__ void __launch_bounds__(THREADS)
 attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ ctx, int64_t n_seq, float p, float scale, uint64_t seed,
                 uint64_t offset) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int BUF = HC * 3 * TILE;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int hc = blockIdx.y;
-  for (int f = tid; f < NBUF * BUF; f += THREADS) smem[f] = 0.f;
+  for (int f = tid; f < HC * 3 * TILE; f += THREADS) smem[f] = 0.f;
   __syncthreads();
-  if (NBUF == 2 && (int64_t)blockIdx.x < n_seq) issue<3>(smem, qkv + (int64_t)blockIdx.x * S * D3, nullptr, hc, tid);
-  int b = 0;
-  for (int64_t seq = blockIdx.x; seq < n_seq; seq += gridDim.x, b ^= (NBUF - 1)) {
-    if (NBUF == 1) {
-      __syncthreads();        // every warp is done with the previous title
-      issue<3>(smem, qkv + seq * S * D3, nullptr, hc, tid);
-    }
-    cp_async_wait_all();
-    __syncthreads();          // this title's tiles are visible (NBUF 2: and every warp is done with the other buffer)
-    if (NBUF == 2 && seq + gridDim.x < n_seq) issue<3>(smem + (b ^ 1) * BUF, qkv + (seq + gridDim.x) * S * D3, nullptr, hc, tid);
-    float* Q = smem + b * BUF + (warp * 3 + 0) * TILE;
-    const float* K = Q + TILE;
-    const float* V = K + TILE;
-    const int colbase = hc * (HC * DH) + warp * DH;
-    round_tiles<3>(Q, lane, seq, colbase, 0.f, 1.f, 0, 0);
+  float* Q = smem + (warp * 3 + 0) * TILE;
+  const float* K = Q + TILE;
+  const float* V = K + TILE;
+  const int colbase = hc * (HC * DH) + warp * DH;
+  for (int64_t seq = blockIdx.x; seq < n_seq; seq += gridDim.x) {
+    __syncwarp();             // every lane is done with the previous title's tiles
+    warp_fetch<3>(Q, qkv + seq * S * D3 + colbase, nullptr, lane, seq * S, colbase, 0.f, 1.f, 0, 0);
     Frag a;
     zero(a);
     gemm_nt(a, Q, K, g, t);
@@ -299,38 +335,38 @@ attn_fwd_kernel(const float* __restrict__ qkv, float* __restrict__ ctx, int64_t 
 }
 
 __global__ void __launch_bounds__(THREADS)
-attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_ctx, float* __restrict__ d_qkv, int64_t n_seq,
-                float p, float scale, uint64_t seed, uint64_t offset) {
+attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_ctx, float* __restrict__ d_qkv,
+                float* __restrict__ d_qkv_t, int64_t ldt, int64_t n_seq, float p, float scale, uint64_t seed, uint64_t offset) {
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int hc = blockIdx.y;
-  constexpr int BUF = HC * 4 * TILE;
-  for (int f = tid; f < NBUF * BUF; f += THREADS) smem[f] = 0.f;
+  for (int f = tid; f < HC * 4 * TILE; f += THREADS) smem[f] = 0.f;
   __syncthreads();
   constexpr float INV_SQRT_DH = 1.f / SQRT_DH;
-  if (NBUF == 2 && (int64_t)blockIdx.x < n_seq)
-    issue<4>(smem, qkv + (int64_t)blockIdx.x * S * D3, d_ctx + (int64_t)blockIdx.x * S * D, hc, tid);
-  int b = 0;
-  for (int64_t seq = blockIdx.x; seq < n_seq; seq += gridDim.x, b ^= (NBUF - 1)) {
-    if (NBUF == 1) {
-      __syncthreads();        // every warp is done with the previous title
-      issue<4>(smem, qkv + seq * S * D3, d_ctx + seq * S * D, hc, tid);
-    }
-    cp_async_wait_all();
-    __syncthreads();          // this title's tiles are visible (NBUF 2: and every warp is done with the other buffer)
-    if (NBUF == 2 && seq + gridDim.x < n_seq)
-      issue<4>(smem + (b ^ 1) * BUF, qkv + (seq + gridDim.x) * S * D3, d_ctx + (seq + gridDim.x) * S * D, hc, tid);
-    float* Q = smem + b * BUF + (warp * 4 + 0) * TILE;
-    float* K = Q + TILE;
-    float* V = K + TILE;
-    float* G = V + TILE;
-    round_tiles<4>(Q, lane, seq, hc * (HC * DH) + warp * DH, p, scale, seed, offset);
+  float* Q = smem + (warp * 4 + 0) * TILE;
+  float* K = Q + TILE;
+  float* V = K + TILE;
+  float* G = V + TILE;
+  const int colbase = hc * (HC * DH) + warp * DH;
+#ifdef NRMS_AMMA_TRACE
+  long long tr[12] = {0};
+#endif
+  for (int64_t seq = blockIdx.x; seq < n_seq; seq += gridDim.x) {
+    AT(0);
+    __syncwarp();             // every lane is done with the previous title's tiles
+    AT(1);
+    AT(2);
+    warp_fetch<4>(Q, qkv + seq * S * D3 + colbase, d_ctx + seq * S * D + colbase, lane, seq * S, colbase, p, scale, seed, offset);
+    AT(3);
     Frag a, dp;
     zero(a);
     gemm_nt(a, Q, K, g, t);
+    AT(4);
     softmax_rows(a, t);                       // a = attn
+    AT(5);
     zero(dp);
     gemm_nt(dp, G, V, g, t);                  // dp = dO V^T
+    AT(6);
     // ds = attn (dp - sum_j attn dp) / sqrt 20, in place over dp
 #pragma unroll
     for (int mt = 0; mt < 2; ++mt)
@@ -349,13 +385,16 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_ctx, 
           for (int e = 0; e < 2; ++e)
             dp[mt][nt][half * 2 + e] = a[mt][nt][half * 2 + e] * (dp[mt][nt][half * 2 + e] - delta) * INV_SQRT_DH;
       }
-    float* out = d_qkv + seq * S * D3 + hc * (HC * DH) + warp * DH;
+    float* out = d_qkv + seq * S * D3 + colbase;
+    float* out_t = d_qkv_t ? d_qkv_t + (int64_t)colbase * ldt + seq * S : nullptr;     // [900, ldt]: row = column of dQKV
     __syncwarp();
     park(V, dp, g, t);                        // V is dead: dS (TF32-rounded) parked as [i][j]
     Frag r;
     zero(r);
     gemm_frag_n(r, dp, K, g, t);              // dQ = dS K
     store_rows(out, D3, r, g, t);
+    if (out_t) store_rows_t(out_t, ldt, K, r, lane, g, t);       // K is dead from here on
+    AT(7);
     __syncwarp();
     // K is dead: the rounding residue dS - tf32(dS) goes there.  The rows of dS sum to ~0 (the softmax Jacobian), and
     // the K-bias gradient is exactly that sum: with dS = hi + lo in the dK contraction it cancels to fp32 accuracy
@@ -372,12 +411,23 @@ attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ d_ctx, 
     gemm_tn(r, V, Q, g, t);                   // dK = (dS_hi + dS_lo)^T Q
     gemm_tn(r, K, Q, g, t);
     store_rows(out + D, D3, r, g, t);
+    if (out_t) store_rows_t(out_t + (int64_t)D * ldt, ldt, K, r, lane, g, t);       // dS_lo in K is dead
+    AT(8);
     __syncwarp();
     park(V, a, g, t);                         // dS is dead: attn parked as [i][j]
     __syncwarp();
     zero(r);
     gemm_tn(r, V, G, g, t);                   // dV = attn^T dO
     store_rows(out + 2 * D, D3, r, g, t);
+    if (out_t) store_rows_t(out_t + (int64_t)2 * D * ldt, ldt, K, r, lane, g, t);
+    AT(9);
+#ifdef NRMS_AMMA_TRACE
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && seq == (int64_t)gridDim.x * 2) {
+      printf("attn_bwd sync+issue/wait/round/S/softmax/dP/dS+dQ/dK/dV cycles:");
+      for (int k_ = 1; k_ < 10; ++k_) printf(" %lld", tr[k_] - tr[k_ - 1]);
+      printf("\n");
+    }
+#endif
   }
 }
 
@@ -394,15 +444,15 @@ int attn_mma_fwd(const float* qkv, float* ctx, int64_t n_seq, float p, uint64_t 
   return NRMS_OK;
 }
 
-int attn_mma_bwd(const float* qkv, const float* d_ctx, float* d_qkv, int64_t n_seq, float p, uint64_t seed, uint64_t offset,
-                 cudaStream_t st) {
+int attn_mma_bwd(const float* qkv, const float* d_ctx, float* d_qkv, float* d_qkv_t, int64_t ldt, int64_t n_seq, float p,
+                 uint64_t seed, uint64_t offset, cudaStream_t st) {
   const size_t smem = amma::NBUF * (size_t)amma::HC * 4 * amma::TILE * sizeof(float);
   static bool configured[64] = {false};
   if (cudaError_t e = set_max_dynamic_smem(amma::attn_bwd_kernel, (int)smem, configured)) return cuda_fail(e, "attn_mma_bwd attr");
   int64_t gx = n_seq < (int64_t)num_sms() * 8 ? n_seq : (int64_t)num_sms() * 8;
   const float scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
-  amma::attn_bwd_kernel<<<dim3((unsigned)gx, H / amma::HC), amma::THREADS, smem, st>>>(qkv, d_ctx, d_qkv, n_seq, p, scale, seed,
-                                                                                       offset);
+  amma::attn_bwd_kernel<<<dim3((unsigned)gx, H / amma::HC), amma::THREADS, smem, st>>>(qkv, d_ctx, d_qkv, d_qkv_t, ldt, n_seq, p, scale,
+                                                                                       seed, offset);
   NRMS_LAUNCH_CHECK("attn_mma_bwd");
   return NRMS_OK;
 }

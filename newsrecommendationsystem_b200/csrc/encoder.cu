@@ -259,8 +259,11 @@ static int encoder_core_bwd(const Stash& s, const BwdWs& w, const float* d_out, 
 #ifndef NRMS_ATTN_BWD_HC20
 #define NRMS_ATTN_BWD_HC20 5        // heads per CTA of the title-length attention backward (measured: 5 -> 807 us, 15 -> 1,086 us per 7,040 titles)
 #endif
+  bool dqkv_t_written = false;
   if (S == 20 && tc && g_train_attn_mma) {
-    if (int rc2 = attn_mma_bwd(s.qkv, w.d_c, w.d_qkv, n_seq, p2, seed, offset, st)) return rc2;
+    // the kernel also leaves dQKV^T in t1 (the K-major operand of the dWqkv contraction below)
+    if (int rc2 = attn_mma_bwd(s.qkv, w.d_c, w.d_qkv, w.t1, w.ldr, n_seq, p2, seed, offset, st)) return rc2;
+    dqkv_t_written = true;
     e = cudaSuccess;
   } else if (S == 20) e = launch_attention_bwd<20, NRMS_ATTN_BWD_HC20>(s.qkv, w.d_c, w.d_qkv, n_seq, p2, seed, offset, st);
   else e = launch_attention_bwd<50, 5>(s.qkv, w.d_c, w.d_qkv, n_seq, p2, seed, offset, st);
@@ -272,7 +275,8 @@ static int encoder_core_bwd(const Stash& s, const BwdWs& w, const float* d_out, 
   NRMS_LAUNCH_CHECK("dbqkv_reduce");
   if (tc) {
     // d_wqkv[900,300] += dQKV^T X
-    if (int rc = transpose_f32(w.d_qkv, D3, w.t1, w.ldr, rows, D3, st)) return rc;
+    if (!dqkv_t_written)
+      if (int rc = transpose_f32(w.d_qkv, D3, w.t1, w.ldr, rows, D3, st)) return rc;
     if (int rc = transpose_f32(s.x, D, w.t2, w.ldr, rows, D, st)) return rc;
     if (int rc = tc_gemm_nt_ex(w.t1, w.ldr, w.t2, w.ldr, nullptr, d_wqkv, D, D3, D, (int)rows,
                                tc_gemm_auto_splits(D3, D, (int)rows), TC_EPI_ATOMIC, st)) return rc;

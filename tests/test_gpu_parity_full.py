@@ -145,10 +145,13 @@ def test_dropout_masks_keep_rate_scale_and_train_forward(dev, lib, golden_sd, pr
     q, k, v = (QKV[:, i * 300:(i + 1) * 300].reshape(n, L, 15, 20).transpose(0, 2, 1, 3).astype(np.float64) for i in range(3))
     e = np.exp(q @ k.transpose(0, 1, 3, 2) / np.sqrt(20.0))
     ctx = ((e / (e.sum(-1, keepdims=True) + 1e-8)) @ v).transpose(0, 2, 1, 3).reshape(rows, 300)
-    big = np.abs(ctx) > 1e-4
+    # the mask is read off entries large enough for the ratio to be meaningful: fp32 rounding of the scores (FP32 mode),
+    # TF32 operands of the title attention (tensor mode: absolute error ~5e-4 on values of ~0.3)
+    big = np.abs(ctx) > (1e-4 if precision == "fp32" else 5e-2)
     kept2 = Cm != 0
     ratio = Cm[big & kept2] / ctx[big & kept2]
-    assert np.all(np.abs(ratio - scale) < 2e-2), (ratio.min(), ratio.max())      # |ctx| > 1e-4: fp32 rounding of the scores
+    assert big.mean() > 0.3
+    assert np.all(np.abs(ratio - scale) < 2e-2), (ratio.min(), ratio.max())
     assert abs(float(np.median(ratio)) - float(scale)) < (1e-6 if precision == "fp32" else 1e-4)
     n2 = int(big.sum())
     rate2 = float((big & kept2).sum()) / n2
