@@ -497,6 +497,65 @@ def main():
             r["tf32_peak_measured"] = tf32_peak
             r["frac_of_tf32_peak"] = r["achieved"] / tf32_peak
 
+    # ---------------------------------------------------------------------------------------------------
+    # single-user latency path (reference src/recommend.py:245-341): side measurement, one GPU
+    # ---------------------------------------------------------------------------------------------------
+    latency = None
+    if rank == 0 and world == 1 and not args.no_train:
+        from newsrecommendationsystem_b200.recommend import Recommender
+        from newsrecommendationsystem_b200 import ops
+        rng = np.random.default_rng(77)
+        n_rows = NEWS_PER_GPU + 1
+        table = torch.randn(n_rows, 300, device=dev) * 0.4
+        table[-1] = 0
+        rec = Recommender(model, [f"N{i}" for i in range(n_rows - 1)], table)
+        hist = rng.integers(0, n_rows, 50).astype(np.int32)
+        latency = dict(what="user vector from 50 cached news vectors + scores of C candidates + ranking, one user per call "
+                            "(nrms_recommend_user: two cluster launches, FP32)", n_table_rows=n_rows)
+        for Cn in (37, 300):
+            cand = rng.integers(0, n_rows, Cn).astype(np.int32)
+            hist_d, cand_d = torch.from_numpy(hist).to(dev), torch.from_numpy(cand).to(dev)
+            ue = model.user_encoder
+            w = (*ue.multihead_self_attention.packed(), ue.additive_attention.linear.weight, ue.additive_attention.linear.bias,
+                 ue.additive_attention.attention_query_vector)
+
+            def call_dev():
+                return ops.recommend_user(table, hist_d, cand_d, *w)
+
+            def call_host():
+                return rec.recommend_rows(hist, cand)[0].cpu()       # host indices in, ranked positions back on the host
+
+            def timed(fn, n, wall):
+                for _ in range(10):
+                    fn()
+                torch.cuda.synchronize()
+                if wall:
+                    t0 = time.perf_counter()
+                    for _ in range(n):
+                        fn()
+                    torch.cuda.synchronize()
+                    return (time.perf_counter() - t0) / n * 1e6
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(n):
+                    fn()
+                b.record()
+                torch.cuda.synchronize()
+                return a.elapsed_time(b) * 1e3 / n
+            side = torch.cuda.Stream()
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    call_dev()
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                call_dev()
+            latency[f"C={Cn}"] = dict(device_us_graph_replay=timed(graph.replay, 200, False),
+                                      call_us_device_indices=timed(call_dev, 200, False),
+                                      e2e_us_host_indices_to_host_ranking=timed(call_host, 200, True))
+        del rec, table
+        torch.cuda.empty_cache()
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         news, imp = make_data(1)
@@ -521,7 +580,7 @@ def main():
                     e2e=dict(value=head["e2e_value"], unit="impressions/s", h2d_bytes_per_step=head["h2d_bytes"],
                              d2h_bytes_per_step=64, ms_per_step=head["e2e_ms_per_step"]),
                     gpu_launches=head["launches"], roofline=roof, roofline_news=roof_news, roofline_score=roof_score,
-                    cpu_baseline=cpu, train=train, train_ln=train_ln, stage_ms=st, metrics=head["metrics"],
+                    cpu_baseline=cpu, train=train, train_ln=train_ln, recommend_latency=latency, stage_ms=st, metrics=head["metrics"],
                     stage_note="news_encode = this rank's titles (incl. the embedding-table projection) + the fp16 pack; news = "
                                "what follows it in the news stage: the NCCL all-gather of the fp16 table and the pad rows",
                     news_per_s=head["n_news"] / ((st.get("news", float("nan")) + st.get("news_encode", 0.0)) / 1e3),

@@ -81,15 +81,23 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler (converged MMA issue)
   const int n_tiles = (N + TG_BN - 1) / TG_BN;
   const int64_t m_tiles = (M + TG_BM - 1) / TG_BM;
-  const int64_t total_tiles = m_tiles * n_tiles * k_splits;   // work items: K split fastest
-  constexpr int BK = F16 ? 2 * TG_BK : TG_BK;          // elements per 128-byte K chunk
-  constexpr int KSTEP = F16 ? 16 : 8;                  // elements per MMA
-  const int all_chunks = (K + BK - 1) / BK;
-  // chunk range of work item w (the host guarantees every split is non-empty)
-  auto chunk_range = [&](int64_t w, int& c0, int& c1) {
-    c0 = (int)(w % k_splits) * chunks_per_split;
-    c1 = c0 + chunks_per_split;
-    if (c1 > all_chunks) c1 = all_chunks;
+  // Work items: a CTA takes ROW BLOCKS (m tile, K split) round-robin and walks ALL n tiles of each one back to back.
+  // (Round 2, from the ncu captures of the training GEMMs: with items dealt out singly, w = blockIdx + k * grid and
+  // n = w % n_tiles, a grid of 148 CTAs and N = 300 (n tiles of 256 and 44 columns) gave every even CTA only wide tiles and
+  // every odd CTA only the 44-column slivers -- half the SMs idle -- and the two n tiles of a row block drifted apart in
+  // time, so the A row block came from DRAM twice: 903 MB read for a 507 MB operand.)
+  // With under half a wave of row blocks (the user-encoder GEMMs: 50 m tiles) the host launches one CTA per (row block,
+  // n tile) instead and the n tiles are dealt out singly again (gridDim > row blocks tells the kernel).
+  const int64_t total_rb = m_tiles * k_splits;
+  const int ng = total_rb >= (int64_t)gridDim.x ? n_tiles : 1;          // n tiles walked back to back by one CTA
+  const int64_t total_groups = total_rb * (n_tiles / ng);
+  const int64_t my_groups = (int64_t)blockIdx.x < total_groups ? (total_groups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t my_items = my_groups * ng;
+  auto item_w = [&](int64_t i) -> int64_t {
+    const int64_t grp = blockIdx.x + (i / ng) * gridDim.x;
+    const int64_t rb = ng == 1 ? grp / n_tiles : grp;
+    const int64_t n = ng == 1 ? grp % n_tiles : i % ng;
+    return ((rb / k_splits) * n_tiles + n) * k_splits + (rb % k_splits);      // K split fastest, as chunk_range expects
   };
 
   if (tid == 0) {
@@ -113,7 +121,8 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // ------------------------------ TMA producer ---------------------------------------
     if (lane == 0) {
       uint32_t it = 0;
-      for (int64_t w = blockIdx.x; w < total_tiles; w += gridDim.x) {
+      for (int64_t i = 0; i < my_items; ++i) {
+        const int64_t w = item_w(i);
         const int64_t t = w / k_splits;
         const int m0 = (int)(t / n_tiles) * TG_BM;
         const int n0 = (int)(t % n_tiles) * TG_BN;
@@ -135,7 +144,8 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const uint32_t el = elect_one_u32();
     const uint64_t desc0 = umma_desc_k_sw128(0);
     uint32_t it = 0, tile_it = 0;
-    for (int64_t w = blockIdx.x; w < total_tiles; w += gridDim.x, ++tile_it) {
+    for (int64_t i = 0; i < my_items; ++i, ++tile_it) {
+      const int64_t w = item_w(i);
       const int64_t t = w / k_splits;
       const int n0 = (int)(t % n_tiles) * TG_BN;
       int n_valid = N - n0;
@@ -175,7 +185,8 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // ------------------------------ epilogue (warps 2..5) ------------------------------
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     uint32_t tile_it = 0;
-    for (int64_t w = blockIdx.x; w < total_tiles; w += gridDim.x, ++tile_it) {
+    for (int64_t i = 0; i < my_items; ++i, ++tile_it) {
+      const int64_t w = item_w(i);
       const int64_t t = w / k_splits;
       const int64_t m0 = (t / n_tiles) * TG_BM;
       const int n0 = (int)(t % n_tiles) * TG_BN;
@@ -548,8 +559,9 @@ static int tc_gemm_launch(const void* A, int64_t lda, const void* B, int64_t ldb
   if (k_splits > chunks) k_splits = chunks;
   const int cps = (chunks + k_splits - 1) / k_splits;
   k_splits = (chunks + cps - 1) / cps;            // every split owns at least one chunk
-  const int64_t items = tiles * k_splits;
+  int64_t items = ((M + TG_BM - 1) / TG_BM) * k_splits;     // row blocks (m tile, K split): see the kernel
   int grid = num_sms();
+  if (2 * items < grid) items *= (N + TG_BN - 1) / TG_BN;    // under half a wave of row blocks: n tiles dealt out singly
   if (items < grid) grid = (int)items;
   if (epi == TC_EPI_STORE_F16_TMA)
     tc_gemm_nt_kernel<true, true><<<grid, TG_THREADS, TG_SMEM_TMA, st>>>(ta, tb, tcm, bias, C, ldc, M, N, K, stage_tx, k_splits,
@@ -574,8 +586,10 @@ int tc_gemm_nt(const float* A, int64_t lda, const float* B, int64_t ldb, const f
 
 // number of K splits that fills the machine for an [M,N] output (weight gradients: few tiles, very long K)
 int tc_gemm_auto_splits(int64_t M, int N, int K) {
-  const int64_t tiles = ((M + TG_BM - 1) / TG_BM) * ((N + TG_BN - 1) / TG_BN);
-  int64_t s = (num_sms() + tiles - 1) / tiles;
+  // row blocks (m tile, K split) are the unit a CTA takes: one wave of them, rounded down so that no CTA gets a second
+  const int64_t m_tiles = (M + TG_BM - 1) / TG_BM;
+  (void)N;
+  int64_t s = num_sms() / m_tiles;
   const int chunks = (K + TG_BK - 1) / TG_BK;
   if (s > chunks / 8) s = chunks / 8;             // keep the main loop long enough to amortise the epilogue
   return s < 1 ? 1 : (int)s;

@@ -20,7 +20,7 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-pytestmark = [pytest.mark.gpu,
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(240),
               pytest.mark.skipif(not torch.cuda.is_available() or torch.cuda.device_count() < 2,
                                  reason="needs two GPUs (gpurun --gpus 2)")]
 
@@ -57,7 +57,7 @@ def _data():
     return news, imp
 
 
-def _eval_worker(rank, world, port, q):
+def _eval_worker(rank, world, port, out_path):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world)
@@ -68,25 +68,24 @@ def _eval_worker(rank, world, port, q):
         host = EvalHost(news, imp["hist_rows"], imp["cand_offsets"], imp["cand_rows"], imp["labels"])
         means = evaluate_tensors(_model(dev), EvalInputs.from_host(host, dev, shard=True))
         if rank == 0:
-            q.put([float(x) for x in means])
+            np.save(out_path, np.asarray([float(x) for x in means]))
     finally:
         dist.destroy_process_group()
 
 
-def test_evaluate_two_ranks_equals_one_rank():
+def test_evaluate_two_ranks_equals_one_rank(tmp_path):
     from newsrecommendationsystem_b200.evaluate import EvalHost, EvalInputs, evaluate_tensors
     dev = torch.device("cuda", 0)
     news, imp = _data()
     host = EvalHost(news, imp["hist_rows"], imp["cand_offsets"], imp["cand_rows"], imp["labels"])
     one = [float(x) for x in evaluate_tensors(_model(dev), EvalInputs.from_host(host, dev))]
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    mp.spawn(_eval_worker, args=(2, _free_port(), q), nprocs=2, join=True)
-    two = q.get(timeout=60)
+    out_path = str(tmp_path / "means.npy")          # results travel through files: a Queue.put of a large array blocks the
+    mp.spawn(_eval_worker, args=(2, _free_port(), out_path), nprocs=2, join=True)      # child until the parent reads
+    two = np.load(out_path)
     np.testing.assert_allclose(two, one, rtol=0, atol=1e-9)      # same kernels on the same rows: only the fp64 sum order differs
 
 
-def _train_worker(rank, world, port, q):
+def _train_worker(rank, world, port, out_path):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world)
@@ -100,8 +99,8 @@ def _train_worker(rank, world, port, q):
         torch.cuda.synchronize()
         if rank == 0:
             # after the step flat_grad holds the all-reduced SUM of the ranks' gradients; the Adam kernel applied 1/world
-            q.put((ts.optimizer.flat_grad.detach().cpu().numpy() / world,
-                   ts.optimizer.flat_param.detach().cpu().numpy()))
+            np.savez(out_path, g=ts.optimizer.flat_grad.detach().cpu().numpy() / world,
+                     p=ts.optimizer.flat_param.detach().cpu().numpy())
     finally:
         dist.destroy_process_group()
 
@@ -113,17 +112,17 @@ def _train_batch():
     return t
 
 
-def test_data_parallel_step_equals_full_batch_step():
+def test_data_parallel_step_equals_full_batch_step(tmp_path):
     from newsrecommendationsystem_b200.train import TrainStep
     dev = torch.device("cuda", 0)
     ts = TrainStep(_model(dev, train=True), lr=1e-4)
     ts.step_tokens(torch.from_numpy(_train_batch()), 5)
     torch.cuda.synchronize()
     g1, p1 = ts.optimizer.flat_grad.detach().cpu().numpy(), ts.optimizer.flat_param.detach().cpu().numpy()
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    mp.spawn(_train_worker, args=(2, _free_port(), q), nprocs=2, join=True)
-    g2, p2 = q.get(timeout=60)
+    out_path = str(tmp_path / "dp.npz")
+    mp.spawn(_train_worker, args=(2, _free_port(), out_path), nprocs=2, join=True)
+    z = np.load(out_path)
+    g2, p2 = z["g"], z["p"]
     # averaged two-rank gradient == full-batch gradient (TF32 contractions and fp32 atomics: up to summation order)
     scale = float(np.abs(g1).max())
     assert float(np.abs(g1 - g2).max()) <= 2e-4 * scale, float(np.abs(g1 - g2).max()) / scale
