@@ -99,6 +99,15 @@ tc_gemm_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const int64_t n = ng == 1 ? grp % n_tiles : i % ng;
     return ((rb / k_splits) * n_tiles + n) * k_splits + (rb % k_splits);      // K split fastest, as chunk_range expects
   };
+  constexpr int BK = F16 ? 2 * TG_BK : TG_BK;          // elements per 128-byte K chunk
+  constexpr int KSTEP = F16 ? 16 : 8;                  // elements per MMA
+  const int all_chunks = (K + BK - 1) / BK;
+  // chunk range of work item w (the host guarantees every split is non-empty)
+  auto chunk_range = [&](int64_t w, int& c0, int& c1) {
+    c0 = (int)(w % k_splits) * chunks_per_split;
+    c1 = c0 + chunks_per_split;
+    if (c1 > all_chunks) c1 = all_chunks;
+  };
 
   if (tid == 0) {
     for (int s = 0; s < TG_STAGES; ++s) {
