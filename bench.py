@@ -76,6 +76,14 @@ class ClockSampler:
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             pass
+        # wait for the first sample: nvidia-smi takes ~1 s to initialise NVML (on every GPU of the box), and that
+        # initialisation stalls kernel launches of ALL ranks -- started right in front of the timed loop it cost the
+        # 8-GPU line 0.6 ms per step on the ranks that waited for rank 0 (e2e, timed later, was faster than resident)
+        t0 = time.time()
+        while self.p is not None and time.time() - t0 < 5.0:
+            if os.path.getsize(self.f.name) > 0:
+                break
+            time.sleep(0.05)
 
     def stop(self):
         if self.p is None:
@@ -300,10 +308,13 @@ def main():
         # the attention launches are bracketed with CUDA events in BOTH loops (same instrumentation; the events are
         # created and pooled during the warm-up)
         lib.nrms_set_option(b"time_k1", 1)
+        # the clock sampler is up and past its NVML initialisation BEFORE the warm-up; it samples through the warm-up, the
+        # timed resident loop and the timed e2e loop
+        sampler = ClockSampler(local_rank) if (rank == 0 and sample_clocks) else None
+        barrier()
         for _ in range(warmup):
             timed_eval(inputs)
         barrier()
-        sampler = ClockSampler(local_rank) if (rank == 0 and sample_clocks) else None
         lib.nrms_set_option(b"time_k1", 1)
         l0 = lib.nrms_launch_count()
         times, means = [], None
