@@ -303,6 +303,10 @@ def main():
             if record_stages:
                 for (n0, a), (n1, b) in zip(marks[:-1], marks[1:]):
                     stage.setdefault(n1, []).append(a.elapsed_time(b))
+                # what the marks do not cover: up to the first mark, and from the last one to the end of the step (the
+                # 8-double all-reduce, where a rank waits for the slowest one, and the read-back of the means)
+                stage.setdefault("pre", []).append(e0.elapsed_time(marks[0][1]))
+                stage.setdefault("allreduce_readback", []).append(marks[-1][1].elapsed_time(e1))
             return e0.elapsed_time(e1), means
 
         # the attention launches are bracketed with CUDA events in BOTH loops (same instrumentation; the events are
@@ -310,7 +314,7 @@ def main():
         lib.nrms_set_option(b"time_k1", 1)
         # the clock sampler is up and past its NVML initialisation BEFORE the warm-up; it samples through the warm-up, the
         # timed resident loop and the timed e2e loop
-        sampler = ClockSampler(local_rank) if (rank == 0 and sample_clocks) else None
+        sampler = ClockSampler(local_rank) if (rank == 0 and sample_clocks and not os.environ.get("NRMS_BENCH_NO_SAMPLER")) else None
         barrier()
         for _ in range(warmup):
             timed_eval(inputs)
@@ -335,11 +339,19 @@ def main():
         clocks = sampler.stop() if sampler else None
         total_ms = max_over_ranks(float(np.sum(times)))
         e2e_ms = max_over_ranks(float(np.sum(e2e_times)))
+        rank_stage = None
+        if world > 1:       # every rank's own stage means: names the rank / stage the others wait for
+            mine = {k: round(float(np.mean(v)), 4) for k, v in stage.items()}
+            for kk, (kms, kn, _) in kstat.items():
+                if kn > 0:
+                    mine[f"{kk}_us_per_launch"] = round(1e3 * kms / kn, 1)
+            rank_stage = [None] * world
+            dist.all_gather_object(rank_stage, mine)
         res = dict(workload=workload, n_news=int(host.n_news), n_impressions=int(n_imp_total),
                    n_candidates=int(host.cand_offsets_host[-1]), ms_per_step=total_ms / steps,
                    value=n_imp_total * steps / (total_ms / 1e3), e2e_ms_per_step=e2e_ms / steps,
                    e2e_value=n_imp_total * steps / (e2e_ms / 1e3), h2d_bytes=int(h2d[0]),
-                   stage_ms={k: float(np.mean(v)) for k, v in stage.items()},
+                   stage_ms={k: float(np.mean(v)) for k, v in stage.items()}, stage_ms_per_rank=rank_stage,
                    metrics=dict(zip(("auc", "mrr", "ndcg5", "ndcg10"), means)), launches=launches, kstat=kstat, clocks=clocks)
         if world > 1:
             # N ranks == 1 rank: rank 0 evaluates the WHOLE workload alone (outside every timed region)
@@ -577,7 +589,7 @@ def main():
             out = dict(n_gpus=world, news=r["n_news"], impressions=r["n_impressions"], candidates=r["n_candidates"],
                        ms_per_step=r["ms_per_step"], value=r["value"], unit="impressions/s",
                        e2e=dict(value=r["e2e_value"], ms_per_step=r["e2e_ms_per_step"], h2d_bytes_per_step=r["h2d_bytes"]),
-                       stage_ms=r["stage_ms"], metrics=r["metrics"])
+                       stage_ms=r["stage_ms"], stage_ms_per_rank=r.get("stage_ms_per_rank"), metrics=r["metrics"])
             for k in ("metrics_1rank", "metrics_match_1rank"):
                 if k in r:
                     out[k] = r[k]
@@ -591,7 +603,8 @@ def main():
                     e2e=dict(value=head["e2e_value"], unit="impressions/s", h2d_bytes_per_step=head["h2d_bytes"],
                              d2h_bytes_per_step=64, ms_per_step=head["e2e_ms_per_step"]),
                     gpu_launches=head["launches"], roofline=roof, roofline_news=roof_news, roofline_score=roof_score,
-                    cpu_baseline=cpu, train=train, train_ln=train_ln, recommend_latency=latency, stage_ms=st, metrics=head["metrics"],
+                    cpu_baseline=cpu, train=train, train_ln=train_ln, recommend_latency=latency, stage_ms=st,
+                    stage_ms_per_rank=head.get("stage_ms_per_rank"), metrics=head["metrics"],
                     stage_note="news_encode = this rank's titles (incl. the embedding-table projection) + the fp16 pack; news = "
                                "what follows it in the news stage: the NCCL all-gather of the fp16 table and the pad rows",
                     news_per_s=head["n_news"] / ((st.get("news", float("nan")) + st.get("news_encode", 0.0)) / 1e3),
