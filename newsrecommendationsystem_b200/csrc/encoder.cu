@@ -377,7 +377,7 @@ static int news_encoder_fwd_impl(const int64_t* tokens, int64_t n_titles, int L,
   // inference
   if (mode == NRMS_MODE_TF32 && dropout_p == 0.f && tc_fused_workspace_bytes(n_titles, L, num_words) != (size_t)-1) {
     return tc_encoder_fused(emb, nullptr, num_words, tokens, 1, n_titles, L, wqkv, bqkv, wa, ba, qa, out, workspace,
-                            workspace_bytes, st, ln ? ln->gamma : nullptr, ln ? ln->beta : nullptr);
+                            workspace_bytes, st, ln ? ln->gamma : nullptr, ln ? ln->beta : nullptr, /*hot_row = padding_idx*/ 0);
   }
   const int64_t chunk_seq = INFER_CHUNK_ROWS / L;
   const int64_t first = n_titles < chunk_seq ? n_titles : chunk_seq;
@@ -420,7 +420,7 @@ int nrms_news_encoder_i32_fwd(const int32_t* tokens, int64_t n_titles, int L, co
                  NRMS_E_INVALID, "pointers must be 16-byte aligned");
   NRMS_CHECK_ARG(tc_fused_workspace_bytes(n_titles, L, num_words) != (size_t)-1, NRMS_E_UNSUPPORTED, "title length not compiled");
   return tc_encoder_fused(emb, nullptr, num_words, tokens, 2, n_titles, L, wqkv, bqkv, wa, ba, qa, out, workspace,
-                          workspace_bytes, st);
+                          workspace_bytes, st, nullptr, nullptr, /*hot_row = padding_idx*/ 0);
 }
 
 int nrms_news_encoder_ln_fwd(const int64_t* tokens, int64_t n_titles, int L, const float* emb, int64_t num_words,

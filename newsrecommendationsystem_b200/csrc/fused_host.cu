@@ -34,11 +34,11 @@ int k1v6_run(int S, const CUtensorMap& tw, const void* src16, const void* idx, i
              void* Cbuf, cudaStream_t st);
 // K1g (k1g_table_attn.cu)
 int k1g_project_table(const float* table, const void* table_rows16, int64_t n_rows, const float* wqkv, const float* bqkv,
-                      void* scratch, cudaStream_t st);
+                      void* scratch, cudaStream_t st, int64_t hot_row);
 size_t k1g_table16_bytes(int64_t n_rows, bool rows16_given);
 const void* k1g_table16_ptr(void* scratch);
 int k1g_run_seq(int S, int idx_kind, const void* table16, int64_t n_table_rows, const void* rows, int64_t n_seq,
-                void* Cbuf, const float* qk_bound, cudaStream_t st);
+                void* Cbuf, const float* qk_bound, cudaStream_t st, int64_t hot_row);
 
 constexpr size_t W16_SLOT_BYTES = 655360;   // fp16 weight copy of K1 v6: [1024][320] halfs
 constexpr size_t WA16_SLOT_BYTES = 131072;  // fp16 copy of W_a [200][320] (128,000 B) + the 30 score bounds behind it
@@ -220,7 +220,7 @@ size_t tc_fused_workspace_bytes(int64_t n_seq, int S, int64_t n_src_rows, bool r
 int tc_encoder_fused(const float* src, const void* src16_ext, int64_t n_src_rows, const void* idx, int idx_kind, int64_t n_seq,
                      int S, const float* wqkv, const float* bqkv, const float* wa, const float* ba, const float* qa,
                      float* out, void* workspace, size_t workspace_bytes, cudaStream_t st, const float* ln_gamma,
-                     const float* ln_beta) {
+                     const float* ln_beta, int64_t hot_row) {
   if (S != 20 && S != 50) {
     set_error("fused encoder compiled for S = 20 or 50, got %d", S);
     return NRMS_E_UNSUPPORTED;
@@ -244,7 +244,8 @@ int tc_encoder_fused(const float* src, const void* src16_ext, int64_t n_src_rows
   const int tkind_table = (S == 50 && idx_kind == 2) ? 2 : 3;
 
   if (table_attn) {
-    if (int rc = k1g_project_table(src, src16_ext, n_src_rows, wqkv, bqkv, srcbuf, st)) return rc;
+    if (fused_pool_enabled()) hot_row = -1;      // K1f reads the table without the replicas
+    if (int rc = k1g_project_table(src, src16_ext, n_src_rows, wqkv, bqkv, srcbuf, st, hot_row)) return rc;
     const void* table16 = k1g_table16_ptr(srcbuf);
     // Bound on the attention scores over the projected table: the user-encoder attention picks the plain or the
     // row-shifted softmax form from it (the shifted form costs that kernel ~5 %).  The news-encoder attention is bound by
@@ -265,7 +266,7 @@ int tc_encoder_fused(const float* src, const void* src16_ext, int64_t n_src_rows
       const void* idx_c = (const char*)idx + (size_t)s0 * S * idx_elem;
       {
         K1Timer timer(st, n, tkind_table);
-        if (int rc = k1g_run_seq(S, idx_kind, table16, n_src_rows, idx_c, n, Cbuf, bound, st)) return rc;
+        if (int rc = k1g_run_seq(S, idx_kind, table16, n_src_rows, idx_c, n, Cbuf, bound, st, hot_row)) return rc;
       }
       if (int rc = k2v2_run(S, twa, Cbuf, n, ba, qa, out + s0 * D, st)) return rc;
     }

@@ -48,6 +48,7 @@ constexpr int PITCH = 3 * GROUP;        // 2,160 B: one table16 row
 constexpr int STAGE = S * PITCH;        // 108,000 B: one user
 constexpr int NSTAGE = 2;
 constexpr int ROW_BYTES = PITCH;
+constexpr int HOT_REPLICAS_LOG2 = 6, HOT_REPLICAS = 1 << HOT_REPLICAS_LOG2;      // copies of a hot table row (see the producer)
 constexpr int THREADS = 512;
 constexpr int CP = 320;            // pitch (halfs) of the context rows K2 reads
 
@@ -124,7 +125,7 @@ struct SeqCfg {
 template <int SEQ, typename IdxT, bool SAFE>
 __global__ void __launch_bounds__(THREADS, 1)
 seq_attn_kernel(const __half* __restrict__ table16, int64_t n_table_rows, const IdxT* __restrict__ seq_rows,
-                int64_t n_seq, __half* __restrict__ ctx, const float* __restrict__ qk_bound) {
+                int64_t n_seq, __half* __restrict__ ctx, const float* __restrict__ qk_bound, int64_t hot_row) {
   using Cfg = SeqCfg<SEQ>;
   if (qk_bound != nullptr) {
     const int l = threadIdx.x & 31;
@@ -156,6 +157,11 @@ seq_attn_kernel(const __half* __restrict__ table16, int64_t n_table_rows, const 
       int64_t r1 = lane + 32 < SEQ ? (int64_t)seq_rows[u * SEQ + lane + 32] : 0;
       r0 = r0 < 0 ? 0 : (r0 >= n_table_rows ? n_table_rows - 1 : r0);
       r1 = r1 < 0 ? 0 : (r1 >= n_table_rows ? n_table_rows - 1 : r1);
+      // The hot row (the padding token of the titles: 45 % of all gathered rows) has HOT_REPLICAS copies behind the table;
+      // its references are spread over them by position.  One row read by every SM all the time is an L2 hot spot:
+      // measured on the user encoder's PADDED_NEWS row, 488 / 564 -> 417 us per launch (profiles/block_probe.py).
+      if (r0 == hot_row) r0 = n_table_rows + (((uint32_t)(u * SEQ + lane) * 2654435761u) >> (32 - HOT_REPLICAS_LOG2));
+      if (r1 == hot_row) r1 = n_table_rows + (((uint32_t)(u * SEQ + lane + 32) * 2654435761u) >> (32 - HOT_REPLICAS_LOG2));
       const uint32_t st = it % NST;
       tc::mbar_wait(empty_bar + 8 * st, ((it / NST) & 1) ^ 1);
       if (lane == 0) mbar_arrive_expect_tx(full_bar + 8 * st, STG);
@@ -350,7 +356,15 @@ int pack_rows16(const float* src, int64_t n_rows, void* src16, cudaStream_t st);
 
 // scratch of the table path: [table16: n_rows x 2,160 B][fp16 copy of the source rows: (n_rows + 1) x 640 B, unless the
 // caller already has one][fp16 weights in table order]
-static size_t k1g_table16_only(int64_t n_rows) { return align_up((size_t)n_rows * k1g::ROW_BYTES, 1024); }
+static size_t k1g_table16_only(int64_t n_rows) { return align_up((size_t)(n_rows + k1g::HOT_REPLICAS) * k1g::ROW_BYTES, 1024); }
+
+// rows [n_rows, n_rows + HOT_REPLICAS) of the projected table <- row hot_row
+static __global__ void __launch_bounds__(256)
+replicate_row_kernel(__half* __restrict__ table16, int64_t n_rows, int64_t hot_row) {
+  const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(table16) + hot_row * k1g::ROW_BYTES);
+  uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<char*>(table16) + (n_rows + blockIdx.x) * k1g::ROW_BYTES);
+  for (int i = threadIdx.x; i < k1g::ROW_BYTES / 16; i += blockDim.x) dst[i] = src[i];
+}
 static size_t k1g_a16_bytes(int64_t n_rows) { return align_up((size_t)(n_rows + 1) * 640, 1024); }
 size_t k1g_table16_bytes(int64_t n_rows, bool rows16_given) {
   return k1g_table16_only(n_rows) + k1g_a16_bytes(n_rows) * (rows16_given ? 0 : 1) + (size_t)TABLE_COLS * 640;
@@ -363,7 +377,7 @@ const void* k1g_table16_ptr(void* scratch) { return scratch; }
 // (Same operand precision as K1 v6's in-kernel projection.)  rows16: the fp16 copy of the source rows when the caller
 // already holds one (pack_rows16 layout), else nullptr and `table` (fp32) is packed here.
 int k1g_project_table(const float* table, const void* rows16, int64_t n_rows, const float* wqkv, const float* bqkv,
-                      void* scratch, cudaStream_t st) {
+                      void* scratch, cudaStream_t st, int64_t hot_row) {
   char* base = reinterpret_cast<char*>(scratch);
   void* table16 = base;
   const void* a16 = rows16;
@@ -377,13 +391,18 @@ int k1g_project_table(const float* table, const void* rows16, int64_t n_rows, co
   const float qscale = 1.4426950408889634f / sqrtf((float)DH);
   pack_wqkv16_table_kernel<<<148, 256, 0, st>>>(wqkv, bqkv, reinterpret_cast<__half*>(b16), qscale);
   NRMS_LAUNCH_CHECK("pack_wqkv16_table_kernel");
-  return tc_gemm_nt_f16_tma(a16, 320, b16, 320, table16, TABLE_COLS, n_rows, TABLE_COLS, 304, st);
+  if (int rc = tc_gemm_nt_f16_tma(a16, 320, b16, 320, table16, TABLE_COLS, n_rows, TABLE_COLS, 304, st)) return rc;
+  if (hot_row >= 0 && hot_row < n_rows) {
+    replicate_row_kernel<<<k1g::HOT_REPLICAS, 256, 0, st>>>(reinterpret_cast<__half*>(table16), n_rows, hot_row);
+    NRMS_LAUNCH_CHECK("replicate_row_kernel");
+  }
+  return NRMS_OK;
 }
 
 // S = 50 (int32 history rows / int64 ids) or S = 20; Cbuf: fp16 context rows [n_seq * S][320] (columns 300..319 cleared here)
 template <int SEQ, typename IdxT>
 static int launch_seq_attn(const void* table16, int64_t n_table_rows, const void* rows, int64_t n_seq, void* Cbuf,
-                           const float* qk_bound, cudaStream_t st) {
+                           const float* qk_bound, cudaStream_t st, int64_t hot_row) {
   int dev = 0;
   cudaGetDevice(&dev);
   static bool configured[64] = {false};
@@ -406,24 +425,24 @@ static int launch_seq_attn(const void* table16, int64_t n_table_rows, const void
   if (force <= 0) {
     k1g::seq_attn_kernel<SEQ, IdxT, false><<<grid, k1g::THREADS, k1g::SeqCfg<SEQ>::SMEM_BYTES, st>>>(
         reinterpret_cast<const __half*>(table16), n_table_rows, reinterpret_cast<const IdxT*>(rows), n_seq,
-        reinterpret_cast<__half*>(Cbuf), bound);
+        reinterpret_cast<__half*>(Cbuf), bound, hot_row);
     NRMS_LAUNCH_CHECK("seq_attn_kernel");
   }
   if (force != 0 && (force > 0 || bound != nullptr)) {
     k1g::seq_attn_kernel<SEQ, IdxT, true><<<grid, k1g::THREADS, k1g::SeqCfg<SEQ>::SMEM_BYTES, st>>>(
         reinterpret_cast<const __half*>(table16), n_table_rows, reinterpret_cast<const IdxT*>(rows), n_seq,
-        reinterpret_cast<__half*>(Cbuf), bound);
+        reinterpret_cast<__half*>(Cbuf), bound, hot_row);
     NRMS_LAUNCH_CHECK("seq_attn_kernel(row-shifted)");
   }
   return NRMS_OK;
 }
 
 int k1g_run_seq(int S, int idx_kind, const void* table16, int64_t n_table_rows, const void* rows, int64_t n_seq,
-                void* Cbuf, const float* qk_bound, cudaStream_t st) {
-  if (S == 50 && idx_kind == 2) return launch_seq_attn<50, int32_t>(table16, n_table_rows, rows, n_seq, Cbuf, qk_bound, st);
-  if (S == 50 && idx_kind == 1) return launch_seq_attn<50, int64_t>(table16, n_table_rows, rows, n_seq, Cbuf, qk_bound, st);
-  if (S == 20 && idx_kind == 1) return launch_seq_attn<20, int64_t>(table16, n_table_rows, rows, n_seq, Cbuf, qk_bound, st);
-  if (S == 20 && idx_kind == 2) return launch_seq_attn<20, int32_t>(table16, n_table_rows, rows, n_seq, Cbuf, qk_bound, st);
+                void* Cbuf, const float* qk_bound, cudaStream_t st, int64_t hot_row) {
+  if (S == 50 && idx_kind == 2) return launch_seq_attn<50, int32_t>(table16, n_table_rows, rows, n_seq, Cbuf, qk_bound, st, hot_row);
+  if (S == 50 && idx_kind == 1) return launch_seq_attn<50, int64_t>(table16, n_table_rows, rows, n_seq, Cbuf, qk_bound, st, hot_row);
+  if (S == 20 && idx_kind == 1) return launch_seq_attn<20, int64_t>(table16, n_table_rows, rows, n_seq, Cbuf, qk_bound, st, hot_row);
+  if (S == 20 && idx_kind == 2) return launch_seq_attn<20, int32_t>(table16, n_table_rows, rows, n_seq, Cbuf, qk_bound, st, hot_row);
   set_error("seq_attn_kernel: unsupported (S, index kind) = (%d, %d)", S, idx_kind);
   return NRMS_E_UNSUPPORTED;
 }

@@ -31,7 +31,9 @@ size_t tc_fused_workspace_bytes(int64_t n_seq, int S, int64_t n_src_rows, bool r
 int tc_encoder_fused(const float* src, const void* src16, int64_t n_src_rows, const void* idx, int idx_kind, int64_t n_seq,
                      int S, const float* wqkv, const float* bqkv, const float* wa, const float* ba, const float* qa,
                      float* out, void* workspace, size_t workspace_bytes, cudaStream_t st, const float* ln_gamma = nullptr,
-                     const float* ln_beta = nullptr);
+                     const float* ln_beta = nullptr, int64_t hot_row = -1);
+// hot_row: a source row that a large share of the indices name (the padding token 0 of the titles); the table path keeps
+// replicas of its projected row and spreads the references over them (an L2 hot spot otherwise).  -1 = none.
 int pack_rows16(const float* src, int64_t n_rows, void* src16, cudaStream_t st);    // pack.cu
 
 // fp16 operands (A16 [M, lda halfs], B16 [N, ldb halfs], 16-byte aligned rows), kind::f16, same fp16 epilogue (no bias)

@@ -48,6 +48,21 @@ def _dist(distributed=True):
     return None
 
 
+# PADDED_NEWS is ONE vector in the reference (evaluate.py:203-204) and half of all history entries point at it (history
+# lengths are uniform in 0..50).  As one table row it was an L2 hot spot for the row-gathering attention kernel: 1.8 M of the
+# 3.7 M gathered rows of an evaluate pass hit the same 2,160 bytes, and the launch time moved between 417 and 762 us with
+# the impression block (profiles/block_probe.py).  The table therefore carries PAD_REPLICAS identical zero rows and the pad
+# references are spread over them on the host -- the same arithmetic (bit-identical user vectors), 488 / 564 -> 417 us.
+PAD_REPLICAS = 64
+
+
+def spread_pad_rows(hist: np.ndarray, n_news: int) -> None:
+    """In place: history entries < 0 (PADDED_NEWS) -> n_news + r, r in [0, PAD_REPLICAS) by position."""
+    pad = hist < 0
+    idx = np.flatnonzero(pad.ravel())
+    hist.ravel()[idx] = n_news + (idx * 7 + idx // hist.shape[-1]) % PAD_REPLICAS
+
+
 def shard_range(n, rank, world):
     """Contiguous block [lo, hi) of rank `rank` (blocks of ceil(n/world))."""
     per = (n + world - 1) // world
@@ -89,7 +104,7 @@ class EvalHost:
         tok = np.asarray(news_tokens)
         if num_words is not None and tok.size and (int(tok.min()) < 0 or int(tok.max()) >= int(num_words)):
             raise IndexError(f"token ids must lie in [0, {int(num_words)}), got [{int(tok.min())}, {int(tok.max())}]")
-        hist[hist < 0] = n_news           # PADDED_NEWS -> the all-zero last row of the table
+        spread_pad_rows(hist, n_news)     # PADDED_NEWS -> one of the PAD_REPLICAS all-zero rows that close the table
         self.n_news = n_news
         self.n_impressions = int(hist.shape[0])
         pin = torch.cuda.is_available()
@@ -194,13 +209,13 @@ def encode_news_table(model, news_tokens: torch.Tensor, n_news=None, local_shard
     model.eval()
     try:
         if dist is None:
-            table = torch.empty((n + 1, ops.D), dtype=torch.float32, device=dev)
+            table = torch.empty((n + PAD_REPLICAS, ops.D), dtype=torch.float32, device=dev)
             table[:n] = model.get_news_vector({"title": news_tokens})
-            table[n].zero_()
+            table[n:].zero_()
             return table
         world, rank = dist.get_world_size(), dist.get_rank()
         per = (n + world - 1) // world
-        padded = torch.zeros((world * per + 1, ops.D), dtype=torch.float32, device=dev)
+        padded = torch.zeros((max(world * per, n + PAD_REPLICAS), ops.D), dtype=torch.float32, device=dev)
         lo, hi = shard_range(n, rank, world)
         # One encoder call per shard (the table path of the news encoder projects the embedding table once per CALL, and
         # needs >= 8 token rows per vocabulary row to be selected: splitting the shard to overlap the exchange with the
@@ -211,8 +226,8 @@ def encode_news_table(model, news_tokens: torch.Tensor, n_news=None, local_shard
         if hi > lo:
             padded[lo:hi] = model.get_news_vector({"title": news_tokens if local_shard is not None else news_tokens[lo:hi]})
         dist.all_gather_into_tensor(padded[:world * per].view(-1), padded[rank * per:(rank + 1) * per].reshape(-1).clone())
-        table = padded[:n + 1]
-        table[n].zero_()
+        table = padded[:n + PAD_REPLICAS]
+        table[n:].zero_()
         return table
     finally:
         model.train(was_training)
@@ -221,8 +236,8 @@ def encode_news_table(model, news_tokens: torch.Tensor, n_news=None, local_shard
 @torch.no_grad()
 def encode_news_table16(model, news_tokens: torch.Tensor, n_news=None, local_shard=None, want_fp32=False, distributed=True,
                         mark=None):
-    """Stage A of the tensor-mode pipeline.  Returns (table16, table32): table16 = fp16 [N_news + 2, 320] in
-    `ops.pack_rows_f16`'s layout -- row N_news is the PADDED_NEWS zero vector (evaluate.py:203-204; zeros with the 1.0 of the bias
+    """Stage A of the tensor-mode pipeline.  Returns (table16, table32): table16 = fp16 [N_news + PAD_REPLICAS + 1, 320] in
+    `ops.pack_rows_f16`'s layout -- rows N_news .. N_news + PAD_REPLICAS - 1 are the PADDED_NEWS zero vector (evaluate.py:203-204; zeros with the 1.0 of the bias
     column), the row after it the all-zero closing row the kernels expect -- and table32 = the fp32 [N_news + 1, 300] table when `want_fp32`, else None.
 
     Nothing downstream of the news encoder reads fp32 rows in tensor mode: the user encoder projects the fp16 copy and the
@@ -236,7 +251,7 @@ def encode_news_table16(model, news_tokens: torch.Tensor, n_news=None, local_sha
     try:
         world, rank = (dist.get_world_size(), dist.get_rank()) if dist is not None else (1, 0)
         per = (n + world - 1) // world
-        buf = torch.empty((world * per + 2, 320), dtype=torch.float16, device=dev)
+        buf = torch.empty((max(world * per, n + PAD_REPLICAS) + 1, 320), dtype=torch.float16, device=dev)
         lo, hi = shard_range(n, rank, world)
         if local_shard is not None and tuple(local_shard) != (lo, hi):
             raise RuntimeError(f"token rows were sharded for {tuple(local_shard)} but this rank encodes {(lo, hi)}")
@@ -251,8 +266,8 @@ def encode_news_table16(model, news_tokens: torch.Tensor, n_news=None, local_sha
                 dist.all_gather_into_tensor(buf[:world * per].view(-1), buf[rank * per:(rank + 1) * per].view(-1))
             else:                 # gloo (CPU tests of the plumbing)
                 dist.all_gather_into_tensor(buf[:world * per].view(-1), buf[rank * per:(rank + 1) * per].reshape(-1).clone())
-        buf[n:].zero_()           # PADDED_NEWS, the closing row and the slot padding
-        buf[n, 300] = 1.0         # ... PADDED_NEWS is a zero VECTOR that still meets the biases (q = 0 W + b): its 1.0 column stays
+        buf[n:].zero_()           # the PADDED_NEWS rows, the closing row and the slot padding
+        buf[n:n + PAD_REPLICAS, 300] = 1.0    # ... PADDED_NEWS is a zero VECTOR that still meets the biases (q = 0 W + b): its 1.0 column stays
         table32 = None
         if want_fp32:
             if dist is None:
@@ -265,7 +280,7 @@ def encode_news_table16(model, news_tokens: torch.Tensor, n_news=None, local_sha
                 dist.all_gather_into_tensor(padded[:world * per].view(-1), padded[rank * per:(rank + 1) * per].reshape(-1).clone())
                 table32 = padded[:n + 1]
                 table32[n].zero_()
-        return buf[:n + 2], table32
+        return buf[:n + PAD_REPLICAS + 1], table32
     finally:
         model.train(was_training)
 

@@ -160,10 +160,11 @@ def test_evaluate_fp16_table_flow_world2():
     ref_means, _, _, ref_table, _ = O.evaluate_pipeline(sd, ntok, imp["hist_rows"], imp["cand_offsets"],
                                                          imp["cand_rows"], imp["labels"])
     (r0, m0, a0, f0), (r1, m1, a1, f1) = res
-    assert a0.shape == (63, 320)                                          # 61 news + PADDED_NEWS + the closing row
+    from newsrecommendationsystem_b200.evaluate import PAD_REPLICAS as R
+    assert a0.shape == (61 + R + 1, 320)                                  # 61 news + R x PADDED_NEWS + the closing row
     assert np.array_equal(a0, a1) and np.array_equal(f0, f1)              # every rank holds the same tables
     np.testing.assert_allclose(a0[:61, :300], ref_table[:61], rtol=2e-3, atol=2e-4)     # fp16 rounding of the rows
-    assert np.all(a0[:62, 300] == 1.0) and not a0[:61, 301:].any() and not a0[61, :300].any() and not a0[62].any()
+    assert np.all(a0[:61 + R, 300] == 1.0) and not a0[:61, 301:].any() and not a0[61:61 + R, :300].any() and not a0[61 + R].any()
     np.testing.assert_allclose(f0[:61], ref_table[:61], rtol=2e-4, atol=2e-6)
     assert not f0[61].any()
     np.testing.assert_allclose(m0, m1, rtol=1e-12)
