@@ -14,6 +14,8 @@ modules (`/root/reference/src/model/NRMS`, torch CPU fp32 + autograd + torch.opt
 and `evaluate.calculate_single_user_metric`) run in the build container by
 `tests/golden/make_golden.py`; the resulting fixtures are committed under
 `tests/golden/` and `tests/test_oracle_golden.py` checks every function here against them.
+The restatements of model/Exp1 and of recommend.py's single-user arithmetic (end of this file) are pinned the same way
+by `tests/golden/make_golden_exp1.py` (live reference `Exp1` / `NRMS` modules) and `tests/test_exp1_recommend.py`.
 
 All `file:line` citations are relative to the reference tree (`/root/reference/`).
 The arithmetic itself lives in third-party, un-vendored PyTorch (requirements.txt:1,

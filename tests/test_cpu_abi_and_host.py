@@ -176,3 +176,24 @@ def test_checkpoint_keeps_the_dropout_stream_position(tmp_path):
     m2.news_encoder = type("E", (), {"dropout_seed": 1, "_dropout_calls": 0})()
     assert checkpoint.load_checkpoint(path, m2) == (7, 0.5)
     assert (m2.news_encoder.dropout_seed, m2.news_encoder._dropout_calls) == (0x5EED, 12345)
+
+
+def test_pad_references_are_spread_over_the_replica_rows():
+    """PADDED_NEWS is PAD_REPLICAS identical zero rows behind the news rows; EvalHost sends every pad (-1) to one of them
+    (an L2 hot spot otherwise) and leaves real rows alone."""
+    from newsrecommendationsystem_b200 import evaluate as E
+    rng = np.random.default_rng(0)
+    n_news = 37
+    hist = rng.integers(0, n_news, size=(200, 50)).astype(np.int64)
+    hist[np.arange(50)[None, :] < rng.integers(0, 51, size=200)[:, None]] = -1
+    ref = hist.copy()
+    tok = rng.integers(1, 90, size=(n_news, 20)).astype(np.int64)
+    offs = np.arange(0, 401, 2, dtype=np.int64)
+    host = E.EvalHost(tok, hist, offs, rng.integers(0, n_news, size=400), np.zeros(400, dtype=np.int8))
+    h = host.hist_rows.numpy()
+    assert np.array_equal(h[ref >= 0], ref[ref >= 0])
+    pads = h[ref < 0]
+    assert pads.min() >= n_news and pads.max() < n_news + E.PAD_REPLICAS
+    assert len(np.unique(pads)) == E.PAD_REPLICAS                       # all replicas are in use
+    assert np.bincount(pads - n_news).max() < 3 * len(pads) / E.PAD_REPLICAS     # and evenly
+    assert np.array_equal(hist, ref)                                    # the caller's array is not modified
