@@ -50,7 +50,7 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-// operand load.  The tiles arrive raw (cp.async); their warp rounds them to TF32 in place once (round_tiles: cvt.rna; a
+// operand load.  The tiles arrive raw (cp.async); their warp rounds them to TF32 in place once (warp_fetch: cvt.rna; a
 // bare fp32 pattern would be truncated by the tensor core) -- one conversion per element instead of one per fragment load
 __device__ __forceinline__ uint32_t ld(const float* p) { return __float_as_uint(*p); }
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {

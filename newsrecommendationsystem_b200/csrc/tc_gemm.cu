@@ -561,7 +561,6 @@ static int tc_gemm_launch(const void* A, int64_t lda, const void* B, int64_t ldb
     if (int rc = make_tmap_k_major(&tb, reinterpret_cast<const float*>(B), N, K, ldb, box_b)) return rc;
   }
   const uint32_t stage_tx = (uint32_t)(box_a + box_b) * TG_BK * 4;       // 128 bytes per row and chunk, either type
-  const int64_t tiles = ((M + TG_BM - 1) / TG_BM) * ((N + TG_BN - 1) / TG_BN);
   const int bk = f16_in ? 2 * TG_BK : TG_BK;
   const int chunks = (K + bk - 1) / bk;
   if (k_splits < 1) k_splits = 1;
