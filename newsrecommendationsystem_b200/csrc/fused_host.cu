@@ -250,11 +250,12 @@ int tc_encoder_fused(const float* src, const void* src16_ext, int64_t n_src_rows
     // Bound on the attention scores over the projected table: the user-encoder attention picks the plain or the
     // row-shifted softmax form from it (the shifted form costs that kernel ~5 %).  The news-encoder attention is bound by
     // its gather and runs the shifted form for free (measured 1.032 vs 1.033 ms per 65,238 titles): no bound pass there.
-    // The bound pass reads the whole projected table (2,160 B per row: 42 us at 65 k rows, 0.33 ms at the 522 k rows of the
-    // 8-GPU weak-scaling line); the shifted form costs the user kernel ~1 us per 1,000 users.  When the table is large
-    // against the call (multi-GPU evaluate: every rank holds ALL news but a 1/N share of the users) the pass is skipped
-    // and the shifted form runs unconditionally.
-    if (S == 50 && 2 * n_src_rows <= 3 * n_seq) {
+    // The bound pass reads the whole projected table (2,160 B per row: 42 us at 65 k rows, 84 us at 130 k, 0.33 ms at the
+    // 522 k rows of the 8-GPU weak-scaling line); the shifted form costs the user kernel ~2.8 us per 1,000 users (measured
+    // at 2 GPUs: 469 vs 418 us per 18,288-user launch).  Only when the table is very large against the call -- more than
+    // 5 rows per user: every rank of an 8-GPU evaluate holds ALL news but a 1/8 share of the users -- is the pass
+    // skipped and the shifted form run unconditionally.
+    if (S == 50 && n_src_rows <= 5 * n_seq) {
       if (int rc = k1f_qk_bound(table16, n_src_rows, bound, st)) return rc;
     } else {
       bound = nullptr;
