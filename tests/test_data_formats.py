@@ -1,0 +1,62 @@
+"""newsrecommendationsystem_b200/data.py against what the LIVE reference dataset classes make of the same files
+(tests/golden/make_golden_data.py: dataset.BaseDataset, evaluate.NewsDataset, evaluate.BehaviorsDataset): integer and
+string work, so everything is compared exactly."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+DATA = os.path.join(ROOT, "tests", "golden", "data")
+
+
+@pytest.fixture(scope="module")
+def gd():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "data_golden.npz"))
+    return {k: z[k] for k in z.files}
+
+
+def test_news_table_matches_reference_news_dataset(gd):
+    from newsrecommendationsystem_b200.data import load_news_parsed
+    news = load_news_parsed(os.path.join(DATA, "news_parsed.tsv"), ("title", "abstract", "category", "subcategory"))
+    assert news.ids == [str(x) for x in gd["news/ids"]]
+    assert np.array_equal(news.title, gd["news/titles"]) and news.title.dtype == np.int64
+    assert news.columns["abstract"].shape == (len(news), 50) and news.columns["category"].shape == (len(news),)
+    # the repeated id maps to its FIRST row (evaluate.py:197-201)
+    assert news.ids[9] == news.ids[2] and news.row_of[news.ids[9]] == 2
+    t = news.token_table_with_pad()
+    assert t.shape == (len(news) + 1, 20) and not t[-1].any()
+    with pytest.raises(ValueError):
+        load_news_parsed(os.path.join(DATA, "news_parsed.tsv"), ("title_entities",))
+
+
+def test_training_rows_reproduce_the_reference_minibatch_tensors(gd):
+    """cand_rows / hist_rows index the token table to exactly the title tensors BaseDataset.__getitem__ stacks
+    (first 50 clicks, left padding with the all-zero title, dataset.py:62-85)."""
+    from newsrecommendationsystem_b200.data import load_news_parsed, load_behaviors_parsed
+    news = load_news_parsed(os.path.join(DATA, "news_parsed.tsv"))
+    tr = load_behaviors_parsed(os.path.join(DATA, "behaviors_parsed.tsv"), news)
+    table = news.token_table_with_pad()
+    assert tr.cand_rows.shape == (7, 3) and tr.hist_rows.shape == (7, 50)
+    assert np.array_equal(table[tr.cand_rows], gd["train/cand_titles"])
+    assert np.array_equal(table[tr.hist_rows], gd["train/clicked_titles"])
+    assert np.array_equal(tr.clicked, np.tile(np.array([1, 0, 0], dtype=np.int8), (7, 1)))
+    assert (tr.hist_rows[0, :47] == len(news)).all() and (tr.hist_rows[2] < len(news)).all()      # 3 clicks / 64 clicks
+
+
+def test_evaluate_rows_match_reference_behaviors(gd):
+    from newsrecommendationsystem_b200.data import load_news_parsed, load_behaviors
+    from newsrecommendationsystem_b200.evaluate import EvalHost
+    news = load_news_parsed(os.path.join(DATA, "news_parsed.tsv"))
+    ev = load_behaviors(os.path.join(DATA, "behaviors.tsv"), news)
+    for k in ("hist_rows", "cand_offsets", "cand_rows", "labels"):
+        assert np.array_equal(getattr(ev, k), gd["eval/" + k]), k
+    assert ev.clicked_news_strings == [str(x) for x in gd["eval/keys"]]
+    assert (ev.hist_rows[0] == -1).all()                                    # empty history -> 50 x PADDED_NEWS
+    assert (ev.hist_rows[3] >= 0).all()                                     # 77 clicks -> the FIRST 50
+    # max_count: the reference breaks BEFORE the max_count-th impression (evaluate.py:247-249)
+    assert len(load_behaviors(os.path.join(DATA, "behaviors.tsv"), news, max_count=4).impression_ids) == 3
+    # and the tables feed the device-resident evaluate as they are
+    host = EvalHost(news.title, ev.hist_rows, ev.cand_offsets, ev.cand_rows, ev.labels, news_ids=news.ids)
+    assert host.n_impressions == 6 and host.n_news == len(news)
