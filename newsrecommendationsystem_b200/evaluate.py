@@ -361,3 +361,22 @@ def evaluate_tensors(model, inputs: EvalInputs, max_count=None, return_details=F
         return means, dict(table=table, user_vectors=user_vec, scores=scores, per_impression=per,
                            impression_range=(lo, hi))
     return means
+
+
+def evaluate(model, directory, num_workers=0, max_count=None):
+    """The reference's entry point (src/evaluate.py:171-272), same signature and return value: evaluate `model` on
+    `directory` (which holds `behaviors.tsv` and `news_parsed.tsv`) -> (AUC, MRR, nDCG@5, nDCG@10).  The files are read once
+    into integer tables (`data.py`); everything after that is the device-resident pipeline above.  `num_workers` (the
+    reference's metric process pool) is accepted and unused: the metrics run on the GPU.  `max_count` as in the reference
+    (`sys.maxsize` or None = all impressions)."""
+    import os
+    import sys
+    from . import data
+    news = data.load_news_parsed(os.path.join(directory, "news_parsed.tsv"))
+    ev = data.load_behaviors(os.path.join(directory, "behaviors.tsv"), news)
+    device = next(model.parameters()).device if hasattr(model, "parameters") else "cpu"
+    inputs = EvalInputs(news.title, ev.hist_rows, ev.cand_offsets, ev.cand_rows, ev.labels, news_ids=news.ids, device=device)
+    if max_count is not None and max_count >= sys.maxsize:
+        max_count = None
+    return evaluate_tensors(model, inputs, max_count=max_count)
+

@@ -60,3 +60,49 @@ def test_evaluate_rows_match_reference_behaviors(gd):
     # and the tables feed the device-resident evaluate as they are
     host = EvalHost(news.title, ev.hist_rows, ev.cand_offsets, ev.cand_rows, ev.labels, news_ids=news.ids)
     assert host.n_impressions == 6 and host.n_news == len(news)
+
+
+def test_evaluate_directory_entry_point_on_cpu_stub(gd, monkeypatch):
+    """evaluate(model, directory, num_workers, max_count) -- the reference's signature (evaluate.py:171-272) -- over the sample
+    files: file reading, first-wins ids, pad spreading and the pipeline plumbing, with the arithmetic of every stage supplied
+    by the oracle's torch port (CPU stand-ins of the library calls, as in test_distributed_cpu.py)."""
+    import sys
+    import torch
+    from newsrecommendationsystem_b200 import evaluate as E, ops, synthetic
+    from oracle import nrms_oracle as O
+    from test_distributed_cpu import _StubModel, _cpu_score_csr, _cpu_rank_metrics
+    monkeypatch.setattr(ops, "score_csr", _cpu_score_csr)
+    monkeypatch.setattr(ops, "rank_metrics", _cpu_rank_metrics)
+    sd = synthetic.init_state_dict(num_words=401, seed=1)
+    model = _StubModel(sd)
+    model.parameters = lambda: iter([torch.zeros(1)])
+    means = E.evaluate(model, DATA, num_workers=4, max_count=sys.maxsize)
+    # (the fixture's history / candidate rows already name the FIRST row of a repeated id)
+    ref_means = O.evaluate_pipeline(sd, gd["news/titles"], gd["eval/hist_rows"], gd["eval/cand_offsets"], gd["eval/cand_rows"],
+                                    gd["eval/labels"])[0]
+    np.testing.assert_allclose(means, ref_means, atol=1e-6)
+    means3 = E.evaluate(model, DATA, 0, max_count=4)                      # impressions 1..3 only
+    ref3 = O.evaluate_pipeline(sd, gd["news/titles"], gd["eval/hist_rows"], gd["eval/cand_offsets"], gd["eval/cand_rows"],
+                               gd["eval/labels"], max_count=4)[0]
+    np.testing.assert_allclose(means3, ref3, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision,atol", [("fp32", 1e-5), ("tf32", 2e-3)])
+def test_evaluate_directory_entry_point_on_gpu(gd, precision, atol):
+    """The same call on the CUDA path (both precision modes) against the oracle's evaluate walk."""
+    import torch
+    from newsrecommendationsystem_b200 import NRMS, NRMSConfig, evaluate as E, synthetic
+    from oracle import nrms_oracle as O
+
+    class Cfg(NRMSConfig):
+        num_words = 401
+    sd = synthetic.init_state_dict(num_words=401, seed=1)
+    m = NRMS(Cfg)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    m.to("cuda:0").eval().set_precision(precision)
+    means = E.evaluate(m, DATA, num_workers=4)
+    ref = O.evaluate_pipeline(sd, gd["news/titles"], gd["eval/hist_rows"], gd["eval/cand_offsets"], gd["eval/cand_rows"],
+                              gd["eval/labels"])[0]
+    np.testing.assert_allclose(means, ref, atol=atol)
+
