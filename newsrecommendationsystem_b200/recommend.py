@@ -11,8 +11,21 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+import csv
+import os
+
 from . import ops
-from .checkpoint import table_from_news2vector
+from .checkpoint import news2vector_from_table, table_from_news2vector
+
+
+def load_target_user(behaviors_path, target_user_id):
+    """The FIRST row of `target_user_id` in a raw `behaviors.tsv` (the reference keeps `.iloc[[0]]` of the user's rows,
+    src/recommend.py:100,159) -> (clicked news ids, impression strings).  An empty history is the reference's `' '`."""
+    with open(behaviors_path, newline="") as f:
+        for rec in csv.reader(f, delimiter="\t", quoting=csv.QUOTE_NONE):
+            if rec[1] == target_user_id:
+                return (rec[3] or " ").split(), rec[4].split()
+    raise KeyError(f"user {target_user_id!r} not found in {behaviors_path}")
 
 
 class Recommender:
@@ -33,6 +46,35 @@ class Recommender:
         """From the reference's cache file content (dict id -> vector + 'PADDED_NEWS', src/recommend.py:211-243)."""
         ids, table = table_from_news2vector(news2vector, device=device)
         return cls(model, ids, table)
+
+    @classmethod
+    def from_directory(cls, model, directory, device=None, batch=2048):
+        """`directory` as the reference's evaluate() takes it (src/recommend.py:197-243): `news2vector.pt` is loaded when it
+        exists, else the news of `news_parsed.tsv` are encoded (`model.get_news_vector`, batches of 2,048 titles) and the
+        cache is written in the reference's format (dict id -> vector + 'PADDED_NEWS')."""
+        from . import data
+        device = device or next(model.parameters()).device
+        cache = os.path.join(directory, "news2vector.pt")
+        if os.path.exists(cache):
+            return cls.from_news2vector(model, torch.load(cache, map_location="cpu", weights_only=False), device)
+        news = data.load_news_parsed(os.path.join(directory, "news_parsed.tsv"))
+        was_training = model.training
+        model.eval()
+        with torch.no_grad():
+            titles = torch.from_numpy(news.title)
+            vec = torch.cat([model.get_news_vector({"title": titles[s:s + batch]}).float().cpu()
+                             for s in range(0, len(news), batch)])
+        model.train(was_training)
+        table = torch.cat([vec, torch.zeros(1, vec.shape[1])])
+        torch.save(news2vector_from_table(news.ids, table), cache)
+        keep = [i for i, nid in enumerate(news.ids) if news.row_of[nid] == i]          # first occurrence of an id wins
+        return cls(model, [news.ids[i] for i in keep], torch.cat([vec[keep], torch.zeros(1, vec.shape[1])]).to(device))
+
+    def recommend_target_user(self, directory, target_user_id):
+        """What the reference's recommend.evaluate(model, directory, ..., target_user_id) returns (:338-340) for the user's
+        first behaviors row: (candidate ids by descending score, y = (score + 1) / 2 in that order)."""
+        clicked, impressions = load_target_user(os.path.join(directory, "behaviors.tsv"), target_user_id)
+        return self.recommend(clicked, impressions)
 
     def history_rows(self, clicked_news):
         """First 50 clicks, LEFT-padded with PADDED_NEWS (src/recommend.py:117-124 = evaluate.py:117-124)."""

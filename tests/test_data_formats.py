@@ -106,3 +106,46 @@ def test_evaluate_directory_entry_point_on_gpu(gd, precision, atol):
                               gd["eval/labels"])[0]
     np.testing.assert_allclose(means, ref, atol=atol)
 
+
+def test_load_target_user_takes_the_first_row(tmp_path):
+    from newsrecommendationsystem_b200.recommend import load_target_user
+    f = tmp_path / "behaviors.tsv"
+    f.write_text("1\tU1\tt\tN1 N2\tN3-0 N4-1\n2\tU2\tt\t\tN5-0\n3\tU1\tt\tN9\tN8-1\n")
+    assert load_target_user(str(f), "U1") == (["N1", "N2"], ["N3-0", "N4-1"])
+    assert load_target_user(str(f), "U2") == ([], ["N5-0"])
+    with pytest.raises(KeyError):
+        load_target_user(str(f), "U7")
+
+
+@pytest.mark.gpu
+def test_recommender_from_directory_and_cache_roundtrip(gd, tmp_path):
+    """Recommender.from_directory on the sample files: encodes the news, writes the reference's news2vector.pt, reloads it,
+    and ranks the first impression of a user like the oracle does."""
+    import shutil
+    import torch
+    from newsrecommendationsystem_b200 import NRMS, NRMSConfig, synthetic
+    from newsrecommendationsystem_b200.recommend import Recommender
+    from oracle import nrms_oracle as O
+
+    class Cfg(NRMSConfig):
+        num_words = 401
+    for name in ("news_parsed.tsv", "behaviors.tsv"):
+        shutil.copy(os.path.join(DATA, name), tmp_path / name)
+    sd = synthetic.init_state_dict(num_words=401, seed=1)
+    m = NRMS(Cfg)
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    m.to("cuda:0").eval().set_precision("fp32")
+    rec = Recommender.from_directory(m, str(tmp_path))
+    cache = torch.load(tmp_path / "news2vector.pt", weights_only=False)
+    assert "PADDED_NEWS" in cache and not cache["PADDED_NEWS"].any() and len(cache) == len(set(gd["news/ids"].tolist())) + 1
+    rec2 = Recommender.from_directory(m, str(tmp_path))                     # now from the cache file
+    table = O.evaluate_pipeline(sd, gd["news/titles"], gd["eval/hist_rows"][:0], gd["eval/cand_offsets"][:1],
+                                gd["eval/cand_rows"][:0], gd["eval/labels"][:0])[3]
+    for r in (rec, rec2):
+        ids, y = r.recommend_target_user(str(tmp_path), "U3")              # impression 4: 77 clicks -> the first 50
+        a, b = int(gd["eval/cand_offsets"][3]), int(gd["eval/cand_offsets"][4])
+        _, y_ref, order_ref = O.recommend_user(sd, table, np.where(gd["eval/hist_rows"][3] < 0, len(table) - 1,
+                                                                   gd["eval/hist_rows"][3]), gd["eval/cand_rows"][a:b])
+        np.testing.assert_allclose(y, y_ref[order_ref], atol=1e-5)
+        assert len(ids) == b - a
+
