@@ -203,7 +203,9 @@ def run_reference(args, rank):
     line = dict(impl="reference", metric="evaluate impressions/s", value=v, unit="impressions/s", n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * IMPRESSIONS_PER_GPU / v,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=workload_config(args.gpus, "cpu"),
+                # the same `config` as the B200 arm prints (it names the WORKLOAD; this arm's own arithmetic is `dtype` f32 and
+                # `cpu_baseline.kind`): the driver compares the two dictionaries
+                config=workload_config(args.gpus, args.precision),
                 cpu_baseline=dict(value=v, unit="impressions/s", cores=last["cores"], kind="port", sample=last["sample"]),
                 e2e=dict(value=v, unit="impressions/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
