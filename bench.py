@@ -207,7 +207,10 @@ def run_reference(args, rank):
                 # `cpu_baseline.kind`): the driver compares the two dictionaries
                 config=workload_config(args.gpus, args.precision),
                 cpu_baseline=dict(value=v, unit="impressions/s", cores=last["cores"], kind="port", sample=last["sample"]),
-                e2e=dict(value=v, unit="impressions/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+                e2e=dict(value=v, unit="impressions/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                # a step is a BOUNDED SAMPLE of the workload: `value` is the sample's rate, `ms_per_step` the time a full pass
+                # would take at that rate (extrapolated), `sample_wall_s_per_step` what a step really took here
+                extrapolated=True, sample_wall_s_per_step=float(np.mean([x[1] for x in vals])))
     print(json.dumps(line), flush=True)
 
 
