@@ -197,3 +197,35 @@ def test_pad_references_are_spread_over_the_replica_rows():
     assert len(np.unique(pads)) == E.PAD_REPLICAS                       # all replicas are in use
     assert np.bincount(pads - n_news).max() < 3 * len(pads) / E.PAD_REPLICAS     # and evenly
     assert np.array_equal(hist, ref)                                    # the caller's array is not modified
+
+
+def test_gemm_work_mapping_covers_every_tile_once():
+    """Restatement of the work mapping of csrc/tc_gemm.cu (host grid rule + the kernel's item_w): a CTA takes row blocks
+    (m tile, K split) and walks all n tiles of each -- or, under half a wave of row blocks, the n tiles are dealt out singly.
+    Every (m tile, n tile, split) must be visited exactly once for every shape the path uses."""
+    SM, BM, BN = 148, 128, 256
+
+    def visited(M, N, k_splits):
+        m_tiles, n_tiles = (M + BM - 1) // BM, (N + BN - 1) // BN
+        items = m_tiles * k_splits
+        grid = SM
+        if 2 * items < grid:
+            items *= n_tiles
+        grid = min(grid, items)
+        total_rb = m_tiles * k_splits
+        ng = n_tiles if total_rb >= grid else 1
+        total_groups = total_rb * (n_tiles // ng)
+        seen = []
+        for b in range(grid):
+            my_groups = (total_groups - b + grid - 1) // grid if b < total_groups else 0
+            for i in range(my_groups * ng):
+                grp = b + (i // ng) * grid
+                rb, n = (grp // n_tiles, grp % n_tiles) if ng == 1 else (grp, i % ng)
+                seen.append(((rb // k_splits) * n_tiles + n) * k_splits + rb % k_splits)
+        return sorted(seen), m_tiles * n_tiles * k_splits
+
+    for M in (1, 61, 128, 129, 1000, 6400, 9472, 65239, 140800, 900, 200):
+        for N in (16, 200, 256, 300, 900, 1080):
+            for ks in (1, 2, 10, 18, 74):
+                seen, total = visited(M, N, ks)
+                assert seen == list(range(total)), (M, N, ks)
